@@ -1,0 +1,180 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt from the REAL reference.
+
+Runs the unmodified reference classes (oracle/ref_shim.py) on seeded synthetic
+batches with the key-seeded weights of oracle/params.py and stores outputs and
+selected gradients.  Must be run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The composite "prefix + alignment head" case follows SURVEY.md 8(c): the ~30 glue
+lines of ChunkAlign_CLS_enc4_align.forward (v10:1032-1084) are restated here, while
+``global_enc`` (embeddings, img_embedding, LayerNorm, encoder, pooler), ``seq_enc``,
+``cls_ensemble``, ``cls_layer[i]``, ``classifier``, ``cls_loss_fct`` and
+``binary_to_mp`` are the reference objects, unchanged.  With P=0 the composite is
+checked against ``model(**batch)`` bit-for-bit before anything is written."""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import params      # noqa: E402
+import ref_shim    # noqa: E402
+import modcr_b200  # noqa: E402,F401
+from modcr_b200 import synth  # noqa: E402
+
+GRAD_KEYS = [
+    "classifier.weight", "classifier.bias", "cls_ensemble.bias",
+    "cls_layer.0.cls_q_proj.bias", "cls_layer.2.align_k_proj.bias", "cls_layer.1.LayerNorm.weight",
+    "cls_layer.0.output.dense.bias",
+    "global_enc.encoder.layer.0.attention.self.query.bias",
+    "global_enc.encoder.layer.0.attention.self.key.bias",
+    "global_enc.encoder.layer.11.attention.self.value.bias",
+    "global_enc.encoder.layer.5.attention.output.LayerNorm.weight",
+    "global_enc.encoder.layer.5.output.dense.bias",
+    "global_enc.encoder.layer.3.intermediate.dense.bias",
+    "global_enc.img_embedding.bias", "global_enc.LayerNorm.weight",
+    "global_enc.embeddings.LayerNorm.bias", "global_enc.pooler.dense.bias",
+    "seq_enc.encoder.layer.0.attention.self.query.bias",
+    "seq_enc.encoder.layer.10.attention.self.query.bias",
+    "seq_enc.encoder.layer.10.attention.self.key.bias",
+    "seq_enc.encoder.layer.11.output.LayerNorm.bias",
+    "seq_enc.encoder.layer.2.attention.output.dense.bias",
+    "seq_enc.img_embedding.bias", "seq_enc.embeddings.LayerNorm.weight",
+    "seq_enc.embeddings.token_type_embeddings.weight",
+]
+GRAD_SLICES = {  # big tensors: keep a [rows, cols] corner
+    "global_enc.encoder.layer.0.attention.self.query.weight": (8, 64),
+    "global_enc.encoder.layer.11.output.dense.weight": (8, 64),
+    "seq_enc.encoder.layer.9.attention.self.value.weight": (8, 64),
+    "seq_enc.encoder.layer.0.intermediate.dense.weight": (8, 64),
+    "global_enc.img_embedding.weight": (8, 64),
+    "cls_layer.1.align_k_proj.weight": (8, 64),
+    "cls_ensemble.weight": (8, 64),
+    "global_enc.embeddings.position_embeddings.weight": (8, 64),
+}
+
+
+def build_reference(ns, seed):
+    cfg = ref_shim.make_config(ns)
+    g = ns.tfm.BertImgModel(cfg)
+    s = ns.v10.SeqBertImgModel(cfg)
+    m = ns.v10.ChunkAlign_CLS_enc4_align(g, s, 4)
+    sd = m.state_dict()
+    params.fill_params(sd, seed)
+    m.load_state_dict(sd)
+    m.eval()
+    return m
+
+
+def composite_forward(ns, m, b, prefix):
+    """Glue of v10:1032-1084 around the reference sub-objects; prefix-aware."""
+    T = b["input_ids"].size(1)
+    N = b["input_ids"].size(0)
+    ge = m.global_enc
+    input_mask = b["input_mask"]
+    emb = ge.embeddings(b["input_ids"], position_ids=None, token_type_ids=b["token_type_ids"])
+    ie = ge.dropout(ge.LayerNorm(ge.img_embedding(b["img_feat"])))
+    emb = torch.cat((emb, ie), 1)
+    hist, gmask = None, input_mask
+    if prefix is not None:
+        P = prefix.shape[1]
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(prefix.shape[0])]
+        gmask = torch.cat([torch.ones(N, P), input_mask], -1)
+    ext = (1.0 - gmask.unsqueeze(1).unsqueeze(2)) * -10000.0
+    enc = ge.encoder(emb, ext, head_mask=[None] * 12, encoder_history_states=hist)
+    global_output = enc[0]
+    global_CLS = ge.pooler(global_output)
+    img_mask = input_mask[:, T:]
+    seq_outputs, chunk_hidden_states = m.seq_enc(
+        b["input_ids"], img_feats=b["img_feat"], img_mask=img_mask, input_mask=input_mask,
+        attention_mask=b["chunk_attention_mask"], position_ids=None, token_type_ids=b["token_type_ids"],
+        head_mask=None, offsets=b["offsets"], gather_index=b["gather_index"])
+    chunk_CLS = seq_outputs[1]
+    CLS = m.cls_ensemble(torch.cat((global_CLS, chunk_CLS), -1))
+    x = torch.cat((global_output[:, 1:T], seq_outputs[0][:, 1:T], chunk_hidden_states[:, 1:T]), dim=1)
+    wm = (1.0 - input_mask[:, 1:T].unsqueeze(1)) * -10000.0
+    wm = torch.cat((wm, wm, wm), -1)
+    for layer in m.cls_layer:
+        CLS, _ = layer(x, CLS, wm)
+    logits = m.classifier(CLS)
+    label = b["label"]
+    loss_cls = m.cls_loss_fct(logits.view(-1, 2), label)
+    logit_expl = ns.v10.binary_to_mp(logits, m.num_labels)
+    pre = logit_expl.max(dim=-1)[1]
+    gold = torch.argmax(label.reshape(-1, m.num_labels), -1)
+    matched = pre == gold
+    aw = torch.stack(seq_outputs[2][-3:], dim=1).sum(1).sum(1)[:, :T, T:]
+    block = aw
+    aw = aw.masked_fill(aw == 0, -1e5)
+    aw = torch.nn.Softmax(dim=-1)(aw)
+    tl = b["total_label"][b["align_pos"] == 1].to(torch.int64)
+    wa = aw[b["align_pos"] == 1, :]
+    align_loss = m.cls_loss_fct(wa, tl)
+    correct = int((torch.argmax(wa, -1) == tl).sum().item())
+    return dict(loss_cls=loss_cls, matched=matched, align_loss=align_loss, correct=correct,
+                total_sum=int(tl.size(0)), logits=logits, logit_expl=logit_expl, pre=pre,
+                align_block=block, global_output=global_output, global_CLS=global_CLS,
+                seq_output=seq_outputs[0], chunk_CLS=chunk_CLS,
+                chunk_hidden_states=chunk_hidden_states, CLS=CLS)
+
+
+def run_case(ns, name, B, T, R, P, seed, wseed, region_pad=0):
+    m = build_reference(ns, wseed)
+    b = synth.make_batch(B=B, T=T, R=R, seed=seed, region_pad=region_pad)
+    prefix = None
+    if P > 0:
+        prefix = synth.make_prefix(12, P, 768, seed=seed + 1).requires_grad_(True)
+    # self-check of the glue at P=0 against the untouched model.forward
+    with torch.no_grad():
+        ref = m(b["input_ids"], b["img_feat"], input_mask=b["input_mask"], label=b["label"],
+                token_type_ids=b["token_type_ids"], offsets=b["offsets"],
+                chunk_attention_mask=b["chunk_attention_mask"], gather_index=b["gather_index"],
+                align_pos=b["align_pos"], total_label=b["total_label"])
+        comp = composite_forward(ns, m, b, None)
+    assert float((ref[0] - comp["loss_cls"]).abs()) == 0.0, "glue self-check (loss_cls)"
+    assert float((ref[2] - comp["align_loss"]).abs()) == 0.0, "glue self-check (align_loss)"
+    assert bool((ref[1] == comp["matched"]).all()) and ref[3] == comp["correct"] and ref[4] == comp["total_sum"]
+
+    m.zero_grad()
+    out = composite_forward(ns, m, b, prefix)
+    (out["loss_cls"] + out["align_loss"]).backward()
+    named = dict(m.named_parameters())
+    grads = {k: named[k].grad.clone() for k in GRAD_KEYS}
+    for k, (r, c) in GRAD_SLICES.items():
+        grads[k + "[:%d,:%d]" % (r, c)] = named[k].grad[:r, :c].clone()
+    if prefix is not None:
+        grads["prefix[:,:,::4]"] = prefix.grad[:, :, ::4].clone()
+    # word embedding grad rows of the ids actually used by sequence 0 (first 8)
+    ids0 = b["input_ids"][0, :8]
+    grads["global_enc.embeddings.word_embeddings.weight[ids0,:64]"] = \
+        named["global_enc.embeddings.word_embeddings.weight"].grad[ids0, :64].clone()
+    gold = dict(
+        meta=dict(B=B, T=T, R=R, P=P, seed=seed, wseed=wseed, region_pad=region_pad),
+        loss_cls=out["loss_cls"].detach(), align_loss=out["align_loss"].detach(),
+        matched=out["matched"], correct=out["correct"], total_sum=out["total_sum"],
+        logits=out["logits"].detach().clone(), logit_expl=out["logit_expl"].detach().clone(), pre=out["pre"].clone(),
+        align_block=out["align_block"].detach().clone(),
+        global_CLS=out["global_CLS"].detach().clone(), chunk_CLS=out["chunk_CLS"].detach().clone(),
+        CLS=out["CLS"].detach().clone(),
+        global_output_sub=out["global_output"].detach()[:, ::7, ::5].clone(),
+        seq_output_sub=out["seq_output"].detach()[:, ::7, ::5].clone(),
+        chunk_hidden_sub=out["chunk_hidden_states"].detach()[:, ::7, ::5].clone(),
+        grads=grads,
+    )
+    path = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(gold, path)
+    print(name, "loss_cls %.6f align_loss %.6f" % (float(gold["loss_cls"]), float(gold["align_loss"])),
+          "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    ns = ref_shim.load()
+    run_case(ns, "cfg1_prefix10", B=2, T=128, R=50, P=10, seed=88, wseed=0)
+    run_case(ns, "cfg1_noprefix", B=2, T=128, R=50, P=0, seed=88, wseed=0)
+    run_case(ns, "ragged_small", B=1, T=40, R=13, P=3, seed=5, wseed=1, region_pad=2)

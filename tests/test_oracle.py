@@ -1,0 +1,178 @@
+"""CPU tests of the oracle restatement: golden vectors produced by the REAL
+reference (oracle/make_golden.py), the real reference itself when it is present
+(build container), the state_dict surface, and the known-answer invariants of
+SURVEY.md section 4."""
+import math
+import os
+
+import pytest
+import torch
+
+import params
+import ref_shim
+import restate
+import statedict
+import modcr_b200  # noqa: F401
+from modcr_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CFG = restate.default_cfg()
+
+
+def _weights(seed):
+    return params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), seed)
+
+
+def _case(name):
+    g = torch.load(os.path.join(GOLD, name + ".pt"))
+    m = g["meta"]
+    b = synth.make_batch(B=m["B"], T=m["T"], R=m["R"], seed=m["seed"], region_pad=m["region_pad"])
+    prefix = synth.make_prefix(12, m["P"], 768, seed=m["seed"] + 1) if m["P"] > 0 else None
+    return g, b, prefix, _weights(m["wseed"])
+
+
+@pytest.mark.parametrize("name", ["ragged_small", "cfg1_prefix10", "cfg1_noprefix"])
+def test_restatement_matches_reference_golden(name):
+    g, b, prefix, sd = _case(name)
+    grad_names = [k for k in g["grads"] if "[" not in k]
+    for k in grad_names:
+        sd[k].requires_grad_(True)
+    if prefix is not None:
+        prefix.requires_grad_(True)
+    (loss_cls, matched, align_loss, correct, total), ex = restate.chunkalign_forward(sd, CFG, b, prefix)
+    # same torch ops on the same machine class: tight tolerances
+    assert abs(float(loss_cls) - float(g["loss_cls"])) < 1e-5
+    assert abs(float(align_loss) - float(g["align_loss"])) < 1e-5
+    assert bool((matched == g["matched"]).all())
+    assert correct == g["correct"] and total == g["total_sum"]
+    torch.testing.assert_close(ex["logits"], g["logits"], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(ex["align_block"], g["align_block"], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(ex["global_output"][:, ::7, ::5], g["global_output_sub"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(ex["seq_output"][:, ::7, ::5], g["seq_output_sub"], atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(ex["chunk_hidden_states"][:, ::7, ::5], g["chunk_hidden_sub"], atol=2e-5, rtol=1e-4)
+    if name == "ragged_small":  # backward too (small case keeps the CPU suite fast)
+        (loss_cls + align_loss).backward()
+        for k in grad_names:
+            torch.testing.assert_close(sd[k].grad, g["grads"][k], atol=2e-6, rtol=2e-3)
+        torch.testing.assert_close(prefix.grad[:, :, ::4], g["grads"]["prefix[:,:,::4]"], atol=2e-6, rtol=2e-3)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_restatement_matches_live_reference_and_state_dict_surface():
+    ns = ref_shim.load()
+    cfg = ref_shim.make_config(ns)
+    m = ns.v10.ChunkAlign_CLS_enc4_align(ns.tfm.BertImgModel(cfg), ns.v10.SeqBertImgModel(cfg), 4)
+    ref_keys = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ref_keys == dict(statedict.chunkalign_keys(CFG))
+    me = ns.v10.ChunkAlign_CLS_enc4_align_ensemble(ns.tfm.BertImgModel(cfg), ns.v10.SeqBertImgModel(cfg), 4)
+    assert {k: tuple(v.shape) for k, v in me.state_dict().items()} == dict(statedict.chunkalign_ensemble_keys(CFG))
+    sd = params.fill_params(m.state_dict(), 3)
+    m.load_state_dict(sd)
+    m.eval()
+    b = synth.make_batch(B=1, T=24, R=7, seed=3)
+    with torch.no_grad():
+        ref = m(b["input_ids"], b["img_feat"], input_mask=b["input_mask"], label=b["label"],
+                token_type_ids=b["token_type_ids"], offsets=b["offsets"],
+                chunk_attention_mask=b["chunk_attention_mask"], gather_index=b["gather_index"],
+                align_pos=b["align_pos"], total_label=b["total_label"])
+        (o, _) = restate.chunkalign_forward({k: v.clone() for k, v in sd.items()}, CFG, b, None)
+    assert float((ref[0] - o[0]).abs()) == 0.0 and float((ref[2] - o[2]).abs()) == 0.0
+    assert bool((ref[1] == o[1]).all()) and ref[3] == o[3] and ref[4] == o[4]
+    # ensemble head
+    sde = params.fill_params(me.state_dict(), 4)
+    me.load_state_dict(sde)
+    me.eval()
+    with torch.no_grad():
+        r2 = me(b["input_ids"], b["img_feat"], input_mask=b["input_mask"], label=b["label_onehot"],
+                token_type_ids=b["token_type_ids"], offsets=b["offsets"],
+                chunk_attention_mask=b["chunk_attention_mask"], gather_index=b["gather_index"],
+                align_pos=b["align_pos"], total_label=b["total_label"])
+        c2, al2 = restate.chunkalign_ensemble_forward({k: v.clone() for k, v in sde.items()}, CFG, b, None)
+    assert float((r2[0] - c2).abs().max()) == 0.0 and float((r2[1] - al2).abs()) == 0.0
+
+
+# ---- known-answer invariants, small shapes ----------------
+def _small():
+    sd = _weights(11)
+    b = synth.make_batch(B=1, T=20, R=6, seed=9)
+    return sd, b
+
+
+def test_masked_prefix_equals_no_prefix_and_live_prefix_differs():
+    sd, b = _small()
+    N, P = 4, 3
+    hist = [torch.randn(N, P, 768) * 0.5 for _ in range(12)]
+    with torch.no_grad():
+        base, _, _ = restate.global_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"], b["input_mask"],
+                                                b["img_feat"], None)
+        masked, _, _ = restate.global_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"],
+                                                  torch.cat([torch.zeros(N, P), b["input_mask"]], -1),
+                                                  b["img_feat"], hist)
+        live, _, _ = restate.global_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"],
+                                                torch.cat([torch.ones(N, P), b["input_mask"]], -1),
+                                                b["img_feat"], hist)
+    assert float((base - masked).abs().max()) == 0.0
+    assert float((base - live).abs().max()) > 1e-3
+
+
+def test_align_loss_near_log_R_and_block_bounds_and_phase_masks():
+    sd, b = _small()
+    with torch.no_grad():
+        (out, ex) = restate.chunkalign_forward(sd, CFG, b, None)
+        (s_out, _, att), _ = restate.seq_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"],
+                                                     b["chunk_attention_mask"], b["input_mask"], b["img_feat"],
+                                                     b["offsets"], b["gather_index"])
+    T, R = 20, 6
+    assert abs(float(out[2]) - math.log(R)) < 0.05
+    blk = ex["align_block"]
+    assert float(blk.sum(-1).max()) <= 36.0 + 1e-4 and float(blk.sum(-1).min()) > 0
+    for l in (9, 10, 11):   # image rows: identity only
+        p = att[l]
+        assert bool((torch.diagonal(p[:, :, T:, T:], dim1=-2, dim2=-1) == 1.0).all())
+        assert float(p[:, :, T:, :T].abs().max()) == 0.0
+    for l in (0, 1, 2):     # phase A: image->text exactly 0, text->text outside chunk exactly 0
+        p = att[l]
+        assert float(p[:, :, T:, :T].abs().max()) == 0.0
+        outside = (b["chunk_attention_mask"] == 0).unsqueeze(1).expand(-1, 12, -1, -1)
+        assert float(p[:, :, :T, :T][outside].abs().max()) == 0.0
+
+
+def test_singleton_chunks_make_chunk_mean_identity():
+    sd, b = _small()
+    N, T = b["input_ids"].shape
+    lens = b["input_mask"][:, :T].sum(-1).long()
+    b2 = dict(b)
+    b2["offsets"] = [[[t] for t in range(1, int(L) - 1)] for L in lens]
+    b2["gather_index"] = [torch.arange(int(L) - 2) for L in lens]
+    q = torch.randn(N, T + 6, 768)
+    assert float((restate.chunk_mean_queries(q, b2["offsets"], b2["gather_index"]) - q).abs().max()) == 0.0
+    assert float((restate.chunk_mean_queries(q, b["offsets"], b["gather_index"]) - q).abs().max()) > 0
+
+
+def test_choice_permutation_permutes_logits():
+    sd, b = _small()
+    perm = torch.tensor([2, 0, 3, 1])
+    b2 = dict(b)
+    for k in ("input_ids", "token_type_ids", "input_mask", "img_feat", "label", "chunk_attention_mask",
+              "total_label", "align_pos"):
+        b2[k] = b[k][perm]
+    b2["gather_index"] = [b["gather_index"][i] for i in perm.tolist()]
+    b2["offsets"] = [b["offsets"][i] for i in perm.tolist()]
+    with torch.no_grad():
+        _, e1 = restate.chunkalign_forward(sd, CFG, b, None)
+        _, e2 = restate.chunkalign_forward(sd, CFG, b2, None)
+    torch.testing.assert_close(e1["logit_expl"][0][perm], e2["logit_expl"][0], atol=1e-6, rtol=1e-5)
+
+
+def test_mc_scorers():
+    torch.manual_seed(0)
+    pooled = torch.randn(8, 16)
+    w, bias = torch.randn(1, 16), torch.randn(1)
+    onehot = torch.tensor([0, 1, 0, 0, 0, 0, 0, 1.0])
+    loss, logits = restate.abstract_scorer(pooled, w, bias, onehot)
+    ref = -(torch.log_softmax(logits, -1) * onehot.view(2, 4)).sum(-1).mean()
+    assert abs(float(loss - ref)) < 1e-6
+    w4, b4 = torch.randn(3, 64), torch.randn(3)
+    loss4, lg4 = restate.choice_flattened_scorer(pooled, w4, b4, torch.tensor([2, 0]))
+    assert lg4.shape == (2, 3) and float(loss4) > 0
