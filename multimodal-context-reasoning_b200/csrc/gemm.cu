@@ -1,0 +1,457 @@
+// Persistent, warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA for sm_100a.
+//
+//   C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )
+//
+// Operand storage ("major") is selected per operand:
+//   A K-major : A stored [M,K] row-major          A MN-major: A stored [K,M] row-major
+//   B K-major : B stored [N,K] row-major          B MN-major: B stored [K,N] row-major
+// which gives forward (K,K), dgrad (K,MN: dX = dY * W with W stored [out,in]) and
+// wgrad (MN,MN: dW = dY^T * X, contraction over the row dimension of both).
+//
+// Roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0  TMA producer for the A/B smem ring            (1 elected thread)
+//   warp 1  tcgen05.mma issuer, accumulators in TMEM      (1 elected thread)
+//   warp 2  TMEM allocator + TMA loader of the optional epilogue input tile
+//   warps 4-7 epilogue: tcgen05.ld -> bias / activation / residual-add / GELU' ->
+//           128B-swizzled smem -> TMA store (or TMA reduce-add for split-K fp32)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "gemm.h"
+
+#include <stdio.h>
+
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace modcr {
+
+struct GemmParams {
+  int M, N, K;
+  int kb_total;   // ceil(K / 64)
+  int kb_per;     // k-blocks per split
+  int split_k;
+  int m_tiles, n_tiles;
+  float alpha;
+  const float* bias;
+  int act;        // 0 none, 1 gelu(erf), 2 tanh
+  int in_op;      // 0 none, 1 add, 2 multiply by gelu'(in)
+  int reduce_add; // output through TMA reduce-add (fp32 accumulate in place)
+};
+
+template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+struct Cfg {
+  static constexpr int BM = 128, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B
+  static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
+  static constexpr int NCHUNK = BN / CHUNK_COLS;
+  static constexpr int OUT_BUFS = HAS_AUX ? 4 : 2;
+  static constexpr int IN_BUFS = HAS_IN ? 2 : 0;
+  static constexpr int EPI_BYTES = (OUT_BUFS + IN_BUFS) * CHUNK_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_MAX = 232448;  // 227 KB
+  static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+  static_assert(!(OUT_F32 && (HAS_AUX || HAS_IN)), "fp32 output has no aux / epilogue-input path");
+};
+
+struct TileCoord {
+  int m, n, kb0, kb1, split;
+};
+
+DEVINL TileCoord decode_tile(const GemmParams& p, int t) {
+  TileCoord c;
+  const int mn = p.m_tiles * p.n_tiles;
+  c.split = t / mn;
+  const int r = t - c.split * mn;
+  c.m = r / p.n_tiles;
+  c.n = r - c.m * p.n_tiles;
+  c.kb0 = c.split * p.kb_per;
+  c.kb1 = min(c.kb0 + p.kb_per, p.kb_total);
+  return c;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+            const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
+  using C = Cfg<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * C::A_BYTES;
+  uint8_t* sOut = sB + STAGES * C::B_BYTES;
+  uint8_t* sIn = sOut + C::OUT_BUFS * C::CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + C::IN_BUFS * C::CHUNK_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* infull = tempty + 2;
+  uint64_t* inempty = infull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (HAS_AUX) tma_prefetch_desc(&tmAux);
+    if (HAS_IN) tma_prefetch_desc(&tmIn);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+      mbar_init(&infull[i], 1);
+      mbar_init(&inempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * C::A_BYTES;
+          uint8_t* b_dst = sB + stage * C::B_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, tc.m * 128);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full[stage], tc.m * 128 + i * 64, kb * 64);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, tc.n * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(b_dst + i * 8192, &tmB, &full[stage], tc.n * BN + i * 64, kb * 64);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, t);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_base = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_desc = A_MN ? make_smem_desc(a_base + k * 2048, 8192, 1024)
+                                         : make_smem_desc(a_base + k * 32, 0, 1024);
+            const uint64_t b_desc = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024)
+                                         : make_smem_desc(b_base + k * 32, 0, 1024);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ epilogue-input loader
+    if (HAS_IN && lane == 0) {
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int c = 0; c < C::NCHUNK; ++c, ++cnt) {
+          const int ib = cnt & 1;
+          mbar_wait(&inempty[ib], ((cnt >> 1) & 1) ^ 1);
+          mbar_expect_tx(&infull[ib], C::CHUNK_BYTES);
+          tma_load_2d(sIn + ib * C::CHUNK_BYTES, &tmIn, &infull[ib], tc.n * BN + c * C::CHUNK_COLS, tc.m * 128);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp - 4;          // TMEM lane quarter == warp % 4
+    const int row = q * 32 + lane;   // row inside the 128-row tile
+    const bool issuer = (threadIdx.x == 128);
+    int it = 0;
+    uint32_t cnt = 0;  // chunk counter (selects smem buffers)
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, t);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
+#pragma unroll 1
+      for (int c = 0; c < C::NCHUNK; ++c, ++cnt) {
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * C::CHUNK_COLS;
+        float v[C::CHUNK_COLS];
+        {
+          uint32_t* r = reinterpret_cast<uint32_t*>(v);
+          tmem_ld_32x32(taddr, r);
+          if (!OUT_F32) tmem_ld_32x32(taddr + 32, r + 32);
+          tmem_ld_wait();
+        }
+        if (c == C::NCHUNK - 1) {  // accumulator fully read: hand the TMEM stage back
+          tc_fence_before();
+          mbar_arrive(&tempty[as]);
+        }
+        const int n0 = tc.n * BN + c * C::CHUNK_COLS;
+#pragma unroll
+        for (int j = 0; j < C::CHUNK_COLS; ++j) {
+          float x = v[j] * p.alpha;
+          if (add_bias && (n0 + j) < p.N) x += __ldg(p.bias + n0 + j);
+          v[j] = x;
+        }
+        const int ob = cnt & 1;
+        uint8_t* out_buf = sOut + ob * C::CHUNK_BYTES;
+        // make sure the TMA store that last used this buffer has finished reading it
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
+          uint8_t* aux_buf = sOut + (2 + ob) * C::CHUNK_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(aux_buf + sw128_offset(row, j)) = pk;
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = tanhf(v[j]);
+        }
+        if (HAS_IN) {
+          const int ib = cnt & 1;
+          mbar_wait(&infull[ib], (cnt >> 1) & 1);
+          const uint8_t* in_buf = sIn + ib * C::CHUNK_BYTES;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(in_buf + sw128_offset(row, j));
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16(w[e]);
+              if (p.in_op == 1) {
+                v[8 * j + 2 * e] += f.x;
+                v[8 * j + 2 * e + 1] += f.y;
+              } else {
+                v[8 * j + 2 * e] *= gelu_erf_grad(f.x);
+                v[8 * j + 2 * e + 1] *= gelu_erf_grad(f.y);
+              }
+            }
+          }
+          mbar_arrive(&inempty[ib]);
+        }
+        if (OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<float4*>(out_buf + sw128_offset(row, j)) = f4;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            *reinterpret_cast<uint4*>(out_buf + sw128_offset(row, j)) = pk;
+          }
+        }
+        fence_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          if (n0 < p.N) {
+            if (p.reduce_add)
+              tma_reduce_add_2d(&tmC, out_buf, n0, tc.m * 128);
+            else
+              tma_store_2d(&tmC, out_buf, n0, tc.m * 128);
+            if (HAS_AUX) tma_store_2d(&tmAux, sOut + (2 + ob) * C::CHUNK_BYTES, n0, tc.m * 128);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------- host
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+static int launch(const GemmDesc& g, cudaStream_t stream) {
+  using C = Cfg<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return MODCR_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB, tmC, tmAux, tmIn;
+  int rc;
+  // A
+  if (!A_MN) rc = make_tmap_2d(&tmA, g.A, 2, g.M, g.K, g.lda, 128, 64);
+  else       rc = make_tmap_2d(&tmA, g.A, 2, g.K, g.M, g.lda, 64, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d(&tmB, g.B, 2, g.N, g.K, g.ldb, BN, 64);
+  else       rc = make_tmap_2d(&tmB, g.B, 2, g.K, g.N, g.ldb, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmC, g.C, OUT_F32 ? 4 : 2, g.M, g.N, g.ldc, 128, C::CHUNK_COLS);
+  if (rc) return rc;
+  tmAux = tmC;
+  tmIn = tmC;
+  if (HAS_AUX) {
+    rc = make_tmap_2d(&tmAux, g.aux, 2, g.M, g.N, g.ldaux, 128, 64);
+    if (rc) return rc;
+  }
+  if (HAS_IN) {
+    rc = make_tmap_2d(&tmIn, g.epi_in, 2, g.M, g.N, g.ld_in, 128, 64);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.kb_total = (g.K + 63) / 64;
+  int split = g.split_k < 1 ? 1 : g.split_k;
+  if (split > p.kb_total) split = p.kb_total;
+  p.kb_per = (p.kb_total + split - 1) / split;
+  split = (p.kb_total + p.kb_per - 1) / p.kb_per;  // no empty splits
+  p.split_k = split;
+  p.m_tiles = (g.M + 127) / 128;
+  p.n_tiles = (g.N + BN - 1) / BN;
+  p.alpha = g.alpha;
+  p.bias = g.bias;
+  p.act = g.act;
+  p.in_op = g.in_op;
+  p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
+  const int total = p.m_tiles * p.n_tiles * p.split_k;
+  int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, tmIn, p);
+  return check_launch("gemm");
+}
+
+int gemm_split_k_heuristic(int M, int N, int K, int bn) {
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int kb = (K + 63) / 64;
+  const int sms = num_sms();
+  if (tiles >= sms) return 1;
+  int s = sms / tiles;
+  if (s > kb / 4) s = kb / 4;  // keep >= 4 k-blocks per split
+  return s < 1 ? 1 : s;
+}
+
+int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) {
+    set_error("gemm: bad shape M=%d N=%d K=%d", g.M, g.N, g.K);
+    return MODCR_ERR_SHAPE;
+  }
+  const bool has_aux = g.aux != nullptr;
+  const bool has_in = g.epi_in != nullptr && g.in_op != 0;
+  if (g.c_fp32) {
+    if (has_aux || has_in) {
+      set_error("gemm: fp32 output does not support aux / epilogue input");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    if (g.split_k > 1 && !g.accumulate) {
+      set_error("gemm: split-K requires accumulate=1 (output must be pre-initialised)");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    if (!g.a_mn && !g.b_mn) return launch<256, false, false, false, false, true>(g, stream);
+    if (!g.a_mn && g.b_mn) return launch<256, false, true, false, false, true>(g, stream);
+    if (g.a_mn && g.b_mn) return launch<256, true, true, false, false, true>(g, stream);
+    set_error("gemm: operand major combination (A MN-major, B K-major) not instantiated");
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  if (g.accumulate || g.split_k > 1) {
+    set_error("gemm: accumulate / split-K need an fp32 output");
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  if (g.a_mn) {
+    set_error("gemm: A MN-major is only instantiated for fp32 (wgrad) output");
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  if (!g.b_mn) {
+    if (has_aux && has_in) {
+      set_error("gemm: aux output and epilogue input together are not instantiated");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    if (has_aux) return launch<256, false, false, true, false, false>(g, stream);
+    if (has_in) return launch<256, false, false, false, true, false>(g, stream);
+    return launch<256, false, false, false, false, false>(g, stream);
+  } else {
+    if (has_aux) {
+      set_error("gemm: aux output with B MN-major is not instantiated");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    if (has_in) return launch<256, false, true, false, true, false>(g, stream);
+    return launch<256, false, true, false, false, false>(g, stream);
+  }
+}
+
+}  // namespace modcr
