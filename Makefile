@@ -16,7 +16,7 @@ build/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -Iinclude -c $< -o $@
 
 $(LIB): $(CU_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
 cuda_tests: build/test_gemm
 

@@ -1,0 +1,206 @@
+/* modcr_b200 -- C ABI of the B200-native (sm_100a) ModCR training / scoring hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference has no FFI
+ * layer (it is pure PyTorch); each entry point therefore names the reference *operator site* it
+ * replaces, and INTEGRATION.md shows the ctypes binding that the reference-side Python modules
+ * (modeling/modeling_bert.py, modeling/modeling_vcr_chunkalign_v10.py, modeling/modeling_utils.py)
+ * use to reach it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (including workspaces); nothing is
+ *     allocated or freed by the library; all work is enqueued on `stream` (a cudaStream_t);
+ *   - activations are bf16, row-major, 16-byte aligned; statistics, losses, masks and parameter
+ *     gradients are fp32; index tensors are int64 exactly as the reference batch contract
+ *     (Data/VCRChunkAlign.py:690-741) delivers them;
+ *   - return value 0 = success, negative = error (enum below); the text of the last error of the
+ *     calling thread is returned by modcr_last_error_string().  Shapes are validated BEFORE launch.
+ *     There is no CPU fallback: on a machine without an sm_100 device every compute entry fails.
+ */
+#ifndef MODCR_B200_H_
+#define MODCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODCR_VERSION 100 /* 0.1.0 */
+
+enum {
+  MODCR_OK = 0,
+  MODCR_ERR_SHAPE = -1,
+  MODCR_ERR_ALIGN = -2,
+  MODCR_ERR_ARCH = -3,
+  MODCR_ERR_CUDA = -4,
+  MODCR_ERR_DRIVER = -5,
+  MODCR_ERR_WORKSPACE = -6,
+  MODCR_ERR_UNSUPPORTED = -7
+};
+
+int modcr_version(void);
+const char* modcr_last_error_string(void);
+
+/* Workspace query.  op: 1 = prefix_attn_bwd {N,S,heads}; 2 = img_embed_ln {rows, feat_dim, H} */
+size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
+
+/* ---------------------------------------------------------------------------------------------
+ * tcgen05 GEMM with fused epilogues:  C[M,N] = epi(alpha * sum_k A[m,k] B[n,k])
+ * Replaces every nn.Linear on the path:
+ *   qkv_gemm        query/key/value        modeling/modeling_bert.py:38-44, v10:57-65
+ *   gemm_bias_res   BertSelfOutput.dense / BertOutput.dense + residual   a_transformers/modeling_bert.py:369-373, 447-451
+ *   gemm_bias_gelu  BertIntermediate       a_transformers/modeling_bert.py:434-437
+ *   pooler          BertPooler (tanh)      a_transformers/modeling_bert.py:640-646
+ *   img_embedding   modeling/modeling_transfomres.py:676-681
+ * and their dgrad / wgrad in the backward pass (autograd of the reference).
+ *   a_mn = 0: A stored [M,K];  a_mn = 1: A stored [K,M]      (same for B with N)
+ *   act: 0 none, 1 GELU(erf), 2 tanh;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in)
+ *   aux: optional bf16 copy of the pre-activation;  c_fp32 + accumulate / split_k: wgrad
+ */
+typedef struct modcr_gemm_desc {
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t lda, ldb, ldc;
+  int32_t a_mn, b_mn, c_fp32, accumulate, split_k;
+  int32_t M, N, K;
+  float alpha;
+  const float* bias;
+  int32_t act;
+  void* aux;
+  int64_t ldaux;
+  const void* epi_in;
+  int64_t ld_in;
+  int32_t in_op;
+} modcr_gemm_desc;
+int modcr_gemm(const modcr_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row maps: logical row m -> physical row (m / rows_per_seq) * seq_stride + row0 + m % rows_per_seq
+ * (rows_per_seq <= 0: identity).  Lets the embedding kernels write text rows [0,T) and region rows
+ * [T,S) of the concatenated [N,S,H] buffer directly (no torch.cat, modeling_transfomres.py:684). */
+typedef struct modcr_rowmap {
+  int32_t rows_per_seq, seq_stride, row0;
+} modcr_rowmap;
+
+/* LayerNorm over the last dim (H % 256 == 0, H <= 1024); BertSelfOutput/BertOutput/img LayerNorm. */
+int modcr_layernorm_fwd(const void* x, modcr_rowmap xmap, const float* gamma, const float* beta, void* y,
+                        modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H, float eps, void* stream);
+/* dbias (optional) receives sum_rows dx = bias gradient of the Linear that produced x. fp32 outputs accumulate. */
+int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, modcr_rowmap xmap, const float* mean,
+                        const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap, float* dgamma,
+                        float* dbeta, float* dbias, int32_t M, int32_t H, void* stream);
+
+/* BertEmbeddings.forward (a_transformers/modeling_bert.py:184-211): gather + sum + LayerNorm. */
+int modcr_txt_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
+                           const float* word, const float* type, const float* pos, const float* gamma,
+                           const float* beta, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t N,
+                           int32_t T, int32_t H, float eps, void* stream);
+int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* input_ids,
+                           const int64_t* token_type_ids, const int64_t* position_ids, const float* word,
+                           const float* type, const float* pos, const float* gamma, const float* mean,
+                           const float* rstd, float* dword, float* dtype, float* dpos, float* dgamma, float* dbeta,
+                           int32_t N, int32_t T, int32_t H, int64_t padding_idx, void* stream);
+
+/* img_embedding + LayerNorm (modeling_transfomres.py:676-681, v10:339-343):
+ *   packed = bf16(feats) zero-padded to Dpad (TMA needs 16-byte row strides; 2054 -> 2112)
+ *   pre    = packed W^T + bias            (tcgen05 GEMM; W is bf16 [H, Dpad])
+ *   y      = use_ln ? LN(pre) : pre       written through ymap
+ * Workspaces `packed` [rows, Dpad] and `pre` [rows, H] are kept for the backward pass. */
+int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t Dpad, const void* W,
+                           const float* bias, const float* gamma, const float* beta, int32_t use_ln, float eps,
+                           void* packed, void* pre, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t H,
+                           void* stream);
+/* dW_pad: fp32 [H, Dpad] (overwritten); dbias/dgamma/dbeta accumulate; dpre: bf16 [rows, H] workspace. */
+int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const void* pre,
+                           const float* mean, const float* rstd, const float* gamma, int32_t use_ln, void* dpre,
+                           float* dW_pad, float* dbias, float* dgamma, float* dbeta, int64_t rows, int32_t Dpad,
+                           int32_t H, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused prefix attention (CaptionBertSelfAttention.forward after the projections:
+ * modeling/modeling_bert.py:46-72, v10:80-104).  K/V = [prefix rows ; sequence rows], never
+ * concatenated in HBM.  mode: 0 key-bias only; 1 seq_enc layers 0-2; 2 seq_enc layers 9-11
+ * (v10:171-232).  head_dim = 64. */
+typedef struct modcr_attn_desc {
+  int32_t N, S, P, heads, T, mode;
+  float scale;
+  const void* qkv;        /* bf16 [N,S,3H] */
+  const void* pkv;        /* bf16 [N,P,2H] or NULL */
+  const float* kbias;     /* fp32 [N,P+S] additive key bias = (1-mask)*-10000 */
+  const uint32_t* cbits;  /* [N,T,cwords] chunk bit mask (modes 1/2) */
+  int32_t cwords;
+  void* ctx;              /* bf16 [N,S,H] */
+  float* lse;             /* fp32 [N,heads,S] */
+  float* probs_img;       /* fp32 [N,heads,T,S-T] or NULL */
+  const void* dctx;       /* backward: bf16 [N,S,H] */
+  const float* dalign;    /* backward: fp32 [N,T,S-T] or NULL */
+  void* dqkv;             /* backward: bf16 [N,S,3H] */
+  void* dpkv;             /* backward: bf16 [N,P,2H] */
+  float* dq_ws;           /* backward workspace, modcr_workspace_bytes(1, {N,S,heads}) */
+} modcr_attn_desc;
+int modcr_prefix_attn_fwd(const modcr_attn_desc* d, void* stream);
+int modcr_prefix_attn_bwd(const modcr_attn_desc* d, void* stream);
+
+/* Chunk-mean queries (v10:66-78), in place on columns [0,H) of the QKV buffer (row stride ld).
+ * chunk_id: int32 [N,T], -1 for tokens outside every chunk.  Self-adjoint: backward = same call on dQ. */
+int modcr_chunk_mean_q(void* q, int64_t ld, int32_t N, int32_t S, int32_t H, const int32_t* chunk_id, int32_t T,
+                       int32_t max_chunks, void* stream);
+
+/* Alignment loss (v10:982-987, 1071-1077).  probs: fp32 [nl,N,heads,T,R]; out[4] = {loss, M, correct, sum}. */
+int modcr_align_softmax_ce_fwd(const float* probs, int32_t nl, int32_t heads, const int64_t* align_pos,
+                               const int64_t* total_label, float* block, float* row_loss, float* out, int32_t N,
+                               int32_t T, int32_t R, void* stream);
+int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label,
+                               const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
+                               void* stream);
+
+/* ClsLayer2 attention pooling (v10:816-829). q bf16 [N,H], k bf16 [N,L,H], mask fp32 [N,L] additive. */
+int modcr_cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int32_t N,
+                            int32_t L, int32_t H, void* stream);
+int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk,
+                            int32_t N, int32_t L, int32_t H, void* stream);
+
+/* Fused multiple-choice classifier + cross-entropy (v10:1063-1069, 363-373;
+ * modeling/modeling_ensemble.py:511-536; modeling/modeling_bert.py:553-567, 690-710). */
+typedef struct modcr_scorer_desc {
+  const void* x;          /* bf16 [rows,K] */
+  const float* W;         /* fp32 [C,K] */
+  const float* b;         /* fp32 [C] or NULL */
+  int32_t rows, K, C, G;  /* CE over the view [rows*C/G, G] */
+  const int64_t* hard;    /* int64 [rows*C/G] or NULL */
+  const float* soft;      /* fp32 [rows*C/G, G] or NULL */
+  float* logits;          /* fp32 [rows,C] */
+  float* loss;            /* fp32 [1] */
+  float* mp;              /* optional fp32 [rows] = softmax(logits)[:,1]  (binary_to_mp) */
+  int64_t* pred;          /* optional int64 [rows/num_choice] */
+  uint8_t* matched;       /* optional uint8 [rows/num_choice] */
+  int32_t num_choice;
+  float gout;
+  void* dx;               /* backward: bf16 [rows,K] */
+  float* dW;              /* backward: fp32 [C,K], accumulates */
+  float* db;              /* backward: fp32 [C], accumulates */
+} modcr_scorer_desc;
+int modcr_mc_scorer_ce_fwd(const modcr_scorer_desc* d, void* stream);
+int modcr_mc_scorer_ce_bwd(const modcr_scorer_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small utilities of the path. */
+int modcr_cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int32_t cols,
+                   int64_t row_step, void* stream);
+int modcr_bf16_to_f32(const void* src, float* dst, int64_t n, int32_t accumulate, void* stream);
+int modcr_colsum(const void* x, int64_t ld, int32_t M, int32_t N, float* out, void* stream);
+int modcr_copy_rows(const void* src, int64_t src_seq_stride, int32_t srow0, void* dst, int64_t dst_seq_stride,
+                    int32_t drow0, int32_t nseq, int32_t nrows, int32_t H, int32_t accumulate, void* stream);
+int modcr_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
+int modcr_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+int modcr_key_bias(const float* mask, float* kbias, int64_t total, void* stream);
+int modcr_chunk_bits(const float* chunk_mask, uint32_t* bits, int32_t N, int32_t T, int32_t cwords, void* stream);
+int modcr_accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int32_t cols,
+                       int32_t accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODCR_B200_H_ */

@@ -1,0 +1,781 @@
+// Fused prefix self-attention for sm_100a (tcgen05 / TMEM / TMA), forward and backward.
+//
+// Replaces CaptionBertSelfAttention.forward (reference modeling/modeling_bert.py:34-75 and
+// modeling/modeling_vcr_chunkalign_v10.py:55-107) after the Q/K/V projections:
+//
+//     probs = softmax(Q K^T / sqrt(d) + mask)     K/V = [prefix rows ; sequence rows]
+//     ctx   = probs V
+//
+// * The learned prefix K/V rows ([N,P,2H], projected from `history_state`) and the sequence
+//   K/V rows (inside the fused [N,S,3H] QKV buffer) are TMA-loaded into ONE shared-memory
+//   tile ([prefix padded to 16 rows ; sequence]); the concatenation is never materialised
+//   in HBM.
+// * One CTA per (q-tile of 128 rows, head, sequence).  S = QK^T is one tcgen05.mma group
+//   (M=128, N=Kp<=512 in slices of <=256, K=64) into TMEM; 128 softmax threads own one row
+//   each (TMEM lane == row): pass 1 max, pass 2 exp/sum and bf16 P into 128B-swizzled shared
+//   memory, optional pass 3 stores the normalised text->region probabilities that feed the
+//   alignment loss (v10:982-987).  O = P V is a second tcgen05.mma group whose accumulator
+//   re-uses TMEM columns [0,64).
+// * The mask zoo of the chunk-aware encoder (v10:171-232) is evaluated in
+//   registers from compact inputs: an additive per-key bias vector, a per-row chunk bit mask
+//   and the mode; the additive -10000 semantics of the reference are reproduced exactly.
+// * Backward: one CTA per (head, sequence), K/V resident in shared memory, outer loop over
+//   128-key blocks, inner loop over 128-row q tiles (Q / dO streamed through a 2-stage TMA
+//   ring).  Per step: S and dP by tcgen05 into TMEM, P = exp(S - lse) and
+//   dS = P * (dP + dAlign - delta) * scale by the row threads into shared memory, then
+//   dV += P^T dO, dK += dS^T Q (accumulated in TMEM across q tiles) and dQ = dS K (flushed to
+//   an fp32 partial when there is more than one key block).
+#include "attn.h"
+
+#include <math.h>
+
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace modcr {
+
+typedef __nv_bfloat16 bf16;
+constexpr float NEG_BIAS = -10000.0f;
+
+struct AttnParams {
+  int N, S, P, Ppad, T, R, heads, H;
+  int Kp;      // key rows seen by the MMAs (multiple of 16): Ppad + round16(S); Ppad = round16(P)
+  int Krows;   // key rows resident in shared memory: Ppad + 64 * ceil(S / 64)
+  int nqt;     // 128-row q tiles
+  int nkb;     // 128-key blocks (backward)
+  int mode;
+  float scale;
+  const float* kbias;
+  const uint32_t* cbits;
+  int cwords;
+  float* lse;
+  float* probs_img;
+  const bf16* ctx;
+  const bf16* dctx;
+  const float* dalign;
+  bf16* dqkv;
+  bf16* dpkv;
+  float* dq_ws;
+};
+
+template <int W>
+DEVINL void tmem_ld_cols(uint32_t taddr, float* v) {
+  if (W == 32)
+    tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+  else
+    tmem_ld_32x16(taddr, reinterpret_cast<uint32_t*>(v));
+}
+
+// additive-mask semantics of SURVEY.md A.2; `sb` is the staged key bias (-inf marks a key
+// row that does not exist: prefix padding, rows >= S, MMA padding)
+template <int MODE>
+DEVINL float masked_score(float acc, float scale, float sb, int kk, int q, bool q_txt, int T, uint32_t w) {
+  float b = sb;
+  if (MODE != 0) {
+    if (kk < T)
+      b = q_txt ? (((w >> (kk & 31)) & 1u) ? 0.f : NEG_BIAS) : NEG_BIAS;
+    else if (MODE == 2 && !q_txt)
+      b = (kk == q) ? 0.f : NEG_BIAS;
+  }
+  return (sb == -INFINITY) ? -INFINITY : fmaf(acc, scale, b);
+}
+
+// stage the per-key bias of sequence n into shared memory, indexed by smem key row
+DEVINL void stage_bias(float* sBias, int count, const AttnParams& p, int n, int tid, int nthreads) {
+  for (int kk = tid; kk < count; kk += nthreads) {
+    float b = -INFINITY;
+    if (kk < p.P)
+      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + kk);
+    else if (kk >= p.Ppad && kk - p.Ppad < p.S)
+      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + p.P + (kk - p.Ppad));
+    sBias[kk] = b;
+  }
+}
+
+// TMA-load the K and V tiles of (n, head): [prefix rows padded to Ppad ; sequence rows]
+DEVINL void load_kv(uint8_t* sK, uint8_t* sV, const CUtensorMap* tmQKV, const CUtensorMap* tmPKV, uint64_t* barK,
+                    uint64_t* barV, const AttnParams& p, int n, int h) {
+  const int nbox = (p.S + 63) >> 6;
+  const int npre = p.Ppad >> 4;
+  const uint32_t bytes = (uint32_t)(npre * 2048 + nbox * 8192);
+  mbar_expect_tx(barK, bytes);
+  for (int i = 0; i < npre; ++i) tma_load_3d(sK + i * 2048, tmPKV, barK, h * 64, i * 16, n);
+  for (int i = 0; i < nbox; ++i) tma_load_3d(sK + p.Ppad * 128 + i * 8192, tmQKV, barK, p.H + h * 64, i * 64, n);
+  mbar_expect_tx(barV, bytes);
+  for (int i = 0; i < npre; ++i) tma_load_3d(sV + i * 2048, tmPKV, barV, p.H + h * 64, i * 16, n);
+  for (int i = 0; i < nbox; ++i)
+    tma_load_3d(sV + p.Ppad * 128 + i * 8192, tmQKV, barV, 2 * p.H + h * 64, i * 64, n);
+}
+
+// ============================================================================ forward
+template <int MODE, int W, int PASS>
+DEVINL void fwd_chunk(const AttnParams& p, uint32_t taddr, const float* sBias, uint8_t* sP, int c0, int row, int q,
+                      bool alive, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row) {
+  float v[W];
+  tmem_ld_cols<W>(taddr + c0, v);
+  tmem_ld_wait();
+  if (PASS == 1) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const float s = masked_score<MODE>(v[j], p.scale, sBias[c0 + j], c0 + j, q, q_txt, p.T, w);
+      m = fmaxf(m, s);
+    }
+  } else if (PASS == 2) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const float s = masked_score<MODE>(v[j], p.scale, sBias[c0 + j], c0 + j, q, q_txt, p.T, w);
+      const float e = alive ? __expf(s - m) : 0.f;
+      sum += e;
+      v[j] = e;
+    }
+    uint8_t* blk = sP + (c0 >> 6) * 16384;
+    const int piece0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < W / 8; ++j) {
+      uint4 pk;
+      pk.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+      pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+      pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+      pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(blk + sw128_offset(row, piece0 + j)) = pk;
+    }
+  } else {
+    if (alive && q_txt) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const int kk = c0 + j;
+        if (kk >= p.T && kk < p.S) {
+          const float s = masked_score<MODE>(v[j], p.scale, sBias[kk], kk, q, q_txt, p.T, w);
+          pimg_row[kk - p.T] = __expf(s - m) * inv;
+        }
+      }
+    }
+  }
+}
+
+template <int TMEM_COLS, int MODE>
+__global__ void __launch_bounds__(160, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPKV,
+                const __grid_constant__ CUtensorMap tmCTX, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nblk = (p.Kp + 63) >> 6;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 16384;
+  uint8_t* sV = sK + p.Krows * 128;
+  uint8_t* sP = sV + p.Krows * 128;
+  float* sBias = reinterpret_cast<float*>(sP + nblk * 16384);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + nblk * 64);
+  uint64_t* bar_qk = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_s = bars + 2;
+  uint64_t* bar_p = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      if (p.P > 0) tma_prefetch_desc(&tmPKV);
+      tma_prefetch_desc(&tmCTX);
+      mbar_init(bar_qk, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<TMEM_COLS>(tmem_slot);
+  } else {
+    stage_bias(sBias, nblk * 64, p, n, tid, 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA + MMA issue
+      const int nbox = (p.S + 63) >> 6;
+      const int npre = p.Ppad >> 4;
+      const uint32_t kv_bytes = (uint32_t)(npre * 2048 + nbox * 8192);
+      mbar_expect_tx(bar_qk, 16384u + kv_bytes);
+      tma_load_3d(sQ, &tmQKV, bar_qk, h * 64, qt * 128, n);
+      tma_load_3d(sQ + 8192, &tmQKV, bar_qk, h * 64, qt * 128 + 64, n);
+      for (int i = 0; i < npre; ++i) tma_load_3d(sK + i * 2048, &tmPKV, bar_qk, h * 64, i * 16, n);
+      for (int i = 0; i < nbox; ++i)
+        tma_load_3d(sK + p.Ppad * 128 + i * 8192, &tmQKV, bar_qk, p.H + h * 64, i * 64, n);
+      mbar_expect_tx(bar_v, kv_bytes);
+      for (int i = 0; i < npre; ++i) tma_load_3d(sV + i * 2048, &tmPKV, bar_v, p.H + h * 64, i * 16, n);
+      for (int i = 0; i < nbox; ++i)
+        tma_load_3d(sV + p.Ppad * 128 + i * 8192, &tmQKV, bar_v, 2 * p.H + h * 64, i * 64, n);
+
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      for (int n0 = 0; n0 < p.Kp; n0 += 256) {
+        const int nn = min(256, p.Kp - n0);
+        const uint32_t idesc = make_idesc_bf16(128, nn, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + n0, make_smem_desc(q_addr + k * 32, 0, 1024),
+                    make_smem_desc(k_addr + n0 * 128 + k * 32, 0, 1024), idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const int ksteps = p.Kp >> 4;
+      for (int ks = 0; ks < ksteps; ++ks)
+        umma_bf16(tmem_base, make_smem_desc(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                  make_smem_desc(v_addr + ks * 2048, 8192, 1024), idesc_pv, ks > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax rows
+    const int row = tid;
+    const int q = qt * 128 + row;
+    const bool alive = q < p.S;
+    const bool warp_alive = (qt * 128 + warp * 32) < p.S;
+    const bool q_txt = q < p.T;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
+    float* pimg_row = nullptr;
+    if (p.probs_img != nullptr && alive && q_txt)
+      pimg_row = p.probs_img + (((size_t)n * p.heads + h) * p.T + q) * p.R;
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float m = -INFINITY, sum = 0.f, inv = 0.f;
+    if (warp_alive) {
+      const int full = p.Kp & ~31;
+      for (int c0 = 0; c0 < full; c0 += 32) {
+        const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+        fwd_chunk<MODE, 32, 1>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+      }
+      if (full < p.Kp) {
+        const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+        fwd_chunk<MODE, 16, 1>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+      }
+      for (int c0 = 0; c0 < full; c0 += 32) {
+        const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+        fwd_chunk<MODE, 32, 2>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+      }
+      if (full < p.Kp) {
+        const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+        fwd_chunk<MODE, 16, 2>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+      }
+      inv = sum > 0.f ? 1.0f / sum : 0.f;
+      if (p.probs_img != nullptr) {  // uniform over the CTA
+        const int first = (p.T >> 5) << 5;
+        for (int c0 = first; c0 < full; c0 += 32) {
+          const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+          fwd_chunk<MODE, 32, 3>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        }
+        if (full < p.Kp && full + 16 > first) {
+          const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+          fwd_chunk<MODE, 16, 3>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        }
+      }
+      if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = m + logf(sum);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    if (warp_alive) {
+      float o[64];
+      tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(o));
+      tmem_ld_32x32(taddr + 32, reinterpret_cast<uint32_t*>(o) + 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 pk;
+        pk.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+        pk.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+        pk.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+        pk.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+        *reinterpret_cast<uint4*>(sQ + sw128_offset(row, j)) = pk;  // Q tile is dead: reuse as staging
+      }
+    }
+    fence_async_smem();
+    named_bar_sync(1, 128);
+    if (tid == 0) {
+      tma_store_3d(&tmCTX, sQ, h * 64, qt * 128, n);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ============================================================================ backward
+template <int MODE>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPKV,
+                const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + p.Krows * 128;
+  uint8_t* sQ = sV + p.Krows * 128;   // 2 stages x 16 KB
+  uint8_t* sDO = sQ + 2 * 16384;      // 2 stages x 16 KB
+  uint8_t* sP = sDO + 2 * 16384;      // 2 blocks of [128 x 64] bf16
+  uint8_t* sDS = sP + 2 * 16384;
+  float* sBias = reinterpret_cast<float*>(sDS + 2 * 16384);
+  float* sDelta = sBias + p.nkb * 128;
+  float* sLse = sDelta + p.nqt * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sLse + p.nqt * 128);
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* qfull = bars + 2;    // [2]
+  uint64_t* qempty = bars + 4;   // [2]
+  uint64_t* bar_sdp = bars + 6;
+  uint64_t* bar_pds = bars + 7;
+  uint64_t* bar_dq = bars + 8;
+  uint64_t* bar_dkv_full = bars + 9;
+  uint64_t* bar_dkv_free = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      if (p.P > 0) tma_prefetch_desc(&tmPKV);
+      tma_prefetch_desc(&tmDO);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qfull[i], 1);
+        mbar_init(&qempty[i], 1);
+      }
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_pds, 128);
+      mbar_init(bar_dq, 1);
+      mbar_init(bar_dkv_full, 1);
+      mbar_init(bar_dkv_free, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  } else if (warp < 4) {
+    stage_bias(sBias, p.nkb * 128, p, n, tid, 128);
+    // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q]
+    for (int r = tid; r < p.nqt * 128; r += 128) {
+      float d = 0.f, l = 0.f;
+      if (r < p.S) {
+        const uint4* po = reinterpret_cast<const uint4*>(p.ctx + ((size_t)n * p.S + r) * p.H + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + ((size_t)n * p.S + r) * p.H + h * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 a = __ldg(po + j), b = __ldg(pd + j);
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = unpack_bf16(aw[e]), fb = unpack_bf16(bw[e]);
+            d = fmaf(fa.x, fb.x, d);
+            d = fmaf(fa.y, fb.y, d);
+          }
+        }
+        if (p.dalign != nullptr && p.probs_img != nullptr && r < p.T) {
+          const float* pi = p.probs_img + (((size_t)n * p.heads + h) * p.T + r) * p.R;
+          const float* da = p.dalign + ((size_t)n * p.T + r) * p.R;
+          for (int j = 0; j < p.R; ++j) d = fmaf(__ldg(pi + j), __ldg(da + j), d);
+        }
+        l = __ldg(p.lse + ((size_t)n * p.heads + h) * p.S + r);
+      }
+      sDelta[r] = d;
+      sLse[r] = l;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // -------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      load_kv(sK, sV, &tmQKV, &tmPKV, bar_k, bar_v, p, n, h);
+      int step = 0;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int qt = 0; qt < p.nqt; ++qt, ++step) {
+          const int s = step & 1;
+          const uint32_t ph = (step >> 1) & 1;
+          mbar_wait(&qempty[s], ph ^ 1);
+          mbar_expect_tx(&qfull[s], 32768);
+          tma_load_3d(sQ + s * 16384, &tmQKV, &qfull[s], h * 64, qt * 128, n);
+          tma_load_3d(sQ + s * 16384 + 8192, &tmQKV, &qfull[s], h * 64, qt * 128 + 64, n);
+          tma_load_3d(sDO + s * 16384, &tmDO, &qfull[s], h * 64, qt * 128, n);
+          tma_load_3d(sDO + s * 16384 + 8192, &tmDO, &qfull[s], h * 64, qt * 128 + 64, n);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // -------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
+      mbar_wait(bar_k, 0);
+      mbar_wait(bar_v, 0);
+      int step = 0;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int nb = min(128, p.Kp - kb * 128);
+        const uint32_t idesc_s = make_idesc_bf16(128, nb, 0, 0);
+        for (int qt = 0; qt < p.nqt; ++qt, ++step) {
+          const int s = step & 1;
+          const uint32_t ph = (step >> 1) & 1;
+          const uint32_t q_addr = smem_u32(sQ + s * 16384), do_addr = smem_u32(sDO + s * 16384);
+          mbar_wait(&qfull[s], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + COL_S, make_smem_desc(q_addr + k * 32, 0, 1024),
+                      make_smem_desc(k_addr + kb * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + COL_DP, make_smem_desc(do_addr + k * 32, 0, 1024),
+                      make_smem_desc(v_addr + kb * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(bar_sdp);
+          mbar_wait(bar_pds, step & 1);
+          if (qt == 0 && kb > 0) mbar_wait(bar_dkv_free, (kb - 1) & 1);
+          tc_fence_after();
+          const uint32_t acc0 = qt > 0 ? 1u : 0u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO
+            umma_bf16(tmem_base + COL_DV, make_smem_desc(p_addr + ks * 2048, 16384, 1024),
+                      make_smem_desc(do_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : acc0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
+            umma_bf16(tmem_base + COL_DK, make_smem_desc(ds_addr + ks * 2048, 16384, 1024),
+                      make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : acc0);
+          const int ksteps = nb >> 4;
+          for (int ks = 0; ks < ksteps; ++ks)  // dQ = dS K_kb
+            umma_bf16(tmem_base + COL_DQ, make_smem_desc(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                      make_smem_desc(k_addr + kb * 16384 + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+          umma_commit(&qempty[s]);
+          umma_commit(bar_dq);
+          if (qt == p.nqt - 1) umma_commit(bar_dkv_full);
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- row threads
+    const int row = tid;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const size_t H3 = (size_t)3 * p.H;
+    int step = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int nb = min(128, p.Kp - kb * 128);
+      for (int qt = 0; qt < p.nqt; ++qt, ++step) {
+        const int q = qt * 128 + row;
+        const bool alive = q < p.S;
+        const bool q_txt = q < p.T;
+        const float lse = sLse[q], delta = sDelta[q];
+        const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
+        const float* darow =
+            (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
+        mbar_wait(bar_sdp, step & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = c * 32;
+          const int kk0 = kb * 128 + c0;
+          float sv[32], dp[32];
+          if (c0 < nb) {
+            tmem_ld_32x32(taddr + COL_S + c0, reinterpret_cast<uint32_t*>(sv));
+            tmem_ld_32x32(taddr + COL_DP + c0, reinterpret_cast<uint32_t*>(dp));
+            tmem_ld_wait();
+            const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int kk = kk0 + j;
+              const float sb = sBias[kk];
+              const float s = masked_score<MODE>(sv[j], p.scale, sb, kk, q, q_txt, p.T, w);
+              const bool valid = alive && (sb != -INFINITY);
+              const float pr = valid ? __expf(s - lse) : 0.f;
+              float g = dp[j];
+              if (darow != nullptr && kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
+              sv[j] = pr;
+              dp[j] = valid ? pr * (g - delta) * p.scale : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sv[j] = 0.f;
+              dp[j] = 0.f;
+            }
+          }
+          uint8_t* pblk = sP + (c0 >> 6) * 16384;
+          uint8_t* dblk = sDS + (c0 >> 6) * 16384;
+          const int piece0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(sv[8 * j + 0], sv[8 * j + 1]);
+            pk.y = pack_bf16(sv[8 * j + 2], sv[8 * j + 3]);
+            pk.z = pack_bf16(sv[8 * j + 4], sv[8 * j + 5]);
+            pk.w = pack_bf16(sv[8 * j + 6], sv[8 * j + 7]);
+            *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = pk;
+            pk.x = pack_bf16(dp[8 * j + 0], dp[8 * j + 1]);
+            pk.y = pack_bf16(dp[8 * j + 2], dp[8 * j + 3]);
+            pk.z = pack_bf16(dp[8 * j + 4], dp[8 * j + 5]);
+            pk.w = pack_bf16(dp[8 * j + 6], dp[8 * j + 7]);
+            *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = pk;
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+
+        // ---- dQ partial of this (key block, q tile)
+        mbar_wait(bar_dq, step & 1);
+        tc_fence_after();
+        {
+          float dq[64];
+          tmem_ld_32x32(taddr + COL_DQ, reinterpret_cast<uint32_t*>(dq));
+          tmem_ld_32x32(taddr + COL_DQ + 32, reinterpret_cast<uint32_t*>(dq) + 32);
+          tmem_ld_wait();
+          if (alive) {
+            float4* ws = reinterpret_cast<float4*>(p.dq_ws + (((size_t)n * p.heads + h) * p.S + q) * 64);
+            if (kb > 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 f = ws[j];
+                dq[4 * j] += f.x;
+                dq[4 * j + 1] += f.y;
+                dq[4 * j + 2] += f.z;
+                dq[4 * j + 3] += f.w;
+              }
+            }
+            if (kb == p.nkb - 1) {
+              uint4* out = reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.S + q) * H3 + h * 64);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 pk;
+                pk.x = pack_bf16(dq[8 * j + 0], dq[8 * j + 1]);
+                pk.y = pack_bf16(dq[8 * j + 2], dq[8 * j + 3]);
+                pk.z = pack_bf16(dq[8 * j + 4], dq[8 * j + 5]);
+                pk.w = pack_bf16(dq[8 * j + 6], dq[8 * j + 7]);
+                out[j] = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ws[j] = make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+            }
+          }
+        }
+        // ---- dK / dV of this key block once the last q tile has been accumulated
+        if (qt == p.nqt - 1) {
+          mbar_wait(bar_dkv_full, kb & 1);
+          tc_fence_after();
+          const int kk = kb * 128 + row;
+          bf16* dk_dst = nullptr;
+          bf16* dv_dst = nullptr;
+          if (kk < p.P) {
+            dk_dst = p.dpkv + ((size_t)n * p.P + kk) * (2 * p.H) + h * 64;
+            dv_dst = dk_dst + p.H;
+          } else if (kk >= p.Ppad && kk - p.Ppad < p.S) {
+            dk_dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64;
+            dv_dst = dk_dst + p.H;
+          }
+#pragma unroll 1
+          for (int which = 0; which < 2; ++which) {
+            float acc[64];
+            const uint32_t col = which == 0 ? COL_DK : COL_DV;
+            tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
+            tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
+            tmem_ld_wait();
+            bf16* dst = which == 0 ? dk_dst : dv_dst;
+            if (dst != nullptr) {
+              uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                uint4 pk;
+                pk.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]);
+                pk.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
+                pk.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]);
+                pk.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
+                out[j] = pk;
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_dkv_free);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<512>(tmem_base);
+}
+
+// ============================================================================ host
+static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
+  if (a.N <= 0 || a.S <= 0 || a.heads <= 0 || a.P < 0 || a.P > 64) {
+    set_error("prefix_attn: bad shape N=%d S=%d P=%d heads=%d (P <= 64)", a.N, a.S, a.P, a.heads);
+    return MODCR_ERR_SHAPE;
+  }
+  if (a.mode < 0 || a.mode > 2) {
+    set_error("prefix_attn: bad mode %d", a.mode);
+    return MODCR_ERR_SHAPE;
+  }
+  if (a.mode != 0 && (a.P != 0 || a.T <= 0 || a.T > a.S || a.cbits == nullptr || a.cwords * 32 < a.T)) {
+    set_error("prefix_attn: chunk modes need P=0, 0<T<=S, a chunk bit mask with cwords*32 >= T");
+    return MODCR_ERR_SHAPE;
+  }
+  if ((a.probs_img != nullptr || a.dalign != nullptr) && (a.P != 0 || a.T <= 0 || a.T >= a.S)) {
+    set_error("prefix_attn: the text->region probability block needs P=0 and 0<T<S");
+    return MODCR_ERR_SHAPE;
+  }
+  if (a.qkv == nullptr || a.kbias == nullptr || (a.P > 0 && a.pkv == nullptr)) {
+    set_error("prefix_attn: null input pointer");
+    return MODCR_ERR_SHAPE;
+  }
+  p.N = a.N; p.S = a.S; p.P = a.P; p.heads = a.heads; p.H = a.heads * 64;
+  p.Ppad = (a.P + 15) & ~15;
+  p.T = a.T; p.R = a.S - a.T;
+  p.Kp = p.Ppad + ((a.S + 15) & ~15);
+  p.Krows = p.Ppad + 64 * ((a.S + 63) / 64);
+  p.nqt = (a.S + 127) / 128;
+  p.nkb = (p.Kp + 127) / 128;
+  p.mode = a.mode; p.scale = a.scale;
+  p.kbias = a.kbias; p.cbits = a.cbits; p.cwords = a.cwords;
+  p.lse = a.lse; p.probs_img = a.probs_img;
+  p.ctx = (const bf16*)a.ctx; p.dctx = (const bf16*)a.dctx; p.dalign = a.dalign;
+  p.dqkv = (bf16*)a.dqkv; p.dpkv = (bf16*)a.dpkv; p.dq_ws = a.dq_ws;
+  if (a.lse == nullptr || a.ctx == nullptr) {
+    set_error("prefix_attn: null ctx / lse pointer");
+    return MODCR_ERR_SHAPE;
+  }
+  if (bwd) {
+    if (a.dctx == nullptr || a.dqkv == nullptr || (a.P > 0 && a.dpkv == nullptr)) {
+      set_error("prefix_attn_bwd: null gradient pointer");
+      return MODCR_ERR_SHAPE;
+    }
+    if (p.nkb > 1 && a.dq_ws == nullptr) {
+      set_error("prefix_attn_bwd: workspace required when P+S > 128");
+      return MODCR_ERR_WORKSPACE;
+    }
+  }
+  return MODCR_OK;
+}
+
+size_t attn_bwd_workspace_bytes(int N, int S, int heads) { return (size_t)N * heads * S * 64 * sizeof(float); }
+
+template <int TMEM_COLS, int MODE>
+static int launch_fwd(const AttnDesc& a, const AttnParams& p, const CUtensorMap& tmQKV, const CUtensorMap& tmPKV,
+                      const CUtensorMap& tmCTX, size_t smem, cudaStream_t stream) {
+  auto kern = attn_fwd_kernel<TMEM_COLS, MODE>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("prefix_attn_fwd: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+      return MODCR_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(p.nqt, p.heads, p.N);
+  kern<<<grid, 160, smem, stream>>>(tmQKV, tmPKV, tmCTX, p);
+  return check_launch("prefix_attn_fwd");
+}
+
+int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
+  AttnParams p;
+  int rc = fill_params(a, p, false);
+  if (rc) return rc;
+  const int nblk = (p.Kp + 63) / 64;
+  const size_t smem = 1024 + 16384 + (size_t)2 * p.Krows * 128 + (size_t)nblk * 16384 + nblk * 64 * 4 + 128;
+  if (p.Kp > 512 || smem > 232448) {
+    set_error("prefix_attn_fwd: P+S=%d too long for the single-pass kernel (smem %zu B)", p.P + p.S, smem);
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmQKV, tmPKV, tmCTX;
+  rc = make_tmap_3d(&tmQKV, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, 64, 64);
+  if (rc) return rc;
+  tmPKV = tmQKV;
+  if (p.P > 0) {
+    rc = make_tmap_3d(&tmPKV, a.pkv, 2, p.N, p.P, 2 * p.H, 2 * p.H, (uint64_t)p.P * 2 * p.H, 16, 64);
+    if (rc) return rc;
+  }
+  rc = make_tmap_3d(&tmCTX, a.ctx, 2, p.N, p.S, p.H, p.H, (uint64_t)p.S * p.H, 128, 64);
+  if (rc) return rc;
+  const bool small = p.Kp <= 256;
+  switch (p.mode) {
+    case 0:
+      return small ? launch_fwd<256, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
+                   : launch_fwd<512, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+    case 1:
+      return small ? launch_fwd<256, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
+                   : launch_fwd<512, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+    default:
+      return small ? launch_fwd<256, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
+                   : launch_fwd<512, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+  }
+}
+
+template <int MODE>
+static int launch_bwd(const AttnParams& p, const CUtensorMap& tmQKV, const CUtensorMap& tmPKV, const CUtensorMap& tmDO,
+                      size_t smem, cudaStream_t stream) {
+  auto kern = attn_bwd_kernel<MODE>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("prefix_attn_bwd: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+      return MODCR_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(p.heads, p.N);
+  kern<<<grid, 192, smem, stream>>>(tmQKV, tmPKV, tmDO, p);
+  return check_launch("prefix_attn_bwd");
+}
+
+int attn_bwd_launch(const AttnDesc& a, cudaStream_t stream) {
+  AttnParams p;
+  int rc = fill_params(a, p, true);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)2 * p.Krows * 128 + 8 * 16384 + (size_t)(p.nkb * 128 + 2 * p.nqt * 128) * 4 + 128;
+  if (smem > 232448) {
+    set_error("prefix_attn_bwd: P+S=%d too long (smem %zu B)", p.P + p.S, smem);
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmQKV, tmPKV, tmDO;
+  rc = make_tmap_3d(&tmQKV, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, 64, 64);
+  if (rc) return rc;
+  tmPKV = tmQKV;
+  if (p.P > 0) {
+    rc = make_tmap_3d(&tmPKV, a.pkv, 2, p.N, p.P, 2 * p.H, 2 * p.H, (uint64_t)p.P * 2 * p.H, 16, 64);
+    if (rc) return rc;
+  }
+  rc = make_tmap_3d(&tmDO, a.dctx, 2, p.N, p.S, p.H, p.H, (uint64_t)p.S * p.H, 64, 64);
+  if (rc) return rc;
+  switch (p.mode) {
+    case 0: return launch_bwd<0>(p, tmQKV, tmPKV, tmDO, smem, stream);
+    case 1: return launch_bwd<1>(p, tmQKV, tmPKV, tmDO, smem, stream);
+    default: return launch_bwd<2>(p, tmQKV, tmPKV, tmDO, smem, stream);
+  }
+}
+
+}  // namespace modcr

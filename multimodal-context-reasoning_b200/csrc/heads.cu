@@ -1,0 +1,662 @@
+// Head kernels of the ModCR hot path (sm_100a): chunk-to-region alignment loss, ClsLayer2
+// attention pooling and the fused multiple-choice classifier + cross-entropy.  HBM / latency
+// bound: warp-shuffle reductions, 128-bit loads, fp32 math.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "ptx.cuh"
+#include "rowops.h"
+#include "tma_host.h"
+
+namespace modcr {
+
+typedef __nv_bfloat16 bf16;
+
+DEVINL float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DEVINL float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+DEVINL void unpack8h(const uint4& u, float* f) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+DEVINL uint4 pack8h(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+// block-wide sum / max over 256 threads (8 warps); `sh` needs 8 floats
+DEVINL float block_sum(float v, float* sh) {
+  v = wsum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) s += sh[i];
+  return s;
+}
+DEVINL float block_max(float v, float* sh) {
+  v = wmax(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = -INFINITY;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) s = fmaxf(s, sh[i]);
+  return s;
+}
+
+// ============================================================================ alignment loss
+constexpr int AL_MAXR = 8;  // R <= 256
+
+// probs: [nl, N, heads, T, R] fp32.  One warp per (n, t) row.
+__global__ void __launch_bounds__(256) align_fwd_kernel(const float* __restrict__ probs, int nl, int heads,
+                                                        const int64_t* __restrict__ align_pos,
+                                                        const int64_t* __restrict__ total_label, float* __restrict__ block,
+                                                        float* __restrict__ row_loss, int N, int T, int R) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N * T) return;
+  const int n = row / T, t = row - n * T;
+  float a[AL_MAXR];
+#pragma unroll
+  for (int i = 0; i < AL_MAXR; ++i) a[i] = 0.f;
+  for (int h = 0; h < heads; ++h) {
+    float tmp[AL_MAXR];
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) tmp[i] = 0.f;
+    for (int l = 0; l < nl; ++l) {
+      const float* src = probs + ((((size_t)l * N + n) * heads + h) * T + t) * R;
+#pragma unroll
+      for (int i = 0; i < AL_MAXR; ++i) {
+        const int r = lane + 32 * i;
+        if (r < R) tmp[i] += __ldg(src + r);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) a[i] += tmp[i];
+  }
+#pragma unroll
+  for (int i = 0; i < AL_MAXR; ++i) {
+    const int r = lane + 32 * i;
+    if (r < R) block[(size_t)row * R + r] = a[i];
+  }
+  float loss = 0.f, correct = 0.f;
+  if (align_pos[row] == 1) {
+    // z = softmax(masked_fill(A == 0, -1e5)) ; loss = logsumexp(z) - z[label]
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        a[i] = (a[i] == 0.f) ? -1e5f : a[i];
+        mx = fmaxf(mx, a[i]);
+      }
+    }
+    mx = wmax(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        a[i] = expf(a[i] - mx);
+        se += a[i];
+      }
+    }
+    se = wsum(se);
+    const int label = (int)total_label[row];
+    float zmax = -INFINITY, zlab = 0.f, s2 = 0.f;
+    int zarg = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        const float z = a[i] / se;
+        a[i] = z;
+        if (z > zmax) {
+          zmax = z;
+          zarg = r;
+        }
+        if (r == label) zlab = z;
+      }
+    }
+    // argmax with first-index tie break
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, zmax, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, zarg, o);
+      if (om > zmax || (om == zmax && oa < zarg)) {
+        zmax = om;
+        zarg = oa;
+      }
+    }
+    zlab = wsum(zlab);
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) s2 += expf(a[i] - zmax);
+    }
+    s2 = wsum(s2);
+    loss = (zmax + logf(s2)) - zlab;
+    correct = (zarg == label) ? 1.f : 0.f;
+  }
+  if (lane == 0) {
+    row_loss[2 * (size_t)row] = loss;
+    row_loss[2 * (size_t)row + 1] = correct;
+  }
+}
+
+// out[0] = mean loss over aligned rows, out[1] = #aligned rows, out[2] = #correct, out[3] = loss sum
+__global__ void __launch_bounds__(256) align_reduce_kernel(const float* __restrict__ row_loss,
+                                                           const int64_t* __restrict__ align_pos, float* __restrict__ out,
+                                                           int rows) {
+  __shared__ float sh[8];
+  float s = 0.f, c = 0.f, m = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    if (align_pos[i] == 1) {
+      s += row_loss[2 * (size_t)i];
+      c += row_loss[2 * (size_t)i + 1];
+      m += 1.f;
+    }
+  }
+  s = block_sum(s, sh);
+  c = block_sum(c, sh);
+  m = block_sum(m, sh);
+  if (threadIdx.x == 0) {
+    out[0] = s / m;
+    out[1] = m;
+    out[2] = c;
+    out[3] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) align_bwd_kernel(const float* __restrict__ block, const int64_t* __restrict__ align_pos,
+                                                        const int64_t* __restrict__ total_label, const float* __restrict__ out,
+                                                        float gout, float* __restrict__ dblock, int N, int T, int R) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N * T) return;
+  float d[AL_MAXR];
+#pragma unroll
+  for (int i = 0; i < AL_MAXR; ++i) d[i] = 0.f;
+  if (align_pos[row] == 1) {
+    const float scale = gout / out[1];
+    float a[AL_MAXR];
+    bool zero[AL_MAXR];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      a[i] = 0.f;
+      zero[i] = true;
+      if (r < R) {
+        const float v = block[(size_t)row * R + r];
+        zero[i] = (v == 0.f);
+        a[i] = zero[i] ? -1e5f : v;
+        mx = fmaxf(mx, a[i]);
+      }
+    }
+    mx = wmax(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i)
+      if (lane + 32 * i < R) {
+        a[i] = expf(a[i] - mx);
+        se += a[i];
+      }
+    se = wsum(se);
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i)
+      if (lane + 32 * i < R) {
+        a[i] /= se;
+        zmax = fmaxf(zmax, a[i]);
+      }
+    zmax = wmax(zmax);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i)
+      if (lane + 32 * i < R) s2 += expf(a[i] - zmax);
+    s2 = wsum(s2);
+    const int label = (int)total_label[row];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      if (r < R) {
+        const float y = expf(a[i] - zmax) / s2;
+        d[i] = (y - (r == label ? 1.f : 0.f)) * scale;  // dL/dz
+        dot += a[i] * d[i];
+      }
+    }
+    dot = wsum(dot);
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) d[i] = zero[i] ? 0.f : a[i] * (d[i] - dot);
+  }
+#pragma unroll
+  for (int i = 0; i < AL_MAXR; ++i) {
+    const int r = lane + 32 * i;
+    if (r < R) dblock[(size_t)row * R + r] = d[i];
+  }
+}
+
+int align_softmax_ce_fwd(const float* probs, int nl, int heads, const int64_t* align_pos, const int64_t* total_label,
+                         float* block, float* row_loss, float* out, int N, int T, int R, cudaStream_t st) {
+  if (R <= 0 || R > 32 * AL_MAXR || N <= 0 || T <= 0 || nl <= 0) {
+    set_error("align_softmax_ce: bad shape N=%d T=%d R=%d (R <= %d)", N, T, R, 32 * AL_MAXR);
+    return MODCR_ERR_SHAPE;
+  }
+  const int rows = N * T;
+  align_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, block, row_loss, N, T, R);
+  align_reduce_kernel<<<1, 256, 0, st>>>(row_loss, align_pos, out, rows);
+  return check_launch("align_softmax_ce_fwd");
+}
+
+int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label, const float* out,
+                         float gout, float* dblock, int N, int T, int R, cudaStream_t st) {
+  if (R <= 0 || R > 32 * AL_MAXR || N <= 0 || T <= 0) {
+    set_error("align_softmax_ce_bwd: bad shape N=%d T=%d R=%d", N, T, R);
+    return MODCR_ERR_SHAPE;
+  }
+  const int rows = N * T;
+  align_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(block, align_pos, total_label, out, gout, dblock, N, T, R);
+  return check_launch("align_softmax_ce_bwd");
+}
+
+// ============================================================================ ClsLayer2 pooling
+constexpr int CP_MAXV = 4;  // H <= 1024
+
+// smem: qs[H] | sc[L] | part[8][H]
+__global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+                                                           const float* __restrict__ mask, float* __restrict__ w,
+                                                           bf16* __restrict__ pooled, int L, int H) {
+  extern __shared__ float sm[];
+  __shared__ float sh[8];
+  float* qs = sm;
+  float* sc = qs + H;
+  float* part = sc + ((L + 3) & ~3);
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  for (int c = threadIdx.x; c < H; c += 256) qs[c] = __bfloat162float(q[(size_t)n * H + c]);
+  __syncthreads();
+  const bf16* kn = k + (size_t)n * L * H;
+  for (int l = warp; l < L; l += 8) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < CP_MAXV; ++i)
+      if (i < nv) {
+        float f[8];
+        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        const float* qq = qs + (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d = fmaf(f[j], qq[j], d);
+      }
+    d = wsum(d);
+    if (lane == 0) sc[l] = d + (mask ? __ldg(mask + (size_t)n * L + l) : 0.f);
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int l = threadIdx.x; l < L; l += 256) mx = fmaxf(mx, sc[l]);
+  mx = block_max(mx, sh);
+  float se = 0.f;
+  for (int l = threadIdx.x; l < L; l += 256) {
+    const float e = expf(sc[l] - mx);
+    sc[l] = e;
+    se += e;
+  }
+  se = block_sum(se, sh);
+  const float inv = 1.f / se;
+  for (int l = threadIdx.x; l < L; l += 256) {
+    const float p = sc[l] * inv;
+    sc[l] = p;
+    w[(size_t)n * L + l] = p;
+  }
+  __syncthreads();
+  float acc[CP_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < CP_MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int l = warp; l < L; l += 8) {
+    const float p = sc[l];
+#pragma unroll
+    for (int i = 0; i < CP_MAXV; ++i)
+      if (i < nv) {
+        float f[8];
+        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p, f[j], acc[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < CP_MAXV; ++i)
+    if (i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[warp * H + (lane + 32 * i) * 8 + j] = acc[i][j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += part[ww * H + c];
+    pooled[(size_t)n * H + c] = __float2bfloat16(s);
+  }
+}
+
+// smem: qs[H] | dps[H] | wv[L] | dsv[L] | part[8][H]
+__global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ q,
+                                                           const bf16* __restrict__ k, const float* __restrict__ w,
+                                                           bf16* __restrict__ dq, bf16* __restrict__ dk, int L, int H) {
+  extern __shared__ float sm[];
+  __shared__ float sh[8];
+  const int Lp = (L + 3) & ~3;
+  float* qs = sm;
+  float* dps = qs + H;
+  float* wv = dps + H;
+  float* dsv = wv + Lp;
+  float* part = dsv + Lp;
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  for (int c = threadIdx.x; c < H; c += 256) {
+    qs[c] = __bfloat162float(q[(size_t)n * H + c]);
+    dps[c] = __bfloat162float(dpooled[(size_t)n * H + c]);
+  }
+  for (int l = threadIdx.x; l < L; l += 256) wv[l] = w[(size_t)n * L + l];
+  __syncthreads();
+  const bf16* kn = k + (size_t)n * L * H;
+  bf16* dkn = dk + (size_t)n * L * H;
+  for (int l = warp; l < L; l += 8) {  // dw[l] = dpooled . k[l]
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < CP_MAXV; ++i)
+      if (i < nv) {
+        float f[8];
+        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        const float* dd = dps + (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d = fmaf(f[j], dd[j], d);
+      }
+    d = wsum(d);
+    if (lane == 0) dsv[l] = d;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int l = threadIdx.x; l < L; l += 256) dot += wv[l] * dsv[l];
+  dot = block_sum(dot, sh);
+  for (int l = threadIdx.x; l < L; l += 256) dsv[l] = wv[l] * (dsv[l] - dot);
+  __syncthreads();
+  float acc[CP_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < CP_MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int l = warp; l < L; l += 8) {
+    const float p = wv[l], ds = dsv[l];
+#pragma unroll
+    for (int i = 0; i < CP_MAXV; ++i)
+      if (i < nv) {
+        float f[8], o[8];
+        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        const float* dd = dps + (lane + 32 * i) * 8;
+        const float* qq = qs + (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = p * dd[j] + ds * qq[j];           // dk[l] = w[l] dpooled + ds[l] q   (k is key and value)
+          acc[i][j] = fmaf(ds, f[j], acc[i][j]);   // dq += ds[l] k[l]
+        }
+        reinterpret_cast<uint4*>(dkn + (size_t)l * H)[lane + 32 * i] = pack8h(o);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < CP_MAXV; ++i)
+    if (i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) part[warp * H + (lane + 32 * i) * 8 + j] = acc[i][j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += part[ww * H + c];
+    dq[(size_t)n * H + c] = __float2bfloat16(s);
+  }
+}
+
+static int cls_pool_check(int N, int L, int H, size_t smem, const char* what) {
+  if (N <= 0 || L <= 0 || H % 256 != 0 || H > 256 * CP_MAXV) {
+    set_error("%s: bad shape N=%d L=%d H=%d", what, N, L, H);
+    return MODCR_ERR_SHAPE;
+  }
+  if (smem > 200 * 1024) {
+    set_error("%s: L=%d needs %zu B of shared memory", what, L, smem);
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  return MODCR_OK;
+}
+
+int cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int N, int L, int H,
+                      cudaStream_t st) {
+  const size_t smem = ((size_t)H + ((L + 3) & ~3) + 8 * (size_t)H) * 4;
+  if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_fwd")) return rc;
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(cls_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  cls_pool_fwd_kernel<<<N, 256, smem, st>>>((const bf16*)q, (const bf16*)k, mask, w, (bf16*)pooled, L, H);
+  return check_launch("cls_pool_attn_fwd");
+}
+
+int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk, int N, int L,
+                      int H, cudaStream_t st) {
+  const size_t smem = (2 * (size_t)H + 2 * ((L + 3) & ~3) + 8 * (size_t)H) * 4;
+  if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_bwd")) return rc;
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(cls_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  cls_pool_bwd_kernel<<<N, 256, smem, st>>>((const bf16*)dpooled, (const bf16*)q, (const bf16*)k, w, (bf16*)dq, (bf16*)dk,
+                                            L, H);
+  return check_launch("cls_pool_attn_bwd");
+}
+
+// ============================================================================ classifier + CE
+constexpr int SC_MAXC = 8;
+
+struct ScorerParams {
+  const bf16* x;
+  const float* W;
+  const float* b;
+  int rows, K, C, G, V;
+  const int64_t* hard;
+  const float* soft;
+  float* logits;
+  float* loss;
+  float* mp;
+  int64_t* pred;
+  uint8_t* matched;
+  int num_choice;
+  float gout;
+  bf16* dx;
+  float* dW;
+  float* db;
+};
+
+DEVINL void scorer_logits(const ScorerParams& p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < p.rows; r += nw) {
+    float acc[SC_MAXC];
+#pragma unroll
+    for (int c = 0; c < SC_MAXC; ++c) acc[c] = 0.f;
+    for (int v = lane; v < (p.K >> 3); v += 32) {
+      float f[8];
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(p.x + (size_t)r * p.K) + v), f);
+#pragma unroll
+      for (int c = 0; c < SC_MAXC; ++c)
+        if (c < p.C) {
+          const float* wr = p.W + (size_t)c * p.K + v * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c] = fmaf(f[j], __ldg(wr + j), acc[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SC_MAXC; ++c)
+      if (c < p.C) {
+        const float s = wsum(acc[c]);
+        if (lane == 0) p.logits[(size_t)r * p.C + c] = s + (p.b ? p.b[c] : 0.f);
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) scorer_fwd_kernel(const ScorerParams p) {
+  __shared__ float sh[8];
+  scorer_logits(p);
+  __syncthreads();
+  float ls = 0.f;
+  for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
+    const float* lg = p.logits + (size_t)v * p.G;
+    float mx = -INFINITY;
+    for (int g = 0; g < p.G; ++g) mx = fmaxf(mx, lg[g]);
+    float se = 0.f;
+    for (int g = 0; g < p.G; ++g) se += expf(lg[g] - mx);
+    const float lse = mx + logf(se);
+    if (p.hard) {
+      ls += lse - lg[(int)p.hard[v]];
+    } else if (p.soft) {
+      for (int g = 0; g < p.G; ++g) ls += p.soft[(size_t)v * p.G + g] * (lse - lg[g]);
+    }
+  }
+  ls = block_sum(ls, sh);
+  if (threadIdx.x == 0 && p.loss) p.loss[0] = ls / (float)p.V;
+  if (p.mp != nullptr && p.C == 2) {  // binary_to_mp (v10:363-373) + argmax + matched (v10:1065-1069)
+    const int nq = p.rows / p.num_choice;
+    for (int b = threadIdx.x; b < nq; b += blockDim.x) {
+      float best = -INFINITY, gbest = -INFINITY;
+      int arg = 0, garg = 0;
+      for (int j = 0; j < p.num_choice; ++j) {
+        const int r = b * p.num_choice + j;
+        const float l0 = p.logits[2 * (size_t)r], l1 = p.logits[2 * (size_t)r + 1];
+        const float mx = fmaxf(l0, l1);
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+        const float pr = e1 / (e0 + e1);
+        p.mp[r] = pr;
+        if (pr > best) {
+          best = pr;
+          arg = j;
+        }
+        const float lab = p.hard ? (float)p.hard[r] : (p.soft ? p.soft[2 * (size_t)r + 1] : 0.f);
+        if (lab > gbest) {
+          gbest = lab;
+          garg = j;
+        }
+      }
+      if (p.pred) p.pred[b] = arg;
+      if (p.matched) p.matched[b] = (arg == garg) ? 1 : 0;
+    }
+  }
+}
+
+// dynamic smem: dl[rows * C]
+__global__ void __launch_bounds__(256) scorer_bwd_kernel(const ScorerParams p) {
+  extern __shared__ float dl[];
+  const float scale = p.gout / (float)p.V;
+  for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
+    const float* lg = p.logits + (size_t)v * p.G;
+    float mx = -INFINITY;
+    for (int g = 0; g < p.G; ++g) mx = fmaxf(mx, lg[g]);
+    float se = 0.f;
+    for (int g = 0; g < p.G; ++g) se += expf(lg[g] - mx);
+    float tsum = 1.f;
+    if (p.soft) {
+      tsum = 0.f;
+      for (int g = 0; g < p.G; ++g) tsum += p.soft[(size_t)v * p.G + g];
+    }
+    for (int g = 0; g < p.G; ++g) {
+      const float y = expf(lg[g] - mx) / se;
+      const float tg = p.hard ? ((int)p.hard[v] == g ? 1.f : 0.f) : p.soft[(size_t)v * p.G + g];
+      dl[(size_t)v * p.G + g] = (y * tsum - tg) * scale;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (p.dx) {
+    for (int r = warp; r < p.rows; r += nw) {
+      for (int v = lane; v < (p.K >> 3); v += 32) {
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < p.C; ++c) {
+          const float d = dl[(size_t)r * p.C + c];
+          const float* wr = p.W + (size_t)c * p.K + v * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(d, __ldg(wr + j), o[j]);
+        }
+        reinterpret_cast<uint4*>(p.dx + (size_t)r * p.K)[v] = pack8h(o);
+      }
+    }
+  }
+  if (p.dW) {
+    for (int i = threadIdx.x; i < p.C * p.K; i += blockDim.x) {
+      const int c = i / p.K, kk = i - c * p.K;
+      float s = 0.f;
+      for (int r = 0; r < p.rows; ++r) s = fmaf(dl[(size_t)r * p.C + c], __bfloat162float(p.x[(size_t)r * p.K + kk]), s);
+      p.dW[i] += s;
+    }
+  }
+  if (p.db) {
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < p.rows; ++r) s += dl[(size_t)r * p.C + c];
+      p.db[c] += s;
+    }
+  }
+}
+
+static int scorer_params(const ScorerDesc& d, ScorerParams& p, const char* what) {
+  if (d.rows <= 0 || d.K <= 0 || d.K % 8 != 0 || d.C <= 0 || d.C > SC_MAXC || d.G <= 0 || (d.rows * d.C) % d.G != 0) {
+    set_error("%s: bad shape rows=%d K=%d C=%d G=%d", what, d.rows, d.K, d.C, d.G);
+    return MODCR_ERR_SHAPE;
+  }
+  if (d.x == nullptr || d.W == nullptr || d.logits == nullptr || (d.hard == nullptr && d.soft == nullptr)) {
+    set_error("%s: null pointer", what);
+    return MODCR_ERR_SHAPE;
+  }
+  if (d.mp != nullptr && (d.C != 2 || d.G != 2 || d.num_choice <= 0 || d.rows % d.num_choice != 0)) {
+    set_error("%s: binary_to_mp needs C=G=2 and rows %% num_choice == 0", what);
+    return MODCR_ERR_SHAPE;
+  }
+  p.x = (const bf16*)d.x; p.W = d.W; p.b = d.b; p.rows = d.rows; p.K = d.K; p.C = d.C; p.G = d.G;
+  p.V = d.rows * d.C / d.G; p.hard = d.hard; p.soft = d.soft; p.logits = d.logits; p.loss = d.loss; p.mp = d.mp;
+  p.pred = d.pred; p.matched = d.matched; p.num_choice = d.num_choice; p.gout = d.gout; p.dx = (bf16*)d.dx; p.dW = d.dW;
+  p.db = d.db;
+  return MODCR_OK;
+}
+
+int mc_scorer_ce_fwd(const ScorerDesc& d, cudaStream_t st) {
+  ScorerParams p;
+  if (int rc = scorer_params(d, p, "mc_scorer_ce_fwd")) return rc;
+  scorer_fwd_kernel<<<1, 256, 0, st>>>(p);
+  return check_launch("mc_scorer_ce_fwd");
+}
+
+int mc_scorer_ce_bwd(const ScorerDesc& d, cudaStream_t st) {
+  ScorerParams p;
+  if (int rc = scorer_params(d, p, "mc_scorer_ce_bwd")) return rc;
+  const size_t smem = (size_t)d.rows * d.C * 4;
+  if (smem > 48 * 1024) {
+    set_error("mc_scorer_ce_bwd: rows*C=%d too large", d.rows * d.C);
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  scorer_bwd_kernel<<<1, 256, smem, st>>>(p);
+  return check_launch("mc_scorer_ce_bwd");
+}
+
+}  // namespace modcr

@@ -1,0 +1,679 @@
+// HBM-bound row kernels of the ModCR hot path (sm_100a): LayerNorm forward/backward, the fused
+// text-embedding gather + LayerNorm (a_transformers/modeling_bert.py:184-211), casts / packing,
+// column sums (bias gradients), row copies between [N,S,H] buffers and the chunk-mean query
+// operator (modeling_vcr_chunkalign_v10.py:66-78).  All activations are bf16, statistics and
+// parameter gradients fp32; every global access is a 128-bit vector access, one warp per row.
+#include "rowops.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace modcr {
+
+typedef __nv_bfloat16 bf16;
+
+DEVINL float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+DEVINL float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+DEVINL void unpack8(const uint4& u, float* f) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+DEVINL uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+DEVINL void load8f(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// physical row of logical row m: rows are grouped `rows_per_seq` at a time, each group starts
+// `seq_stride` rows after the previous one, offset by `row0` (writes text rows / region rows of
+// the concatenated [N,S,H] buffer without a torch.cat)
+DEVINL int64_t map_row(int m, const RowMap& r) {
+  if (r.rows_per_seq <= 0) return m;
+  const int s = m / r.rows_per_seq;
+  return (int64_t)s * r.seq_stride + r.row0 + (m - s * r.rows_per_seq);
+}
+
+constexpr int LN_MAXV = 4;  // up to 4 x 8 x 32 = 1024 columns
+
+// ---------------------------------------------------------------------------- LayerNorm fwd
+// y = (x - mean) * rstd * gamma + beta ; two-pass statistics in fp32 registers
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, RowMap xmap, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y, RowMap ymap,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int H,
+                                                     float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = H >> 8;  // vectors per lane
+  const bf16* xr = x + map_row(warp, xmap) * H;
+  float v[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + lane + 32 * i);
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  const float mu = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mu;
+        q += d * d;
+      }
+    }
+  const float rs = rsqrtf(warp_sum(q) / H + eps);
+  bf16* yr = y + map_row(warp, ymap) * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      const int c = (lane + 32 * i) * 8;
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+      reinterpret_cast<uint4*>(yr)[lane + 32 * i] = pack8(o);
+    }
+  if (lane == 0) {
+    if (mean) mean[warp] = mu;
+    if (rstd) rstd[warp] = rs;
+  }
+}
+
+// ---------------------------------------------------------------------------- LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dx (bias of the Linear
+// that produced x, fused here so no extra pass over dx is needed)
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x,
+                                                     RowMap xmap, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                     bf16* __restrict__ dx, RowMap dxmap, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
+  __shared__ float red[8][32 * 8 + 1];
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  const int wstride = gridDim.x * 8;
+  float ag[LN_MAXV][8], ab[LN_MAXV][8], ax[LN_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = ax[i][j] = 0.f;
+  float gm[LN_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) load8f(gamma + (lane + 32 * i) * 8, gm[i]);
+
+  for (int m = blockIdx.x * 8 + wib; m < M; m += wstride) {
+    const bf16* dyr = dy + map_row(m, dymap) * H;
+    const bf16* xr = x + map_row(m, xmap) * H;
+    const float mu = __ldg(mean + m), rs = __ldg(rstd + m);
+    float g[LN_MAXV][8], xh[LN_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        float d[8], xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + lane + 32 * i), d);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + lane + 32 * i), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = d[j] * gm[i][j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          ag[i][j] += d[j] * xh[i][j];
+          ab[i][j] += d[j];
+        }
+      }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+    bf16* dxr = dx + map_row(m, dxmap) * H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+          ax[i][j] += o[j];
+        }
+        reinterpret_cast<uint4*>(dxr)[lane + 32 * i] = pack8(o);
+      }
+  }
+  // cross-warp reduction of the three column accumulators, then one atomic per column per CTA
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;  // uniform
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      if (i < nv) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : ax[i][j]);
+        __syncthreads();
+        // 256 threads: thread t sums column t of this 256-column slab
+        const int t = threadIdx.x;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][t];
+        // slab i covers columns (lane + 32 i) * 8 + j  ->  t = lane*8 + j
+        const int col = ((t >> 3) + 32 * i) * 8 + (t & 7);
+        atomicAdd(dst + col, s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- text embedding + LN
+// e = word[ids] + type[tt] + pos[t] (fp32 tables), y = LN(e) written into rows [0,T) of [N,S,H]
+__global__ void __launch_bounds__(256) txt_embed_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
+                                                            const int64_t* __restrict__ pos_ids,
+                                                            const float* __restrict__ word, const float* __restrict__ type,
+                                                            const float* __restrict__ pos, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            RowMap ymap, float* __restrict__ mean, float* __restrict__ rstd,
+                                                            int M, int T, int H, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = H >> 8;
+  const int64_t id = ids[warp];
+  const int64_t tt = tts ? tts[warp] : 0;
+  const int64_t ps = pos_ids ? pos_ids[warp] : (warp % T);
+  float v[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      const int c = (lane + 32 * i) * 8;
+      float a[8], b[8], d[8];
+      load8f(word + id * H + c, a);
+      load8f(type + tt * H + c, b);
+      load8f(pos + ps * H + c, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] = (a[j] + b[j]) + d[j];  // reference order: (word + type) + position
+        s += v[i][j];
+      }
+    }
+  const float mu = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mu;
+        q += d * d;
+      }
+    }
+  const float rs = rsqrtf(warp_sum(q) / H + eps);
+  bf16* yr = y + map_row(warp, ymap) * H;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      const int c = (lane + 32 * i) * 8;
+      float g[8], b[8], o[8];
+      load8f(gamma + c, g);
+      load8f(beta + c, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
+      reinterpret_cast<uint4*>(yr)[lane + 32 * i] = pack8(o);
+    }
+  if (lane == 0) {
+    mean[warp] = mu;
+    rstd[warp] = rs;
+  }
+}
+
+// backward: recompute e, LN backward, scatter-add into the fp32 table gradients (padding row skipped)
+__global__ void __launch_bounds__(256) txt_embed_bwd_kernel(
+    const bf16* __restrict__ dy, RowMap dymap, const int64_t* __restrict__ ids, const int64_t* __restrict__ tts,
+    const int64_t* __restrict__ pos_ids, const float* __restrict__ word, const float* __restrict__ type,
+    const float* __restrict__ pos, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ rstd, float* __restrict__ dword, float* __restrict__ dtype, float* __restrict__ dpos,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int T, int H, int64_t padding_idx) {
+  __shared__ float red[8][32 * 8 + 1];
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  const int wstride = gridDim.x * 8;
+  float ag[LN_MAXV][8], ab[LN_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  for (int m = blockIdx.x * 8 + wib; m < M; m += wstride) {
+    const int64_t id = ids[m];
+    const int64_t tt = tts ? tts[m] : 0;
+    const int64_t ps = pos_ids ? pos_ids[m] : (m % T);
+    const bf16* dyr = dy + map_row(m, dymap) * H;
+    const float mu = __ldg(mean + m), rs = __ldg(rstd + m);
+    float g[LN_MAXV][8], xh[LN_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+        float d[8], a[8], b[8], e[8], gmv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + lane + 32 * i), d);
+        load8f(word + id * H + c, a);
+        load8f(type + tt * H + c, b);
+        load8f(pos + ps * H + c, e);
+        load8f(gamma + c, gmv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (((a[j] + b[j]) + e[j]) - mu) * rs;
+          g[i][j] = d[j] * gmv[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          ag[i][j] += d[j] * xh[i][j];
+          ab[i][j] += d[j];
+        }
+      }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float o = rs * (g[i][j] - s1 - xh[i][j] * s2);
+          if (id != padding_idx) atomicAdd(dword + id * H + c + j, o);
+          atomicAdd(dtype + tt * H + c + j, o);
+          atomicAdd(dpos + ps * H + c + j, o);
+        }
+      }
+  }
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which == 0 ? dgamma : dbeta;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      if (i < nv) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : ab[i][j];
+        __syncthreads();
+        const int t = threadIdx.x;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][t];
+        const int col = ((t >> 3) + 32 * i) * 8 + (t & 7);
+        atomicAdd(dst + col, s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- casts / packing
+// dst[r, 0:cols] = bf16(src[r, 0:cols]) ; dst[r, cols:ld_dst] = 0   (region features 2054 -> 2112, weights)
+__global__ void cast_pad_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
+                                int64_t rows, int cols, int64_t row_step) {
+  const int64_t total = rows * (ld_dst >> 3);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (ld_dst >> 3);
+    const int c = (int)(i - r * (ld_dst >> 3)) * 8;
+    const float* s = src + r * row_step * ld_src + c;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c + j < cols) ? __ldg(s + j) : 0.f;
+    *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = pack8(f);
+  }
+}
+
+// dst(fp32) [+]= src(bf16) elementwise (used for gradients that must come back as fp32)
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n8, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src) + i), f);
+    float4* d = reinterpret_cast<float4*>(dst) + 2 * i;
+    if (accumulate) {
+      const float4 a = d[0], b = d[1];
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+// dst[r, c] (+)= src[r, c] for c < cols (fp32; un-pads the region-embedding weight gradient)
+__global__ void accum_f32_2d_kernel(float* __restrict__ dst, int64_t ld_dst, const float* __restrict__ src, int64_t ld_src,
+                                    int64_t rows, int cols, int accumulate) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = __ldg(src + r * ld_src + c);
+    float* d = dst + r * ld_dst + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------- column sums
+// out[c] += sum_r x[r, c]    (bias gradients); block = 8 warps x 256 columns, rows strided by grid.y
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int64_t ld, int M, int N,
+                                                     float* __restrict__ out) {
+  __shared__ float red[8][32 * 8 + 1];
+  const int wib = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < N) {
+    for (int r = blockIdx.y * 8 + wib; r < M; r += gridDim.y * 8) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (int64_t)r * ld + c)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][t];
+  const int col = blockIdx.x * 256 + t;
+  if (col < N) atomicAdd(out + col, s);
+}
+
+// ---------------------------------------------------------------------------- row copies
+// dst[seq, drow0 + r, :] (+)= src[seq, srow0 + r, :]   for r < nrows   (bf16, H % 8 == 0)
+__global__ void copy_rows_kernel(const bf16* __restrict__ src, int64_t src_seq_stride, int srow0, bf16* __restrict__ dst,
+                                 int64_t dst_seq_stride, int drow0, int nseq, int nrows, int H, int accumulate) {
+  const int hv = H >> 3;
+  const int64_t total = (int64_t)nseq * nrows * hv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % hv);
+    const int64_t rr = i / hv;
+    const int r = (int)(rr % nrows);
+    const int64_t s = rr / nrows;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (s * src_seq_stride + srow0 + r) * H) + v);
+    uint4* d = reinterpret_cast<uint4*>(dst + (s * dst_seq_stride + drow0 + r) * H) + v;
+    if (accumulate) {
+      float a[8], b[8];
+      unpack8(u, a);
+      unpack8(*d, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+      *d = pack8(a);
+    } else {
+      *d = u;
+    }
+  }
+}
+
+// y = a + b (bf16, elementwise)
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), fa);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b) + i), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+    reinterpret_cast<uint4*>(y)[i] = pack8(fa);
+  }
+}
+
+// dx = dy * (1 - y^2)   (pooler tanh backward), rows strided
+__global__ void tanh_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ dx, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= (1.f - b[j] * b[j]);
+    reinterpret_cast<uint4*>(dx)[i] = pack8(a);
+  }
+}
+
+// ---------------------------------------------------------------------------- masks
+// kbias[n, k] = (1 - mask[n, k]) * -10000   (modeling_transfomres.py:628-641, no dtype cast)
+__global__ void key_bias_kernel(const float* __restrict__ mask, float* __restrict__ kbias, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    kbias[i] = (1.0f - mask[i]) * -10000.0f;
+}
+
+// bits[n, q, w] bit j = (chunk_mask[n, q, 32 w + j] != 0)
+// Exactness: the reference adds (1 - C) * -10000 with C in {0, 1} (v10:289-296); a bit reproduces it exactly.
+__global__ void chunk_bits_kernel(const float* __restrict__ cmask, uint32_t* __restrict__ bits, int N, int T, int cwords) {
+  const int64_t total = (int64_t)N * T * cwords;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % cwords);
+    const int64_t row = i / cwords;
+    const float* src = cmask + row * T + w * 32;
+    uint32_t b = 0;
+    for (int j = 0; j < 32; ++j)
+      if (w * 32 + j < T && src[j] != 0.f) b |= (1u << j);
+    bits[i] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------- chunk-mean queries
+// In place on the Q columns of the fused QKV buffer (row stride ld): for tokens t in [1, 1+len[n]),
+// Q[n,t,:] <- mean over tokens of the same chunk id (v10:66-78).  The operator is self-adjoint, so
+// the backward pass applies the same kernel to dQ.  One CTA per (sequence, 128-column slab); chunk
+// sums are accumulated in token order in fp32 shared memory.
+__global__ void __launch_bounds__(128) chunk_mean_kernel(bf16* __restrict__ q, int64_t ld, int S, const int32_t* __restrict__ chunk_id,
+                                                         int T, int max_chunks) {
+  extern __shared__ float csm[];
+  float* sums = csm;                                            // [max_chunks][128]
+  int* cnt = reinterpret_cast<int*>(csm + (size_t)max_chunks * 128);  // [max_chunks]
+  const int n = blockIdx.y;
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const int32_t* cid = chunk_id + (size_t)n * T;
+  for (int i = threadIdx.x; i < max_chunks; i += 128) cnt[i] = 0;
+  for (int i = threadIdx.x; i < max_chunks * 128; i += 128) sums[i] = 0.f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += 128) {
+    const int c = cid[t];
+    if (c >= 0 && c < max_chunks) atomicAdd(&cnt[c], 1);
+  }
+  bf16* base = q + (size_t)n * S * ld + col;
+  for (int t = 0; t < T; ++t) {
+    const int c = cid[t];
+    if (c >= 0 && c < max_chunks) sums[c * 128 + threadIdx.x] += __bfloat162float(base[(size_t)t * ld]);
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const int c = cid[t];
+    if (c >= 0 && c < max_chunks) base[(size_t)t * ld] = __float2bfloat16(sums[c * 128 + threadIdx.x] / (float)cnt[c]);
+  }
+}
+
+// ============================================================================ host launchers
+static inline int blocks_for(int64_t work, int per_block, int cap = 148 * 16) {
+  int64_t b = (work + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+static int check_h(int H, const char* what) {
+  if (H <= 0 || H % 256 != 0 || H > 256 * LN_MAXV) {
+    set_error("%s: hidden size %d must be a multiple of 256 and <= %d", what, H, 256 * LN_MAXV);
+    return MODCR_ERR_SHAPE;
+  }
+  return MODCR_OK;
+}
+
+int layernorm_fwd(const void* x, RowMap xmap, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
+                  float* rstd, int M, int H, float eps, cudaStream_t st) {
+  if (int rc = check_h(H, "layernorm_fwd")) return rc;
+  if (M <= 0) return MODCR_OK;
+  ln_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, xmap, gamma, beta, (bf16*)y, ymap, mean, rstd, M, H, eps);
+  return check_launch("layernorm_fwd");
+}
+
+int layernorm_bwd(const void* dy, RowMap dymap, const void* x, RowMap xmap, const float* mean, const float* rstd,
+                  const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias, int M, int H,
+                  cudaStream_t st) {
+  if (int rc = check_h(H, "layernorm_bwd")) return rc;
+  if (M <= 0) return MODCR_OK;
+  const int grid = blocks_for(M, 8 * 8, 148 * 4);
+  ln_bwd_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, dymap, (const bf16*)x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap,
+                                      dgamma, dbeta, dbias, M, H);
+  return check_launch("layernorm_bwd");
+}
+
+int txt_embed_ln_fwd(const int64_t* ids, const int64_t* tts, const int64_t* pos_ids, const float* word, const float* type,
+                     const float* pos, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
+                     float* rstd, int N, int T, int H, float eps, cudaStream_t st) {
+  if (int rc = check_h(H, "txt_embed_ln_fwd")) return rc;
+  const int M = N * T;
+  if (M <= 0) return MODCR_OK;
+  txt_embed_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, tts, pos_ids, word, type, pos, gamma, beta, (bf16*)y, ymap, mean,
+                                                    rstd, M, T, H, eps);
+  return check_launch("txt_embed_ln_fwd");
+}
+
+int txt_embed_ln_bwd(const void* dy, RowMap dymap, const int64_t* ids, const int64_t* tts, const int64_t* pos_ids,
+                     const float* word, const float* type, const float* pos, const float* gamma, const float* mean,
+                     const float* rstd, float* dword, float* dtype, float* dpos, float* dgamma, float* dbeta, int N, int T,
+                     int H, int64_t padding_idx, cudaStream_t st) {
+  if (int rc = check_h(H, "txt_embed_ln_bwd")) return rc;
+  const int M = N * T;
+  if (M <= 0) return MODCR_OK;
+  const int grid = blocks_for(M, 8 * 4, 148 * 4);
+  txt_embed_bwd_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, dymap, ids, tts, pos_ids, word, type, pos, gamma, mean, rstd,
+                                             dword, dtype, dpos, dgamma, dbeta, M, T, H, padding_idx);
+  return check_launch("txt_embed_ln_bwd");
+}
+
+int cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int cols, int64_t row_step,
+             cudaStream_t st) {
+  if (ld_dst % 8 != 0 || cols > ld_dst || rows < 0) {
+    set_error("cast_pad: ld_dst=%lld must be a multiple of 8 and >= cols=%d", (long long)ld_dst, cols);
+    return MODCR_ERR_SHAPE;
+  }
+  if (rows == 0) return MODCR_OK;
+  cast_pad_kernel<<<blocks_for(rows * (ld_dst / 8), 256), 256, 0, st>>>(src, ld_src, (bf16*)dst, ld_dst, rows, cols,
+                                                                         row_step);
+  return check_launch("cast_pad");
+}
+
+int bf16_to_f32(const void* src, float* dst, int64_t n, int accumulate, cudaStream_t st) {
+  if (n % 8 != 0) {
+    set_error("bf16_to_f32: n=%lld must be a multiple of 8", (long long)n);
+    return MODCR_ERR_SHAPE;
+  }
+  if (n == 0) return MODCR_OK;
+  bf16_to_f32_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)src, dst, n / 8, accumulate);
+  return check_launch("bf16_to_f32");
+}
+
+int accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int cols, int accumulate,
+                 cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return MODCR_OK;
+  accum_f32_2d_kernel<<<blocks_for(rows * cols, 256), 256, 0, st>>>(dst, ld_dst, src, ld_src, rows, cols, accumulate);
+  return check_launch("accum_f32_2d");
+}
+
+int colsum(const void* x, int64_t ld, int M, int N, float* out, cudaStream_t st) {
+  if (N % 8 != 0 || ld % 8 != 0) {
+    set_error("colsum: N=%d and ld=%lld must be multiples of 8", N, (long long)ld);
+    return MODCR_ERR_SHAPE;
+  }
+  if (M <= 0) return MODCR_OK;
+  dim3 grid((N + 255) / 256, blocks_for(M, 8 * 16, 148));
+  colsum_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ld, M, N, out);
+  return check_launch("colsum");
+}
+
+int copy_rows(const void* src, int64_t src_seq_stride, int srow0, void* dst, int64_t dst_seq_stride, int drow0, int nseq,
+              int nrows, int H, int accumulate, cudaStream_t st) {
+  if (H % 8 != 0) {
+    set_error("copy_rows: H=%d must be a multiple of 8", H);
+    return MODCR_ERR_SHAPE;
+  }
+  if (nseq <= 0 || nrows <= 0) return MODCR_OK;
+  copy_rows_kernel<<<blocks_for((int64_t)nseq * nrows * (H / 8), 256), 256, 0, st>>>(
+      (const bf16*)src, src_seq_stride, srow0, (bf16*)dst, dst_seq_stride, drow0, nseq, nrows, H, accumulate);
+  return check_launch("copy_rows");
+}
+
+int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st) {
+  if (n % 8 != 0) {
+    set_error("add_bf16: n=%lld must be a multiple of 8", (long long)n);
+    return MODCR_ERR_SHAPE;
+  }
+  if (n == 0) return MODCR_OK;
+  add_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
+  return check_launch("add_bf16");
+}
+
+int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st) {
+  if (n % 8 != 0) {
+    set_error("tanh_bwd: n=%lld must be a multiple of 8", (long long)n);
+    return MODCR_ERR_SHAPE;
+  }
+  if (n == 0) return MODCR_OK;
+  tanh_bwd_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (bf16*)dx, n / 8);
+  return check_launch("tanh_bwd");
+}
+
+int key_bias(const float* mask, float* kbias, int64_t total, cudaStream_t st) {
+  if (total <= 0) return MODCR_OK;
+  key_bias_kernel<<<blocks_for(total, 256), 256, 0, st>>>(mask, kbias, total);
+  return check_launch("key_bias");
+}
+
+int chunk_bits(const float* cmask, uint32_t* bits, int N, int T, int cwords, cudaStream_t st) {
+  if (cwords * 32 < T) {
+    set_error("chunk_bits: cwords=%d too small for T=%d", cwords, T);
+    return MODCR_ERR_SHAPE;
+  }
+  if (N <= 0) return MODCR_OK;
+  chunk_bits_kernel<<<blocks_for((int64_t)N * T * cwords, 256), 256, 0, st>>>(cmask, bits, N, T, cwords);
+  return check_launch("chunk_bits");
+}
+
+int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_id, int T, int max_chunks,
+                 cudaStream_t st) {
+  if (H % 128 != 0 || T > S || max_chunks <= 0) {
+    set_error("chunk_mean_q: bad shape H=%d T=%d S=%d max_chunks=%d", H, T, S, max_chunks);
+    return MODCR_ERR_SHAPE;
+  }
+  const size_t smem = (size_t)max_chunks * 128 * 4 + (size_t)max_chunks * 4;
+  if (smem > 200 * 1024) {
+    set_error("chunk_mean_q: %d chunks need %zu B of shared memory", max_chunks, smem);
+    return MODCR_ERR_UNSUPPORTED;
+  }
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(chunk_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("chunk_mean_q: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return MODCR_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  dim3 grid(H / 128, N);
+  chunk_mean_kernel<<<grid, 128, smem, st>>>((bf16*)q, ld, S, chunk_id, T, max_chunks);
+  return check_launch("chunk_mean_q");
+}
+
+}  // namespace modcr

@@ -1,0 +1,83 @@
+// Internal C++ interface of the HBM-bound row kernels (rowops.cu) and head kernels (heads.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace modcr {
+
+// Logical row m -> physical row (m / rows_per_seq) * seq_stride + row0 + m % rows_per_seq.
+// rows_per_seq <= 0 means identity.
+struct RowMap {
+  int rows_per_seq = 0;
+  int seq_stride = 0;
+  int row0 = 0;
+};
+
+int layernorm_fwd(const void* x, RowMap xmap, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
+                  float* rstd, int M, int H, float eps, cudaStream_t st);
+int layernorm_bwd(const void* dy, RowMap dymap, const void* x, RowMap xmap, const float* mean, const float* rstd,
+                  const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias, int M, int H,
+                  cudaStream_t st);
+int txt_embed_ln_fwd(const int64_t* ids, const int64_t* tts, const int64_t* pos_ids, const float* word, const float* type,
+                     const float* pos, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
+                     float* rstd, int N, int T, int H, float eps, cudaStream_t st);
+int txt_embed_ln_bwd(const void* dy, RowMap dymap, const int64_t* ids, const int64_t* tts, const int64_t* pos_ids,
+                     const float* word, const float* type, const float* pos, const float* gamma, const float* mean,
+                     const float* rstd, float* dword, float* dtype, float* dpos, float* dgamma, float* dbeta, int N, int T,
+                     int H, int64_t padding_idx, cudaStream_t st);
+int cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int cols, int64_t row_step,
+             cudaStream_t st);
+int bf16_to_f32(const void* src, float* dst, int64_t n, int accumulate, cudaStream_t st);
+int accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int cols, int accumulate,
+                 cudaStream_t st);
+int colsum(const void* x, int64_t ld, int M, int N, float* out, cudaStream_t st);
+int copy_rows(const void* src, int64_t src_seq_stride, int srow0, void* dst, int64_t dst_seq_stride, int drow0, int nseq,
+              int nrows, int H, int accumulate, cudaStream_t st);
+int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st);
+int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
+int key_bias(const float* mask, float* kbias, int64_t total, cudaStream_t st);
+int chunk_bits(const float* cmask, uint32_t* bits, int N, int T, int cwords, cudaStream_t st);
+int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_id, int T, int max_chunks,
+                 cudaStream_t st);
+
+// ---- heads.cu
+// Alignment loss (v10:982-987): A = sum over `nslices` slices of probs_img, masked_fill(A==0,-1e5),
+// softmax over R, rows with align_pos==1, CE(probabilities, total_label) -- double softmax as written.
+//   probs: fp32 [nl, N, heads, T, R]; block: [N,T,R]; row_loss: [N*T, 2]; out: [4] = {loss, M, correct, loss sum}
+int align_softmax_ce_fwd(const float* probs, int nl, int heads, const int64_t* align_pos, const int64_t* total_label,
+                         float* block, float* row_loss, float* out, int N, int T, int R, cudaStream_t st);
+int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label, const float* out,
+                         float gout, float* dblock, int N, int T, int R, cudaStream_t st);
+
+// ClsLayer2 attention pooling (v10:816-829): w = softmax(q k^T + mask) (no 1/sqrt(d)), pooled = w k
+int cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int N, int L, int H,
+                      cudaStream_t st);
+int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk, int N, int L,
+                      int H, cudaStream_t st);
+
+// Fused small classifier + cross-entropy (+ binary_to_mp / argmax / matched):
+//   logits[r, c] = x[r,:] . W[c,:] + b[c]            x bf16 [rows,K], W fp32 [C,K], C <= 8
+//   CE over the view [rows*C/G, G]; hard labels (int64) or soft labels (fp32 [rows*C/G, G]).
+struct ScorerDesc {
+  const void* x = nullptr;
+  const float* W = nullptr;
+  const float* b = nullptr;
+  int rows = 0, K = 0, C = 0, G = 0;
+  const int64_t* hard = nullptr;
+  const float* soft = nullptr;
+  float* logits = nullptr;     // [rows, C]
+  float* loss = nullptr;       // [1]
+  float* mp = nullptr;         // optional [rows/num_choice, num_choice] = softmax(logits)[:,1] (C == 2)
+  int64_t* pred = nullptr;     // optional [rows/num_choice] argmax of mp
+  uint8_t* matched = nullptr;  // optional [rows/num_choice] pred == argmax(label group)
+  int num_choice = 4;
+  // backward
+  float gout = 1.f;
+  void* dx = nullptr;          // bf16 [rows, K]
+  float* dW = nullptr;         // fp32 [C, K] accumulate
+  float* db = nullptr;         // fp32 [C] accumulate
+};
+int mc_scorer_ce_fwd(const ScorerDesc& d, cudaStream_t st);
+int mc_scorer_ce_bwd(const ScorerDesc& d, cudaStream_t st);
+
+}  // namespace modcr
