@@ -1,0 +1,379 @@
+"""Host-side execution engine of the hot path: explicit forward / backward programs over the
+CUDA kernels (``ops``), with the activations each backward needs kept in caller-owned buffers.
+
+The reference runs this path as eager PyTorch autograd over cuBLAS / ATen kernels
+(modeling/modeling_bert.py:25-155, modeling/modeling_transfomres.py:471-727,
+modeling/modeling_vcr_chunkalign_v10.py:45-373, 801-837, 1016-1165).  Here every arithmetic step is
+one of our sm_100a kernels; PyTorch only owns memory, streams and the autograd *edges* between
+the few coarse ``torch.autograd.Function`` nodes defined in ``functions.py``.
+
+Layout in HBM (all row-major, bf16 unless noted):
+  hidden states      [N, S, H]      S = T text rows followed by R region rows (no torch.cat)
+  fused QKV          [N, S, 3H]     Q | K | V column blocks, heads are 64-column slices
+  prefix K/V         [N, P, 2H]     K | V of the per-layer ``history_state`` rows
+  FFN activations    [N*S, I]       pre-GELU (kept for GELU') and post-GELU
+  LN statistics      fp32 [N*S]     mean / rstd per row
+  parameter grads    fp32, produced directly by the tcgen05 wgrad GEMM (TN, fp32 out)
+"""
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+NUM_SMS = 148
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _zeros(shape, dtype, dev):
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+# --------------------------------------------------------------------------------------------
+class ParamStore:
+    """fp32 master parameters (the module's ``nn.Parameter`` objects, reference state_dict names)
+    plus lazily refreshed bf16 operand copies for the tensor-core kernels."""
+
+    def __init__(self, named):
+        self.named = dict(named)
+        self._cache = {}
+
+    def f32(self, name):
+        return self.named[name]
+
+    def has(self, name):
+        return name in self.named
+
+    def _key(self, names):
+        return tuple((self.named[n].data_ptr(), self.named[n]._version) for n in names)
+
+    def bf16(self, name):
+        ent = self._cache.get(name)
+        key = self._key((name,))
+        if ent is None or ent[0] != key:
+            ent = (key, ops.to_bf16(self.named[name].detach()))
+            self._cache[name] = ent
+        return ent[1]
+
+    def qkv(self, pfx):
+        """Concatenated [3H,H] bf16 weight and [3H] fp32 bias of attention.self.{query,key,value}."""
+        names = [pfx + n + s for n in ("query", "key", "value") for s in (".weight", ".bias")]
+        ent = self._cache.get(pfx + "#qkv")
+        key = self._key(names)
+        if ent is None or ent[0] != key:
+            ws = [self.named[pfx + n + ".weight"].detach() for n in ("query", "key", "value")]
+            H = ws[0].shape[1]
+            W = _empty((3 * H, H), BF16, ws[0].device)
+            for i, w in enumerate(ws):
+                ops.cast_pad(w.contiguous(), H, W[i * H:], H, H, H)
+            b = torch.cat([self.named[pfx + n + ".bias"].detach() for n in ("query", "key", "value")]).contiguous()
+            ent = (key, W, b)
+            self._cache[pfx + "#qkv"] = ent
+        return ent[1], ent[2]
+
+    def padded(self, name, Dpad):
+        ent = self._cache.get(name + "#pad")
+        key = self._key((name,))
+        if ent is None or ent[0] != key:
+            w = self.named[name].detach().contiguous()
+            out = _empty((w.shape[0], Dpad), BF16, w.device)
+            ops.cast_pad(w, w.shape[1], out, Dpad, w.shape[0], w.shape[1])
+            ent = (key, out)
+            self._cache[name + "#pad"] = ent
+        return ent[1]
+
+
+def _split_k(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    if tiles >= NUM_SMS:
+        return 1
+    return max(1, min(NUM_SMS // tiles, kb // 4))
+
+
+def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None):
+    """dW[out_f, in_f] = dY^T X  (fp32; split-K through TMA reduce-add when the tile grid is small).
+    With ``out`` given the product is accumulated into it."""
+    dev = dY.device
+    if out is not None:
+        ops.gemm(dY, X, out, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1,
+                 split_k=_split_k(out_f, in_f, rows))
+        return out
+    sk = _split_k(out_f, in_f, rows)
+    if sk > 1:
+        dW = _zeros((out_f, in_f), F32, dev)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1, split_k=sk)
+    else:
+        dW = _empty((out_f, in_f), F32, dev)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1)
+    return dW
+
+
+# -------------------------------------------------------------------------------------------- FFN block
+def ffn_fwd(ps, pfx, a, M, H, I, eps, save):
+    """BertIntermediate + BertOutput (a_transformers/modeling_bert.py:434-437, 447-451)."""
+    dev = a.device
+    W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
+    gact = _empty((M, I), BF16, dev)
+    u = _empty((M, I), BF16, dev) if save is not None else None
+    ops.gemm(a, W1, gact, M, I, H, bias=ps.f32(pfx + "intermediate.dense.bias"), act=1, aux=u)
+    pre2 = _empty((M, H), BF16, dev)
+    ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a, in_op=1)
+    y = _empty((M, H), BF16, dev)
+    mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+    ops.layernorm_fwd(pre2, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), y, mean2,
+                      rstd2, M, H, eps)
+    if save is not None:
+        save.update(a=a, u=u, gact=gact, pre2=pre2, mean2=mean2, rstd2=rstd2)
+    return y
+
+
+def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads):
+    """Returns d(a) given d(y)."""
+    dev = dy.device
+    W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
+    g2 = _empty((M, H), BF16, dev)
+    dgam, dbet, db2 = _zeros((H,), F32, dev), _zeros((H,), F32, dev), _zeros((H,), F32, dev)
+    ops.layernorm_bwd(dy, sv["pre2"], sv["mean2"], sv["rstd2"], ps.f32(pfx + "output.LayerNorm.weight"), g2, dgam, dbet,
+                      db2, M, H)
+    grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
+    grads[pfx + "output.dense.bias"] = db2
+    grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M)
+    du = _empty((M, I), BF16, dev)
+    ops.gemm(g2, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)           # (g2 W2) * GELU'(u)
+    db1 = _zeros((I,), F32, dev)
+    ops.colsum(du, I, M, I, db1)
+    grads[pfx + "intermediate.dense.bias"] = db1
+    grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M)
+    da = _empty((M, H), BF16, dev)
+    ops.gemm(du, W1, da, M, H, I, b_mn=1, epi_in=g2, in_op=1)                # + residual branch
+    return da
+
+
+# -------------------------------------------------------------------------------------------- attention block
+class AttnCfg:
+    """Static description of one self-attention call."""
+    __slots__ = ("N", "S", "H", "heads", "P", "T", "mode", "kbias", "cbits", "cwords", "chunk_id", "max_chunks")
+
+    def __init__(self, N, S, H, heads, P=0, T=0, mode=0, kbias=None, cbits=None, cwords=0, chunk_id=None,
+                 max_chunks=0):
+        self.N, self.S, self.H, self.heads, self.P, self.T, self.mode = N, S, H, heads, P, T, mode
+        self.kbias, self.cbits, self.cwords, self.chunk_id, self.max_chunks = kbias, cbits, cwords, chunk_id, max_chunks
+
+
+def attention_fwd(ps, pfx, x, hist, ac, eps, save, do_chunk_cross=False, probs_img=None):
+    """CaptionBertAttention: self-attention with prefix (modeling/modeling_bert.py:34-93, v10:55-129)
+    followed by BertSelfOutput.  ``x`` [N*S,H]; ``hist`` [N*P,H] or None."""
+    dev = x.device
+    N, S, H, heads, P = ac.N, ac.S, ac.H, ac.heads, ac.P
+    M = N * S
+    Wqkv, bqkv = ps.qkv(pfx + "self.")
+    qkv = _empty((M, 3 * H), BF16, dev)
+    ops.gemm(x, Wqkv, qkv, M, 3 * H, H, bias=bqkv)
+    pkv = None
+    if P > 0:
+        pkv = _empty((N * P, 2 * H), BF16, dev)
+        ops.gemm(hist, Wqkv[H:], pkv, N * P, 2 * H, H, bias=bqkv[H:])
+    if do_chunk_cross:
+        ops.chunk_mean_q(qkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)
+    ctx = _empty((M, H), BF16, dev)
+    lse = _empty((N, heads, S), F32, dev)
+    ops.prefix_attn_fwd(N, S, P, heads, ac.T, ac.mode, qkv, pkv, ac.kbias, ac.cbits, ac.cwords, ctx, lse, probs_img)
+    pre1 = _empty((M, H), BF16, dev)
+    ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
+             epi_in=x, in_op=1)
+    a = _empty((M, H), BF16, dev)
+    mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+    ops.layernorm_fwd(pre1, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), a, mean1,
+                      rstd1, M, H, eps)
+    if save is not None:
+        save.update(x=x, hist=hist, qkv=qkv, pkv=pkv, ctx=ctx, lse=lse, pre1=pre1, mean1=mean1, rstd1=rstd1,
+                    chunk=do_chunk_cross, probs_img=probs_img)
+    return a
+
+
+def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None):
+    """Returns (dx, dhist)."""
+    dev = da.device
+    N, S, H, heads, P = ac.N, ac.S, ac.H, ac.heads, ac.P
+    M = N * S
+    Wqkv, _ = ps.qkv(pfx + "self.")
+    g1 = _empty((M, H), BF16, dev)
+    dgam, dbet, dbo = _zeros((H,), F32, dev), _zeros((H,), F32, dev), _zeros((H,), F32, dev)
+    ops.layernorm_bwd(da, sv["pre1"], sv["mean1"], sv["rstd1"], ps.f32(pfx + "output.LayerNorm.weight"), g1, dgam, dbet,
+                      dbo, M, H)
+    grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
+    grads[pfx + "output.dense.bias"] = dbo
+    grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M)
+    dctx = _empty((M, H), BF16, dev)
+    ops.gemm(g1, ps.bf16(pfx + "output.dense.weight"), dctx, M, H, H, b_mn=1)
+    dqkv = _empty((M, 3 * H), BF16, dev)
+    dpkv = _empty((N * P, 2 * H), BF16, dev) if P > 0 else None
+    if ws is None:
+        ws = _empty((ops.attn_bwd_workspace_bytes(N, S, heads) // 4,), F32, dev)
+    use_align = dalign if sv["probs_img"] is not None else None
+    ops.prefix_attn_bwd(N, S, P, heads, ac.T, ac.mode, sv["qkv"], sv["pkv"], ac.kbias, ac.cbits, ac.cwords, sv["ctx"],
+                        sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws)
+    if sv["chunk"]:
+        ops.chunk_mean_q(dqkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)   # self-adjoint operator
+    dbqkv = _zeros((3 * H,), F32, dev)
+    ops.colsum(dqkv, 3 * H, M, 3 * H, dbqkv)
+    dWqkv = wgrad(dqkv, sv["x"], 3 * H, H, M)
+    dhist = None
+    if P > 0:
+        ops.colsum(dpkv, 2 * H, N * P, 2 * H, dbqkv[H:])
+        wgrad(dpkv, sv["hist"], 2 * H, H, N * P, out=dWqkv[H:])
+        dhist = _empty((N * P, H), BF16, dev)
+        ops.gemm(dpkv, Wqkv[H:], dhist, N * P, H, 2 * H, b_mn=1)
+    for i, n in enumerate(("query", "key", "value")):
+        grads[pfx + "self." + n + ".weight"] = dWqkv[i * H:(i + 1) * H]
+        grads[pfx + "self." + n + ".bias"] = dbqkv[i * H:(i + 1) * H]
+    dx = _empty((M, H), BF16, dev)
+    ops.gemm(dqkv, Wqkv, dx, M, H, 3 * H, b_mn=1, epi_in=g1, in_op=1)
+    return dx, dhist
+
+
+def layer_fwd(ps, pfx, x, hist, ac, I, eps, save, do_chunk_cross=False, probs_img=None):
+    """CaptionBertLayer.forward (modeling/modeling_transfomres.py:481-489, v10:140-150)."""
+    a = attention_fwd(ps, pfx + "attention.", x, hist, ac, eps, save, do_chunk_cross, probs_img)
+    return ffn_fwd(ps, pfx, a, ac.N * ac.S, ac.H, I, eps, save)
+
+
+def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None):
+    da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, ac.H, I, grads)
+    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws)
+
+
+# -------------------------------------------------------------------------------------------- embeddings
+def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, save):
+    """BertEmbeddings + img_embedding (+LayerNorm) written into one [N,S,H] buffer
+    (a_transformers/modeling_bert.py:184-211; modeling_transfomres.py:676-684; v10:339-345)."""
+    dev = input_ids.device
+    N, T = input_ids.shape
+    H = cfg["H"]
+    R = 0 if img_feats is None else img_feats.shape[1]
+    S = T + R
+    x0 = _empty((N, S, H), BF16, dev)
+    tmean, trstd = _empty((N * T,), F32, dev), _empty((N * T,), F32, dev)
+    tmap = ops.rowmap(T, S, 0)
+    ids = input_ids.contiguous()
+    tts = None if token_type_ids is None else token_type_ids.contiguous()
+    pos = None if position_ids is None else position_ids.expand(N, T).contiguous()
+    ops.txt_embed_ln_fwd(ids, tts, pos, ps.f32("embeddings.word_embeddings.weight"),
+                         ps.f32("embeddings.token_type_embeddings.weight"),
+                         ps.f32("embeddings.position_embeddings.weight"), ps.f32("embeddings.LayerNorm.weight"),
+                         ps.f32("embeddings.LayerNorm.bias"), x0, tmap, tmean, trstd, N, T, H, cfg["eps"])
+    sv = dict(ids=ids, tts=tts, pos=pos, tmean=tmean, trstd=trstd, N=N, T=T, R=R, S=S)
+    if R > 0:
+        D = img_feats.shape[2]
+        Dpad = (D + 63) // 64 * 64
+        rows = N * R
+        feats = img_feats.contiguous()
+        packed = _empty((rows, Dpad), BF16, dev)
+        pre = _empty((rows, H), BF16, dev)
+        imean, irstd = _empty((rows,), F32, dev), _empty((rows,), F32, dev)
+        use_ln = cfg["use_img_layernorm"]
+        ops.img_embed_ln_fwd(feats, rows, D, Dpad, ps.padded("img_embedding.weight", Dpad),
+                             ps.f32("img_embedding.bias"),
+                             ps.f32("LayerNorm.weight") if use_ln else None,
+                             ps.f32("LayerNorm.bias") if use_ln else None, use_ln, cfg["img_eps"], packed, pre, x0,
+                             ops.rowmap(R, S, T), imean, irstd, H)
+        sv.update(packed=packed, pre=pre, imean=imean, irstd=irstd, D=D, Dpad=Dpad)
+    if save is not None:
+        save.update(sv)
+    return x0
+
+
+def embeddings_bwd(ps, cfg, sv, dx0, grads):
+    dev = dx0.device
+    N, T, R, S, H = sv["N"], sv["T"], sv["R"], sv["S"], cfg["H"]
+    word = ps.f32("embeddings.word_embeddings.weight")
+    type_ = ps.f32("embeddings.token_type_embeddings.weight")
+    pos = ps.f32("embeddings.position_embeddings.weight")
+    dw, dt, dp = torch.zeros_like(word), torch.zeros_like(type_), torch.zeros_like(pos)
+    dg, db = _zeros((H,), F32, dev), _zeros((H,), F32, dev)
+    ops.txt_embed_ln_bwd(dx0, ops.rowmap(T, S, 0), sv["ids"], sv["tts"], sv["pos"], word, type_, pos,
+                         ps.f32("embeddings.LayerNorm.weight"), sv["tmean"], sv["trstd"], dw, dt, dp, dg, db, N, T, H,
+                         cfg["pad_token_id"])
+    grads["embeddings.word_embeddings.weight"] = dw
+    grads["embeddings.token_type_embeddings.weight"] = dt
+    grads["embeddings.position_embeddings.weight"] = dp
+    grads["embeddings.LayerNorm.weight"], grads["embeddings.LayerNorm.bias"] = dg, db
+    if R > 0:
+        rows, D, Dpad = N * R, sv["D"], sv["Dpad"]
+        use_ln = cfg["use_img_layernorm"]
+        dpre = _empty((rows, H), BF16, dev)
+        dWp = _empty((H, Dpad), F32, dev)
+        dbias = _zeros((H,), F32, dev)
+        dgi, dbi = (_zeros((H,), F32, dev), _zeros((H,), F32, dev)) if use_ln else (None, None)
+        ops.img_embed_ln_bwd(dx0, ops.rowmap(R, S, T), sv["packed"], sv["pre"], sv["imean"], sv["irstd"],
+                             ps.f32("LayerNorm.weight") if use_ln else None, use_ln, dpre, dWp, dbias, dgi, dbi, rows,
+                             Dpad, H)
+        dW = _empty((H, D), F32, dev)
+        ops.accum_f32_2d(dW, D, dWp, Dpad, H, D)
+        grads["img_embedding.weight"], grads["img_embedding.bias"] = dW, dbias
+        if use_ln:
+            grads["LayerNorm.weight"], grads["LayerNorm.bias"] = dgi, dbi
+
+
+# -------------------------------------------------------------------------------------------- pooler
+def pooler_fwd(ps, h, N, S, H, out=None, ldc=None):
+    """BertPooler (a_transformers/modeling_bert.py:640-646): tanh(W h[:,0] + b); reads row 0 of every
+    sequence in place (lda = S*H) and can write into a column block of a wider buffer."""
+    if out is None:
+        out = _empty((N, H), BF16, h.device)
+    ops.gemm(h, ps.bf16("pooler.dense.weight"), out, N, H, H, lda=S * H, ldc=ldc, bias=ps.f32("pooler.dense.bias"),
+             act=2)
+    return out
+
+
+def pooler_bwd(ps, h, pooled, dpooled, N, S, H, dh, grads):
+    """Accumulates the gradient of row 0 into ``dh`` [N,S,H]."""
+    dev = h.device
+    dpre = _empty((N, H), BF16, dev)
+    ops.tanh_bwd(dpooled, pooled, dpre)
+    db = _zeros((H,), F32, dev)
+    ops.colsum(dpre, H, N, H, db)
+    grads["pooler.dense.bias"] = db
+    grads["pooler.dense.weight"] = wgrad(dpre, h, H, H, N, ldx=S * H)
+    d0 = _empty((N, H), BF16, dev)
+    ops.gemm(dpre, ps.bf16("pooler.dense.weight"), d0, N, H, H, b_mn=1)
+    ops.copy_rows(d0, 1, 0, dh, S, 0, N, 1, H, accumulate=True)
+
+
+# -------------------------------------------------------------------------------------------- masks
+def make_key_bias(mask2d):
+    """(1 - mask) * -10000 (modeling_transfomres.py:628-641; no dtype cast)."""
+    m = mask2d.to(F32).contiguous()
+    kb = torch.empty_like(m)
+    ops.key_bias(m, kb)
+    return kb
+
+
+def make_chunk_bits(chunk_mask):
+    N, T, _ = chunk_mask.shape
+    cwords = (T + 31) // 32
+    bits = _empty((N, T, cwords), torch.int32, chunk_mask.device)
+    ops.chunk_bits(chunk_mask.to(F32).contiguous(), bits, N, T, cwords)
+    return bits, cwords
+
+
+def pack_chunk_ids(gather_index, T, device):
+    """Ragged ``gather_index`` (list of N int64 tensors, chunk id of tokens 1..L-2,
+    Data/VCRChunkAlign.py:666-670) -> int32 [N,T] with -1 outside the chunked span, plus the
+    largest chunk count.  One host-side pack and one H2D copy per batch."""
+    N = len(gather_index)
+    lens = [int(g.numel()) for g in gather_index]
+    flat = torch.cat([g.reshape(-1) for g in gather_index]) if N else torch.zeros(0, dtype=torch.int64)
+    flat = flat.to("cpu") if flat.is_cuda else flat
+    out = torch.full((N, T), -1, dtype=torch.int32)
+    off, mx = 0, 0
+    for n, L in enumerate(lens):
+        if L:
+            seg = flat[off:off + L]
+            out[n, 1:1 + L] = seg.to(torch.int32)
+            mx = max(mx, int(seg.max()) + 1)
+        off += L
+    return out.to(device, non_blocking=True), max(mx, 1)

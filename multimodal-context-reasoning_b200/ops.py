@@ -1,0 +1,245 @@
+"""Tensor-level wrappers over the C ABI (``include/modcr_b200.h``).
+
+Each function takes CUDA tensors that the caller owns (PyTorch is only the memory
+and stream plumbing), validates what the C side cannot see (dtype / device /
+contiguity) and enqueues the kernel on the current stream.  There is no fallback
+path: without the shared library or an sm_100 device these raise ``RuntimeError``.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AttnDesc, GemmDesc, RowMap, ScorerDesc
+
+BF16, F32, I64 = torch.bfloat16, torch.float32, torch.int64
+IDENT = RowMap(0, 0, 0)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError("modcr_b200: %s must be a CUDA tensor (no CPU path)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("modcr_b200: %s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def rowmap(rows_per_seq=0, seq_stride=0, row0=0):
+    return RowMap(rows_per_seq, seq_stride, row0)
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=None, act=0, aux=None,
+         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None):
+    """C[M,N] = epi(alpha * A B^T); operands are raw 2-D views described by (ptr, ld)."""
+    d = GemmDesc()
+    d.A, d.B, d.C = A.data_ptr(), B.data_ptr(), C_.data_ptr()
+    d.lda = lda if lda is not None else (M if a_mn else K)
+    d.ldb = ldb if ldb is not None else (N if b_mn else K)
+    d.ldc = ldc if ldc is not None else N
+    d.a_mn, d.b_mn = a_mn, b_mn
+    d.c_fp32 = 1 if C_.dtype == F32 else 0
+    d.accumulate, d.split_k = accumulate, split_k
+    d.M, d.N, d.K = M, N, K
+    d.alpha = alpha
+    d.bias = _p(bias)
+    d.act = act
+    d.aux = _p(aux)
+    d.ldaux = ldaux if ldaux is not None else N
+    d.epi_in = _p(epi_in)
+    d.ld_in = ld_in if ld_in is not None else N
+    d.in_op = in_op if epi_in is not None else 0
+    _lib.check(_lib.load().modcr_gemm(C.byref(d), _stream()), "gemm")
+    return C_
+
+
+# --------------------------------------------------------------------------- LayerNorm / embeddings
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, eps, xmap=IDENT, ymap=IDENT):
+    _lib.check(_lib.load().modcr_layernorm_fwd(_p(x), xmap, _p(gamma), _p(beta), _p(y), ymap, _p(mean), _p(rstd),
+                                               M, H, eps, _stream()), "layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dbias, M, H, dymap=IDENT, xmap=IDENT, dxmap=IDENT):
+    _lib.check(_lib.load().modcr_layernorm_bwd(_p(dy), dymap, _p(x), xmap, _p(mean), _p(rstd), _p(gamma), _p(dx),
+                                               dxmap, _p(dgamma), _p(dbeta), _p(dbias), M, H, _stream()),
+               "layernorm_bwd")
+
+
+def txt_embed_ln_fwd(ids, tts, pos_ids, word, type_, pos, gamma, beta, y, ymap, mean, rstd, N, T, H, eps):
+    _chk(ids, I64, "input_ids")
+    _chk(tts, I64, "token_type_ids")
+    _chk(pos_ids, I64, "position_ids")
+    _lib.check(_lib.load().modcr_txt_embed_ln_fwd(_p(ids), _p(tts), _p(pos_ids), _p(word), _p(type_), _p(pos),
+                                                  _p(gamma), _p(beta), _p(y), ymap, _p(mean), _p(rstd), N, T, H, eps,
+                                                  _stream()), "txt_embed_ln_fwd")
+
+
+def txt_embed_ln_bwd(dy, dymap, ids, tts, pos_ids, word, type_, pos, gamma, mean, rstd, dword, dtype, dpos, dgamma,
+                     dbeta, N, T, H, padding_idx):
+    _lib.check(_lib.load().modcr_txt_embed_ln_bwd(_p(dy), dymap, _p(ids), _p(tts), _p(pos_ids), _p(word), _p(type_),
+                                                  _p(pos), _p(gamma), _p(mean), _p(rstd), _p(dword), _p(dtype),
+                                                  _p(dpos), _p(dgamma), _p(dbeta), N, T, H, padding_idx, _stream()),
+               "txt_embed_ln_bwd")
+
+
+def img_embed_ln_fwd(feats, rows, D, Dpad, W, bias, gamma, beta, use_ln, eps, packed, pre, y, ymap, mean, rstd, H):
+    _chk(feats, F32, "img_feats")
+    _lib.check(_lib.load().modcr_img_embed_ln_fwd(_p(feats), rows, D, Dpad, _p(W), _p(bias), _p(gamma), _p(beta),
+                                                  int(use_ln), eps, _p(packed), _p(pre), _p(y), ymap, _p(mean),
+                                                  _p(rstd), H, _stream()), "img_embed_ln_fwd")
+
+
+def img_embed_ln_bwd(dy, dymap, packed, pre, mean, rstd, gamma, use_ln, dpre, dW_pad, dbias, dgamma, dbeta, rows,
+                     Dpad, H):
+    _lib.check(_lib.load().modcr_img_embed_ln_bwd(_p(dy), dymap, _p(packed), _p(pre), _p(mean), _p(rstd), _p(gamma),
+                                                  int(use_ln), _p(dpre), _p(dW_pad), _p(dbias), _p(dgamma),
+                                                  _p(dbeta), rows, Dpad, H, _stream()), "img_embed_ln_bwd")
+
+
+# --------------------------------------------------------------------------- attention
+def _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, dctx=None,
+               dalign=None, dqkv=None, dpkv=None, dq_ws=None):
+    d = AttnDesc()
+    d.N, d.S, d.P, d.heads, d.T, d.mode = N, S, P, heads, T, mode
+    d.scale = 0.125
+    d.qkv, d.pkv, d.kbias, d.cbits, d.cwords = _p(qkv), _p(pkv), _p(kbias), _p(cbits), cwords
+    d.ctx, d.lse, d.probs_img = _p(ctx), _p(lse), _p(probs_img)
+    d.dctx, d.dalign, d.dqkv, d.dpkv, d.dq_ws = _p(dctx), _p(dalign), _p(dqkv), _p(dpkv), _p(dq_ws)
+    return d
+
+
+def prefix_attn_fwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None):
+    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img)
+    _lib.check(_lib.load().modcr_prefix_attn_fwd(C.byref(d), _stream()), "prefix_attn_fwd")
+
+
+def prefix_attn_bwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
+                    dpkv, dq_ws):
+    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
+                   dpkv, dq_ws)
+    _lib.check(_lib.load().modcr_prefix_attn_bwd(C.byref(d), _stream()), "prefix_attn_bwd")
+
+
+def attn_bwd_workspace_bytes(N, S, heads):
+    dims = (C.c_int64 * 3)(N, S, heads)
+    return int(_lib.load().modcr_workspace_bytes(1, dims, 3))
+
+
+def chunk_mean_q(q, ld, N, S, H, chunk_id, T, max_chunks):
+    _chk(chunk_id, torch.int32, "chunk_id")
+    _lib.check(_lib.load().modcr_chunk_mean_q(_p(q), ld, N, S, H, _p(chunk_id), T, max_chunks, _stream()),
+               "chunk_mean_q")
+
+
+# --------------------------------------------------------------------------- heads
+def align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, block, row_loss, out, N, T, R):
+    _chk(align_pos, I64, "align_pos")
+    _chk(total_label, I64, "total_label")
+    _lib.check(_lib.load().modcr_align_softmax_ce_fwd(_p(probs), nl, heads, _p(align_pos), _p(total_label), _p(block),
+                                                      _p(row_loss), _p(out), N, T, R, _stream()),
+               "align_softmax_ce_fwd")
+
+
+def align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T, R):
+    _lib.check(_lib.load().modcr_align_softmax_ce_bwd(_p(block), _p(align_pos), _p(total_label), _p(out), gout,
+                                                      _p(dblock), N, T, R, _stream()), "align_softmax_ce_bwd")
+
+
+def cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H):
+    _lib.check(_lib.load().modcr_cls_pool_attn_fwd(_p(q), _p(k), _p(mask), _p(w), _p(pooled), N, L, H, _stream()),
+               "cls_pool_attn_fwd")
+
+
+def cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H):
+    _lib.check(_lib.load().modcr_cls_pool_attn_bwd(_p(dpooled), _p(q), _p(k), _p(w), _p(dq), _p(dk), N, L, H,
+                                                   _stream()), "cls_pool_attn_bwd")
+
+
+def _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None, num_choice=4,
+                 gout=1.0, dx=None, dW=None, db=None):
+    d = ScorerDesc()
+    d.x, d.W, d.b = _p(x), _p(W), _p(b)
+    d.rows, d.K, d.C, d.G = rows, K, Cc, G
+    d.hard, d.soft, d.logits, d.loss = _p(hard), _p(soft), _p(logits), _p(loss)
+    d.mp, d.pred, d.matched, d.num_choice = _p(mp), _p(pred), _p(matched), num_choice
+    d.gout, d.dx, d.dW, d.db = gout, _p(dx), _p(dW), _p(db)
+    return d
+
+
+def mc_scorer_ce_fwd(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None,
+                     num_choice=4):
+    _chk(hard, I64, "labels")
+    _chk(soft, F32, "soft labels")
+    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice)
+    _lib.check(_lib.load().modcr_mc_scorer_ce_fwd(C.byref(d), _stream()), "mc_scorer_ce_fwd")
+
+
+def mc_scorer_ce_bwd(x, W, b, rows, K, Cc, G, hard, soft, logits, gout, dx, dW, db):
+    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, None, gout=gout, dx=dx, dW=dW, db=db)
+    _lib.check(_lib.load().modcr_mc_scorer_ce_bwd(C.byref(d), _stream()), "mc_scorer_ce_bwd")
+
+
+# --------------------------------------------------------------------------- utilities
+def cast_pad(src, ld_src, dst, ld_dst, rows, cols, row_step=1):
+    _chk(src, F32, "cast_pad src")
+    _lib.check(_lib.load().modcr_cast_pad(_p(src), ld_src, _p(dst), ld_dst, rows, cols, row_step, _stream()),
+               "cast_pad")
+
+
+def to_bf16(src):
+    """fp32 [rows, cols] (contiguous) -> new bf16 tensor of the same shape (cols % 8 == 0)."""
+    src = src.contiguous()
+    cols = src.shape[-1]
+    rows = src.numel() // cols
+    dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+    if cols % 8 == 0:
+        cast_pad(src, cols, dst, cols, rows, cols)
+    else:  # 1-D / odd shapes: flat view, numel % 8 == 0 required
+        cast_pad(src, src.numel(), dst, src.numel(), 1, src.numel())
+    return dst
+
+
+def bf16_to_f32(src, dst, accumulate=False):
+    _lib.check(_lib.load().modcr_bf16_to_f32(_p(src), _p(dst), src.numel(), int(accumulate), _stream()),
+               "bf16_to_f32")
+
+
+def colsum(x, ld, M, N, out):
+    _lib.check(_lib.load().modcr_colsum(_p(x), ld, M, N, _p(out), _stream()), "colsum")
+
+
+def copy_rows(src, src_seq_stride, srow0, dst, dst_seq_stride, drow0, nseq, nrows, H, accumulate=False):
+    _lib.check(_lib.load().modcr_copy_rows(_p(src), src_seq_stride, srow0, _p(dst), dst_seq_stride, drow0, nseq,
+                                           nrows, H, int(accumulate), _stream()), "copy_rows")
+
+
+def add_bf16(a, b, y):
+    _lib.check(_lib.load().modcr_add_bf16(_p(a), _p(b), _p(y), a.numel(), _stream()), "add_bf16")
+
+
+def tanh_bwd(dy, y, dx):
+    _lib.check(_lib.load().modcr_tanh_bwd(_p(dy), _p(y), _p(dx), dy.numel(), _stream()), "tanh_bwd")
+
+
+def key_bias(mask, kbias):
+    _chk(mask, F32, "attention mask")
+    _lib.check(_lib.load().modcr_key_bias(_p(mask), _p(kbias), mask.numel(), _stream()), "key_bias")
+
+
+def chunk_bits(cmask, bits, N, T, cwords):
+    _chk(cmask, F32, "chunk_attention_mask")
+    _lib.check(_lib.load().modcr_chunk_bits(_p(cmask), _p(bits), N, T, cwords, _stream()), "chunk_bits")
+
+
+def accum_f32_2d(dst, ld_dst, src, ld_src, rows, cols, accumulate=False):
+    _lib.check(_lib.load().modcr_accum_f32_2d(_p(dst), ld_dst, _p(src), ld_src, rows, cols, int(accumulate),
+                                              _stream()), "accum_f32_2d")

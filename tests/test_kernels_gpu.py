@@ -1,0 +1,469 @@
+"""GPU parity tests of every CUDA kernel, called through the C ABI (ctypes), against plain
+PyTorch fp32 references of the same op evaluated on the same (bf16-rounded) inputs.
+
+Tolerances: bf16 outputs are compared with a normalised max error (max|a-b| / max|b|) of 2e-2
+(1.5e-2 typical bf16 rounding of a long fp32-accumulated contraction); fp32 statistics /
+losses with 1e-4..1e-3; index / mask work bit-exactly."""
+import math
+
+import pytest
+import torch
+
+import modcr_b200  # noqa: F401
+from modcr_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NEG = -10000.0
+
+
+def nerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------------------- GEMM via ctypes
+def test_gemm_forward_variants():
+    M, N, K = 712, 768, 2304
+    A, B = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res = rnd(M, N, seed=4)
+    ref = A.float() @ B.float().t() + bias
+    C = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, B, C, M, N, K, bias=bias)
+    assert nerr(C, ref) < 1e-2
+    ops.gemm(A, B, C, M, N, K, bias=bias, epi_in=res, in_op=1)
+    assert nerr(C, ref + res.float()) < 1e-2
+    aux = torch.empty_like(C)
+    ops.gemm(A, B, C, M, N, K, bias=bias, act=1, aux=aux)
+    assert nerr(aux, ref) < 1e-2 and nerr(C, torch.nn.functional.gelu(ref)) < 1e-2
+    # strided A (pooler reads row 0 of every sequence: lda = S*H)
+    S_, H = 5, 256
+    X = rnd(64, S_, H, seed=5)
+    Wp = rnd(H, H, scale=0.05, seed=6)
+    out = torch.empty(64, H, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(X, Wp, out, 64, H, H, lda=S_ * H, act=2)
+    assert nerr(out, torch.tanh(X[:, 0].float() @ Wp.float().t())) < 1e-2
+
+
+def test_gemm_backward_variants():
+    M, N, K = 712, 768, 1024   # dY [M,N], W [N,K], X [M,K]
+    dY, W, X = rnd(M, N, seed=1), rnd(N, K, scale=0.05, seed=2), rnd(M, K, seed=3)
+    dX = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(dY, W, dX, M, K, N, b_mn=1)                               # dgrad: dX = dY W
+    assert nerr(dX, dY.float() @ W.float()) < 1e-2
+    dW = torch.zeros(N, K, dtype=torch.float32, device=DEV)
+    ops.gemm(dY, X, dW, N, K, M, a_mn=1, b_mn=1)                       # wgrad: dW = dY^T X
+    assert nerr(dW, dY.float().t() @ X.float()) < 1e-3
+    ops.gemm(dY, X, dW, N, K, M, a_mn=1, b_mn=1, accumulate=1)         # accumulate (TMA reduce-add)
+    assert nerr(dW, 2 * (dY.float().t() @ X.float())) < 1e-3
+
+
+# ------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("H", [768, 1024])
+def test_layernorm_fwd_bwd(H):
+    M = 1000
+    x = rnd(M, H, scale=2.0, seed=1)
+    gamma = (1 + 0.1 * torch.randn(H)).to(DEV)
+    beta = (0.1 * torch.randn(H)).to(DEV)
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, 1e-12)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (H,), gr, br, 1e-12)
+    assert nerr(y, yr) < 1e-2
+    torch.testing.assert_close(mean, xr.mean(-1), atol=1e-5, rtol=1e-5)
+    dy = rnd(M, H, seed=2)
+    yr.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db, dbias = (torch.zeros(H, device=DEV) for _ in range(3))
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, dbias, M, H)
+    assert nerr(dx, xr.grad) < 1e-2
+    assert nerr(dg, gr.grad) < 1e-3 and nerr(db, br.grad) < 1e-3
+    assert nerr(dbias, xr.grad.sum(0)) < 2e-2   # sum of bf16-rounded... compared to fp32 sum
+
+
+def test_layernorm_rowmap_writes_into_concat_buffer():
+    N, T, R, H = 3, 5, 4, 256
+    S = T + R
+    x = rnd(N * R, H, seed=1)
+    gamma, beta = torch.ones(H, device=DEV), torch.zeros(H, device=DEV)
+    buf = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = torch.empty(N * R, device=DEV), torch.empty(N * R, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, buf, mean, rstd, N * R, H, 1e-12, ymap=ops.rowmap(R, S, T))
+    ref = torch.nn.functional.layer_norm(x.float(), (H,)).view(N, R, H)
+    assert nerr(buf[:, T:], ref) < 1e-2
+    assert float(buf[:, :T].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------- embeddings
+def test_txt_embed_ln_fwd_bwd():
+    N, T, R, H, V = 4, 9, 3, 768, 500
+    S = T + R
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, V, (N, T), generator=g).to(DEV)
+    ids[0, -2:] = 0   # padding rows (padding_idx = 0 receives no gradient)
+    tts = torch.randint(0, 2, (N, T), generator=g).to(DEV)
+    word = (0.02 * torch.randn(V, H, generator=g)).to(DEV)
+    type_ = (0.02 * torch.randn(2, H, generator=g)).to(DEV)
+    pos = (0.02 * torch.randn(512, H, generator=g)).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(H, generator=g)).to(DEV)
+    buf = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = torch.empty(N * T, device=DEV), torch.empty(N * T, device=DEV)
+    ymap = ops.rowmap(T, S, 0)
+    ops.txt_embed_ln_fwd(ids, tts, None, word, type_, pos, gamma, beta, buf, ymap, mean, rstd, N, T, H, 1e-12)
+    wr, tr, pr = (t.clone().requires_grad_(True) for t in (word, type_, pos))
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    e = torch.nn.functional.embedding(ids, wr, padding_idx=0) + tr[tts] + pr[torch.arange(T, device=DEV)][None]
+    yr = torch.nn.functional.layer_norm(e, (H,), gr, br, 1e-12)
+    assert nerr(buf[:, :T], yr) < 1e-2
+    dy = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    dy[:, :T] = rnd(N, T, H, seed=5)
+    yr.backward(dy[:, :T].float())
+    dw, dt, dp = torch.zeros_like(word), torch.zeros_like(type_), torch.zeros_like(pos)
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.txt_embed_ln_bwd(dy, ymap, ids, tts, None, word, type_, pos, gamma, mean, rstd, dw, dt, dp, dg, db, N, T, H, 0)
+    assert nerr(dw, wr.grad) < 1e-3 and nerr(dt, tr.grad) < 1e-3 and nerr(dp, pr.grad) < 1e-3
+    assert float(dw[0].abs().max()) == 0.0
+    assert nerr(dg, gr.grad) < 1e-3 and nerr(db, br.grad) < 1e-3
+
+
+def test_img_embed_ln_fwd_bwd():
+    N, T, R, H, D = 3, 4, 50, 768, 2054
+    Dpad, S = 2112, 4 + 50
+    feats = torch.randn(N, R, D, generator=torch.Generator().manual_seed(1)).to(DEV)
+    W = (0.02 * torch.randn(H, D, generator=torch.Generator().manual_seed(2))).to(DEV)
+    bias = (0.02 * torch.randn(H, generator=torch.Generator().manual_seed(3))).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(H)).to(DEV), (0.1 * torch.randn(H)).to(DEV)
+    Wb = torch.zeros(H, Dpad, dtype=torch.bfloat16, device=DEV)
+    ops.cast_pad(W, D, Wb, Dpad, H, D)
+    assert torch.equal(Wb[:, :D], W.to(torch.bfloat16)) and float(Wb[:, D:].abs().max()) == 0.0
+    rows = N * R
+    packed = torch.empty(rows, Dpad, dtype=torch.bfloat16, device=DEV)
+    pre = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    buf = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    ymap = ops.rowmap(R, S, T)
+    ops.img_embed_ln_fwd(feats, rows, D, Dpad, Wb, bias, gamma, beta, 1, 1e-12, packed, pre, buf, ymap, mean, rstd, H)
+    fr = feats.to(torch.bfloat16).float()
+    Wr = W.to(torch.bfloat16).float().requires_grad_(True)
+    br_ = bias.clone().requires_grad_(True)
+    gr, ber = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(fr @ Wr.t() + br_, (H,), gr, ber, 1e-12)
+    assert nerr(buf[:, T:], yr) < 1.5e-2
+    dy = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    dy[:, T:] = rnd(N, R, H, seed=7)
+    yr.backward(dy[:, T:].float())
+    dpre = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    dWp = torch.zeros(H, Dpad, dtype=torch.float32, device=DEV)
+    dbias, dg, db = (torch.zeros(H, device=DEV) for _ in range(3))
+    ops.img_embed_ln_bwd(dy, ymap, packed, pre, mean, rstd, gamma, 1, dpre, dWp, dbias, dg, db, rows, Dpad, H)
+    assert nerr(dWp[:, :D], Wr.grad) < 2e-2
+    assert nerr(dbias, br_.grad) < 2e-2 and nerr(dg, gr.grad) < 1e-2 and nerr(db, ber.grad) < 1e-2
+    dW = torch.zeros(H, D, device=DEV)
+    ops.accum_f32_2d(dW, D, dWp, Dpad, H, D)
+    assert torch.equal(dW, dWp[:, :D])
+
+
+# ------------------------------------------------------------------------------- attention
+def _chunk_mask(N, T, lens, seed):
+    g = torch.Generator().manual_seed(seed)
+    cm = torch.zeros(N, T, T)
+    for n in range(N):
+        L = int(lens[n])
+        m = torch.eye(L)
+        m[0], m[L - 1] = 1.0, 1.0
+        t = 1
+        while t <= L - 2:
+            run = min(int(torch.randint(1, 5, (1,), generator=g)), L - 1 - t)
+            m[t:t + run, t:t + run] = 1.0
+            t += run
+        cm[n, :L, :L] = m
+    return cm
+
+
+def _dense_mask(mode, N, S, T, P, key_mask, cm):
+    """additive [N,1,S,P+S] mask exactly as the reference builds it (v10:171-232, modeling_transfomres.py:628-641)."""
+    ext = ((1.0 - key_mask) * NEG)[:, None, None, :]
+    if mode == 0:
+        return ext.expand(N, 1, S, P + S).clone()
+    R = S - T
+    am = ext.repeat(1, 1, S, 1)
+    am[:, :, :T, :T] = ((1.0 - cm) * NEG)[:, None]
+    am[:, :, T:, :T] = NEG
+    if mode == 2:
+        im = torch.cat((torch.zeros(N, R, T, device=cm.device), torch.eye(R, device=cm.device)[None].repeat(N, 1, 1)), -1)
+        am[:, :, T:, :] = ((1.0 - im) * NEG)[:, None]
+    return am
+
+
+def _attn_ref(qkv, pkv, am, heads, T, dctx, dalign):
+    N, S, H3 = qkv.shape
+    H = H3 // 3
+    q, k, v = qkv.float().split(H, dim=-1)
+    if pkv is not None:
+        pk, pv = pkv.float().split(H, dim=-1)
+        k, v = torch.cat([pk, k], 1), torch.cat([pv, v], 1)
+
+    def heads_(t):
+        return t.view(N, -1, heads, 64).permute(0, 2, 1, 3)
+    scores = heads_(q) @ heads_(k).transpose(-1, -2) / 8.0 + am
+    probs = torch.softmax(scores, -1)
+    ctx = (probs @ heads_(v)).permute(0, 2, 1, 3).reshape(N, S, H)
+    loss = (ctx * dctx.float()).sum()
+    if dalign is not None:
+        loss = loss + (probs[:, :, :T, T:].sum(1) * dalign).sum()
+    return ctx, probs, loss, torch.logsumexp(scores.detach(), -1)
+
+
+@pytest.mark.parametrize("mode,P,S,T", [(0, 0, 178, 128), (0, 10, 178, 128), (1, 0, 178, 128), (2, 0, 178, 128),
+                                        (0, 64, 256, 0), (2, 0, 300, 200), (0, 10, 300, 200), (0, 0, 40, 0),
+                                        (0, 3, 130, 0)])
+def test_prefix_attention_fwd_bwd(mode, P, S, T):
+    N, heads = 3, 4
+    H = heads * 64
+    g = torch.Generator().manual_seed(mode * 100 + P + S)
+    qkv = rnd(N, S, 3 * H, seed=11 + mode)
+    pkv = rnd(N, P, 2 * H, seed=12) if P > 0 else None
+    key_mask = torch.ones(N, P + S)
+    lens = [S] * N
+    if T > 0:
+        lens = [T, max(T // 2, 3), max(T - 7, 3)]
+        for n in range(N):
+            key_mask[n, P + lens[n]:P + T] = 0.0
+        key_mask[1, P + S - 5:] = 0.0       # some padded regions on one sequence
+    else:
+        key_mask[1, P + S - 9:] = 0.0
+    key_mask = key_mask.to(DEV)
+    cm = _chunk_mask(N, T, lens, 5).to(DEV) if mode != 0 else None
+    cwords = (T + 31) // 32 if mode != 0 else 0
+    kbias = torch.empty(N, P + S, device=DEV)
+    ops.key_bias(key_mask, kbias)
+    assert torch.equal(kbias, (1.0 - key_mask) * NEG)
+    cbits = None
+    if mode != 0:
+        cbits = torch.zeros(N, T, cwords, dtype=torch.int32, device=DEV)
+        ops.chunk_bits(cm, cbits, N, T, cwords)
+        # bit-exact packing check
+        unpacked = ((cbits.unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).reshape(N, T, cwords * 32)[:, :, :T]
+        assert torch.equal(unpacked.float(), cm)
+    want_align = mode == 2
+    R = S - T
+    ctx = torch.empty(N, S, H, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(N, heads, S, device=DEV)
+    probs_img = torch.zeros(N, heads, T, R, device=DEV) if want_align else None
+    ops.prefix_attn_fwd(N, S, P, heads, T if (mode != 0 or want_align) else 0, mode, qkv, pkv, kbias, cbits, cwords,
+                        ctx, lse, probs_img)
+    dctx = rnd(N, S, H, seed=13)
+    dalign = (torch.randn(N, T, R, generator=g) * 0.5).to(DEV) if want_align else None
+    qkv_r = qkv.float().requires_grad_(True)
+    pkv_r = pkv.float().requires_grad_(True) if P > 0 else None
+    am = _dense_mask(mode, N, S, T, P, key_mask, cm)
+    ctx_r, probs_r, loss, lse_r = _attn_ref(qkv_r, pkv_r, am, heads, T, dctx, dalign)
+    assert nerr(ctx, ctx_r) < 1.5e-2
+    torch.testing.assert_close(lse, lse_r, atol=2e-3, rtol=1e-4)
+    if want_align:
+        torch.testing.assert_close(probs_img, probs_r[:, :, :T, T:].detach(), atol=2e-5, rtol=1e-3)
+        # exact zeros where the reference has exact zeros (masked_fill(A == 0) relies on it)
+        assert torch.equal(probs_img == 0, probs_r[:, :, :T, T:] == 0)
+    loss.backward()
+    dqkv = torch.zeros(N, S, 3 * H, dtype=torch.bfloat16, device=DEV)
+    dpkv = torch.zeros(N, P, 2 * H, dtype=torch.bfloat16, device=DEV) if P > 0 else None
+    ws = torch.empty(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, device=DEV)
+    ops.prefix_attn_bwd(N, S, P, heads, T if (mode != 0 or want_align) else 0, mode, qkv, pkv, kbias, cbits, cwords,
+                        ctx, lse, probs_img, dctx, dalign, dqkv, dpkv, ws)
+    gq, gk, gv = qkv_r.grad.split(H, -1)
+    dq, dk, dv = dqkv.split(H, -1)
+    assert nerr(dv, gv) < 2e-2, "dV"
+    assert nerr(dk, gk) < 2e-2, "dK"
+    assert nerr(dq, gq) < 2e-2, "dQ"
+    if P > 0:
+        assert nerr(dpkv, pkv_r.grad) < 2e-2, "dprefix"
+
+
+def test_chunk_mean_q_matches_index_add_gather():
+    N, T, S, H = 4, 37, 50, 256
+    g = torch.Generator().manual_seed(3)
+    qkv = rnd(N, S, 3 * H, seed=4)
+    ref = qkv.clone().float()
+    chunk_id = torch.full((N, T), -1, dtype=torch.int32)
+    max_chunks = 1
+    for n in range(N):
+        L = int(torch.randint(6, T + 1, (1,), generator=g))
+        ids, t, c = [], 1, 0
+        while t <= L - 2:
+            run = min(int(torch.randint(1, 5, (1,), generator=g)), L - 1 - t)
+            ids += [c] * run
+            t += run
+            c += 1
+        gi = torch.tensor(ids)
+        chunk_id[n, 1:1 + len(ids)] = gi.int()
+        max_chunks = max(max_chunks, c)
+        q = ref[n, 1:1 + len(ids), :H]
+        cs = torch.zeros(c, H, device=DEV).index_add(0, gi.to(DEV), q)
+        cnt = torch.bincount(gi, minlength=c).to(DEV).float()
+        ref[n, 1:1 + len(ids), :H] = (cs / cnt[:, None])[gi.to(DEV)]
+    before = qkv.clone()
+    ops.chunk_mean_q(qkv, 3 * H, N, S, H, chunk_id.to(DEV), T, max_chunks)
+    assert nerr(qkv[..., :H], ref[..., :H]) < 1e-2
+    assert torch.equal(qkv[..., H:], before[..., H:])                     # K / V untouched
+    untouched = (chunk_id < 0).to(DEV)
+    assert torch.equal(qkv[:, :T, :H][untouched], before[:, :T, :H][untouched])   # CLS / SEP / pad rows bit-exact
+    assert torch.equal(qkv[:, T:], before[:, T:])                         # region rows bit-exact
+
+
+# ------------------------------------------------------------------------------- heads
+def test_align_softmax_ce_fwd_bwd():
+    nl, N, heads, T, R = 3, 5, 12, 20, 50
+    g = torch.Generator().manual_seed(0)
+    probs = torch.rand(nl, N, heads, T, R, generator=g)
+    probs[:, :, :, :, 40:] = 0.0          # padded regions: exact zeros -> masked_fill branch
+    probs = (probs / probs.sum(-1, keepdim=True).clamp_min(1e-6) * 0.3).to(DEV)
+    total_label = torch.zeros(N, T, dtype=torch.int64)
+    for n in range(N):
+        pos = torch.randperm(T - 2, generator=g)[:4] + 1
+        total_label[n, pos] = torch.randint(1, 40, (4,), generator=g)
+    align_pos = (total_label != 0).long()
+    total_label, align_pos = total_label.to(DEV), align_pos.to(DEV)
+    block = torch.empty(N, T, R, device=DEV)
+    row_loss = torch.empty(N * T, 2, device=DEV)
+    out = torch.empty(4, device=DEV)
+    ops.align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, block, row_loss, out, N, T, R)
+    pr = probs.clone().requires_grad_(True)
+    blk = pr.permute(1, 0, 2, 3, 4).sum(1).sum(1)
+    w = torch.softmax(blk.masked_fill(blk == 0, -1e5), -1)
+    wa, tl = w[align_pos == 1], total_label[align_pos == 1]
+    loss = torch.nn.functional.cross_entropy(wa, tl)
+    torch.testing.assert_close(block, blk.detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(out[0], loss.detach(), atol=1e-5, rtol=1e-5)
+    assert int(out[1]) == int(tl.numel()) and int(out[2]) == int((wa.argmax(-1) == tl).sum())
+    loss.backward()
+    dblock = torch.empty(N, T, R, device=DEV)
+    ops.align_softmax_ce_bwd(block, align_pos, total_label, out, 1.0, dblock, N, T, R)
+    torch.testing.assert_close(dblock, pr.grad[0, :, 0], atol=1e-7, rtol=1e-3)
+
+
+@pytest.mark.parametrize("L,H", [(381, 768), (57, 1024)])
+def test_cls_pool_attn_fwd_bwd(L, H):
+    N = 6
+    q, k = rnd(N, H, scale=0.3, seed=1), rnd(N, L, H, scale=0.3, seed=2)
+    mask = torch.zeros(N, L)
+    mask[:, L - 11:] = NEG
+    mask = mask.to(DEV)
+    w = torch.empty(N, L, device=DEV)
+    pooled = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    ops.cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H)
+    qr, kr = q.float().requires_grad_(True), k.float().requires_grad_(True)
+    wr = torch.softmax((qr[:, None] @ kr.transpose(1, 2)) + mask[:, None], -1)
+    pr = (wr @ kr).squeeze(1)
+    torch.testing.assert_close(w, wr.squeeze(1).detach(), atol=1e-5, rtol=1e-3)
+    assert nerr(pooled, pr) < 1e-2
+    dp = rnd(N, H, seed=3)
+    pr.backward(dp.float())
+    dq = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    dk = torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV)
+    ops.cls_pool_attn_bwd(dp, q, k, w, dq, dk, N, L, H)
+    assert nerr(dq, qr.grad) < 1.5e-2 and nerr(dk, kr.grad) < 1.5e-2
+
+
+def test_mc_scorer_ce_hard_labels_binary_to_mp():
+    B, nc, H = 8, 4, 768
+    rows = B * nc
+    x = rnd(rows, H, seed=1)
+    W = (0.05 * torch.randn(2, H)).to(DEV)
+    b = (0.05 * torch.randn(2)).to(DEV)
+    correct = torch.randint(0, nc, (B,))
+    label = torch.zeros(rows, dtype=torch.int64)
+    label[torch.arange(B) * nc + correct] = 1
+    label = label.to(DEV)
+    logits = torch.empty(rows, 2, device=DEV)
+    loss = torch.empty(1, device=DEV)
+    mp = torch.empty(rows, device=DEV)
+    pred = torch.empty(B, dtype=torch.int64, device=DEV)
+    matched = torch.empty(B, dtype=torch.uint8, device=DEV)
+    ops.mc_scorer_ce_fwd(x, W, b, rows, H, 2, 2, label, None, logits, loss, mp, pred, matched, nc)
+    xr = x.float().requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lr = xr @ Wr.t() + br
+    loss_r = torch.nn.functional.cross_entropy(lr, label)
+    mp_r = torch.softmax(lr, 1)[:, 1].reshape(-1, nc)
+    torch.testing.assert_close(logits, lr.detach(), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(loss[0], loss_r.detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(mp.view(-1, nc), mp_r.detach(), atol=1e-5, rtol=1e-4)
+    assert torch.equal(pred, mp_r.argmax(-1))
+    assert torch.equal(matched.bool(), mp_r.argmax(-1) == label.view(-1, nc).argmax(-1))
+    loss_r.backward()
+    dx = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    dW, db = torch.zeros(2, H, device=DEV), torch.zeros(2, device=DEV)
+    ops.mc_scorer_ce_bwd(x, W, b, rows, H, 2, 2, label, None, logits, 1.0, dx, dW, db)
+    assert nerr(dx, xr.grad) < 1e-2 and nerr(dW, Wr.grad) < 1e-4 and nerr(db, br.grad) < 1e-4
+
+
+def test_mc_scorer_ce_soft_labels_and_choice_flattened():
+    B, nc, H = 8, 4, 768
+    rows = B * nc
+    x = rnd(rows, H, seed=1)
+    # Abstract_Specific: Linear(H -> 1).view(-1, 4), CE with a float one-hot target
+    W = (0.05 * torch.randn(1, H)).to(DEV)
+    b = (0.05 * torch.randn(1)).to(DEV)
+    onehot = torch.zeros(B, nc)
+    onehot[torch.arange(B), torch.randint(0, nc, (B,))] = 1.0
+    onehot = onehot.to(DEV)
+    logits = torch.empty(rows, 1, device=DEV)
+    loss = torch.empty(1, device=DEV)
+    ops.mc_scorer_ce_fwd(x, W, b, rows, H, 1, nc, None, onehot, logits, loss)
+    xr = x.float().requires_grad_(True)
+    lr = (xr @ W.t() + b).view(-1, nc)
+    loss_r = torch.nn.functional.cross_entropy(lr, onehot)
+    torch.testing.assert_close(loss[0], loss_r.detach(), atol=1e-5, rtol=1e-5)
+    loss_r.backward()
+    dx = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    dW, db = torch.zeros(1, H, device=DEV), torch.zeros(1, device=DEV)
+    ops.mc_scorer_ce_bwd(x, W, b, rows, H, 1, nc, None, onehot, logits, 1.0, dx, dW, db)
+    assert nerr(dx, xr.grad) < 1e-2
+    # ImageBertForMultipleChoice: pooled.view(B, 4H) -> Linear(4H -> num_labels) -> CE
+    W4 = (0.02 * torch.randn(nc, nc * H)).to(DEV)
+    lab = torch.randint(0, nc, (B,)).to(DEV)
+    logits4 = torch.empty(B, nc, device=DEV)
+    ops.mc_scorer_ce_fwd(x, W4, None, B, nc * H, nc, nc, lab, None, logits4, loss)
+    lr4 = x.float().view(B, nc * H) @ W4.t()
+    torch.testing.assert_close(logits4, lr4, atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(loss[0], torch.nn.functional.cross_entropy(lr4, lab), atol=1e-5, rtol=1e-5)
+
+
+def test_copy_rows_colsum_add_tanh():
+    N, S, T, H = 3, 9, 6, 256
+    a, b = rnd(N, S, H, seed=1), rnd(N, S, H, seed=2)
+    X = torch.zeros(N, 3 * (T - 1), H, dtype=torch.bfloat16, device=DEV)
+    ops.copy_rows(a, S, 1, X, 3 * (T - 1), 0, N, T - 1, H)
+    ops.copy_rows(b, S, 1, X, 3 * (T - 1), T - 1, N, T - 1, H)
+    assert torch.equal(X[:, :T - 1], a[:, 1:T]) and torch.equal(X[:, T - 1:2 * (T - 1)], b[:, 1:T])
+    acc = a.clone()
+    ops.copy_rows(X, 3 * (T - 1), T - 1, acc, S, 1, N, T - 1, H, accumulate=True)
+    assert nerr(acc[:, 1:T], a[:, 1:T].float() + b[:, 1:T].float()) < 1e-2
+    cs = torch.zeros(H, device=DEV)
+    ops.colsum(a, H, N * S, H, cs)
+    assert nerr(cs, a.float().view(-1, H).sum(0)) < 1e-4
+    y = torch.empty_like(a)
+    ops.add_bf16(a, b, y)
+    assert torch.equal(y, (a.float() + b.float()).to(torch.bfloat16))
+    t = torch.tanh(a.float()).to(torch.bfloat16)
+    dx = torch.empty_like(a)
+    ops.tanh_bwd(b, t, dx)
+    assert nerr(dx, b.float() * (1 - t.float() ** 2)) < 1e-2
+
+
+def test_errors_are_reported_not_swallowed():
+    x = rnd(8, 100, seed=1)
+    with pytest.raises(RuntimeError, match="multiple of 256"):
+        ops.layernorm_fwd(x, x, x, x, None, None, 8, 100, 1e-12)
+    with pytest.raises(RuntimeError):
+        ops.prefix_attn_fwd(1, 600, 0, 2, 0, 0, x, None, x, None, 0, x, x)
