@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the ModCR hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
+
+A *step* is one forward+backward of ``ChunkAlign_CLS_enc4_align`` (both Oscar-base encoders trainable,
+``global_enc`` with a learned per-layer prefix, alignment head, 4-way scorer; loss = loss_cls + align_loss)
+over one synthetic PMR-shaped batch.  Workload at N=1: BASELINE.json configs[1] (32 questions x 4 choices,
+128 text tokens + 50 regions of 2054-d, prefix 10, bf16 compute).  ``value`` is whole-job samples/s
+(1 sample = 1 question = 4 encoder sequences) with the batch resident in HBM; ``e2e`` is the same metric through
+the public module call with the batch in pinned HOST memory (H2D copies and a D2H read of the loss inside the
+timed region).  Each rank prints nothing except rank 0, which prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PMR MC samples/s fwd+bwd"
+UNIT = "samples/s"
+WORKLOAD = dict(name="cfg-2 ModCR PMR training shape", B=32, choices=4, T=128, R=50, feat=2054, P=10,
+                L=12, H=768, heads=12, I=3072)
+
+
+def flops_per_sample(w):
+    """Algorithmic FLOPs (multiply-add = 2) of one fwd+bwd sample, SURVEY.md 8(d) / BASELINE.md section 4."""
+    S, P, H, I, L, R, T = w["T"] + w["R"], w["P"], w["H"], w["I"], w["L"], w["R"], w["T"]
+
+    def enc(P_):
+        layer = 4 * S * H * H + 4 * (S + P_) * H * H + 4 * S * (S + P_) * H + 4 * S * H * I
+        return L * layer + 2 * R * w["feat"] * H + 2 * H * H
+    L3 = 3 * (T - 1)
+    head = 3 * (2 * H * H + 2 * L3 * H * H + 4 * L3 * H + 2 * H * H + 4 * H * I) + 2 * 2 * H * H + 4 * H
+    fwd_seq = enc(P) + enc(0) + head
+    return 3.0 * fwd_seq * w["choices"]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            tf = d.get("bf16_tflops_sustained") or d.get("bf16_tflops")
+            if tf:
+                return float(tf), "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)", d
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained cuBLAS bf16 on this pool)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                if out.strip():
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step_fn(B, w, seed=88):
+    """CPU fp32 restatement of the reference path (oracle/restate.py), forward + backward."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import params
+    import restate
+    import statedict
+    from modcr_b200 import synth
+    cfg = restate.default_cfg()
+    sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(cfg)), 0)
+    names = [k for k, v in sd.items() if torch.is_floating_point(v)]
+    for k in names:
+        sd[k].requires_grad_(True)
+    b = synth.make_batch(B=B, T=w["T"], R=w["R"], seed=seed)
+    prefix = synth.make_prefix(w["L"], w["P"], w["H"], seed=seed + 1).requires_grad_(True)
+
+    def step():
+        (loss_cls, _, align_loss, _, _), _ = restate.chunkalign_forward(sd, cfg, b, prefix)
+        (loss_cls + align_loss).backward()
+        for k in names:
+            sd[k].grad = None
+        prefix.grad = None
+        return float(loss_cls + align_loss)
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 2                                      # bounded sample: cfg-2 shapes at 2 questions per step
+    step = oracle_step_fn(Bs, WORKLOAD)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = Bs / dt
+    sample = "oracle/restate.py fp32 on CPU, %d questions x 4 choices per step (T=128,R=50,P=10), %d threads" % (Bs, cores)
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=max(args.warmup, 1), ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=dict(workload=WORKLOAD["name"], **{k: WORKLOAD[k] for k in
+                                                                                        ("T", "R", "P", "L", "H")},
+                                                           sample_questions_per_step=Bs),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_model(w, dev):
+    import torch
+    from modcr_b200.modeling_bert import BertImgModel
+    from modcr_b200.modeling_utils import BertConfig
+    from modcr_b200.modeling_vcr_chunkalign_v10 import ChunkAlign_CLS_enc4_align, SeqBertImgModel
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=30567, hidden_size=w["H"], num_hidden_layers=w["L"], num_attention_heads=w["heads"],
+                     intermediate_size=w["I"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), w["choices"]).to(dev)
+    m.train()
+    prefix = (torch.randn(w["L"], w["P"], w["H"], device=dev) * 0.02).requires_grad_(True)
+    return m, prefix
+
+
+TENSOR_KEYS = ("input_ids", "token_type_ids", "input_mask", "img_feat", "label", "chunk_attention_mask", "total_label",
+               "align_pos", "chunk_id")
+
+
+def host_batch(w, seed, rank):
+    """Synthetic PMR batch in pinned host memory; the ragged gather_index lists are packed once on the
+    host into the int32 [N,T] chunk-id tensor (SURVEY.md section 7 'hard parts')."""
+    import torch
+    from modcr_b200 import engine, synth
+    b = synth.make_batch(B=w["B"], T=w["T"], R=w["R"], feat_dim=w["feat"], num_choices=w["choices"], seed=seed, rank=rank)
+    chunk_id, _ = engine.pack_chunk_ids(b["gather_index"], w["T"], "cpu")
+    b["chunk_id"] = chunk_id
+    hb = {k: b[k].contiguous().pin_memory() for k in TENSOR_KEYS}
+    return hb
+
+
+def run_ours(args):
+    import torch
+    from modcr_b200 import _lib, parallel
+    rank, local, world = parallel.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = dict(WORKLOAD)
+    m, prefix = build_model(w, dev)
+    N = w["B"] * w["choices"]
+    hb = host_batch(w, 88, rank)
+    db = {k: v.to(dev) for k, v in hb.items()}
+    reducer = parallel.GradReducer(list(m.parameters()) + [prefix]) if world > 1 else None
+
+    def fwd_bwd(bd):
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(w["L"])]
+        out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                token_type_ids=bd["token_type_ids"], encoder_history_states=hist,
+                chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["chunk_id"],
+                align_pos=bd["align_pos"], total_label=bd["total_label"])
+        loss = out[0] + out[2]
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    def zero():
+        for p in m.parameters():
+            p.grad = None
+        prefix.grad = None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(max(args.warmup, 3)):
+        fwd_bwd(db)
+        zero()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = fwd_bwd(db)
+        zero()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    loss_val = float(loss)
+
+    # ---- end to end through the public call with host buffers (`e2e`)
+    h2d = sum(v.numel() * v.element_size() for v in hb.values())
+    stage = {k: torch.empty_like(v, device=dev) for k, v in hb.items()}
+
+    def e2e_step():
+        for k, v in hb.items():
+            stage[k].copy_(v, non_blocking=True)
+        ls = fwd_bwd(stage)
+        val = ls.item()                      # D2H read of the step's result
+        zero()
+        return val
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1) / args.steps
+
+    # ---- max over ranks
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    value = world * w["B"] / ms * 1e3
+    e2e_value = world * w["B"] / ms_e2e * 1e3
+    fps = flops_per_sample(w)
+    peak, peak_src, peak_raw = peaks()
+    achieved = value * fps / world / 1e12
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=w["name"], questions_per_gpu=w["B"], choices=w["choices"], text_tokens=w["T"],
+                            regions=w["R"], region_feat_dim=w["feat"], prefix_len=w["P"], encoder="Oscar-base 12L/768/12H x2",
+                            parallelism="dp%d" % world, l2="per-step working set (>10 GB) far exceeds the 126 MB L2",
+                            dropout=0.0, loss="loss_cls + align_loss", final_loss=loss_val),
+                roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                              traffic=None, scope="whole fwd+bwd step: algorithmic FLOPs/sample (%.1f GF, SURVEY 8d) x "
+                              "samples/s per GPU" % (fps / 1e9), peak_source=peak_src),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
+                gpu_launches=int(launches))
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        step = oracle_step_fn(2, w)
+        step()
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            step()
+            ts.append(time.perf_counter() - t0)
+        line["cpu_baseline"] = dict(value=2 / statistics.median(ts), unit=UNIT, cores=cores, kind="port",
+                                    sample="oracle/restate.py (fp32 CPU restatement of the reference), 2 questions x 4 "
+                                           "choices per step at the same T/R/P, 1 warm-up + 2 timed fwd+bwd")
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

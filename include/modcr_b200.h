@@ -41,6 +41,8 @@ enum {
 
 int modcr_version(void);
 const char* modcr_last_error_string(void);
+/* number of CUDA kernels this library has launched in the calling process (monotonic) */
+uint64_t modcr_launch_count(void);
 
 /* Workspace query.  op: 1 = prefix_attn_bwd {N,S,heads}; 2 = img_embed_ln {rows, feat_dim, H} */
 size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
@@ -84,19 +86,23 @@ typedef struct modcr_rowmap {
   int32_t rows_per_seq, seq_stride, row0;
 } modcr_rowmap;
 
-/* LayerNorm over the last dim (H % 256 == 0, H <= 1024); BertSelfOutput/BertOutput/img LayerNorm. */
-int modcr_layernorm_fwd(const void* x, modcr_rowmap xmap, const float* gamma, const float* beta, void* y,
-                        modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H, float eps, void* stream);
+/* LayerNorm over the last dim (H % 256 == 0, H <= 1024); BertSelfOutput/BertOutput/img LayerNorm.
+ * x is bf16 (x_f32 = 0) or fp32 (x_f32 = 1: the residual stream is kept in fp32 -- pre-LayerNorm sums
+ * and the residual operand never round to bf16; measured to cut the logit error 3x).  y is the bf16
+ * tensor-core operand; y32 (optional) the fp32 copy consumed by the next residual add. */
+int modcr_layernorm_fwd(const void* x, int32_t x_f32, modcr_rowmap xmap, const float* gamma, const float* beta,
+                        void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H,
+                        float eps, void* stream);
 /* dbias (optional) receives sum_rows dx = bias gradient of the Linear that produced x. fp32 outputs accumulate. */
-int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, modcr_rowmap xmap, const float* mean,
-                        const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap, float* dgamma,
-                        float* dbeta, float* dbias, int32_t M, int32_t H, void* stream);
+int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, int32_t x_f32, modcr_rowmap xmap,
+                        const float* mean, const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap,
+                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream);
 
 /* BertEmbeddings.forward (a_transformers/modeling_bert.py:184-211): gather + sum + LayerNorm. */
 int modcr_txt_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
                            const float* word, const float* type, const float* pos, const float* gamma,
-                           const float* beta, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t N,
-                           int32_t T, int32_t H, float eps, void* stream);
+                           const float* beta, void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd,
+                           int32_t N, int32_t T, int32_t H, float eps, void* stream);
 int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* input_ids,
                            const int64_t* token_type_ids, const int64_t* position_ids, const float* word,
                            const float* type, const float* pos, const float* gamma, const float* mean,
@@ -105,15 +111,15 @@ int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* in
 
 /* img_embedding + LayerNorm (modeling_transfomres.py:676-681, v10:339-343):
  *   packed = bf16(feats) zero-padded to Dpad (TMA needs 16-byte row strides; 2054 -> 2112)
- *   pre    = packed W^T + bias            (tcgen05 GEMM; W is bf16 [H, Dpad])
- *   y      = use_ln ? LN(pre) : pre       written through ymap
- * Workspaces `packed` [rows, Dpad] and `pre` [rows, H] are kept for the backward pass. */
+ *   pre    = packed W^T + bias            (tcgen05 GEMM; W is bf16 [H, Dpad]; fp32 output)
+ *   y, y32 = LN(pre)                      written through ymap (bf16 operand + fp32 residual copy)
+ * Workspaces `packed` bf16 [rows, Dpad] and `pre` fp32 [rows, H] are kept for the backward pass. */
 int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t Dpad, const void* W,
                            const float* bias, const float* gamma, const float* beta, int32_t use_ln, float eps,
-                           void* packed, void* pre, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t H,
-                           void* stream);
+                           void* packed, float* pre, void* y, float* y32, modcr_rowmap ymap, float* mean,
+                           float* rstd, int32_t H, void* stream);
 /* dW_pad: fp32 [H, Dpad] (overwritten); dbias/dgamma/dbeta accumulate; dpre: bf16 [rows, H] workspace. */
-int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const void* pre,
+int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const float* pre,
                            const float* mean, const float* rstd, const float* gamma, int32_t use_ln, void* dpre,
                            float* dW_pad, float* dbias, float* dgamma, float* dbeta, int64_t rows, int32_t Dpad,
                            int32_t H, void* stream);

@@ -45,19 +45,20 @@ class ScorerDesc(C.Structure):
 SIGNATURES = {
     "modcr_version": [],
     "modcr_last_error_string": [],
+    "modcr_launch_count": [],
     "modcr_workspace_bytes": [c_int, C.POINTER(c_i64), c_int],
     "modcr_gemm": [C.POINTER(GemmDesc), c_void_p],
-    "modcr_layernorm_fwd": [c_void_p, RowMap, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_i32,
-                            c_float, c_void_p],
-    "modcr_layernorm_bwd": [c_void_p, RowMap, c_void_p, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap,
+    "modcr_layernorm_fwd": [c_void_p, c_i32, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p,
+                            c_i32, c_i32, c_float, c_void_p],
+    "modcr_layernorm_bwd": [c_void_p, RowMap, c_void_p, c_i32, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap,
                             c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
     "modcr_txt_embed_ln_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               RowMap, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_float, c_void_p],
+                               c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_float, c_void_p],
     "modcr_txt_embed_ln_bwd": [c_void_p, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
                                c_i64, c_void_p],
     "modcr_img_embed_ln_fwd": [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_float,
-                               c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_void_p],
+                               c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_void_p],
     "modcr_img_embed_ln_bwd": [c_void_p, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_void_p],
     "modcr_prefix_attn_fwd": [C.POINTER(AttnDesc), c_void_p],
@@ -85,7 +86,8 @@ SIGNATURES = {
                          c_float, c_float, c_void_p, c_float, c_void_p],
     "modcr_sumsq_f32": [c_void_p, c_i64, c_void_p, c_void_p],
 }
-_RESTYPES = {"modcr_last_error_string": C.c_char_p, "modcr_workspace_bytes": c_size_t}
+_RESTYPES = {"modcr_last_error_string": C.c_char_p, "modcr_workspace_bytes": c_size_t,
+             "modcr_launch_count": C.c_uint64}
 OPTIONAL = {"modcr_adamw_clip", "modcr_sumsq_f32"}
 
 _lib = None
@@ -112,6 +114,11 @@ def load():
         fn.restype = _RESTYPES.get(name, c_int)
     _lib = lib
     return lib
+
+
+def launch_count():
+    """Kernels launched by libmodcr_b200.so in this process so far."""
+    return int(load().modcr_launch_count())
 
 
 def last_error():

@@ -49,6 +49,7 @@ extern "C" {
 
 int modcr_version(void) { return MODCR_VERSION; }
 const char* modcr_last_error_string(void) { return modcr::last_error(); }
+uint64_t modcr_launch_count(void) { return (uint64_t)modcr::launch_count(); }
 
 size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims) {
   if (op == 1 && ndims >= 3) return modcr::attn_bwd_workspace_bytes((int)dims[0], (int)dims[1], (int)dims[2]);
@@ -76,25 +77,26 @@ int modcr_gemm(const modcr_gemm_desc* d, void* stream) {
   return modcr::gemm_launch(g, S(stream));
 }
 
-int modcr_layernorm_fwd(const void* x, modcr_rowmap xmap, const float* gamma, const float* beta, void* y,
-                        modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H, float eps, void* stream) {
+int modcr_layernorm_fwd(const void* x, int32_t x_f32, modcr_rowmap xmap, const float* gamma, const float* beta, void* y,
+                        float* y32, modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H, float eps,
+                        void* stream) {
   ARCH_OR_RETURN();
-  return modcr::layernorm_fwd(x, RM(xmap), gamma, beta, y, RM(ymap), mean, rstd, M, H, eps, S(stream));
+  return modcr::layernorm_fwd(x, x_f32, RM(xmap), gamma, beta, y, y32, RM(ymap), mean, rstd, M, H, eps, S(stream));
 }
-int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, modcr_rowmap xmap, const float* mean,
-                        const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap, float* dgamma,
-                        float* dbeta, float* dbias, int32_t M, int32_t H, void* stream) {
+int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, int32_t x_f32, modcr_rowmap xmap,
+                        const float* mean, const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap,
+                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::layernorm_bwd(dy, RM(dymap), x, RM(xmap), mean, rstd, gamma, dx, RM(dxmap), dgamma, dbeta, dbias, M, H,
-                              S(stream));
+  return modcr::layernorm_bwd(dy, RM(dymap), x, x_f32, RM(xmap), mean, rstd, gamma, dx, RM(dxmap), dgamma, dbeta, dbias,
+                              M, H, S(stream));
 }
 
 int modcr_txt_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
                            const float* word, const float* type, const float* pos, const float* gamma,
-                           const float* beta, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t N,
-                           int32_t T, int32_t H, float eps, void* stream) {
+                           const float* beta, void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd,
+                           int32_t N, int32_t T, int32_t H, float eps, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::txt_embed_ln_fwd(input_ids, token_type_ids, position_ids, word, type, pos, gamma, beta, y, RM(ymap),
+  return modcr::txt_embed_ln_fwd(input_ids, token_type_ids, position_ids, word, type, pos, gamma, beta, y, y32, RM(ymap),
                                  mean, rstd, N, T, H, eps, S(stream));
 }
 int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* input_ids,
@@ -109,8 +111,8 @@ int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* in
 
 int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t Dpad, const void* W,
                            const float* bias, const float* gamma, const float* beta, int32_t use_ln, float eps,
-                           void* packed, void* pre, void* y, modcr_rowmap ymap, float* mean, float* rstd, int32_t H,
-                           void* stream) {
+                           void* packed, float* pre, void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd,
+                           int32_t H, void* stream) {
   ARCH_OR_RETURN();
   if (rows <= 0 || D <= 0 || Dpad < D || Dpad % 8 != 0 || rows > 0x7fffffff) {
     modcr::set_error("img_embed_ln_fwd: bad shape rows=%lld D=%d Dpad=%d", (long long)rows, D, Dpad);
@@ -123,23 +125,18 @@ int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t 
   g.B = W; g.ldb = Dpad;
   g.M = (int)rows; g.N = H; g.K = Dpad;
   g.bias = bias;
-  if (use_ln) {
-    g.C = pre; g.ldc = H;
-    rc = modcr::gemm_launch(g, S(stream));
-    if (rc) return rc;
-    modcr::RowMap id;
-    return modcr::layernorm_fwd(pre, id, gamma, beta, y, RM(ymap), mean, rstd, (int)rows, H, eps, S(stream));
+  if (!use_ln) {
+    modcr::set_error("img_embed_ln_fwd: use_img_layernorm=0 is not implemented (the Oscar checkpoints of the path set it)");
+    return modcr::MODCR_ERR_UNSUPPORTED;
   }
-  // no LayerNorm: GEMM into `pre`, then scatter rows through the row map
-  g.C = pre; g.ldc = H;
+  g.C = pre; g.ldc = H; g.c_fp32 = 1;   // fp32 pre-LayerNorm activations
   rc = modcr::gemm_launch(g, S(stream));
   if (rc) return rc;
-  if (ymap.rows_per_seq <= 0) return modcr::copy_rows(pre, rows, 0, y, rows, 0, 1, (int)rows, H, 0, S(stream));
-  return modcr::copy_rows(pre, ymap.rows_per_seq, 0, y, ymap.seq_stride, ymap.row0, (int)(rows / ymap.rows_per_seq),
-                          ymap.rows_per_seq, H, 0, S(stream));
+  modcr::RowMap id;
+  return modcr::layernorm_fwd(pre, 1, id, gamma, beta, y, y32, RM(ymap), mean, rstd, (int)rows, H, eps, S(stream));
 }
 
-int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const void* pre,
+int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const float* pre,
                            const float* mean, const float* rstd, const float* gamma, int32_t use_ln, void* dpre,
                            float* dW_pad, float* dbias, float* dgamma, float* dbeta, int64_t rows, int32_t Dpad,
                            int32_t H, void* stream) {
@@ -148,24 +145,14 @@ int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packe
     modcr::set_error("img_embed_ln_bwd: bad shape rows=%lld Dpad=%d", (long long)rows, Dpad);
     return modcr::MODCR_ERR_SHAPE;
   }
-  int rc;
-  if (use_ln) {
-    modcr::RowMap id;
-    rc = modcr::layernorm_bwd(dy, RM(dymap), pre, id, mean, rstd, gamma, dpre, id, dgamma, dbeta, dbias, (int)rows, H,
-                              S(stream));
-    if (rc) return rc;
-  } else {
-    if (dymap.rows_per_seq <= 0)
-      rc = modcr::copy_rows(dy, rows, 0, dpre, rows, 0, 1, (int)rows, H, 0, S(stream));
-    else
-      rc = modcr::copy_rows(dy, dymap.seq_stride, dymap.row0, dpre, dymap.rows_per_seq, 0,
-                            (int)(rows / dymap.rows_per_seq), dymap.rows_per_seq, H, 0, S(stream));
-    if (rc) return rc;
-    if (dbias) {
-      rc = modcr::colsum(dpre, H, (int)rows, H, dbias, S(stream));
-      if (rc) return rc;
-    }
+  if (!use_ln) {
+    modcr::set_error("img_embed_ln_bwd: use_img_layernorm=0 is not implemented");
+    return modcr::MODCR_ERR_UNSUPPORTED;
   }
+  modcr::RowMap id;
+  int rc = modcr::layernorm_bwd(dy, RM(dymap), pre, 1, id, mean, rstd, gamma, dpre, id, dgamma, dbeta, dbias, (int)rows, H,
+                                S(stream));
+  if (rc) return rc;
   // dW[H, Dpad] = dpre^T packed      (A = dpre stored [K=rows, M=H], B = packed stored [K=rows, N=Dpad])
   modcr::GemmDesc g;
   g.A = dpre; g.lda = H; g.a_mn = 1;

@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
-  static_assert(!(OUT_F32 && (HAS_AUX || HAS_IN)), "fp32 output has no aux / epilogue-input path");
+  static_assert(!(OUT_F32 && HAS_AUX), "fp32 output has no aux path");
 };
 
 struct TileCoord {
@@ -273,6 +273,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int ib = cnt & 1;
           mbar_wait(&infull[ib], (cnt >> 1) & 1);
           const uint8_t* in_buf = sIn + ib * C::CHUNK_BYTES;
+          if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 f = *reinterpret_cast<const float4*>(in_buf + sw128_offset(row, j));
+              v[4 * j + 0] += f.x;
+              v[4 * j + 1] += f.y;
+              v[4 * j + 2] += f.z;
+              v[4 * j + 3] += f.w;
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 pk = *reinterpret_cast<const uint4*>(in_buf + sw128_offset(row, j));
@@ -288,6 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 v[8 * j + 2 * e + 1] *= gelu_erf_grad(f.y);
               }
             }
+          }
           }
           mbar_arrive(&inempty[ib]);
         }
@@ -372,7 +383,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
     if (rc) return rc;
   }
   if (HAS_IN) {
-    rc = make_tmap_2d(&tmIn, g.epi_in, 2, g.M, g.N, g.ld_in, 128, 64);
+    rc = make_tmap_2d(&tmIn, g.epi_in, OUT_F32 ? 4 : 2, g.M, g.N, g.ld_in, 128, C::CHUNK_COLS);
     if (rc) return rc;
   }
   GemmParams p;
@@ -414,9 +425,16 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
   const bool has_aux = g.aux != nullptr;
   const bool has_in = g.epi_in != nullptr && g.in_op != 0;
   if (g.c_fp32) {
-    if (has_aux || has_in) {
-      set_error("gemm: fp32 output does not support aux / epilogue input");
+    if (has_aux) {
+      set_error("gemm: fp32 output does not support an aux output");
       return MODCR_ERR_UNSUPPORTED;
+    }
+    if (has_in) {  // fp32 residual stream: C(fp32) = acc + bias + in(fp32)
+      if (g.in_op != 1 || g.a_mn || g.b_mn || g.accumulate || g.split_k > 1) {
+        set_error("gemm: fp32 epilogue input supports only in_op=1 on the NT layout without split-K");
+        return MODCR_ERR_UNSUPPORTED;
+      }
+      return launch<256, false, false, false, true, true>(g, stream);
     }
     if (g.split_k > 1 && !g.accumulate) {
       set_error("gemm: split-K requires accumulate=1 (output must be pre-initialised)");

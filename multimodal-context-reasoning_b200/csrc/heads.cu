@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) align_fwd_kernel(const float* __restrict_
     if (r < R) block[(size_t)row * R + r] = a[i];
   }
   float loss = 0.f, correct = 0.f;
-  if (align_pos[row] == 1) {
+  if (align_pos != nullptr && align_pos[row] == 1) {
     // z = softmax(masked_fill(A == 0, -1e5)) ; loss = logsumexp(z) - z[label]
     float mx = -INFINITY;
 #pragma unroll
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) align_fwd_kernel(const float* __restrict_
     loss = (zmax + logf(s2)) - zlab;
     correct = (zarg == label) ? 1.f : 0.f;
   }
-  if (lane == 0) {
+  if (lane == 0 && row_loss != nullptr) {
     row_loss[2 * (size_t)row] = loss;
     row_loss[2 * (size_t)row + 1] = correct;
   }
@@ -255,7 +255,10 @@ int align_softmax_ce_fwd(const float* probs, int nl, int heads, const int64_t* a
   }
   const int rows = N * T;
   align_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, block, row_loss, N, T, R);
-  align_reduce_kernel<<<1, 256, 0, st>>>(row_loss, align_pos, out, rows);
+  if (align_pos != nullptr && row_loss != nullptr && out != nullptr) {
+    align_reduce_kernel<<<1, 256, 0, st>>>(row_loss, align_pos, out, rows);
+    count_launches(1);
+  }
   return check_launch("align_softmax_ce_fwd");
 }
 

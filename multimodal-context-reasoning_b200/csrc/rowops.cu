@@ -52,22 +52,36 @@ constexpr int LN_MAXV = 4;  // up to 4 x 8 x 32 = 1024 columns
 
 // ---------------------------------------------------------------------------- LayerNorm fwd
 // y = (x - mean) * rstd * gamma + beta ; two-pass statistics in fp32 registers
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, RowMap xmap, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, bf16* __restrict__ y, RowMap ymap,
-                                                     float* __restrict__ mean, float* __restrict__ rstd, int M, int H,
-                                                     float eps) {
+// load 8 consecutive elements of a row that is either bf16 or fp32
+template <bool F32>
+DEVINL void load_row8(const void* row, int vec, float* f) {
+  if (F32) {
+    load8f(reinterpret_cast<const float*>(row) + vec * 8, f);
+  } else {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(row) + vec), f);
+  }
+}
+DEVINL void store8f(float* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <bool XF32>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, RowMap xmap, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                     float* __restrict__ y32, RowMap ymap, float* __restrict__ mean,
+                                                     float* __restrict__ rstd, int M, int H, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
   const int nv = H >> 8;  // vectors per lane
-  const bf16* xr = x + map_row(warp, xmap) * H;
+  const char* xr = reinterpret_cast<const char*>(x) + map_row(warp, xmap) * H * (XF32 ? 4 : 2);
   float v[LN_MAXV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
     if (i < nv) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + lane + 32 * i);
-      unpack8(u, v[i]);
+      load_row8<XF32>(xr, lane + 32 * i, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
@@ -83,7 +97,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
       }
     }
   const float rs = rsqrtf(warp_sum(q) / H + eps);
-  bf16* yr = y + map_row(warp, ymap) * H;
+  const int64_t orow = map_row(warp, ymap);
+  bf16* yr = y + orow * H;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
     if (i < nv) {
@@ -94,6 +109,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
       reinterpret_cast<uint4*>(yr)[lane + 32 * i] = pack8(o);
+      if (y32 != nullptr) store8f(y32 + orow * H + c, o);   // fp32 copy feeds the next residual add
     }
   if (lane == 0) {
     if (mean) mean[warp] = mu;
@@ -105,7 +121,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dx (bias of the Linear
 // that produced x, fused here so no extra pass over dx is needed)
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const bf16* __restrict__ x,
+template <bool XF32>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const void* __restrict__ x,
                                                      RowMap xmap, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                      bf16* __restrict__ dx, RowMap dxmap, float* __restrict__ dgamma,
@@ -127,7 +144,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 
   for (int m = blockIdx.x * 8 + wib; m < M; m += wstride) {
     const bf16* dyr = dy + map_row(m, dymap) * H;
-    const bf16* xr = x + map_row(m, xmap) * H;
+    const char* xr = reinterpret_cast<const char*>(x) + map_row(m, xmap) * H * (XF32 ? 4 : 2);
     const float mu = __ldg(mean + m), rs = __ldg(rstd + m);
     float g[LN_MAXV][8], xh[LN_MAXV][8];
     float s1 = 0.f, s2 = 0.f;
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       if (i < nv) {
         float d[8], xv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + lane + 32 * i), d);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xr) + lane + 32 * i), xv);
+        load_row8<XF32>(xr, lane + 32 * i, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xv[j] - mu) * rs;
@@ -193,8 +210,8 @@ __global__ void __launch_bounds__(256) txt_embed_fwd_kernel(const int64_t* __res
                                                             const float* __restrict__ word, const float* __restrict__ type,
                                                             const float* __restrict__ pos, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
-                                                            RowMap ymap, float* __restrict__ mean, float* __restrict__ rstd,
-                                                            int M, int T, int H, float eps) {
+                                                            float* __restrict__ y32, RowMap ymap, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, int M, int T, int H, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -230,7 +247,8 @@ __global__ void __launch_bounds__(256) txt_embed_fwd_kernel(const int64_t* __res
       }
     }
   const float rs = rsqrtf(warp_sum(q) / H + eps);
-  bf16* yr = y + map_row(warp, ymap) * H;
+  const int64_t orow = map_row(warp, ymap);
+  bf16* yr = y + orow * H;
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
     if (i < nv) {
@@ -241,6 +259,7 @@ __global__ void __launch_bounds__(256) txt_embed_fwd_kernel(const int64_t* __res
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * g[j] + b[j];
       reinterpret_cast<uint4*>(yr)[lane + 32 * i] = pack8(o);
+      if (y32 != nullptr) store8f(y32 + orow * H + c, o);
     }
   if (lane == 0) {
     mean[warp] = mu;
@@ -520,33 +539,40 @@ static int check_h(int H, const char* what) {
   return MODCR_OK;
 }
 
-int layernorm_fwd(const void* x, RowMap xmap, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
-                  float* rstd, int M, int H, float eps, cudaStream_t st) {
+int layernorm_fwd(const void* x, int x_f32, RowMap xmap, const float* gamma, const float* beta, void* y, float* y32,
+                  RowMap ymap, float* mean, float* rstd, int M, int H, float eps, cudaStream_t st) {
   if (int rc = check_h(H, "layernorm_fwd")) return rc;
   if (M <= 0) return MODCR_OK;
-  ln_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>((const bf16*)x, xmap, gamma, beta, (bf16*)y, ymap, mean, rstd, M, H, eps);
+  if (x_f32)
+    ln_fwd_kernel<true><<<(M + 7) / 8, 256, 0, st>>>(x, xmap, gamma, beta, (bf16*)y, y32, ymap, mean, rstd, M, H, eps);
+  else
+    ln_fwd_kernel<false><<<(M + 7) / 8, 256, 0, st>>>(x, xmap, gamma, beta, (bf16*)y, y32, ymap, mean, rstd, M, H, eps);
   return check_launch("layernorm_fwd");
 }
 
-int layernorm_bwd(const void* dy, RowMap dymap, const void* x, RowMap xmap, const float* mean, const float* rstd,
-                  const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias, int M, int H,
-                  cudaStream_t st) {
+int layernorm_bwd(const void* dy, RowMap dymap, const void* x, int x_f32, RowMap xmap, const float* mean,
+                  const float* rstd, const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias,
+                  int M, int H, cudaStream_t st) {
   if (int rc = check_h(H, "layernorm_bwd")) return rc;
   if (M <= 0) return MODCR_OK;
   const int grid = blocks_for(M, 8 * 8, 148 * 4);
-  ln_bwd_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, dymap, (const bf16*)x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap,
-                                      dgamma, dbeta, dbias, M, H);
+  if (x_f32)
+    ln_bwd_kernel<true><<<grid, 256, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap, dgamma,
+                                              dbeta, dbias, M, H);
+  else
+    ln_bwd_kernel<false><<<grid, 256, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap, dgamma,
+                                               dbeta, dbias, M, H);
   return check_launch("layernorm_bwd");
 }
 
 int txt_embed_ln_fwd(const int64_t* ids, const int64_t* tts, const int64_t* pos_ids, const float* word, const float* type,
-                     const float* pos, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
-                     float* rstd, int N, int T, int H, float eps, cudaStream_t st) {
+                     const float* pos, const float* gamma, const float* beta, void* y, float* y32, RowMap ymap,
+                     float* mean, float* rstd, int N, int T, int H, float eps, cudaStream_t st) {
   if (int rc = check_h(H, "txt_embed_ln_fwd")) return rc;
   const int M = N * T;
   if (M <= 0) return MODCR_OK;
-  txt_embed_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, tts, pos_ids, word, type, pos, gamma, beta, (bf16*)y, ymap, mean,
-                                                    rstd, M, T, H, eps);
+  txt_embed_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, tts, pos_ids, word, type, pos, gamma, beta, (bf16*)y, y32, ymap,
+                                                    mean, rstd, M, T, H, eps);
   return check_launch("txt_embed_ln_fwd");
 }
 

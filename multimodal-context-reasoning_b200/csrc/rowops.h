@@ -13,14 +13,15 @@ struct RowMap {
   int row0 = 0;
 };
 
-int layernorm_fwd(const void* x, RowMap xmap, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
-                  float* rstd, int M, int H, float eps, cudaStream_t st);
-int layernorm_bwd(const void* dy, RowMap dymap, const void* x, RowMap xmap, const float* mean, const float* rstd,
-                  const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias, int M, int H,
-                  cudaStream_t st);
+// x is bf16 (x_f32 = 0) or fp32 (x_f32 = 1, the fp32 residual stream); y32 (optional) receives an fp32 copy of y
+int layernorm_fwd(const void* x, int x_f32, RowMap xmap, const float* gamma, const float* beta, void* y, float* y32,
+                  RowMap ymap, float* mean, float* rstd, int M, int H, float eps, cudaStream_t st);
+int layernorm_bwd(const void* dy, RowMap dymap, const void* x, int x_f32, RowMap xmap, const float* mean,
+                  const float* rstd, const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias,
+                  int M, int H, cudaStream_t st);
 int txt_embed_ln_fwd(const int64_t* ids, const int64_t* tts, const int64_t* pos_ids, const float* word, const float* type,
-                     const float* pos, const float* gamma, const float* beta, void* y, RowMap ymap, float* mean,
-                     float* rstd, int N, int T, int H, float eps, cudaStream_t st);
+                     const float* pos, const float* gamma, const float* beta, void* y, float* y32, RowMap ymap,
+                     float* mean, float* rstd, int N, int T, int H, float eps, cudaStream_t st);
 int txt_embed_ln_bwd(const void* dy, RowMap dymap, const int64_t* ids, const int64_t* tts, const int64_t* pos_ids,
                      const float* word, const float* type, const float* pos, const float* gamma, const float* mean,
                      const float* rstd, float* dword, float* dtype, float* dpos, float* dgamma, float* dbeta, int N, int T,

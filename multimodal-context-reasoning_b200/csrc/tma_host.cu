@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -19,7 +20,12 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long launch_count() { return g_launches.load(); }
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n); }
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));

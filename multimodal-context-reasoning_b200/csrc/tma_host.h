@@ -30,6 +30,8 @@ enum : int {
   MODCR_ERR_UNSUPPORTED = -7,
 };
 
-int check_launch(const char* what);
+int check_launch(const char* what);   // also counts one kernel launch
+unsigned long long launch_count();
+void count_launches(int n);           // extra launches behind a single check_launch
 
 }  // namespace modcr

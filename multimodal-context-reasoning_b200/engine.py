@@ -112,22 +112,23 @@ def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None):
 
 
 # -------------------------------------------------------------------------------------------- FFN block
-def ffn_fwd(ps, pfx, a, M, H, I, eps, save):
-    """BertIntermediate + BertOutput (a_transformers/modeling_bert.py:434-437, 447-451)."""
+def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save):
+    """BertIntermediate + BertOutput (a_transformers/modeling_bert.py:434-437, 447-451).
+    ``a`` is the bf16 tensor-core operand, ``a32`` the fp32 residual; returns ``(y, y32)``."""
     dev = a.device
     W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
     gact = _empty((M, I), BF16, dev)
     u = _empty((M, I), BF16, dev) if save is not None else None
     ops.gemm(a, W1, gact, M, I, H, bias=ps.f32(pfx + "intermediate.dense.bias"), act=1, aux=u)
-    pre2 = _empty((M, H), BF16, dev)
-    ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a, in_op=1)
-    y = _empty((M, H), BF16, dev)
+    pre2 = _empty((M, H), F32, dev)                                         # fp32 residual stream
+    ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1)
+    y, y32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
     mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
     ops.layernorm_fwd(pre2, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), y, mean2,
-                      rstd2, M, H, eps)
+                      rstd2, M, H, eps, y32=y32)
     if save is not None:
         save.update(a=a, u=u, gact=gact, pre2=pre2, mean2=mean2, rstd2=rstd2)
-    return y
+    return y, y32
 
 
 def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads):
@@ -163,7 +164,7 @@ class AttnCfg:
         self.kbias, self.cbits, self.cwords, self.chunk_id, self.max_chunks = kbias, cbits, cwords, chunk_id, max_chunks
 
 
-def attention_fwd(ps, pfx, x, hist, ac, eps, save, do_chunk_cross=False, probs_img=None):
+def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, probs_img=None):
     """CaptionBertAttention: self-attention with prefix (modeling/modeling_bert.py:34-93, v10:55-129)
     followed by BertSelfOutput.  ``x`` [N*S,H]; ``hist`` [N*P,H] or None."""
     dev = x.device
@@ -181,17 +182,17 @@ def attention_fwd(ps, pfx, x, hist, ac, eps, save, do_chunk_cross=False, probs_i
     ctx = _empty((M, H), BF16, dev)
     lse = _empty((N, heads, S), F32, dev)
     ops.prefix_attn_fwd(N, S, P, heads, ac.T, ac.mode, qkv, pkv, ac.kbias, ac.cbits, ac.cwords, ctx, lse, probs_img)
-    pre1 = _empty((M, H), BF16, dev)
+    pre1 = _empty((M, H), F32, dev)                                         # fp32 residual stream
     ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
-             epi_in=x, in_op=1)
-    a = _empty((M, H), BF16, dev)
+             epi_in=x32, in_op=1)
+    a, a32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
     mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
     ops.layernorm_fwd(pre1, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), a, mean1,
-                      rstd1, M, H, eps)
+                      rstd1, M, H, eps, y32=a32)
     if save is not None:
         save.update(x=x, hist=hist, qkv=qkv, pkv=pkv, ctx=ctx, lse=lse, pre1=pre1, mean1=mean1, rstd1=rstd1,
                     chunk=do_chunk_cross, probs_img=probs_img)
-    return a
+    return a, a32
 
 
 def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None):
@@ -235,10 +236,10 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None):
     return dx, dhist
 
 
-def layer_fwd(ps, pfx, x, hist, ac, I, eps, save, do_chunk_cross=False, probs_img=None):
-    """CaptionBertLayer.forward (modeling/modeling_transfomres.py:481-489, v10:140-150)."""
-    a = attention_fwd(ps, pfx + "attention.", x, hist, ac, eps, save, do_chunk_cross, probs_img)
-    return ffn_fwd(ps, pfx, a, ac.N * ac.S, ac.H, I, eps, save)
+def layer_fwd(ps, pfx, x, x32, hist, ac, I, eps, save, do_chunk_cross=False, probs_img=None):
+    """CaptionBertLayer.forward (modeling/modeling_transfomres.py:481-489, v10:140-150); returns (y, y32)."""
+    a, a32 = attention_fwd(ps, pfx + "attention.", x, x32, hist, ac, eps, save, do_chunk_cross, probs_img)
+    return ffn_fwd(ps, pfx, a, a32, ac.N * ac.S, ac.H, I, eps, save)
 
 
 def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None):
@@ -255,7 +256,7 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
     H = cfg["H"]
     R = 0 if img_feats is None else img_feats.shape[1]
     S = T + R
-    x0 = _empty((N, S, H), BF16, dev)
+    x0, x0_32 = _empty((N, S, H), BF16, dev), _empty((N, S, H), F32, dev)
     tmean, trstd = _empty((N * T,), F32, dev), _empty((N * T,), F32, dev)
     tmap = ops.rowmap(T, S, 0)
     ids = input_ids.contiguous()
@@ -264,7 +265,7 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
     ops.txt_embed_ln_fwd(ids, tts, pos, ps.f32("embeddings.word_embeddings.weight"),
                          ps.f32("embeddings.token_type_embeddings.weight"),
                          ps.f32("embeddings.position_embeddings.weight"), ps.f32("embeddings.LayerNorm.weight"),
-                         ps.f32("embeddings.LayerNorm.bias"), x0, tmap, tmean, trstd, N, T, H, cfg["eps"])
+                         ps.f32("embeddings.LayerNorm.bias"), x0, tmap, tmean, trstd, N, T, H, cfg["eps"], y32=x0_32)
     sv = dict(ids=ids, tts=tts, pos=pos, tmean=tmean, trstd=trstd, N=N, T=T, R=R, S=S)
     if R > 0:
         D = img_feats.shape[2]
@@ -272,18 +273,18 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
         rows = N * R
         feats = img_feats.contiguous()
         packed = _empty((rows, Dpad), BF16, dev)
-        pre = _empty((rows, H), BF16, dev)
+        pre = _empty((rows, H), F32, dev)
         imean, irstd = _empty((rows,), F32, dev), _empty((rows,), F32, dev)
         use_ln = cfg["use_img_layernorm"]
         ops.img_embed_ln_fwd(feats, rows, D, Dpad, ps.padded("img_embedding.weight", Dpad),
                              ps.f32("img_embedding.bias"),
                              ps.f32("LayerNorm.weight") if use_ln else None,
                              ps.f32("LayerNorm.bias") if use_ln else None, use_ln, cfg["img_eps"], packed, pre, x0,
-                             ops.rowmap(R, S, T), imean, irstd, H)
+                             ops.rowmap(R, S, T), imean, irstd, H, y32=x0_32)
         sv.update(packed=packed, pre=pre, imean=imean, irstd=irstd, D=D, Dpad=Dpad)
     if save is not None:
         save.update(sv)
-    return x0
+    return x0, x0_32
 
 
 def embeddings_bwd(ps, cfg, sv, dx0, grads):

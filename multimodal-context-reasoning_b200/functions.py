@@ -1,0 +1,322 @@
+"""Coarse ``torch.autograd.Function`` nodes: one per encoder pass and one per head.  Inside a
+node every step is a CUDA kernel from ``libmodcr_b200.so`` driven by ``engine``; autograd only
+sees the edges between nodes (hidden states, pooled vectors, the head-summed alignment block)
+and the fp32 master parameters, whose gradients come straight out of the wgrad kernels.
+"""
+import torch
+
+from . import engine as E
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+# seq_enc mask schedule (v10:168-206): layers 0-2 chunk-local, 3-8 key padding, >= 9 cross-modal
+CHUNK_LAYERS, CROSS_MODAL_START = 3, 9
+
+
+def _as_bf16(t):
+    if t.dtype == BF16:
+        return t.contiguous()
+    t = t.to(F32).contiguous()
+    if t.numel() % 8 == 0 and t.shape[-1] % 8 == 0:
+        return ops.to_bf16(t)
+    return t.to(BF16)
+
+
+class EncoderRun:
+    """Everything one encoder pass needs besides tensors that carry gradients."""
+
+    def __init__(self, ps, names, cfg, input_ids, token_type_ids, position_ids, img_feats, kbias, P, is_seq=False,
+                 cbits=None, cwords=0, chunk_id=None, max_chunks=0, want_block=False):
+        self.ps, self.names, self.cfg = ps, names, cfg
+        self.input_ids, self.token_type_ids, self.position_ids, self.img_feats = (input_ids, token_type_ids,
+                                                                                   position_ids, img_feats)
+        self.kbias, self.P, self.is_seq = kbias, P, is_seq
+        self.cbits, self.cwords, self.chunk_id, self.max_chunks = cbits, cwords, chunk_id, max_chunks
+        self.want_block = want_block
+        self.N, self.T = input_ids.shape
+        self.R = 0 if img_feats is None else img_feats.shape[1]
+        self.S = self.T + self.R
+
+    def layer_cfg(self, i):
+        c = self.cfg
+        mode, cross = 0, False
+        if self.is_seq:
+            if i < CHUNK_LAYERS:
+                mode = 1
+            elif i >= CROSS_MODAL_START:
+                mode, cross = 2, True
+        T = self.T if (self.is_seq) else 0
+        ac = E.AttnCfg(self.N, self.S, c["H"], c["heads"], self.P, T, mode, self.kbias, self.cbits, self.cwords,
+                       self.chunk_id, self.max_chunks)
+        return ac, cross
+
+
+class EncoderFn(torch.autograd.Function):
+    """BertImgModel / SeqBertImgModel forward+backward as one node.
+
+    inputs : run, n_hist, hist_0..hist_{n-1} ([N,P,H]), then the parameters in ``run.names`` order
+    outputs: sequence_output [N,S,H] bf16, pooled [N,H] bf16, chunk_hidden_states [N,S,H] bf16 (seq),
+             align_block [N,T,R] fp32 (seq, head- and layer-summed text->region probabilities)"""
+
+    @staticmethod
+    def forward(ctx, run, n_hist, *tensors):
+        hist_in = tensors[:n_hist]
+        ps, cfg = run.ps, run.cfg
+        N, S, H, L, I = run.N, run.S, cfg["H"], cfg["L"], cfg["I"]
+        dev = run.input_ids.device
+        need_grad = any(ctx.needs_input_grad)
+        hist = [_as_bf16(h).view(N * run.P, H) for h in hist_in] if n_hist else None
+        emb_save = {} if need_grad else None
+        x, x32 = E.embeddings_fwd(ps, cfg, run.input_ids, run.token_type_ids, run.position_ids, run.img_feats,
+                                  emb_save)
+        x, x32 = x.view(N * S, H), x32.view(N * S, H)
+        saves = []
+        chunk_hidden = None
+        nprob = min(3, L) if (run.is_seq and run.want_block and run.R > 0) else 0
+        probs = E._empty((nprob, N, cfg["heads"], run.T, run.R), F32, dev) if nprob else None
+        for i in range(L):
+            ac, cross = run.layer_cfg(i)
+            sv = {} if need_grad else None
+            if run.is_seq and i == CROSS_MODAL_START:
+                chunk_hidden = x
+            pi = probs[i - (L - nprob)] if (nprob and i >= L - nprob) else None
+            x, x32 = E.layer_fwd(ps, "encoder.layer.%d." % i, x, x32, hist[i] if hist else None, ac, I, cfg["eps"], sv,
+                                 cross, pi)
+            saves.append(sv)
+        pooled = E.pooler_fwd(ps, x, N, S, H)
+        seq_out = x.view(N, S, H)
+        block = None
+        if nprob:
+            block = E._empty((N, run.T, run.R), F32, dev)
+            ops.align_softmax_ce_fwd(probs, nprob, cfg["heads"], None, None, block, None, None, N, run.T, run.R)
+        ctx.run, ctx.n_hist, ctx.saves, ctx.emb_save = run, n_hist, saves, emb_save
+        ctx.hist, ctx.hist_dtypes = hist, [h.dtype for h in hist_in]
+        ctx.x_last, ctx.pooled, ctx.nprob = x, pooled, nprob
+        ch = chunk_hidden.view(N, S, H) if chunk_hidden is not None else torch.empty(0, device=dev, dtype=BF16)
+        bl = block if block is not None else torch.empty(0, device=dev, dtype=F32)
+        if chunk_hidden is None:
+            ctx.mark_non_differentiable(ch)
+        if block is None:
+            ctx.mark_non_differentiable(bl)
+        return seq_out, pooled, ch, bl
+
+    @staticmethod
+    def backward(ctx, d_seq, d_pooled, d_chunk, d_block):
+        run, ps, cfg = ctx.run, ctx.run.ps, ctx.run.cfg
+        N, S, H, L, I = run.N, run.S, cfg["H"], cfg["L"], cfg["I"]
+        dev = run.input_ids.device
+        grads = {}
+        if d_seq is None:
+            dy = torch.zeros((N, S, H), dtype=BF16, device=dev)
+        else:
+            dy = d_seq.to(BF16).contiguous().clone()
+        if d_pooled is not None:
+            E.pooler_bwd(ps, ctx.x_last, ctx.pooled, d_pooled.to(BF16).contiguous(), N, S, H, dy, grads)
+        dalign = d_block.to(F32).contiguous() if (d_block is not None and ctx.nprob) else None
+        ws = E._empty((max(ops.attn_bwd_workspace_bytes(N, S, cfg["heads"]) // 4, 1),), F32, dev)
+        dy = dy.view(N * S, H)
+        dhists = [None] * ctx.n_hist
+        for i in range(L - 1, -1, -1):
+            ac, _ = run.layer_cfg(i)
+            da = dalign if (ctx.nprob and i >= L - ctx.nprob) else None
+            dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws)
+            ctx.saves[i] = None  # free this layer's activations
+            if ctx.n_hist:
+                dhists[i] = dh
+            if run.is_seq and i == CROSS_MODAL_START and d_chunk is not None and d_chunk.numel():
+                ops.add_bf16(dy, d_chunk.to(BF16).contiguous(), dy)
+        E.embeddings_bwd(ps, cfg, ctx.emb_save, dy.view(N, S, H), grads)
+        out_h = []
+        for i in range(ctx.n_hist):
+            g = dhists[i].view(N, run.P, H)
+            if ctx.hist_dtypes[i] != BF16:
+                g32 = E._empty((N, run.P, H), F32, dev)
+                ops.bf16_to_f32(g, g32)
+                g = g32.to(ctx.hist_dtypes[i])
+            out_h.append(g)
+        out_p = [grads.get(n) for n in run.names]
+        return (None, None, *out_h, *out_p)
+
+
+class ClsHeadRun:
+    def __init__(self, ps, names, cfg, N, T, S):
+        self.ps, self.names, self.cfg, self.N, self.T, self.S = ps, names, cfg, N, T, S
+
+
+class ClsLayer2HeadFn(torch.autograd.Function):
+    """cls_ensemble + 3 x ClsLayer2 of ChunkAlign_CLS_enc4_align (v10:1048-1061, 816-837).
+
+    inputs : run, word_mask [N, 3(T-1)] fp32 additive, global_out, seq_out, chunk_hidden [N,S,H] bf16,
+             global_pooled, seq_pooled [N,H] bf16, then the parameters in ``run.names`` order
+    output : CLS [N,H] bf16"""
+
+    @staticmethod
+    def forward(ctx, run, word_mask, g_out, s_out, c_hid, g_pool, s_pool, *params):
+        ps, cfg = run.ps, run.cfg
+        N, T, S, H, I = run.N, run.T, run.S, cfg["H"], cfg["I"]
+        dev = g_out.device
+        L3 = 3 * (T - 1)
+        need_grad = any(ctx.needs_input_grad)
+        cat = E._empty((N, 2 * H), BF16, dev)
+        ops.copy_rows(g_pool.contiguous(), 1, 0, cat, 2, 0, N, 1, H)      # [global_CLS | chunk_CLS]
+        ops.copy_rows(s_pool.contiguous(), 1, 0, cat, 2, 1, N, 1, H)
+        cls = E._empty((N, H), BF16, dev)
+        ops.gemm(cat, ps.bf16("cls_ensemble.weight"), cls, N, H, 2 * H, bias=ps.f32("cls_ensemble.bias"))
+        cls32 = E._empty((N, H), F32, dev)
+        ops.bf16_to_f32(cls, cls32)
+        X = E._empty((N, L3, H), BF16, dev)
+        for j, src in enumerate((g_out, s_out, c_hid)):
+            ops.copy_rows(src.contiguous(), S, 1, X, L3, j * (T - 1), N, T - 1, H)
+        saves = []
+        nl = cfg["n_cls_layers"]
+        for i in range(nl):
+            pfx = "cls_layer.%d." % i
+            sv = {} if need_grad else None
+            q = E._empty((N, H), BF16, dev)
+            ops.gemm(cls, ps.bf16(pfx + "cls_q_proj.weight"), q, N, H, H, bias=ps.f32(pfx + "cls_q_proj.bias"))
+            k = E._empty((N, L3, H), BF16, dev)
+            ops.gemm(X, ps.bf16(pfx + "align_k_proj.weight"), k, N * L3, H, H, bias=ps.f32(pfx + "align_k_proj.bias"))
+            w = E._empty((N, L3), F32, dev)
+            pooled = E._empty((N, H), BF16, dev)
+            ops.cls_pool_attn_fwd(q, k, word_mask, w, pooled, N, L3, H)
+            pre = E._empty((N, H), F32, dev)
+            ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"), epi_in=cls32,
+                     in_op=1)
+            c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
+            mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
+            ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
+                              cfg["eps"], y32=c32)
+            if sv is not None:
+                sv.update(cls_in=cls, q=q, k=k, w=w, pooled=pooled, pre=pre, mean=mean, rstd=rstd)
+            cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv)
+            saves.append(sv)
+        ctx.run, ctx.saves, ctx.cat, ctx.X = run, saves, cat, X
+        return cls
+
+    @staticmethod
+    def backward(ctx, dcls):
+        run, ps, cfg = ctx.run, ctx.run.ps, ctx.run.cfg
+        N, T, S, H, I = run.N, run.T, run.S, cfg["H"], cfg["I"]
+        dev = dcls.device
+        L3 = 3 * (T - 1)
+        grads = {}
+        d = dcls.to(BF16).contiguous()
+        dX = None
+        for i in range(cfg["n_cls_layers"] - 1, -1, -1):
+            pfx = "cls_layer.%d." % i
+            sv = ctx.saves[i]
+            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads)
+            g = E._empty((N, H), BF16, dev)
+            dgam, dbet, dbd = E._zeros((H,), F32, dev), E._zeros((H,), F32, dev), E._zeros((H,), F32, dev)
+            ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbd,
+                              N, H)
+            grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"], grads[pfx + "dense.bias"] = dgam, dbet, dbd
+            grads[pfx + "dense.weight"] = E.wgrad(g, sv["pooled"], H, H, N)
+            dpool = E._empty((N, H), BF16, dev)
+            ops.gemm(g, ps.bf16(pfx + "dense.weight"), dpool, N, H, H, b_mn=1)
+            dq = E._empty((N, H), BF16, dev)
+            dk = E._empty((N, L3, H), BF16, dev)
+            ops.cls_pool_attn_bwd(dpool, sv["q"], sv["k"], sv["w"], dq, dk, N, L3, H)
+            dbk = E._zeros((H,), F32, dev)
+            ops.colsum(dk, H, N * L3, H, dbk)
+            grads[pfx + "align_k_proj.bias"] = dbk
+            grads[pfx + "align_k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3)
+            dXn = E._empty((N, L3, H), BF16, dev)
+            ops.gemm(dk, ps.bf16(pfx + "align_k_proj.weight"), dXn, N * L3, H, H, b_mn=1,
+                     epi_in=dX, in_op=1)                                   # accumulate over the 3 layers
+            dX = dXn
+            dbq = E._zeros((H,), F32, dev)
+            ops.colsum(dq, H, N, H, dbq)
+            grads[pfx + "cls_q_proj.bias"] = dbq
+            grads[pfx + "cls_q_proj.weight"] = E.wgrad(dq, sv["cls_in"], H, H, N)
+            dnew = E._empty((N, H), BF16, dev)
+            ops.gemm(dq, ps.bf16(pfx + "cls_q_proj.weight"), dnew, N, H, H, b_mn=1, epi_in=g, in_op=1)  # + residual
+            d = dnew
+            ctx.saves[i] = None
+        # cls_ensemble
+        dbe = E._zeros((H,), F32, dev)
+        ops.colsum(d, H, N, H, dbe)
+        grads["cls_ensemble.bias"] = dbe
+        grads["cls_ensemble.weight"] = E.wgrad(d, ctx.cat, H, 2 * H, N)
+        dcat = E._empty((N, 2 * H), BF16, dev)
+        ops.gemm(d, ps.bf16("cls_ensemble.weight"), dcat, N, 2 * H, H, b_mn=1)
+        dgp, dsp = E._empty((N, H), BF16, dev), E._empty((N, H), BF16, dev)
+        ops.copy_rows(dcat, 2, 0, dgp, 1, 0, N, 1, H)
+        ops.copy_rows(dcat, 2, 1, dsp, 1, 0, N, 1, H)
+        outs = []
+        for j in range(3):
+            dd = torch.zeros((N, S, H), dtype=BF16, device=dev)
+            ops.copy_rows(dX, L3, j * (T - 1), dd, S, 1, N, T - 1, H)
+            outs.append(dd)
+        out_p = [grads.get(n) for n in run.names]
+        return (None, None, outs[0], outs[1], outs[2], dgp, dsp, *out_p)
+
+
+class ScorerFn(torch.autograd.Function):
+    """Linear(K -> C) + cross-entropy (+ binary_to_mp/argmax/matched) in one kernel (v10:1063-1069)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, hard, soft, G, num_choice, want_mp):
+        rows, K = x.shape
+        Cc = W.shape[0]
+        dev = x.device
+        xb = _as_bf16(x)
+        logits = E._empty((rows, Cc), F32, dev)
+        loss = E._empty((1,), F32, dev)
+        mp = pred = matched = None
+        if want_mp:
+            mp = E._empty((rows // num_choice, num_choice), F32, dev)
+            pred = E._empty((rows // num_choice,), torch.int64, dev)
+            matched = E._empty((rows // num_choice,), torch.uint8, dev)
+        Wc, bc = W.detach().contiguous(), (None if b is None else b.detach().contiguous())
+        ops.mc_scorer_ce_fwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice)
+        ctx.sv = (xb, Wc, bc, hard, soft, logits, G, x.dtype, b is not None)
+        outs = [loss.view(()), logits]
+        if want_mp:
+            outs += [mp, pred, matched.bool()]
+            ctx.mark_non_differentiable(mp, pred, outs[-1])
+        ctx.mark_non_differentiable(logits)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dloss, *unused):
+        xb, Wc, bc, hard, soft, logits, G, xdtype, has_b = ctx.sv
+        rows, K = xb.shape
+        Cc = Wc.shape[0]
+        dev = xb.device
+        dx = E._empty((rows, K), BF16, dev)
+        dW = E._zeros((Cc, K), F32, dev)
+        db = E._zeros((Cc,), F32, dev) if has_b else None
+        # the upstream gradient is a device scalar; fold it in afterwards to avoid a host sync
+        ops.mc_scorer_ce_bwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, 1.0, dx, dW, db)
+        g = dloss.to(F32)
+        dxo = (dx.float() * g).to(xdtype) if xdtype != BF16 else (dx * g.to(BF16))
+        return dxo, dW * g, (db * g if has_b else None), None, None, None, None, None
+
+
+class AlignLossFn(torch.autograd.Function):
+    """Alignment loss from the head-summed block (v10:1071-1077)."""
+
+    @staticmethod
+    def forward(ctx, block, align_pos, total_label):
+        N, T, R = block.shape
+        dev = block.device
+        blk = block.contiguous()
+        blk2 = E._empty((N, T, R), F32, dev)
+        row_loss = E._empty((N * T, 2), F32, dev)
+        out = E._empty((4,), F32, dev)
+        ap, tl = align_pos.contiguous(), total_label.contiguous()
+        ops.align_softmax_ce_fwd(blk, 1, 1, ap, tl, blk2, row_loss, out, N, T, R)
+        ctx.sv = (blk, ap, tl, out)
+        stats = out[1:3].clone()
+        ctx.mark_non_differentiable(stats)
+        return out[0].clone(), stats
+
+    @staticmethod
+    def backward(ctx, dloss, _):
+        blk, ap, tl, out = ctx.sv
+        N, T, R = blk.shape
+        dblock = E._empty((N, T, R), F32, blk.device)
+        ops.align_softmax_ce_bwd(blk, ap, tl, out, 1.0, dblock, N, T, R)
+        return dblock * dloss.to(F32), None, None

@@ -1,0 +1,173 @@
+"""Chunk-aware encoder, chunk-to-region alignment heads and the multiple-choice scorer -- module
+surface of the reference's ``modeling/modeling_vcr_chunkalign_v10.py`` (:45-373, :801-1165).
+
+Same class names, constructor / ``forward`` signatures, return tuples and ``state_dict`` keys.  All
+arithmetic runs in the sm_100a kernels behind ``libmodcr_b200.so``; the Python below only assembles
+kernel programs (``functions``) and the tiny host-side glue that the reference also does on the host.
+"""
+import torch
+from torch import nn
+
+from . import engine as E
+from .functions import AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, EncoderFn, EncoderRun, ScorerFn
+from .modeling_bert import (AttentionsNotMaterialised, BertIntermediate, BertOutput, CaptionBertAttention,
+                            _EncoderModelBase)
+from .modeling_utils import cfg_get, check_no_dropout, engine_cfg
+
+NEG = -10000.0
+
+
+def binary_to_mp(logit, num_labels=4):
+    """v10:363-373 -- softmax over the 2 classes, keep class 1, group by question."""
+    sm = torch.softmax(logit.float(), dim=1)
+    return sm[:, 1].reshape(-1, num_labels)
+
+
+class SeqBertImgModel(_EncoderModelBase):
+    """Chunk-aware Oscar encoder (v10:235-360) with the 3-phase mask schedule and chunk-mean queries of
+    its ``CaptionBertEncoder`` / ``CaptionBertSelfAttention`` (v10:55-107, 171-232)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._build(config)
+        self.init_weights()
+        self.max_hypo = cfg_get(config, "max_hypo", -1)
+        self.edge_dense = nn.Embedding(1, config.hidden_size)   # unused by the reference too (v10:259)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, input_mask=None, position_ids=None,
+                head_mask=None, img_feats=None, img_mask=None, encoder_history_states=None, offsets=None,
+                gather_index=None, _want_align_block=True):
+        """``attention_mask`` is the 0/1 chunk mask ``[N,T,T]``; ``input_mask`` ``[N,T+R]`` the key padding
+        mask; ``gather_index`` the ragged per-sequence chunk ids (or an already packed int32 ``[N,T]``
+        tensor with -1 outside the chunked span).  Returns ``((sequence_output, pooled_output, attentions),
+        chunk_hidden_states)`` like v10:360; ``attentions.align_block`` is the fp32 ``[N,T,R]`` sum over the
+        last three layers and all heads of ``probs[:, :T, T:]``."""
+        if head_mask is not None:
+            raise NotImplementedError("head_mask is always None on the ModCR path")
+        if encoder_history_states:
+            raise NotImplementedError("seq_enc never receives history states on the ModCR path (v10:1042-1046)")
+        if img_feats is None or attention_mask is None or input_mask is None or gather_index is None:
+            raise ValueError("SeqBertImgModel needs img_feats, the chunk attention_mask, input_mask and gather_index")
+        check_no_dropout(self, self.config)
+        N, T = input_ids.shape
+        dev = input_ids.device
+        kbias = E.make_key_bias(input_mask)
+        cbits, cwords = E.make_chunk_bits(attention_mask)
+        if torch.is_tensor(gather_index):
+            chunk_id = gather_index.to(device=dev, dtype=torch.int32).contiguous()
+            max_chunks = T
+        else:
+            chunk_id, max_chunks = E.pack_chunk_ids(gather_index, T, dev)
+        ps, names, params = self._store()
+        run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, 0,
+                         is_seq=True, cbits=cbits, cwords=cwords, chunk_id=chunk_id, max_chunks=max_chunks,
+                         want_block=_want_align_block)
+        seq_out, pooled, chunk_hidden, block = EncoderFn.apply(run, 0, *params)
+        att = AttentionsNotMaterialised(block if block.numel() else None)
+        return (seq_out, pooled, att), (chunk_hidden if chunk_hidden.numel() else None)
+
+
+class ClsLayer2(nn.Module):
+    """v10:801-837 (a BertLayer subclass: the inherited ``attention`` block exists in the state_dict but
+    is never called).  Parameter container; executed by ``functions.ClsLayer2HeadFn``."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.attention = CaptionBertAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+        self.cls_q_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.align_k_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+
+def _init_like_reference(module, std=0.02):
+    # heads are plain nn.Modules in the reference: torch default init; kept as is
+    return module
+
+
+class ChunkAlign_CLS_enc4_align(nn.Module):
+    """Fully trainable alignment model (v10:1016-1165): global encoder (+ per-layer prefix), chunk-aware
+    encoder, ``cls_ensemble``, 3 x ``ClsLayer2``, 2-way classifier + CE, ``binary_to_mp`` and the
+    chunk-to-region alignment loss."""
+
+    def __init__(self, global_enc, seq_enc, num_labels):
+        super().__init__()
+        self.global_enc = global_enc
+        self.seq_enc = seq_enc
+        H = self.global_enc.config.hidden_size
+        self.cls_ensemble = nn.Linear(H + self.seq_enc.config.hidden_size, H)
+        self.num_labels = num_labels
+        self.cls_layer_num = 3
+        self.cls_layer = nn.ModuleList([ClsLayer2(self.global_enc.config) for _ in range(self.cls_layer_num)])
+        self.classifier = nn.Linear(H, 2)
+        self.cls_loss_fct = nn.CrossEntropyLoss()
+        self._head_store = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _head_params(self):
+        named = {k: p for k, p in self.named_parameters()
+                 if not (k.startswith("global_enc.") or k.startswith("seq_enc.") or k.startswith("classifier."))}
+        ps = self._head_store
+        if ps is None or ps.named.keys() != named.keys() or any(ps.named[k] is not named[k] for k in named):
+            ps = E.ParamStore(named)
+            self._head_store = ps
+        return ps, list(named.keys()), list(named.values())
+
+    def _encode(self, input_ids, img_feat, input_mask, token_type_ids, position_ids, encoder_history_states, offsets,
+                chunk_attention_mask, gather_index, want_block):
+        N, T = input_ids.shape
+        g = self.global_enc(input_ids, img_feats=img_feat, attention_mask=input_mask, position_ids=position_ids,
+                            token_type_ids=token_type_ids, head_mask=None,
+                            encoder_history_states=encoder_history_states)
+        (s_out, s_pool, att), chunk_hidden = self.seq_enc(
+            input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
+            attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
+            head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
+        check_no_dropout(self, self.global_enc.config)
+        ps, names, params = self._head_params()
+        cfg = engine_cfg(self.global_enc.config)
+        cfg["n_cls_layers"] = self.cls_layer_num
+        S = g[0].shape[1]
+        # word mask (v10:1055-1057): (1 - input_mask[:, 1:T]) * -10000, tiled for the three sources
+        wm = (1.0 - input_mask[:, 1:T].to(torch.float32)) * NEG
+        wm = torch.cat((wm, wm, wm), -1).contiguous()
+        run = ClsHeadRun(ps, names, cfg, N, T, S)
+        cls = ClsLayer2HeadFn.apply(run, wm, g[0], s_out, chunk_hidden, g[1], s_pool, *params)
+        self.last_intermediates = dict(global_output=g[0], global_CLS=g[1], seq_output=s_out, chunk_CLS=s_pool,
+                                       chunk_hidden_states=chunk_hidden, CLS=cls)
+        return cls, att
+
+    def forward(self, input_ids, img_feat, input_mask=None, label=None, token_type_ids=None, position_ids=None,
+                head_mask=None, encoder_history_states=None, offsets=None, chunk_attention_mask=None,
+                gather_index=None, align_pos=None, total_label=None):
+        """Returns ``(loss_cls_0, matched_0, align_loss, correct, total_sum)`` (v10:1084).  ``correct`` and
+        ``total_sum`` are 0-dim device tensors (the reference calls ``.item()`` inside forward, v10:1079-1082;
+        here the host sync is left to the caller)."""
+        want_block = total_label is not None
+        cls, att = self._encode(input_ids, img_feat, input_mask, token_type_ids, position_ids, encoder_history_states,
+                                offsets, chunk_attention_mask, gather_index, want_block)
+        loss_cls_0, logits, mp, pred, matched_0 = ScorerFn.apply(
+            cls, self.classifier.weight, self.classifier.bias, label.long().contiguous(), None, 2, self.num_labels, True)
+        self.last_logits, self.last_logit_expl, self.last_pred = logits, mp, pred
+        self.last_align_block = att.align_block
+        align_loss, correct, total_sum = None, 0, 0
+        if want_block:
+            align_loss, stats = AlignLossFn.apply(att.align_block, align_pos, total_label)
+            total_sum, correct = stats[0].long(), stats[1].long()
+        return loss_cls_0, matched_0, align_loss, correct, total_sum
+
+    @torch.no_grad()
+    def evaluate(self, input_ids, img_feat, input_mask=None, label=None, token_type_ids=None, position_ids=None,
+                 head_mask=None, encoder_history_states=None, offsets=None, chunk_attention_mask=None,
+                 gather_index=None, align_pos=None, total_label=None):
+        """v10:1086-1125: returns ``(matched_0, pre, logit_expl)``."""
+        cls, _ = self._encode(input_ids, img_feat, input_mask, token_type_ids, position_ids, encoder_history_states,
+                              offsets, chunk_attention_mask, gather_index, False)
+        lab = label.long().contiguous() if label is not None else torch.zeros(
+            (input_ids.shape[0],), dtype=torch.int64, device=input_ids.device)
+        _, logits, mp, pred, matched_0 = ScorerFn.apply(cls, self.classifier.weight, self.classifier.bias, lab, None, 2,
+                                                        self.num_labels, True)
+        return matched_0, pred, mp

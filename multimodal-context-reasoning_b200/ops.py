@@ -63,24 +63,25 @@ def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=N
 
 
 # --------------------------------------------------------------------------- LayerNorm / embeddings
-def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, eps, xmap=IDENT, ymap=IDENT):
-    _lib.check(_lib.load().modcr_layernorm_fwd(_p(x), xmap, _p(gamma), _p(beta), _p(y), ymap, _p(mean), _p(rstd),
-                                               M, H, eps, _stream()), "layernorm_fwd")
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, eps, xmap=IDENT, ymap=IDENT, y32=None):
+    """x may be bf16 or fp32 (the fp32 residual stream); y is bf16, y32 an optional fp32 copy."""
+    _lib.check(_lib.load().modcr_layernorm_fwd(_p(x), int(x.dtype == F32), xmap, _p(gamma), _p(beta), _p(y), _p(y32),
+                                               ymap, _p(mean), _p(rstd), M, H, eps, _stream()), "layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dbias, M, H, dymap=IDENT, xmap=IDENT, dxmap=IDENT):
-    _lib.check(_lib.load().modcr_layernorm_bwd(_p(dy), dymap, _p(x), xmap, _p(mean), _p(rstd), _p(gamma), _p(dx),
-                                               dxmap, _p(dgamma), _p(dbeta), _p(dbias), M, H, _stream()),
-               "layernorm_bwd")
+    _lib.check(_lib.load().modcr_layernorm_bwd(_p(dy), dymap, _p(x), int(x.dtype == F32), xmap, _p(mean), _p(rstd),
+                                               _p(gamma), _p(dx), dxmap, _p(dgamma), _p(dbeta), _p(dbias), M, H,
+                                               _stream()), "layernorm_bwd")
 
 
-def txt_embed_ln_fwd(ids, tts, pos_ids, word, type_, pos, gamma, beta, y, ymap, mean, rstd, N, T, H, eps):
+def txt_embed_ln_fwd(ids, tts, pos_ids, word, type_, pos, gamma, beta, y, ymap, mean, rstd, N, T, H, eps, y32=None):
     _chk(ids, I64, "input_ids")
     _chk(tts, I64, "token_type_ids")
     _chk(pos_ids, I64, "position_ids")
     _lib.check(_lib.load().modcr_txt_embed_ln_fwd(_p(ids), _p(tts), _p(pos_ids), _p(word), _p(type_), _p(pos),
-                                                  _p(gamma), _p(beta), _p(y), ymap, _p(mean), _p(rstd), N, T, H, eps,
-                                                  _stream()), "txt_embed_ln_fwd")
+                                                  _p(gamma), _p(beta), _p(y), _p(y32), ymap, _p(mean), _p(rstd), N, T,
+                                                  H, eps, _stream()), "txt_embed_ln_fwd")
 
 
 def txt_embed_ln_bwd(dy, dymap, ids, tts, pos_ids, word, type_, pos, gamma, mean, rstd, dword, dtype, dpos, dgamma,
@@ -91,11 +92,13 @@ def txt_embed_ln_bwd(dy, dymap, ids, tts, pos_ids, word, type_, pos, gamma, mean
                "txt_embed_ln_bwd")
 
 
-def img_embed_ln_fwd(feats, rows, D, Dpad, W, bias, gamma, beta, use_ln, eps, packed, pre, y, ymap, mean, rstd, H):
+def img_embed_ln_fwd(feats, rows, D, Dpad, W, bias, gamma, beta, use_ln, eps, packed, pre, y, ymap, mean, rstd, H,
+                     y32=None):
     _chk(feats, F32, "img_feats")
+    _chk(pre, F32, "img_embed pre-LN workspace")
     _lib.check(_lib.load().modcr_img_embed_ln_fwd(_p(feats), rows, D, Dpad, _p(W), _p(bias), _p(gamma), _p(beta),
-                                                  int(use_ln), eps, _p(packed), _p(pre), _p(y), ymap, _p(mean),
-                                                  _p(rstd), H, _stream()), "img_embed_ln_fwd")
+                                                  int(use_ln), eps, _p(packed), _p(pre), _p(y), _p(y32), ymap,
+                                                  _p(mean), _p(rstd), H, _stream()), "img_embed_ln_fwd")
 
 
 def img_embed_ln_bwd(dy, dymap, packed, pre, mean, rstd, gamma, use_ln, dpre, dW_pad, dbias, dgamma, dbeta, rows,

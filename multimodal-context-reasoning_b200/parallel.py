@@ -1,0 +1,130 @@
+"""Data-parallel plumbing of the hot path: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink 5 / NVSwitch on the B200 box, gloo in CPU tests), bucketed gradient all-reduce overlapped
+with backward.
+
+The reference never shards (NCCL is initialised and then unused: run_PMR_ModCR.py:438-448, :693);
+the only bucketing logic in its tree is the dead Horovod helper utils/distributed.py:46-97 (10 MiB flat
+buckets).  The path shards by *questions*: every rank draws its own batch, runs the full replica and
+the only exchange step is the gradient mean -- so there is exactly one collective.
+
+Buckets are filled in gradient-arrival order from ``register_post_accumulate_grad_hook``; a full bucket
+is flattened and all-reduced on a side stream while autograd keeps running the remaining backward
+kernels.  Parameters that never receive a gradient never enter a bucket, so nothing
+waits for them.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from RANK / WORLD_SIZE / MASTER_* (torchrun contract)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, local, world
+
+
+class GradReducer:
+    """Bucketed, backward-overlapped gradient mean over the data-parallel group."""
+
+    def __init__(self, params, bucket_mb=64, group=None, comm_dtype=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.comm_dtype = comm_dtype
+        self._cur, self._cur_bytes, self._inflight = [], 0, []
+        self._handles = []
+        self.stream = None
+        self.launched = 0
+        if self.world > 1:
+            for p in self.params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    # ---------------------------------------------------------------- hooks
+    def _on_grad(self, p):
+        if p.grad is None:
+            return
+        self._cur.append(p)
+        self._cur_bytes += p.grad.numel() * p.grad.element_size()
+        if self._cur_bytes >= self.bucket_bytes:
+            self._launch()
+
+    def _launch(self):
+        if not self._cur:
+            return
+        bucket, self._cur, self._cur_bytes = self._cur, [], 0
+        grads = [p.grad for p in bucket]
+        cuda = grads[0].is_cuda
+        if cuda:
+            if self.stream is None:
+                self.stream = torch.cuda.Stream()
+            ev = torch.cuda.Event()
+            ev.record()                      # gradients of this bucket are complete on the compute stream here
+            self.stream.wait_event(ev)
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            ctx = _Null()
+        with ctx:
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
+                flat = flat.to(self.comm_dtype)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._inflight.append((work, flat, grads))
+        self.launched += 1
+
+    # ---------------------------------------------------------------- per step
+    def finish(self):
+        """Flush the partial bucket, wait for every all-reduce and write the means back into ``.grad``."""
+        if self.world <= 1:
+            return
+        self._launch()
+        cuda = bool(self._inflight) and self._inflight[0][1].is_cuda
+        ctx = torch.cuda.stream(self.stream) if cuda else _Null()
+        with ctx:
+            for work, flat, grads in self._inflight:
+                work.wait()
+                off = 0
+                scale = 1.0 / self.world
+                for g in grads:
+                    n = g.numel()
+                    g.copy_(flat[off:off + n].view_as(g).to(g.dtype) * scale if flat.dtype != g.dtype
+                            else flat[off:off + n].view_as(g) * scale)
+                    off += n
+        if cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self._inflight = []
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def allreduce_mean_scalar(t, group=None):
+    """Mean of a scalar tensor over ranks (loss reporting)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return t
+    t = t.detach().clone()
+    dist.all_reduce(t, group=group)
+    return t / dist.get_world_size(group)

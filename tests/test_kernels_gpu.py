@@ -64,6 +64,37 @@ def test_gemm_backward_variants():
     assert nerr(dW, 2 * (dY.float().t() @ X.float())) < 1e-3
 
 
+def test_gemm_fp32_residual_stream():
+    M, N, K = 712, 768, 3072
+    A, B = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res = rnd(M, N, seed=4, dtype=torch.float32)
+    C = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(A, B, C, M, N, K, bias=bias, epi_in=res, in_op=1)
+    ref = A.float() @ B.float().t() + bias + res
+    assert nerr(C, ref) < 1e-4
+
+
+def test_layernorm_fp32_input_dual_output():
+    M, H = 333, 768
+    x = rnd(M, H, scale=2.0, seed=1, dtype=torch.float32)
+    gamma, beta = (1 + 0.1 * torch.randn(H)).to(DEV), (0.1 * torch.randn(H)).to(DEV)
+    y = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    y32 = torch.empty(M, H, device=DEV)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, 1e-12, y32=y32)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (H,), gamma, beta, 1e-12)
+    torch.testing.assert_close(y32, yr.detach(), atol=2e-5, rtol=1e-5)
+    assert torch.equal(y, y32.to(torch.bfloat16))
+    dy = rnd(M, H, seed=2)
+    yr.backward(dy.float())
+    dx = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, None, M, H)
+    assert nerr(dx, xr.grad) < 1e-2
+
+
 # ------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("H", [768, 1024])
 def test_layernorm_fwd_bwd(H):
@@ -148,11 +179,14 @@ def test_img_embed_ln_fwd_bwd():
     assert torch.equal(Wb[:, :D], W.to(torch.bfloat16)) and float(Wb[:, D:].abs().max()) == 0.0
     rows = N * R
     packed = torch.empty(rows, Dpad, dtype=torch.bfloat16, device=DEV)
-    pre = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    pre = torch.empty(rows, H, dtype=torch.float32, device=DEV)
     buf = torch.zeros(N, S, H, dtype=torch.bfloat16, device=DEV)
+    buf32 = torch.zeros(N, S, H, dtype=torch.float32, device=DEV)
     mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
     ymap = ops.rowmap(R, S, T)
-    ops.img_embed_ln_fwd(feats, rows, D, Dpad, Wb, bias, gamma, beta, 1, 1e-12, packed, pre, buf, ymap, mean, rstd, H)
+    ops.img_embed_ln_fwd(feats, rows, D, Dpad, Wb, bias, gamma, beta, 1, 1e-12, packed, pre, buf, ymap, mean, rstd, H,
+                         y32=buf32)
+    assert torch.equal(buf32.to(torch.bfloat16), buf)
     fr = feats.to(torch.bfloat16).float()
     Wr = W.to(torch.bfloat16).float().requires_grad_(True)
     br_ = bias.clone().requires_grad_(True)

@@ -1,0 +1,143 @@
+"""End-to-end GPU parity of the drop-in modules against golden vectors produced by the REAL reference
+(oracle/make_golden.py, fp32 CPU) on identical weights and synthetic inputs.
+
+Tolerances (BASELINE.json north_star): logits within 2e-2 absolute (bf16 compute, fp32 accumulate)
+against the fp32 reference, identical argmax choice, bit-exact masking / indexing.  Gradients are
+compared with a normalised max error (bf16 activations through 12 layers)."""
+import os
+
+import pytest
+import torch
+
+import params
+import restate
+import statedict
+import modcr_b200  # noqa: F401
+from modcr_b200 import synth
+from modcr_b200.modeling_bert import BertImgModel
+from modcr_b200.modeling_utils import BertConfig
+from modcr_b200.modeling_vcr_chunkalign_v10 import ChunkAlign_CLS_enc4_align, SeqBertImgModel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CFG = restate.default_cfg()
+DEV = "cuda"
+
+
+def nerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-9))
+
+
+def build(wseed):
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), 4)
+    ref_keys = dict(statedict.chunkalign_keys(CFG))
+    own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert own == ref_keys, "state_dict surface differs from the reference"
+    sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), wseed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV)
+
+
+def run_case(name):
+    g = torch.load(os.path.join(GOLD, name + ".pt"))
+    meta = g["meta"]
+    m = build(meta["wseed"])
+    b = synth.make_batch(B=meta["B"], T=meta["T"], R=meta["R"], seed=meta["seed"], region_pad=meta["region_pad"])
+    bd = synth.to_device(b, DEV)
+    N = b["input_ids"].shape[0]
+    prefix, hist = None, None
+    if meta["P"] > 0:
+        prefix = synth.make_prefix(12, meta["P"], 768, seed=meta["seed"] + 1).to(DEV).requires_grad_(True)
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(12)]
+    m.train()
+    out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+            token_type_ids=bd["token_type_ids"], encoder_history_states=hist, offsets=b["offsets"],
+            chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"],
+            align_pos=bd["align_pos"], total_label=bd["total_label"])
+    return g, m, out, prefix
+
+
+@pytest.mark.parametrize("name", ["ragged_small", "cfg1_noprefix", "cfg1_prefix10"])
+def test_chunkalign_forward_backward_matches_reference_golden(name):
+    g, m, out, prefix = run_case(name)
+    loss_cls, matched, align_loss, correct, total = out
+    rep = dict(dloss=abs(float(loss_cls) - float(g["loss_cls"])), dalign=abs(float(align_loss) - float(g["align_loss"])),
+               dlogits=float((m.last_logits.cpu() - g["logits"]).abs().max()),
+               dexpl=float((m.last_logit_expl.cpu() - g["logit_expl"]).abs().max()),
+               dblock=float((m.last_align_block.cpu() - g["align_block"]).abs().max()))
+    li = m.last_intermediates
+    inter = dict(g_out=nerr(li["global_output"][:, ::7, ::5], g["global_output_sub"]),
+                 s_out=nerr(li["seq_output"][:, ::7, ::5], g["seq_output_sub"]),
+                 c_hid=nerr(li["chunk_hidden_states"][:, ::7, ::5], g["chunk_hidden_sub"]),
+                 g_cls=nerr(li["global_CLS"], g["global_CLS"]), s_cls=nerr(li["chunk_CLS"], g["chunk_CLS"]),
+                 CLS=nerr(li["CLS"], g["CLS"]))
+    print(name, rep, inter)
+    assert rep["dblock"] < 2e-2, rep
+    assert rep["dlogits"] < 2e-2, rep                    # north_star tolerance
+    assert rep["dloss"] < 1e-2 and rep["dalign"] < 1e-2, rep
+    assert bool((m.last_pred.cpu() == g["pre"]).all()), "argmax choice differs"
+    assert bool((matched.cpu() == g["matched"]).all())
+    assert int(total) == g["total_sum"]                  # bit-exact row selection (align_pos indexing)
+    assert abs(int(correct) - g["correct"]) <= 1         # argmax over near-uniform rows at random init
+    (loss_cls + align_loss).backward()
+    named = dict(m.named_parameters())
+    worst = {}
+    for k, ref in g["grads"].items():
+        if k.startswith("prefix"):
+            got = prefix.grad[:, :, ::4]
+        elif "[" in k:
+            base, sl = k.split("[", 1)
+            gr = named[base].grad
+            if sl.startswith("ids0"):
+                ids0 = synth.make_batch(B=g["meta"]["B"], T=g["meta"]["T"], R=g["meta"]["R"], seed=g["meta"]["seed"],
+                                        region_pad=g["meta"]["region_pad"])["input_ids"][0, :8]
+                got = gr[ids0.to(DEV), :64]
+            else:
+                r, c = sl.rstrip("]").split(",")
+                got = gr[:int(r.strip(":")), :int(c.strip(":"))]
+        else:
+            got = named[k].grad
+        assert got is not None, k
+        if k.endswith("attention.self.key.bias"):
+            # softmax is invariant to a per-query constant, so d/d(key.bias) is exactly zero in exact arithmetic
+            # (the reference holds ~1e-9 rounding noise): check ours is noise-sized next to query.bias instead
+            qb = named[k.replace("key.bias", "query.bias")].grad
+            assert float(got.abs().max()) <= 0.05 * float(qb.abs().max()) + 1e-6, k
+            continue
+        worst[k] = nerr(got, ref)
+    print(name, "grad nerr:", {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:8]})
+    # full tensors: 6e-2; 8x64 corner slices are normalised by a much smaller max: 1e-1
+    bad = {k: v for k, v in worst.items() if v > (1e-1 if "[" in k else 6e-2)}
+    assert not bad, bad
+    # parameters the reference never gives a gradient
+    none_grad = [k for k, p in named.items() if p.grad is None]
+    assert all((".attention." in k and k.startswith("cls_layer.")) or k == "seq_enc.edge_dense.weight" for k in none_grad), none_grad
+
+
+def test_eval_no_grad_and_prefix_invariants():
+    g, m, out, _ = run_case("ragged_small")
+    m.eval()
+    meta = g["meta"]
+    b = synth.make_batch(B=meta["B"], T=meta["T"], R=meta["R"], seed=meta["seed"], region_pad=meta["region_pad"])
+    bd = synth.to_device(b, DEV)
+    N = b["input_ids"].shape[0]
+    with torch.no_grad():
+        base = m.global_enc(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=bd["input_mask"],
+                            img_feats=bd["img_feat"])[0]
+        prefix = synth.make_prefix(12, 5, 768, seed=3).to(DEV)
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(12)]
+        # masked-out prefix == no prefix, bit for bit
+        mask0 = torch.cat([torch.zeros(N, 5, device=DEV), bd["input_mask"]], -1)
+        off = m.global_enc(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=mask0,
+                           img_feats=bd["img_feat"], encoder_history_states=hist)[0]
+        assert torch.equal(base, off)
+        # a live prefix changes the output (item 2)
+        on = m.global_enc(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=bd["input_mask"],
+                          img_feats=bd["img_feat"], encoder_history_states=hist)[0]
+        assert float((on.float() - base.float()).abs().max()) > 1e-3
+        matched, pre, expl = m.evaluate(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                                        token_type_ids=bd["token_type_ids"], offsets=b["offsets"],
+                                        chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"])
+        assert expl.shape == (meta["B"], 4) and pre.shape == (meta["B"],)
