@@ -1,0 +1,113 @@
+"""CPU tests of the host-side logic: module surface / state_dict keys, checkpoint helpers, chunk-id packing,
+FLOP accounting and the bench JSON helpers."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+import restate
+import statedict
+import modcr_b200  # noqa: F401
+from modcr_b200 import engine, synth
+from modcr_b200.modeling_bert import BertImgModel, ImageBertForMultipleChoice
+from modcr_b200.modeling_utils import BertConfig
+from modcr_b200.modeling_vcr_chunkalign_v10 import ChunkAlign_CLS_enc4_align, SeqBertImgModel, binary_to_mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = restate.default_cfg()
+
+
+def small_cfg(**kw):
+    d = dict(vocab_size=64, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+             max_position_embeddings=32, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, img_feature_dim=24)
+    d.update(kw)
+    return BertConfig(**d)
+
+
+def test_state_dict_surface_matches_reference_key_list():
+    cfg = BertConfig(vocab_size=CFG["vocab_size"])
+    m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), 4)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(statedict.chunkalign_keys(CFG))
+    n_params = sum(p.numel() for p in m.parameters())
+    assert abs(n_params - 250.0e6) < 1.0e6          # 250.0 M parameters
+
+
+def test_init_weights_follow_bert_init():
+    torch.manual_seed(0)
+    g = BertImgModel(small_cfg())
+    assert float(g.embeddings.word_embeddings.weight[0].abs().max()) == 0.0          # padding row zeroed
+    assert float(g.encoder.layer[0].attention.self.query.bias.abs().max()) == 0.0
+    assert abs(float(g.encoder.layer[0].intermediate.dense.weight.std()) - 0.02) < 2e-3
+    assert float((g.LayerNorm.weight - 1).abs().max()) == 0.0
+
+
+def test_save_and_from_pretrained_roundtrip_and_gamma_beta_rename(tmp_path):
+    torch.manual_seed(1)
+    g = BertImgModel(small_cfg())
+    g.save_pretrained(str(tmp_path))
+    h = BertImgModel.from_pretrained(str(tmp_path), config=small_cfg())
+    for (k1, v1), (k2, v2) in zip(g.state_dict().items(), h.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    sd = {("bert." + k).replace("LayerNorm.weight", "LayerNorm.gamma").replace("LayerNorm.bias", "LayerNorm.beta"): v
+          for k, v in g.state_dict().items()}
+    h2 = BertImgModel.from_pretrained(None, config=small_cfg(), state_dict=sd)
+    assert not h2.load_info["missing_keys"]
+    assert torch.equal(h2.embeddings.LayerNorm.weight, g.embeddings.LayerNorm.weight)
+
+
+def test_resize_token_embeddings_keeps_old_rows():
+    g = BertImgModel(small_cfg())
+    old = g.embeddings.word_embeddings.weight.detach().clone()
+    g.resize_token_embeddings(64 + 45)                # the 45 "<|detN|>" tokens of run_PMR_ModCR.py:715
+    assert g.embeddings.word_embeddings.weight.shape == (109, 256)
+    assert torch.equal(g.embeddings.word_embeddings.weight[:64], old)
+    assert g.config.vocab_size == 109
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    g = BertImgModel(small_cfg())
+    ids = torch.randint(1, 60, (2, 6))
+    with pytest.raises(RuntimeError):
+        g(ids, img_feats=torch.randn(2, 3, 24), attention_mask=torch.ones(2, 9))
+
+
+def test_training_dropout_is_not_silently_dropped():
+    g = BertImgModel(small_cfg(hidden_dropout_prob=0.3))
+    g.train()
+    with pytest.raises(NotImplementedError, match="dropout"):
+        g(torch.randint(1, 60, (2, 6)), img_feats=torch.randn(2, 3, 24), attention_mask=torch.ones(2, 9))
+
+
+def test_pack_chunk_ids_is_bit_exact():
+    b = synth.make_batch(B=2, T=40, R=5, seed=4)
+    ids, mx = engine.pack_chunk_ids(b["gather_index"], 40, "cpu")
+    assert ids.dtype == torch.int32 and ids.shape == (8, 40)
+    for n, gi in enumerate(b["gather_index"]):
+        L = gi.numel()
+        assert torch.equal(ids[n, 1:1 + L].long(), gi)
+        assert int(ids[n, 0]) == -1 and bool((ids[n, 1 + L:] == -1).all())
+        # chunk ids agree with the offsets lists of the collate contract (Data/VCRChunkAlign.py:664-670)
+        for c, toks in enumerate(b["offsets"][n]):
+            assert all(int(ids[n, t]) == c for t in toks)
+    assert mx == max(int(g.max()) + 1 for g in b["gather_index"])
+
+
+def test_binary_to_mp_matches_oracle():
+    x = torch.randn(8, 2)
+    assert torch.equal(binary_to_mp(x, 4), restate.binary_to_mp(x, 4))
+
+
+def test_bench_flop_accounting_matches_survey():
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    gf = bench.flops_per_sample(bench.WORKLOAD) / 1e9
+    assert abs(gf - 778.4) < 1.0                       # 778.4 GF fwd+bwd per sample at cfg-1/2
+    peak, src, _ = bench.peaks()
+    assert peak > 100 and isinstance(src, str)
+
+
+def test_multiple_choice_head_surface():
+    m = ImageBertForMultipleChoice(small_cfg(num_labels=4, num_choice=4))
+    assert m.classifier.weight.shape == (4, 4 * 256)
