@@ -162,11 +162,12 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
                                void* stream);
 
-/* ClsLayer2 attention pooling (v10:816-829). q bf16 [N,H], k bf16 [N,L,H], mask fp32 [N,L] additive. */
-int modcr_cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int32_t N,
-                            int32_t L, int32_t H, void* stream);
-int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk,
+/* ClsLayer2 attention pooling (v10:816-829). q [N,H], k [N,L,H] bf16 (qk_f32=0) or fp32 (qk_f32=1: the unscaled
+ * 768-dim scores are the most rounding-sensitive spot of the path), mask fp32 [N,L] additive. */
+int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,
                             int32_t N, int32_t L, int32_t H, void* stream);
+int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int32_t qk_f32, const float* w, void* dq,
+                            void* dk, int32_t N, int32_t L, int32_t H, void* stream);
 
 /* Fused multiple-choice classifier + cross-entropy (v10:1063-1069, 363-373;
  * modeling/modeling_ensemble.py:511-536; modeling/modeling_bert.py:553-567, 690-710). */

@@ -66,28 +66,34 @@ DEVINL void tmem_ld_cols(uint32_t taddr, float* v) {
     tmem_ld_32x16(taddr, reinterpret_cast<uint32_t*>(v));
 }
 
-// additive-mask semantics of SURVEY.md A.2; `sb` is the staged key bias (-inf marks a key
-// row that does not exist: prefix padding, rows >= S, MMA padding)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr float NEG2 = NEG_BIAS * LOG2E;  // the additive -10000 in the log2 domain
+
+// Additive-mask semantics of SURVEY.md A.2, evaluated in the log2 domain:
+//   s2 = (q.k * scale + bias) * log2(e) = fma(acc, scale*log2e, bias*log2e)
+// `b2` is the staged key bias (already times log2e; -inf marks a key row that does not exist:
+// prefix padding, rows >= S, MMA padding), so exp2(s2 - max) of a missing key is exactly 0 and an
+// additive -10000 underflows to exactly 0 like in the fp32 reference.
 template <int MODE>
-DEVINL float masked_score(float acc, float scale, float sb, int kk, int q, bool q_txt, int T, uint32_t w) {
-  float b = sb;
+DEVINL float masked_s2(float acc, float c1, float b2, int kk, int q, bool q_txt, int T, uint32_t w) {
   if (MODE != 0) {
     if (kk < T)
-      b = q_txt ? (((w >> (kk & 31)) & 1u) ? 0.f : NEG_BIAS) : NEG_BIAS;
+      b2 = q_txt ? (((w >> (kk & 31)) & 1u) ? 0.f : NEG2) : NEG2;
     else if (MODE == 2 && !q_txt)
-      b = (kk == q) ? 0.f : NEG_BIAS;
+      b2 = (b2 == -INFINITY) ? b2 : ((kk == q) ? 0.f : NEG2);
   }
-  return (sb == -INFINITY) ? -INFINITY : fmaf(acc, scale, b);
+  return fmaf(acc, c1, b2);
 }
 
-// stage the per-key bias of sequence n into shared memory, indexed by smem key row
+// stage the per-key bias (times log2e) of sequence n into shared memory, indexed by smem key row
 DEVINL void stage_bias(float* sBias, int count, const AttnParams& p, int n, int tid, int nthreads) {
   for (int kk = tid; kk < count; kk += nthreads) {
     float b = -INFINITY;
     if (kk < p.P)
-      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + kk);
+      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + kk) * LOG2E;
     else if (kk >= p.Ppad && kk - p.Ppad < p.S)
-      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + p.P + (kk - p.Ppad));
+      b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + p.P + (kk - p.Ppad)) * LOG2E;
     sBias[kk] = b;
   }
 }
@@ -108,27 +114,33 @@ DEVINL void load_kv(uint8_t* sK, uint8_t* sV, const CUtensorMap* tmQKV, const CU
 }
 
 // ============================================================================ forward
+struct FwdLayout {
+  int off_k, off_v, off_bias, off_bars;  // byte offsets from the 1024-aligned base (Q tile at 0)
+  int off_p[8];                          // P blocks (16 KB each); block 0 overlays Q, block 1 overlays K when it fits
+};
+
 template <int MODE, int W, int PASS>
-DEVINL void fwd_chunk(const AttnParams& p, uint32_t taddr, const float* sBias, uint8_t* sP, int c0, int row, int q,
-                      bool alive, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row) {
+DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float* sBias, uint8_t* blk, int c0, int row,
+                      int q, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row) {
   float v[W];
   tmem_ld_cols<W>(taddr + c0, v);
+  float bb[W];
+#pragma unroll
+  for (int j = 0; j < W / 4; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + 4 * j);
+    bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+  }
   tmem_ld_wait();
   if (PASS == 1) {
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const float s = masked_score<MODE>(v[j], p.scale, sBias[c0 + j], c0 + j, q, q_txt, p.T, w);
-      m = fmaxf(m, s);
-    }
+    for (int j = 0; j < W; ++j) m = fmaxf(m, masked_s2<MODE>(v[j], c1, bb[j], c0 + j, q, q_txt, p.T, w));
   } else if (PASS == 2) {
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const float s = masked_score<MODE>(v[j], p.scale, sBias[c0 + j], c0 + j, q, q_txt, p.T, w);
-      const float e = alive ? __expf(s - m) : 0.f;
+      const float e = fast_ex2(masked_s2<MODE>(v[j], c1, bb[j], c0 + j, q, q_txt, p.T, w) - m);
       sum += e;
       v[j] = e;
     }
-    uint8_t* blk = sP + (c0 >> 6) * 16384;
     const int piece0 = (c0 & 63) >> 3;
 #pragma unroll
     for (int j = 0; j < W / 8; ++j) {
@@ -140,32 +152,29 @@ DEVINL void fwd_chunk(const AttnParams& p, uint32_t taddr, const float* sBias, u
       *reinterpret_cast<uint4*>(blk + sw128_offset(row, piece0 + j)) = pk;
     }
   } else {
-    if (alive && q_txt) {
+    if (pimg_row != nullptr) {
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const int kk = c0 + j;
-        if (kk >= p.T && kk < p.S) {
-          const float s = masked_score<MODE>(v[j], p.scale, sBias[kk], kk, q, q_txt, p.T, w);
-          pimg_row[kk - p.T] = __expf(s - m) * inv;
-        }
+        if (kk >= p.T && kk < p.S)
+          pimg_row[kk - p.T] = fast_ex2(masked_s2<MODE>(v[j], c1, bb[j], kk, q, q_txt, p.T, w) - m) * inv;
       }
     }
   }
 }
 
 template <int TMEM_COLS, int MODE>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, (TMEM_COLS == 256 ? 2 : 1))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPKV,
-                const __grid_constant__ CUtensorMap tmCTX, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmCTX, const AttnParams p, const FwdLayout lay) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nblk = (p.Kp + 63) >> 6;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 16384;
-  uint8_t* sV = sK + p.Krows * 128;
-  uint8_t* sP = sV + p.Krows * 128;
-  float* sBias = reinterpret_cast<float*>(sP + nblk * 16384);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + nblk * 64);
+  uint8_t* sK = smem + lay.off_k;
+  uint8_t* sV = smem + lay.off_v;
+  float* sBias = reinterpret_cast<float*>(smem + lay.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
   uint64_t* bar_qk = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_s = bars + 2;
@@ -177,6 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const float c1 = p.scale * LOG2E;
 
   if (warp == 4) {
     if (lane == 0) {
@@ -219,7 +229,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
       mbar_wait(bar_qk, 0);
       tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), s_addr = smem_u32(smem);
       for (int n0 = 0; n0 < p.Kp; n0 += 256) {
         const int nn = min(256, p.Kp - n0);
         const uint32_t idesc = make_idesc_bf16(128, nn, 0, 0);
@@ -235,7 +245,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
       const int ksteps = p.Kp >> 4;
       for (int ks = 0; ks < ksteps; ++ks)
-        umma_bf16(tmem_base, make_smem_desc(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+        umma_bf16(tmem_base, make_smem_desc(s_addr + lay.off_p[ks >> 2] + (ks & 3) * 32, 0, 1024),
                   make_smem_desc(v_addr + ks * 2048, 8192, 1024), idesc_pv, ks > 0 ? 1u : 0u);
       umma_commit(bar_o);
     }
@@ -252,46 +262,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     if (p.probs_img != nullptr && alive && q_txt)
       pimg_row = p.probs_img + (((size_t)n * p.heads + h) * p.T + q) * p.R;
 
-    mbar_wait(bar_s, 0);
+    mbar_wait(bar_s, 0);   // S complete: the Q and K tiles are dead, P blocks 0/1 may overlay them
     tc_fence_after();
     float m = -INFINITY, sum = 0.f, inv = 0.f;
     if (warp_alive) {
       const int full = p.Kp & ~31;
       for (int c0 = 0; c0 < full; c0 += 32) {
         const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-        fwd_chunk<MODE, 32, 1>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row);
       }
       if (full < p.Kp) {
         const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-        fwd_chunk<MODE, 16, 1>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row);
       }
       for (int c0 = 0; c0 < full; c0 += 32) {
         const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-        fwd_chunk<MODE, 32, 2>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 32, 2>(p, c1, taddr, sBias, smem + lay.off_p[c0 >> 6], c0, row, q, q_txt, w, m, sum, inv,
+                               pimg_row);
       }
       if (full < p.Kp) {
         const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-        fwd_chunk<MODE, 16, 2>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, smem + lay.off_p[full >> 6], full, row, q, q_txt, w, m, sum, inv,
+                               pimg_row);
       }
       inv = sum > 0.f ? 1.0f / sum : 0.f;
       if (p.probs_img != nullptr) {  // uniform over the CTA
         const int first = (p.T >> 5) << 5;
         for (int c0 = first; c0 < full; c0 += 32) {
           const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-          fwd_chunk<MODE, 32, 3>(p, taddr, sBias, sP, c0, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+          fwd_chunk<MODE, 32, 3>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row);
         }
         if (full < p.Kp && full + 16 > first) {
           const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-          fwd_chunk<MODE, 16, 3>(p, taddr, sBias, sP, full, row, q, alive, q_txt, w, m, sum, inv, pimg_row);
+          fwd_chunk<MODE, 16, 3>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row);
         }
       }
-      if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = m + logf(sum);
+      if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
     }
     fence_async_smem();
     tc_fence_before();
     mbar_arrive(bar_p);
 
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o, 0);   // O complete: every P block is dead, block 0 (== the Q tile) becomes the staging tile
     tc_fence_after();
     if (warp_alive) {
       float o[64];
@@ -305,7 +317,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         pk.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
         pk.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
         pk.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
-        *reinterpret_cast<uint4*>(sQ + sw128_offset(row, j)) = pk;  // Q tile is dead: reuse as staging
+        *reinterpret_cast<uint4*>(sQ + sw128_offset(row, j)) = pk;
       }
     }
     fence_async_smem();
@@ -322,8 +334,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 }
 
 // ============================================================================ backward
+// Row threads: 8 warps.  Warp w owns TMEM lanes 32*(w&3) (= q rows of the tile) and the key-column half (w>>2)
+// of every 128-key block, so two warps share each SM sub-partition's latency.
+template <int MODE, bool SAFE>
+DEVINL void bwd_chunk(const AttnParams& p, float c1, uint32_t taddr_s, uint32_t taddr_dp, const float* sBias,
+                      uint8_t* pblk, uint8_t* dblk, int c0, int kk0, int nb, int row, int q, bool q_txt, uint32_t w,
+                      float lse2, float delta, const float* darow) {
+  float sv[32], dp[32], bb[32];
+  tmem_ld_32x32(taddr_s + c0, reinterpret_cast<uint32_t*>(sv));
+  tmem_ld_32x32(taddr_dp + c0, reinterpret_cast<uint32_t*>(dp));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sBias + kk0 + 4 * j);
+    bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int kk = kk0 + j;
+    float acc = sv[j], g = dp[j];
+    if (SAFE && c0 + j >= nb) {  // TMEM columns beyond this block's MMA width hold stale data
+      acc = 0.f;
+      g = 0.f;
+    }
+    const float pr = fast_ex2(masked_s2<MODE>(acc, c1, bb[j], kk, q, q_txt, p.T, w) - lse2);
+    if (darow != nullptr && kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
+    sv[j] = pr;
+    dp[j] = pr * (g - delta) * p.scale;
+  }
+  const int piece0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    pk.x = pack_bf16(sv[8 * j + 0], sv[8 * j + 1]);
+    pk.y = pack_bf16(sv[8 * j + 2], sv[8 * j + 3]);
+    pk.z = pack_bf16(sv[8 * j + 4], sv[8 * j + 5]);
+    pk.w = pack_bf16(sv[8 * j + 6], sv[8 * j + 7]);
+    *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = pk;
+    pk.x = pack_bf16(dp[8 * j + 0], dp[8 * j + 1]);
+    pk.y = pack_bf16(dp[8 * j + 2], dp[8 * j + 3]);
+    pk.z = pack_bf16(dp[8 * j + 4], dp[8 * j + 5]);
+    pk.w = pack_bf16(dp[8 * j + 6], dp[8 * j + 7]);
+    *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = pk;
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPKV,
                 const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -353,9 +410,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y;
+  const float c1 = p.scale * LOG2E;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       if (p.P > 0) tma_prefetch_desc(&tmPKV);
@@ -367,19 +425,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_init(&qempty[i], 1);
       }
       mbar_init(bar_sdp, 1);
-      mbar_init(bar_pds, 128);
+      mbar_init(bar_pds, 256);
       mbar_init(bar_dq, 1);
       mbar_init(bar_dkv_full, 1);
-      mbar_init(bar_dkv_free, 128);
+      mbar_init(bar_dkv_free, 256);
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
-  } else if (warp < 4) {
-    stage_bias(sBias, p.nkb * 128, p, n, tid, 128);
-    // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q]
-    for (int r = tid; r < p.nqt * 128; r += 128) {
-      float d = 0.f, l = 0.f;
+  } else if (warp < 8) {
+    stage_bias(sBias, p.nkb * 128, p, n, tid, 256);
+    // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q] (log2 domain, +inf for dead rows)
+    for (int r = tid; r < p.nqt * 128; r += 256) {
+      float d = 0.f, l = INFINITY;
       if (r < p.S) {
         const uint4* po = reinterpret_cast<const uint4*>(p.ctx + ((size_t)n * p.S + r) * p.H + h * 64);
         const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + ((size_t)n * p.S + r) * p.H + h * 64);
@@ -399,7 +457,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const float* da = p.dalign + ((size_t)n * p.T + r) * p.R;
           for (int j = 0; j < p.R; ++j) d = fmaf(__ldg(pi + j), __ldg(da + j), d);
         }
-        l = __ldg(p.lse + ((size_t)n * p.heads + h) * p.S + r);
+        l = __ldg(p.lse + ((size_t)n * p.heads + h) * p.S + r) * LOG2E;
       }
       sDelta[r] = d;
       sLse[r] = l;
@@ -410,7 +468,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // -------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       load_kv(sK, sV, &tmQKV, &tmPKV, bar_k, bar_v, p, n, h);
@@ -428,7 +486,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // -------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
@@ -479,8 +537,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else {
     // -------------------------------------------------------------------- row threads
-    const int row = tid;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int row = tid & 127;
+    const int half = tid >> 7;   // key-column half of every 128-key block
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t H3 = (size_t)3 * p.H;
     int step = 0;
     for (int kb = 0; kb < p.nkb; ++kb) {
@@ -489,76 +548,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q = qt * 128 + row;
         const bool alive = q < p.S;
         const bool q_txt = q < p.T;
-        const float lse = sLse[q], delta = sDelta[q];
+        const float lse2 = sLse[q], delta = sDelta[q];
         const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
         const float* darow =
             (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
         mbar_wait(bar_sdp, step & 1);
         tc_fence_after();
+        uint8_t* pblk = sP + half * 16384;
+        uint8_t* dblk = sDS + half * 16384;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = c * 32;
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = half * 64 + i * 32;
           const int kk0 = kb * 128 + c0;
-          float sv[32], dp[32];
-          if (c0 < nb) {
-            tmem_ld_32x32(taddr + COL_S + c0, reinterpret_cast<uint32_t*>(sv));
-            tmem_ld_32x32(taddr + COL_DP + c0, reinterpret_cast<uint32_t*>(dp));
-            tmem_ld_wait();
-            const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int kk = kk0 + j;
-              const float sb = sBias[kk];
-              const float s = masked_score<MODE>(sv[j], p.scale, sb, kk, q, q_txt, p.T, w);
-              const bool valid = alive && (sb != -INFINITY);
-              const float pr = valid ? __expf(s - lse) : 0.f;
-              float g = dp[j];
-              if (darow != nullptr && kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
-              sv[j] = pr;
-              dp[j] = valid ? pr * (g - delta) * p.scale : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sv[j] = 0.f;
-              dp[j] = 0.f;
-            }
-          }
-          uint8_t* pblk = sP + (c0 >> 6) * 16384;
-          uint8_t* dblk = sDS + (c0 >> 6) * 16384;
-          const int piece0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            pk.x = pack_bf16(sv[8 * j + 0], sv[8 * j + 1]);
-            pk.y = pack_bf16(sv[8 * j + 2], sv[8 * j + 3]);
-            pk.z = pack_bf16(sv[8 * j + 4], sv[8 * j + 5]);
-            pk.w = pack_bf16(sv[8 * j + 6], sv[8 * j + 7]);
-            *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = pk;
-            pk.x = pack_bf16(dp[8 * j + 0], dp[8 * j + 1]);
-            pk.y = pack_bf16(dp[8 * j + 2], dp[8 * j + 3]);
-            pk.z = pack_bf16(dp[8 * j + 4], dp[8 * j + 5]);
-            pk.w = pack_bf16(dp[8 * j + 6], dp[8 * j + 7]);
-            *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = pk;
-          }
+          const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
+          if (c0 + 32 <= nb)
+            bwd_chunk<MODE, false>(p, c1, taddr + COL_S, taddr + COL_DP, sBias, pblk, dblk, c0, kk0, nb, row, q, q_txt, w,
+                                   lse2, delta, darow);
+          else
+            bwd_chunk<MODE, true>(p, c1, taddr + COL_S, taddr + COL_DP, sBias, pblk, dblk, c0, kk0, nb, row, q, q_txt, w,
+                                  lse2, delta, darow);
         }
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar_pds);
 
-        // ---- dQ partial of this (key block, q tile)
+        // ---- dQ partial of this (key block, q tile): this thread owns 32 of the 64 columns
         mbar_wait(bar_dq, step & 1);
         tc_fence_after();
         {
-          float dq[64];
-          tmem_ld_32x32(taddr + COL_DQ, reinterpret_cast<uint32_t*>(dq));
-          tmem_ld_32x32(taddr + COL_DQ + 32, reinterpret_cast<uint32_t*>(dq) + 32);
+          float dq[32];
+          tmem_ld_32x32(taddr + COL_DQ + half * 32, reinterpret_cast<uint32_t*>(dq));
           tmem_ld_wait();
           if (alive) {
-            float4* ws = reinterpret_cast<float4*>(p.dq_ws + (((size_t)n * p.heads + h) * p.S + q) * 64);
+            float4* ws = reinterpret_cast<float4*>(p.dq_ws + (((size_t)n * p.heads + h) * p.S + q) * 64 + half * 32);
             if (kb > 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+              for (int j = 0; j < 8; ++j) {
                 const float4 f = ws[j];
                 dq[4 * j] += f.x;
                 dq[4 * j + 1] += f.y;
@@ -567,9 +592,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               }
             }
             if (kb == p.nkb - 1) {
-              uint4* out = reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.S + q) * H3 + h * 64);
+              uint4* out = reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.S + q) * H3 + h * 64 + half * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 uint4 pk;
                 pk.x = pack_bf16(dq[8 * j + 0], dq[8 * j + 1]);
                 pk.y = pack_bf16(dq[8 * j + 2], dq[8 * j + 3]);
@@ -579,43 +604,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) ws[j] = make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) ws[j] = make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
             }
           }
         }
-        // ---- dK / dV of this key block once the last q tile has been accumulated
+        // ---- dK (half 0) / dV (half 1) of this key block once the last q tile has been accumulated
         if (qt == p.nqt - 1) {
           mbar_wait(bar_dkv_full, kb & 1);
           tc_fence_after();
           const int kk = kb * 128 + row;
-          bf16* dk_dst = nullptr;
-          bf16* dv_dst = nullptr;
-          if (kk < p.P) {
-            dk_dst = p.dpkv + ((size_t)n * p.P + kk) * (2 * p.H) + h * 64;
-            dv_dst = dk_dst + p.H;
-          } else if (kk >= p.Ppad && kk - p.Ppad < p.S) {
-            dk_dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64;
-            dv_dst = dk_dst + p.H;
-          }
-#pragma unroll 1
-          for (int which = 0; which < 2; ++which) {
-            float acc[64];
-            const uint32_t col = which == 0 ? COL_DK : COL_DV;
-            tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
-            tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
-            tmem_ld_wait();
-            bf16* dst = which == 0 ? dk_dst : dv_dst;
-            if (dst != nullptr) {
-              uint4* out = reinterpret_cast<uint4*>(dst);
+          bf16* dst = nullptr;
+          if (kk < p.P)
+            dst = p.dpkv + ((size_t)n * p.P + kk) * (2 * p.H) + h * 64 + half * p.H;
+          else if (kk >= p.Ppad && kk - p.Ppad < p.S)
+            dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64 + half * p.H;
+          float acc[64];
+          const uint32_t col = half == 0 ? COL_DK : COL_DV;
+          tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
+          tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
+          tmem_ld_wait();
+          if (dst != nullptr) {
+            uint4* out = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                uint4 pk;
-                pk.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]);
-                pk.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
-                pk.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]);
-                pk.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
-                out[j] = pk;
-              }
+            for (int j = 0; j < 8; ++j) {
+              uint4 pk;
+              pk.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]);
+              pk.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
+              pk.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]);
+              pk.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
+              out[j] = pk;
             }
           }
           tc_fence_before();
@@ -626,7 +643,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<512>(tmem_base);
+  if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
 
 // ============================================================================ host
@@ -684,7 +701,7 @@ size_t attn_bwd_workspace_bytes(int N, int S, int heads) { return (size_t)N * he
 
 template <int TMEM_COLS, int MODE>
 static int launch_fwd(const AttnDesc& a, const AttnParams& p, const CUtensorMap& tmQKV, const CUtensorMap& tmPKV,
-                      const CUtensorMap& tmCTX, size_t smem, cudaStream_t stream) {
+                      const CUtensorMap& tmCTX, size_t smem, const FwdLayout& lay, cudaStream_t stream) {
   auto kern = attn_fwd_kernel<TMEM_COLS, MODE>;
   static size_t attr = 0;
   if (smem > attr) {
@@ -696,7 +713,7 @@ static int launch_fwd(const AttnDesc& a, const AttnParams& p, const CUtensorMap&
     attr = smem;
   }
   dim3 grid(p.nqt, p.heads, p.N);
-  kern<<<grid, 160, smem, stream>>>(tmQKV, tmPKV, tmCTX, p);
+  kern<<<grid, 160, smem, stream>>>(tmQKV, tmPKV, tmCTX, p, lay);
   return check_launch("prefix_attn_fwd");
 }
 
@@ -705,7 +722,21 @@ int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
   int rc = fill_params(a, p, false);
   if (rc) return rc;
   const int nblk = (p.Kp + 63) / 64;
-  const size_t smem = 1024 + 16384 + (size_t)2 * p.Krows * 128 + (size_t)nblk * 16384 + nblk * 64 * 4 + 128;
+  // shared-memory plan: Q tile | K | V | extra P blocks | bias | barriers.  P block 0 overlays the Q tile and
+  // P block 1 the K tile (both dead once S = QK^T has completed), which keeps cfg-2 under 113 KB -> 2 CTAs / SM.
+  FwdLayout lay;
+  int off = 16384;
+  lay.off_k = off; off += p.Krows * 128;
+  lay.off_v = off; off += p.Krows * 128;
+  for (int j = 0; j < 8; ++j) lay.off_p[j] = 0;
+  for (int j = 0; j < nblk && j < 8; ++j) {
+    if (j == 0) lay.off_p[j] = 0;
+    else if (j == 1 && p.Krows * 128 >= 16384) lay.off_p[j] = lay.off_k;
+    else { lay.off_p[j] = off; off += 16384; }
+  }
+  lay.off_bias = off; off += nblk * 64 * 4;
+  lay.off_bars = (off + 15) & ~15;
+  const size_t smem = 1024 + (size_t)lay.off_bars + 128;
   if (p.Kp > 512 || smem > 232448) {
     set_error("prefix_attn_fwd: P+S=%d too long for the single-pass kernel (smem %zu B)", p.P + p.S, smem);
     return MODCR_ERR_UNSUPPORTED;
@@ -723,14 +754,14 @@ int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
   const bool small = p.Kp <= 256;
   switch (p.mode) {
     case 0:
-      return small ? launch_fwd<256, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
-                   : launch_fwd<512, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+      return small ? launch_fwd<256, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream)
+                   : launch_fwd<512, 0>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream);
     case 1:
-      return small ? launch_fwd<256, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
-                   : launch_fwd<512, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+      return small ? launch_fwd<256, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream)
+                   : launch_fwd<512, 1>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream);
     default:
-      return small ? launch_fwd<256, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, stream)
-                   : launch_fwd<512, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, stream);
+      return small ? launch_fwd<256, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream)
+                   : launch_fwd<512, 2>(a, p, tmQKV, tmPKV, tmCTX, smem, lay, stream);
   }
 }
 
@@ -748,7 +779,7 @@ static int launch_bwd(const AttnParams& p, const CUtensorMap& tmQKV, const CUten
     attr = smem;
   }
   dim3 grid(p.heads, p.N);
-  kern<<<grid, 192, smem, stream>>>(tmQKV, tmPKV, tmDO, p);
+  kern<<<grid, 320, smem, stream>>>(tmQKV, tmPKV, tmDO, p);
   return check_launch("prefix_attn_bwd");
 }
 

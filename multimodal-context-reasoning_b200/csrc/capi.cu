@@ -208,15 +208,15 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
   return modcr::align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T, R, S(stream));
 }
 
-int modcr_cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int32_t N,
-                            int32_t L, int32_t H, void* stream) {
-  ARCH_OR_RETURN();
-  return modcr::cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H, S(stream));
-}
-int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk,
+int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,
                             int32_t N, int32_t L, int32_t H, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H, S(stream));
+  return modcr::cls_pool_attn_fwd(q, k, qk_f32, mask, w, pooled, N, L, H, S(stream));
+}
+int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int32_t qk_f32, const float* w, void* dq,
+                            void* dk, int32_t N, int32_t L, int32_t H, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::cls_pool_attn_bwd(dpooled, q, k, qk_f32, w, dq, dk, N, L, H, S(stream));
 }
 
 static void to_scorer(const modcr_scorer_desc* d, modcr::ScorerDesc& s) {

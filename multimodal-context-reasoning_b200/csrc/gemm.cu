@@ -8,12 +8,13 @@
 // which gives forward (K,K), dgrad (K,MN: dX = dY * W with W stored [out,in]) and
 // wgrad (MN,MN: dW = dY^T * X, contraction over the row dimension of both).
 //
-// Roles (256 threads, 1 CTA / SM, persistent over tiles):
+// Roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0  TMA producer for the A/B smem ring            (1 elected thread)
 //   warp 1  tcgen05.mma issuer, accumulators in TMEM      (1 elected thread)
 //   warp 2  TMEM allocator + TMA loader of the optional epilogue input tile
-//   warps 4-7 epilogue: tcgen05.ld -> bias / activation / residual-add / GELU' ->
-//           128B-swizzled smem -> TMA store (or TMA reduce-add for split-K fp32)
+//   warps 4-11 epilogue in two groups of four warps (group g takes column chunks g, g+2, ...):
+//           tcgen05.ld -> bias / activation / residual-add / GELU' -> 128B-swizzled smem ->
+//           TMA store (or TMA reduce-add for split-K fp32); each group owns one out / aux / in buffer
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "gemm.h"
 
@@ -77,7 +78,7 @@ DEVINL TileCoord decode_tile(const GemmParams& p, int t) {
 }
 
 template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
             const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
@@ -116,7 +117,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
       mbar_init(&infull[i], 1);
       mbar_init(&inempty[i], 128);
     }
@@ -198,25 +199,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ epilogue-input loader
+    // chunk c of a tile belongs to epilogue group (c & 1); each group owns one input buffer
     if (HAS_IN && lane == 0) {
-      uint32_t cnt = 0;
+      uint32_t cntg[2] = {0, 0};
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
-        for (int c = 0; c < C::NCHUNK; ++c, ++cnt) {
-          const int ib = cnt & 1;
-          mbar_wait(&inempty[ib], ((cnt >> 1) & 1) ^ 1);
-          mbar_expect_tx(&infull[ib], C::CHUNK_BYTES);
-          tma_load_2d(sIn + ib * C::CHUNK_BYTES, &tmIn, &infull[ib], tc.n * BN + c * C::CHUNK_COLS, tc.m * 128);
+        for (int c = 0; c < C::NCHUNK; ++c) {
+          const int g = c & 1;
+          mbar_wait(&inempty[g], (cntg[g] & 1) ^ 1);
+          mbar_expect_tx(&infull[g], C::CHUNK_BYTES);
+          tma_load_2d(sIn + g * C::CHUNK_BYTES, &tmIn, &infull[g], tc.n * BN + c * C::CHUNK_COLS, tc.m * 128);
+          ++cntg[g];
         }
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int q = warp - 4;          // TMEM lane quarter == warp % 4
+    // ------------------------------------------------------------ epilogue (2 groups x 4 warps)
+    // group g handles chunks c = g, g+2, ... of every tile; both groups read the same TMEM stage.
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;          // TMEM lane quarter == warp % 4
     const int row = q * 32 + lane;   // row inside the 128-row tile
-    const bool issuer = (threadIdx.x == 128);
+    const bool issuer = (q == 0 && lane == 0);
+    const uint32_t bar_id = 1 + g;
+    uint8_t* out_buf = sOut + g * C::CHUNK_BYTES;
+    uint8_t* aux_buf = sOut + (2 + g) * C::CHUNK_BYTES;
+    const uint8_t* in_buf = sIn + g * C::CHUNK_BYTES;
     int it = 0;
-    uint32_t cnt = 0;  // chunk counter (selects smem buffers)
+    uint32_t cnt = 0;  // chunks handled by this group
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, t);
       const int as = it & 1;
@@ -225,7 +234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
 #pragma unroll 1
-      for (int c = 0; c < C::NCHUNK; ++c, ++cnt) {
+      for (int c = g; c < C::NCHUNK; c += 2, ++cnt) {
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * C::CHUNK_COLS;
         float v[C::CHUNK_COLS];
         {
@@ -234,24 +243,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (!OUT_F32) tmem_ld_32x32(taddr + 32, r + 32);
           tmem_ld_wait();
         }
-        if (c == C::NCHUNK - 1) {  // accumulator fully read: hand the TMEM stage back
+        if (c + 2 >= C::NCHUNK) {  // this group's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
           mbar_arrive(&tempty[as]);
         }
         const int n0 = tc.n * BN + c * C::CHUNK_COLS;
+        if (p.alpha != 1.0f) {
 #pragma unroll
-        for (int j = 0; j < C::CHUNK_COLS; ++j) {
-          float x = v[j] * p.alpha;
-          if (add_bias && (n0 + j) < p.N) x += __ldg(p.bias + n0 + j);
-          v[j] = x;
+          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] *= p.alpha;
         }
-        const int ob = cnt & 1;
-        uint8_t* out_buf = sOut + ob * C::CHUNK_BYTES;
-        // make sure the TMA store that last used this buffer has finished reading it
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        if (add_bias) {
+          if (n0 + C::CHUNK_COLS <= p.N) {
+#pragma unroll
+            for (int j = 0; j < C::CHUNK_COLS / 4; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+              v[4 * j + 0] += b4.x;
+              v[4 * j + 1] += b4.y;
+              v[4 * j + 2] += b4.z;
+              v[4 * j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < C::CHUNK_COLS; ++j)
+              if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+          }
+        }
+        // the TMA stores that last used this group's buffers must have finished reading them
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
         if (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
-          uint8_t* aux_buf = sOut + (2 + ob) * C::CHUNK_BYTES;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 pk;
@@ -264,15 +284,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = gelu_fast(v[j]);
         } else if (p.act == 2) {
 #pragma unroll
           for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = tanhf(v[j]);
         }
         if (HAS_IN) {
-          const int ib = cnt & 1;
-          mbar_wait(&infull[ib], (cnt >> 1) & 1);
-          const uint8_t* in_buf = sIn + ib * C::CHUNK_BYTES;
+          mbar_wait(&infull[g], cnt & 1);
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -284,23 +302,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 pk = *reinterpret_cast<const uint4*>(in_buf + sw128_offset(row, j));
-            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+            for (int j = 0; j < 8; ++j) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(in_buf + sw128_offset(row, j));
+              const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16(w[e]);
-              if (p.in_op == 1) {
-                v[8 * j + 2 * e] += f.x;
-                v[8 * j + 2 * e + 1] += f.y;
-              } else {
-                v[8 * j + 2 * e] *= gelu_erf_grad(f.x);
-                v[8 * j + 2 * e + 1] *= gelu_erf_grad(f.y);
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16(w[e]);
+                if (p.in_op == 1) {
+                  v[8 * j + 2 * e] += f.x;
+                  v[8 * j + 2 * e + 1] += f.y;
+                } else {
+                  v[8 * j + 2 * e] *= gelu_grad_fast(f.x);
+                  v[8 * j + 2 * e + 1] *= gelu_grad_fast(f.y);
+                }
               }
             }
           }
-          }
-          mbar_arrive(&inempty[ib]);
+          mbar_arrive(&inempty[g]);
         }
         if (OUT_F32) {
 #pragma unroll
@@ -320,14 +338,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         fence_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (issuer) {
           if (n0 < p.N) {
             if (p.reduce_add)
               tma_reduce_add_2d(&tmC, out_buf, n0, tc.m * 128);
             else
               tma_store_2d(&tmC, out_buf, n0, tc.m * 128);
-            if (HAS_AUX) tma_store_2d(&tmAux, sOut + (2 + ob) * C::CHUNK_BYTES, n0, tc.m * 128);
+            if (HAS_AUX) tma_store_2d(&tmAux, aux_buf, n0, tc.m * 128);
           }
           tma_store_commit();
         }
@@ -403,7 +421,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
   p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, tmIn, p);
+  kern<<<grid, 384, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, tmIn, p);
   return check_launch("gemm");
 }
 

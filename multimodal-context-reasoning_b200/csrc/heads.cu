@@ -276,8 +276,26 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
 // ============================================================================ ClsLayer2 pooling
 constexpr int CP_MAXV = 4;  // H <= 1024
 
+// 8 consecutive elements of a bf16 or fp32 row (q and k are kept in fp32: the scores are unscaled 768-dim dot
+// products, the most rounding-sensitive spot of the path)
+template <bool F32>
+DEVINL void ld8(const void* row, int vec, float* f) {
+  if (F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row) + 2 * vec);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row) + 2 * vec + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8h(__ldg(reinterpret_cast<const uint4*>(row) + vec), f);
+  }
+}
+template <bool F32>
+DEVINL float ld1(const void* base, size_t i) {
+  return F32 ? reinterpret_cast<const float*>(base)[i] : __bfloat162float(reinterpret_cast<const bf16*>(base)[i]);
+}
+
 // smem: qs[H] | sc[L] | part[8][H]
-__global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+template <bool F32>
+__global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const void* __restrict__ q, const void* __restrict__ k,
                                                            const float* __restrict__ mask, float* __restrict__ w,
                                                            bf16* __restrict__ pooled, int L, int H) {
   extern __shared__ float sm[];
@@ -288,16 +306,17 @@ __global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const bf16* __restric
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = H >> 8;
-  for (int c = threadIdx.x; c < H; c += 256) qs[c] = __bfloat162float(q[(size_t)n * H + c]);
+  constexpr int ES = F32 ? 4 : 2;
+  for (int c = threadIdx.x; c < H; c += 256) qs[c] = ld1<F32>(q, (size_t)n * H + c);
   __syncthreads();
-  const bf16* kn = k + (size_t)n * L * H;
+  const char* kn = reinterpret_cast<const char*>(k) + (size_t)n * L * H * ES;
   for (int l = warp; l < L; l += 8) {
     float d = 0.f;
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
         float f[8];
-        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
         const float* qq = qs + (lane + 32 * i) * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) d = fmaf(f[j], qq[j], d);
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const bf16* __restric
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
         float f[8];
-        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p, f[j], acc[i][j]);
       }
@@ -355,8 +374,9 @@ __global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const bf16* __restric
 }
 
 // smem: qs[H] | dps[H] | wv[L] | dsv[L] | part[8][H]
-__global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ q,
-                                                           const bf16* __restrict__ k, const float* __restrict__ w,
+template <bool F32>
+__global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const void* __restrict__ q,
+                                                           const void* __restrict__ k, const float* __restrict__ w,
                                                            bf16* __restrict__ dq, bf16* __restrict__ dk, int L, int H) {
   extern __shared__ float sm[];
   __shared__ float sh[8];
@@ -369,13 +389,14 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = H >> 8;
+  constexpr int ES = F32 ? 4 : 2;
   for (int c = threadIdx.x; c < H; c += 256) {
-    qs[c] = __bfloat162float(q[(size_t)n * H + c]);
+    qs[c] = ld1<F32>(q, (size_t)n * H + c);
     dps[c] = __bfloat162float(dpooled[(size_t)n * H + c]);
   }
   for (int l = threadIdx.x; l < L; l += 256) wv[l] = w[(size_t)n * L + l];
   __syncthreads();
-  const bf16* kn = k + (size_t)n * L * H;
+  const char* kn = reinterpret_cast<const char*>(k) + (size_t)n * L * H * ES;
   bf16* dkn = dk + (size_t)n * L * H;
   for (int l = warp; l < L; l += 8) {  // dw[l] = dpooled . k[l]
     float d = 0.f;
@@ -383,7 +404,7 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
         float f[8];
-        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
         const float* dd = dps + (lane + 32 * i) * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) d = fmaf(f[j], dd[j], d);
@@ -408,7 +429,7 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
         float f[8], o[8];
-        unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + lane + 32 * i), f);
+        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
         const float* dd = dps + (lane + 32 * i) * 8;
         const float* qq = qs + (lane + 32 * i) * 8;
 #pragma unroll
@@ -446,30 +467,37 @@ static int cls_pool_check(int N, int L, int H, size_t smem, const char* what) {
   return MODCR_OK;
 }
 
-int cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int N, int L, int H,
-                      cudaStream_t st) {
+int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
+                      int H, cudaStream_t st) {
   const size_t smem = ((size_t)H + ((L + 3) & ~3) + 8 * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_fwd")) return rc;
   static size_t attr = 0;
   if (smem > attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(cls_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cls_pool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cls_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  cls_pool_fwd_kernel<<<N, 256, smem, st>>>((const bf16*)q, (const bf16*)k, mask, w, (bf16*)pooled, L, H);
+  if (qk_f32)
+    cls_pool_fwd_kernel<true><<<N, 256, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
+  else
+    cls_pool_fwd_kernel<false><<<N, 256, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
   return check_launch("cls_pool_attn_fwd");
 }
 
-int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk, int N, int L,
-                      int H, cudaStream_t st) {
+int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,
+                      int N, int L, int H, cudaStream_t st) {
   const size_t smem = (2 * (size_t)H + 2 * ((L + 3) & ~3) + 8 * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_bwd")) return rc;
   static size_t attr = 0;
   if (smem > attr && smem > 48 * 1024) {
-    cudaFuncSetAttribute(cls_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cls_pool_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cls_pool_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  cls_pool_bwd_kernel<<<N, 256, smem, st>>>((const bf16*)dpooled, (const bf16*)q, (const bf16*)k, w, (bf16*)dq, (bf16*)dk,
-                                            L, H);
+  if (qk_f32)
+    cls_pool_bwd_kernel<true><<<N, 256, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
+  else
+    cls_pool_bwd_kernel<false><<<N, 256, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
   return check_launch("cls_pool_attn_bwd");
 }
 

@@ -205,6 +205,45 @@ DEVINL float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+DEVINL float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+DEVINL float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Fast erf-GELU and its derivative sharing one exponential (Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt(2)  =>  exp(-z^2) = exp(-x^2/2)
+// which is also the Gaussian of GELU'(x) = Phi(x) + x phi(x).  1 MUFU.EX2 + 1 MUFU.RCP + ~12 FMA per element.
+DEVINL void gelu_pair_fast(float x, float& g, float& gp) {
+  const float ax = fabsf(x);
+  const float e = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2/2)
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
+  g = x * cdf;
+  gp = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+DEVINL float gelu_fast(float x) {
+  float g, gp;
+  gelu_pair_fast(x, g, gp);
+  return g;
+}
+DEVINL float gelu_grad_fast(float x) {
+  float g, gp;
+  gelu_pair_fast(x, g, gp);
+  return gp;
+}
+
 // byte offset of 16-byte piece `piece` (0..7) of row `row` inside a 128B-swizzled
 // [rows x 128 B] tile whose base is 1024 B aligned
 DEVINL uint32_t sw128_offset(uint32_t row, uint32_t piece) { return row * 128u + ((piece ^ (row & 7u)) << 4); }

@@ -121,83 +121,78 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dx (bias of the Linear
 // that produced x, fused here so no extra pass over dx is needed)
-template <bool XF32>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const void* __restrict__ x,
-                                                     RowMap xmap, const float* __restrict__ mean,
-                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                     bf16* __restrict__ dx, RowMap dxmap, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, float* __restrict__ dbias, int M, int H) {
-  __shared__ float red[8][32 * 8 + 1];
+constexpr int LNB_WARPS = 12;  // 384 threads, one persistent CTA per SM
+template <bool XF32, int NV>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const void* __restrict__ x, RowMap xmap,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+              bf16* __restrict__ dx, RowMap dxmap, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dbias, int M, int H) {
+  __shared__ float red[LNB_WARPS][32 * 8 + 1];
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nv = H >> 8;
-  const int wstride = gridDim.x * 8;
-  float ag[LN_MAXV][8], ab[LN_MAXV][8], ax[LN_MAXV][8];
+  const int wstride = gridDim.x * LNB_WARPS;
+  float ag[NV][8], ab[NV][8], ax[NV][8], gm[NV][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = ax[i][j] = 0.f;
-  float gm[LN_MAXV][8];
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv) load8f(gamma + (lane + 32 * i) * 8, gm[i]);
-
-  for (int m = blockIdx.x * 8 + wib; m < M; m += wstride) {
+    load8f(gamma + (lane + 32 * i) * 8, gm[i]);
+  }
+  for (int m = blockIdx.x * LNB_WARPS + wib; m < M; m += wstride) {
     const bf16* dyr = dy + map_row(m, dymap) * H;
     const char* xr = reinterpret_cast<const char*>(x) + map_row(m, xmap) * H * (XF32 ? 4 : 2);
     const float mu = __ldg(mean + m), rs = __ldg(rstd + m);
-    float g[LN_MAXV][8], xh[LN_MAXV][8];
+    float d[NV][8], xh[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {  // issue every load of the row before any arithmetic
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + lane + 32 * i), d[i]);
+      load_row8<XF32>(xr, lane + 32 * i, xh[i]);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-      if (i < nv) {
-        float d[8], xv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dyr) + lane + 32 * i), d);
-        load_row8<XF32>(xr, lane + 32 * i, xv);
+    for (int i = 0; i < NV; ++i) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = d[j] * gm[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          ag[i][j] += d[j] * xh[i][j];
-          ab[i][j] += d[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xh[i][j] - mu) * rs;
+        const float g = d[i][j] * gm[i][j];
+        s1 += g;
+        s2 = fmaf(g, xh[i][j], s2);
+        ag[i][j] = fmaf(d[i][j], xh[i][j], ag[i][j]);
+        ab[i][j] += d[i][j];
       }
+    }
     s1 = warp_sum(s1) / H;
     s2 = warp_sum(s2) / H;
     bf16* dxr = dx + map_row(m, dxmap) * H;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i)
-      if (i < nv) {
-        float o[8];
+    for (int i = 0; i < NV; ++i) {
+      float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
-          ax[i][j] += o[j];
-        }
-        reinterpret_cast<uint4*>(dxr)[lane + 32 * i] = pack8(o);
+      for (int j = 0; j < 8; ++j) {
+        o[j] = rs * (d[i][j] * gm[i][j] - s1 - xh[i][j] * s2);
+        ax[i][j] += o[j];
       }
+      reinterpret_cast<uint4*>(dxr)[lane + 32 * i] = pack8(o);
+    }
   }
   // cross-warp reduction of the three column accumulators, then one atomic per column per CTA
   for (int which = 0; which < 3; ++which) {
     float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
     if (dst == nullptr) continue;  // uniform
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
-      if (i < nv) {
-        __syncthreads();
+    for (int i = 0; i < NV; ++i) {
+      __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : ax[i][j]);
-        __syncthreads();
-        // 256 threads: thread t sums column t of this 256-column slab
-        const int t = threadIdx.x;
+      for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : ax[i][j]);
+      __syncthreads();
+      const int t = threadIdx.x;
+      if (t < 256) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][t];
+        for (int w = 0; w < LNB_WARPS; ++w) s += red[w][t];
         // slab i covers columns (lane + 32 i) * 8 + j  ->  t = lane*8 + j
-        const int col = ((t >> 3) + 32 * i) * 8 + (t & 7);
-        atomicAdd(dst + col, s);
+        atomicAdd(dst + ((t >> 3) + 32 * i) * 8 + (t & 7), s);
       }
     }
   }
@@ -279,11 +274,11 @@ __global__ void __launch_bounds__(256) txt_embed_bwd_kernel(
   const int lane = threadIdx.x & 31;
   const int nv = H >> 8;
   const int wstride = gridDim.x * 8;
-  float ag[LN_MAXV][8], ab[LN_MAXV][8];
+  float ag[LN_MAXV][8], ab[LN_MAXV][8], at0[LN_MAXV][8], at1[LN_MAXV][8];
 #pragma unroll
   for (int i = 0; i < LN_MAXV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = at0[i][j] = at1[i][j] = 0.f;
   for (int m = blockIdx.x * 8 + wib; m < M; m += wstride) {
     const int64_t id = ids[m];
     const int64_t tt = tts ? tts[m] : 0;
@@ -322,19 +317,22 @@ __global__ void __launch_bounds__(256) txt_embed_bwd_kernel(
         for (int j = 0; j < 8; ++j) {
           const float o = rs * (g[i][j] - s1 - xh[i][j] * s2);
           if (id != padding_idx) atomicAdd(dword + id * H + c + j, o);
-          atomicAdd(dtype + tt * H + c + j, o);
+          if (tt == 0) at0[i][j] += o;                 // the two hot token-type rows are reduced per CTA
+          else if (tt == 1) at1[i][j] += o;
+          else atomicAdd(dtype + tt * H + c + j, o);
           atomicAdd(dpos + ps * H + c + j, o);
         }
       }
   }
-  for (int which = 0; which < 2; ++which) {
-    float* dst = which == 0 ? dgamma : dbeta;
+  for (int which = 0; which < 4; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : (which == 2 ? dtype : dtype + H));
 #pragma unroll
     for (int i = 0; i < LN_MAXV; ++i) {
       if (i < nv) {
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : ab[i][j];
+        for (int j = 0; j < 8; ++j)
+          red[wib][lane * 8 + j] = which == 0 ? ag[i][j] : (which == 1 ? ab[i][j] : (which == 2 ? at0[i][j] : at1[i][j]));
         __syncthreads();
         const int t = threadIdx.x;
         float s = 0.f;
@@ -555,13 +553,17 @@ int layernorm_bwd(const void* dy, RowMap dymap, const void* x, int x_f32, RowMap
                   int M, int H, cudaStream_t st) {
   if (int rc = check_h(H, "layernorm_bwd")) return rc;
   if (M <= 0) return MODCR_OK;
-  const int grid = blocks_for(M, 8 * 8, 148 * 4);
-  if (x_f32)
-    ln_bwd_kernel<true><<<grid, 256, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap, dgamma,
-                                              dbeta, dbias, M, H);
-  else
-    ln_bwd_kernel<false><<<grid, 256, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, dxmap, dgamma,
-                                               dbeta, dbias, M, H);
+  const int grid = blocks_for(M, LNB_WARPS, 148);
+  const int nv = H >> 8;
+#define LNB_LAUNCH(F32, NV)                                                                                          \
+  ln_bwd_kernel<F32, NV><<<grid, LNB_WARPS * 32, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, \
+                                                          dxmap, dgamma, dbeta, dbias, M, H)
+  if (x_f32) {
+    if (nv == 1) LNB_LAUNCH(true, 1); else if (nv == 2) LNB_LAUNCH(true, 2); else if (nv == 3) LNB_LAUNCH(true, 3); else LNB_LAUNCH(true, 4);
+  } else {
+    if (nv == 1) LNB_LAUNCH(false, 1); else if (nv == 2) LNB_LAUNCH(false, 2); else if (nv == 3) LNB_LAUNCH(false, 3); else LNB_LAUNCH(false, 4);
+  }
+#undef LNB_LAUNCH
   return check_launch("layernorm_bwd");
 }
 
@@ -583,7 +585,7 @@ int txt_embed_ln_bwd(const void* dy, RowMap dymap, const int64_t* ids, const int
   if (int rc = check_h(H, "txt_embed_ln_bwd")) return rc;
   const int M = N * T;
   if (M <= 0) return MODCR_OK;
-  const int grid = blocks_for(M, 8 * 4, 148 * 4);
+  const int grid = blocks_for(M, 8 * 4, 148 * 2);
   txt_embed_bwd_kernel<<<grid, 256, 0, st>>>((const bf16*)dy, dymap, ids, tts, pos_ids, word, type, pos, gamma, mean, rstd,
                                              dword, dtype, dpos, dgamma, dbeta, M, T, H, padding_idx);
   return check_launch("txt_embed_ln_bwd");

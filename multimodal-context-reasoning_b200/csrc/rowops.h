@@ -51,10 +51,11 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
                          float gout, float* dblock, int N, int T, int R, cudaStream_t st);
 
 // ClsLayer2 attention pooling (v10:816-829): w = softmax(q k^T + mask) (no 1/sqrt(d)), pooled = w k
-int cls_pool_attn_fwd(const void* q, const void* k, const float* mask, float* w, void* pooled, int N, int L, int H,
-                      cudaStream_t st);
-int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, const float* w, void* dq, void* dk, int N, int L,
+// q [N,H] and k [N,L,H] are bf16 (qk_f32 = 0) or fp32 (qk_f32 = 1)
+int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
                       int H, cudaStream_t st);
+int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,
+                      int N, int L, int H, cudaStream_t st);
 
 // Fused small classifier + cross-entropy (+ binary_to_mp / argmax / matched):
 //   logits[r, c] = x[r,:] . W[c,:] + b[c]            x bf16 [rows,K], W fp32 [C,K], C <= 8

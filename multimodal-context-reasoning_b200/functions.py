@@ -173,9 +173,9 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         for i in range(nl):
             pfx = "cls_layer.%d." % i
             sv = {} if need_grad else None
-            q = E._empty((N, H), BF16, dev)
+            q = E._empty((N, H), F32, dev)             # q, k stay fp32: unscaled 768-dim scores (v10:822)
             ops.gemm(cls, ps.bf16(pfx + "cls_q_proj.weight"), q, N, H, H, bias=ps.f32(pfx + "cls_q_proj.bias"))
-            k = E._empty((N, L3, H), BF16, dev)
+            k = E._empty((N, L3, H), F32, dev)
             ops.gemm(X, ps.bf16(pfx + "align_k_proj.weight"), k, N * L3, H, H, bias=ps.f32(pfx + "align_k_proj.bias"))
             w = E._empty((N, L3), F32, dev)
             pooled = E._empty((N, H), BF16, dev)

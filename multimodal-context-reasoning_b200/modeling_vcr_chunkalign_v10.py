@@ -136,8 +136,10 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         wm = torch.cat((wm, wm, wm), -1).contiguous()
         run = ClsHeadRun(ps, names, cfg, N, T, S)
         cls = ClsLayer2HeadFn.apply(run, wm, g[0], s_out, chunk_hidden, g[1], s_pool, *params)
-        self.last_intermediates = dict(global_output=g[0], global_CLS=g[1], seq_output=s_out, chunk_CLS=s_pool,
-                                       chunk_hidden_states=chunk_hidden, CLS=cls)
+        # detached debug views (never keep the autograd graph of a finished step alive)
+        self.last_intermediates = dict(global_output=g[0].detach(), global_CLS=g[1].detach(), seq_output=s_out.detach(),
+                                       chunk_CLS=s_pool.detach(), chunk_hidden_states=chunk_hidden.detach(),
+                                       CLS=cls.detach())
         return cls, att
 
     def forward(self, input_ids, img_feat, input_mask=None, label=None, token_type_ids=None, position_ids=None,
@@ -152,7 +154,7 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         loss_cls_0, logits, mp, pred, matched_0 = ScorerFn.apply(
             cls, self.classifier.weight, self.classifier.bias, label.long().contiguous(), None, 2, self.num_labels, True)
         self.last_logits, self.last_logit_expl, self.last_pred = logits, mp, pred
-        self.last_align_block = att.align_block
+        self.last_align_block = None if att.align_block is None else att.align_block.detach()
         align_loss, correct, total_sum = None, 0, 0
         if want_block:
             align_loss, stats = AlignLossFn.apply(att.align_block, align_pos, total_label)

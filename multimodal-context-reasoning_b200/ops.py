@@ -158,13 +158,15 @@ def align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T,
 
 
 def cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H):
-    _lib.check(_lib.load().modcr_cls_pool_attn_fwd(_p(q), _p(k), _p(mask), _p(w), _p(pooled), N, L, H, _stream()),
-               "cls_pool_attn_fwd")
+    if q.dtype != k.dtype:
+        raise RuntimeError("modcr_b200: cls_pool q and k must share a dtype")
+    _lib.check(_lib.load().modcr_cls_pool_attn_fwd(_p(q), _p(k), int(k.dtype == F32), _p(mask), _p(w), _p(pooled), N, L,
+                                                   H, _stream()), "cls_pool_attn_fwd")
 
 
 def cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H):
-    _lib.check(_lib.load().modcr_cls_pool_attn_bwd(_p(dpooled), _p(q), _p(k), _p(w), _p(dq), _p(dk), N, L, H,
-                                                   _stream()), "cls_pool_attn_bwd")
+    _lib.check(_lib.load().modcr_cls_pool_attn_bwd(_p(dpooled), _p(q), _p(k), int(k.dtype == F32), _p(w), _p(dq),
+                                                   _p(dk), N, L, H, _stream()), "cls_pool_attn_bwd")
 
 
 def _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None, num_choice=4,

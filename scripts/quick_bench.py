@@ -29,7 +29,7 @@ def step():
     for p in m.parameters(): p.grad = None
     prefix.grad = None
     return loss
-for _ in range(3): step()
+for _ in range(int(os.environ.get("WARM", 3))): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter(); e0.record()

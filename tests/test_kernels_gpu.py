@@ -385,10 +385,10 @@ def test_align_softmax_ce_fwd_bwd():
     torch.testing.assert_close(dblock, pr.grad[0, :, 0], atol=1e-7, rtol=1e-3)
 
 
-@pytest.mark.parametrize("L,H", [(381, 768), (57, 1024)])
-def test_cls_pool_attn_fwd_bwd(L, H):
+@pytest.mark.parametrize("L,H,dt", [(381, 768, torch.bfloat16), (57, 1024, torch.bfloat16), (381, 768, torch.float32)])
+def test_cls_pool_attn_fwd_bwd(L, H, dt):
     N = 6
-    q, k = rnd(N, H, scale=0.3, seed=1), rnd(N, L, H, scale=0.3, seed=2)
+    q, k = rnd(N, H, scale=0.3, seed=1, dtype=dt), rnd(N, L, H, scale=0.3, seed=2, dtype=dt)
     mask = torch.zeros(N, L)
     mask[:, L - 11:] = NEG
     mask = mask.to(DEV)
