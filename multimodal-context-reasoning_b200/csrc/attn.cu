@@ -554,12 +554,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
         mbar_wait(bar_sdp, step & 1);
         tc_fence_after();
-        uint8_t* pblk = sP + half * 16384;
-        uint8_t* dblk = sDS + half * 16384;
+        // this thread's two 32-column chunks of the 128-key block are interleaved with the other half's
+        // (c0 = 32*half and 32*half + 64) so that a partial last block stays balanced between the two warps
+        const bool warp_alive = (qt * 128 + (warp & 3) * 32) < p.S;
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-          const int c0 = half * 64 + i * 32;
+          const int c0 = half * 32 + i * 64;
           const int kk0 = kb * 128 + c0;
+          uint8_t* pblk = sP + (c0 >> 6) * 16384;
+          uint8_t* dblk = sDS + (c0 >> 6) * 16384;
+          if (!warp_alive || c0 >= nb) {
+            // dead q rows (rows >= S) or key columns beyond this block: P = dS = 0, no TMEM traffic, no math
+            const int piece0 = (c0 & 63) >> 3;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = z;
+              *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = z;
+            }
+            continue;
+          }
           const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
           if (c0 + 32 <= nb)
             bwd_chunk<MODE, false>(p, c1, taddr + COL_S, taddr + COL_DP, sBias, pblk, dblk, c0, kk0, nb, row, q, q_txt, w,
