@@ -16,9 +16,16 @@
 //           tcgen05.ld -> bias / activation / residual-add / GELU' -> 128B-swizzled smem ->
 //           TMA store (or TMA reduce-add for split-K fp32); each group owns one out / aux / in buffer
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// NCTA = 2 runs the same roles on CTA pairs (cluster of 2, tcgen05 cta_group::2): the pair owns a 256 x BN
+// output tile, each CTA loads its own 128 A rows and HALF of the B tile (BN/2 rows), the leader CTA issues
+// M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM, and each CTA runs the epilogue
+// of its own 128 rows.  Per CTA that is 32 KB of operand traffic per k-block instead of 48 KB for the same
+// 128 x 256 x 64 MACs, which is what lifts the kernel off the L2->SM bandwidth limit (ncu: profiles/).
 #include "gemm.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -38,11 +45,12 @@ struct GemmParams {
   int reduce_add; // output through TMA reduce-add (fp32 accumulate in place)
 };
 
-template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
 struct Cfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int BN_LOAD = BN / NCTA;          // B rows this CTA loads
+  static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B
   static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
@@ -59,12 +67,14 @@ struct Cfg {
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
   static_assert(!(OUT_F32 && HAS_AUX), "fp32 output has no aux path");
+  static_assert(NCTA == 1 || NCTA == 2, "CTA pairs at most");
 };
 
 struct TileCoord {
   int m, n, kb0, kb1, split;
 };
 
+// `m` counts 128 * NCTA row groups (p.m_tiles of them)
 DEVINL TileCoord decode_tile(const GemmParams& p, int t) {
   TileCoord c;
   const int mn = p.m_tiles * p.n_tiles;
@@ -77,12 +87,12 @@ DEVINL TileCoord decode_tile(const GemmParams& p, int t) {
   return c;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
             const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
-  using C = Cfg<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,6 +112,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles * p.split_k;
+  // work is distributed over CTA groups (single CTAs or pairs); `rank` is this CTA's half of the pair
+  const int rank = NCTA == 2 ? (int)cluster_ctarank() : 0;
+  const int group = blockIdx.x / NCTA;
+  const int ngroups = gridDim.x / NCTA;
+  const bool leader = rank == 0;
+  constexpr int EPI_ARRIVALS = NCTA == 2 ? 16 : 256;   // pairs: one (remote) arrive per epilogue warp
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -117,15 +133,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], EPI_ARRIVALS);
       mbar_init(&infull[i], 1);
       mbar_init(&inempty[i], 128);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (NCTA == 2) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -134,25 +154,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = group; t < total_tiles; t += ngroups) {
         const TileCoord tc = decode_tile(p, t);
+        const int m0 = (tc.m * NCTA + rank) * 128;            // this CTA's A rows
+        const int n0 = tc.n * BN + rank * C::BN_LOAD;         // this CTA's share of the B rows
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * C::A_BYTES;
           uint8_t* b_dst = sB + stage * C::B_BYTES;
-          if (!A_MN) {
-            tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, tc.m * 128);
-          } else {
+          if constexpr (NCTA == 2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the pair
+            if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+            const uint32_t bar = mapa_rank(smem_u32(&full[stage]), 0);
+            if (!A_MN) {
+              tma_load_2d_pair(a_dst, &tmA, bar, kb * 64, m0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full[stage], tc.m * 128 + i * 64, kb * 64);
-          }
-          if (!B_MN) {
-            tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, tc.n * BN);
-          } else {
+              for (int i = 0; i < 2; ++i) tma_load_2d_pair(a_dst + i * 8192, &tmA, bar, m0 + i * 64, kb * 64);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(b_dst, &tmB, bar, kb * 64, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(b_dst + i * 8192, &tmB, &full[stage], tc.n * BN + i * 64, kb * 64);
+              for (int i = 0; i < C::BN_LOAD / 64; ++i)
+                tma_load_2d_pair(b_dst + i * 8192, &tmB, bar, n0 + i * 64, kb * 64);
+            }
+          } else {
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * 64, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) tma_load_2d(a_dst + i * 8192, &tmA, &full[stage], m0 + i * 64, kb * 64);
+            }
+            if (!B_MN) {
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * 64, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(b_dst + i * 8192, &tmB, &full[stage], n0 + i * 64, kb * 64);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -162,13 +203,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ------------------------------------------------------------ MMA issuer (pairs: leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(128 * NCTA, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = group; t < total_tiles; t += ngroups, ++it) {
         const TileCoord tc = decode_tile(p, t);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -186,15 +227,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                          : make_smem_desc(a_base + k * 32, 0, 1024);
             const uint64_t b_desc = B_MN ? make_smem_desc(b_base + k * 2048, 8192, 1024)
                                          : make_smem_desc(b_base + k * 32, 0, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            if (NCTA == 2) umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (NCTA == 2) umma_commit_pair(&empty[stage], 3);
+          else umma_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (NCTA == 2) umma_commit_pair(&tfull[as], 3);
+        else umma_commit(&tfull[as]);
       }
     }
   } else if (warp == 2) {
@@ -202,13 +248,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // chunk c of a tile belongs to epilogue group (c & 1); each group owns one input buffer
     if (HAS_IN && lane == 0) {
       uint32_t cntg[2] = {0, 0};
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = group; t < total_tiles; t += ngroups) {
         const TileCoord tc = decode_tile(p, t);
+        const int m0 = (tc.m * NCTA + rank) * 128;
         for (int c = 0; c < C::NCHUNK; ++c) {
           const int g = c & 1;
           mbar_wait(&inempty[g], (cntg[g] & 1) ^ 1);
           mbar_expect_tx(&infull[g], C::CHUNK_BYTES);
-          tma_load_2d(sIn + g * C::CHUNK_BYTES, &tmIn, &infull[g], tc.n * BN + c * C::CHUNK_COLS, tc.m * 128);
+          tma_load_2d(sIn + g * C::CHUNK_BYTES, &tmIn, &infull[g], tc.n * BN + c * C::CHUNK_COLS, m0);
           ++cntg[g];
         }
       }
@@ -223,11 +270,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t bar_id = 1 + g;
     uint8_t* out_buf = sOut + g * C::CHUNK_BYTES;
     uint8_t* aux_buf = sOut + (2 + g) * C::CHUNK_BYTES;
-    const uint8_t* in_buf = sIn + g * C::CHUNK_BYTES;
+    const uint32_t out_s = smem_u32(out_buf), aux_s = smem_u32(aux_buf), in_s = smem_u32(sIn + g * C::CHUNK_BYTES);
     int it = 0;
     uint32_t cnt = 0;  // chunks handled by this group
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    const uint32_t tempty_r0 = NCTA == 2 ? mapa_rank(smem_u32(&tempty[0]), 0) : 0u;
+    const uint32_t tempty_r1 = NCTA == 2 ? mapa_rank(smem_u32(&tempty[1]), 0) : 0u;
+    for (int t = group; t < total_tiles; t += ngroups, ++it) {
       const TileCoord tc = decode_tile(p, t);
+      const int m0 = (tc.m * NCTA + rank) * 128;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull[as], aphase);
@@ -245,7 +295,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (c + 2 >= C::NCHUNK) {  // this group's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
-          mbar_arrive(&tempty[as]);
+          if constexpr (NCTA == 2) {   // to the leader's barrier, one arrive per warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(as ? tempty_r1 : tempty_r0);
+          } else {
+            mbar_arrive(&tempty[as]);
+          }
         }
         const int n0 = tc.n * BN + c * C::CHUNK_COLS;
         if (p.alpha != 1.0f) {
@@ -279,7 +334,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
             pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(aux_buf + sw128_offset(row, j)) = pk;
+            sts128(aux_s + sw128_offset(row, j), pk.x, pk.y, pk.z, pk.w);
           }
         }
         if (p.act == 1) {
@@ -294,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 f = *reinterpret_cast<const float4*>(in_buf + sw128_offset(row, j));
+              const float4 f = lds128f(in_s + sw128_offset(row, j));
               v[4 * j + 0] += f.x;
               v[4 * j + 1] += f.y;
               v[4 * j + 2] += f.z;
@@ -303,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(in_buf + sw128_offset(row, j));
+              const uint4 pk = lds128(in_s + sw128_offset(row, j));
               const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -323,8 +378,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (OUT_F32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 f4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<float4*>(out_buf + sw128_offset(row, j)) = f4;
+            sts128f(out_s + sw128_offset(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         } else {
 #pragma unroll
@@ -334,7 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
             pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
             pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(out_buf + sw128_offset(row, j)) = pk;
+            sts128(out_s + sw128_offset(row, j), pk.x, pk.y, pk.z, pk.w);
           }
         }
         fence_async_smem();
@@ -342,10 +396,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (issuer) {
           if (n0 < p.N) {
             if (p.reduce_add)
-              tma_reduce_add_2d(&tmC, out_buf, n0, tc.m * 128);
+              tma_reduce_add_2d(&tmC, out_buf, n0, m0);
             else
-              tma_store_2d(&tmC, out_buf, n0, tc.m * 128);
-            if (HAS_AUX) tma_store_2d(&tmAux, aux_buf, n0, tc.m * 128);
+              tma_store_2d(&tmC, out_buf, n0, m0);
+            if (HAS_AUX) tma_store_2d(&tmAux, aux_buf, n0, m0);
           }
           tma_store_commit();
         }
@@ -354,8 +408,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (issuer) tma_store_wait_all<0>();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (NCTA == 2) {
+    // neither CTA may exit (or free TMEM) while its peer can still arrive on its barriers / read its smem
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------- host
@@ -370,10 +430,20 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
-static int launch(const GemmDesc& g, cudaStream_t stream) {
-  using C = Cfg<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+// MODCR_GEMM_NCTA=1 forces the single-CTA kernel (A/B comparison of the two data paths; default: CTA pairs)
+static int g_ncta = 0;
+static int gemm_ncta() {
+  if (g_ncta == 0) {
+    const char* e = getenv("MODCR_GEMM_NCTA");
+    g_ncta = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return g_ncta;
+}
+
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+static int launch_n(const GemmDesc& g, cudaStream_t stream) {
+  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  auto kern = gemm_kernel<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -389,7 +459,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
   if (!A_MN) rc = make_tmap_2d(&tmA, g.A, 2, g.M, g.K, g.lda, 128, 64);
   else       rc = make_tmap_2d(&tmA, g.A, 2, g.K, g.M, g.lda, 64, 64);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_2d(&tmB, g.B, 2, g.N, g.K, g.ldb, BN, 64);
+  if (!B_MN) rc = make_tmap_2d(&tmB, g.B, 2, g.N, g.K, g.ldb, C::BN_LOAD, 64);
   else       rc = make_tmap_2d(&tmB, g.B, 2, g.K, g.N, g.ldb, 64, 64);
   if (rc) return rc;
   rc = make_tmap_2d(&tmC, g.C, OUT_F32 ? 4 : 2, g.M, g.N, g.ldc, 128, C::CHUNK_COLS);
@@ -412,7 +482,7 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
   p.kb_per = (p.kb_total + split - 1) / split;
   split = (p.kb_total + p.kb_per - 1) / p.kb_per;  // no empty splits
   p.split_k = split;
-  p.m_tiles = (g.M + 127) / 128;
+  p.m_tiles = (g.M + 128 * NCTA - 1) / (128 * NCTA);
   p.n_tiles = (g.N + BN - 1) / BN;
   p.alpha = g.alpha;
   p.bias = g.bias;
@@ -420,9 +490,32 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
   p.in_op = g.in_op;
   p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
   const int total = p.m_tiles * p.n_tiles * p.split_k;
-  int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, 384, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, tmIn, p);
+  const int groups_max = num_sms() / NCTA;
+  const int groups = total < groups_max ? total : groups_max;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * NCTA, 1, 1);
+  cfg.blockDim = dim3(384, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmAux, tmIn, p);
+  if (e != cudaSuccess) {
+    set_error("gemm: launch failed: %s", cudaGetErrorString(e));
+    return MODCR_ERR_CUDA;
+  }
   return check_launch("gemm");
+}
+
+template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+static int launch(const GemmDesc& g, cudaStream_t stream) {
+  if (gemm_ncta() == 2) return launch_n<2, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>(g, stream);
+  return launch_n<1, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>(g, stream);
 }
 
 int gemm_split_k_heuristic(int M, int N, int K, int bn) {

@@ -161,6 +161,62 @@ DEVINL void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
 }
 DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2)
+DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset inside CTA `rank` of this cluster
+DEVINL uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose completion bytes are signalled on a barrier of the pair's
+// leader CTA (`bar_cluster_addr` = mapa_rank(barrier, 0))
+DEVINL void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"((uint64_t)m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int NCOLS>
+DEVINL void tmem_alloc_pair(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+DEVINL void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), each CTA holding half of the B rows
+DEVINL void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in every CTA of `mask`
+DEVINL void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
@@ -216,32 +272,57 @@ DEVINL float fast_rcp(float x) {
   return y;
 }
 
-// Fast erf-GELU and its derivative sharing one exponential (Abramowitz-Stegun 7.1.26, |erf error| < 1.5e-7):
-//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt(2)  =>  exp(-z^2) = exp(-x^2/2)
-// which is also the Gaussian of GELU'(x) = Phi(x) + x phi(x).  1 MUFU.EX2 + 1 MUFU.RCP + ~12 FMA per element.
-DEVINL void gelu_pair_fast(float x, float& g, float& gp) {
-  const float ax = fabsf(x);
-  const float e = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2/2)
-  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
-  g = x * cdf;
-  gp = fmaf(x * 0.3989422804014327f, e, cdf);
+DEVINL float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Fast erf-GELU: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) = 0.5 (1 + tanh(p(x))) with p = atanh(erf(x / sqrt 2)) fitted by
+// the odd quintic x (c0 + c1 x^2 + c2 x^4) (minimax on the GELU error over |x| <= 8: |Phi error| < 5.1e-5,
+// |gelu error| < 2.6e-5; x^2 is clamped where tanh has saturated so the negative c2 never bends p back).
+// With MUFU.TANH (relative error 2^-11) the total |gelu error| stays below 2.5e-4 |x|, an order of magnitude
+// under the bf16 rounding of the stored activation.  7 FP ops + 1 MUFU per element (the Abramowitz-Stegun
+// form used before needed 15 + 2 and made the FFN epilogues issue-bound, ncu: profiles/).
+DEVINL float gelu_tanh_arg(float x, float& x2) {
+  x2 = x * x;
+  const float x2c = fminf(x2, 50.0f);
+  float q = fmaf(x2c, -3.51517510e-04f, 3.70056508e-02f);
+  q = fmaf(x2c, q, 7.97507879e-01f);
+  return x * q;
 }
 DEVINL float gelu_fast(float x) {
-  float g, gp;
-  gelu_pair_fast(x, g, gp);
-  return g;
+  float x2;
+  const float t = fast_tanh(gelu_tanh_arg(x, x2));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
+// GELU'(x) = Phi(x) + x phi(x), phi(x) = exp(-x^2 / 2) / sqrt(2 pi)
 DEVINL float gelu_grad_fast(float x) {
-  float g, gp;
-  gelu_pair_fast(x, g, gp);
-  return gp;
+  float x2;
+  const float t = fast_tanh(gelu_tanh_arg(x, x2));
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  const float e = fast_ex2(-0.72134752044448170f * x2);
+  return fmaf(x * e, 0.3989422804014327f, cdf);
+}
+
+// explicit shared-state-space 128-bit accesses (a generic pointer derived from the aligned dynamic-smem base makes
+// the compiler emit generic LD/ST, which issue slower than LDS/STS)
+DEVINL void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+DEVINL void sts128f(uint32_t addr, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+DEVINL float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 
 // byte offset of 16-byte piece `piece` (0..7) of row `row` inside a 128B-swizzled
