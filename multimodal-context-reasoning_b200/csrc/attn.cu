@@ -336,46 +336,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // ============================================================================ backward
 // Row threads: 8 warps.  Warp w owns TMEM lanes 32*(w&3) (= q rows of the tile) and the key-column half (w>>2)
 // of every 128-key block, so two warps share each SM sub-partition's latency.
-template <int MODE, bool SAFE>
-DEVINL void bwd_chunk(const AttnParams& p, float c1, uint32_t taddr_s, uint32_t taddr_dp, const float* sBias,
-                      uint8_t* pblk, uint8_t* dblk, int c0, int kk0, int nb, int row, int q, bool q_txt, uint32_t w,
-                      float lse2, float delta, const float* darow) {
-  float sv[32], dp[32], bb[32];
-  tmem_ld_32x32(taddr_s + c0, reinterpret_cast<uint32_t*>(sv));
-  tmem_ld_32x32(taddr_dp + c0, reinterpret_cast<uint32_t*>(dp));
+//
+// Schedule (one step = one (key block, q tile) pair, steps run kb-major):
+//   MMA thread :  S/dP(0) | for i: for each 64-key sub-block c: wait "S/dP(i,c) consumed" -> issue S/dP(i+1,c)
+//                 | wait P/dS(i) -> issue dV,dK,dQ(i) -> commit "free(i)"
+//   row threads:  for i: for c: wait S/dP(i,c) -> tcgen05.ld -> arrive "consumed" -> P, dS math into registers
+//                 | wait free(i-1) -> read out whatever step i-1 completed (dQ, dK/dV) -> store P/dS(i) -> arrive
+// Every thread's two 32-column chunks lie in different 64-key sub-blocks, and S/dP of a sub-block is its own MMA
+// group with its own barrier, so the product for step i+1 is re-issued as soon as the registers hold step i's
+// values: the exp / dS math of step i runs while the tensor core computes S/dP(i+1) and dV/dK/dQ(i-1).  With at most two q tiles (S <= 256) the dQ accumulators
+// of both tiles stay resident in TMEM across key blocks (columns 256.. and 448..), so dQ is written once, as bf16,
+// and the fp32 workspace round trip disappears; longer sequences flush dQ per step through the workspace.
+// P and dS of one 32-column chunk from the S / dP accumulator values already in registers.
+// DALIGN: the chunk overlaps the region columns and the alignment-loss gradient has to be added to dP.
+template <int MODE, bool SAFE, bool DALIGN>
+DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, const float* sBias, int c0, int kk0,
+                           int nb, int q, bool q_txt, uint32_t w, float lse2, float delta_s, const float* darow,
+                           uint32_t* pp, uint32_t* dd) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b4 = *reinterpret_cast<const float4*>(sBias + kk0 + 4 * j);
-    bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
-  }
-  tmem_ld_wait();
+  for (int g4 = 0; g4 < 8; ++g4) {   // 4 columns at a time keeps the live register set small
+    const float4 b4 = *reinterpret_cast<const float4*>(sBias + kk0 + 4 * g4);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    float pr[4], ds[4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int kk = kk0 + j;
-    float acc = sv[j], g = dp[j];
-    if (SAFE && c0 + j >= nb) {  // TMEM columns beyond this block's MMA width hold stale data
-      acc = 0.f;
-      g = 0.f;
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * g4 + e;
+      const int kk = kk0 + j;
+      float acc = sv[j], g = dp[j];
+      if (SAFE && c0 + j >= nb) {  // TMEM columns beyond this block's MMA width hold stale data
+        acc = 0.f;
+        g = 0.f;
+      }
+      pr[e] = fast_ex2(masked_s2<MODE>(acc, c1, bb[e], kk, q, q_txt, p.T, w) - lse2);
+      if (DALIGN) {
+        if (kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
+      }
+      ds[e] = pr[e] * fmaf(g, p.scale, -delta_s);   // dS = P (dP - delta) scale
     }
-    const float pr = fast_ex2(masked_s2<MODE>(acc, c1, bb[j], kk, q, q_txt, p.T, w) - lse2);
-    if (darow != nullptr && kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
-    sv[j] = pr;
-    dp[j] = pr * (g - delta) * p.scale;
-  }
-  const int piece0 = (c0 & 63) >> 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 pk;
-    pk.x = pack_bf16(sv[8 * j + 0], sv[8 * j + 1]);
-    pk.y = pack_bf16(sv[8 * j + 2], sv[8 * j + 3]);
-    pk.z = pack_bf16(sv[8 * j + 4], sv[8 * j + 5]);
-    pk.w = pack_bf16(sv[8 * j + 6], sv[8 * j + 7]);
-    *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = pk;
-    pk.x = pack_bf16(dp[8 * j + 0], dp[8 * j + 1]);
-    pk.y = pack_bf16(dp[8 * j + 2], dp[8 * j + 3]);
-    pk.z = pack_bf16(dp[8 * j + 4], dp[8 * j + 5]);
-    pk.w = pack_bf16(dp[8 * j + 6], dp[8 * j + 7]);
-    *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = pk;
+    pp[2 * g4] = pack_bf16(pr[0], pr[1]);
+    pp[2 * g4 + 1] = pack_bf16(pr[2], pr[3]);
+    dd[2 * g4] = pack_bf16(ds[0], ds[1]);
+    dd[2 * g4 + 1] = pack_bf16(ds[2], ds[3]);
   }
 }
 
@@ -399,21 +400,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_v = bars + 1;
   uint64_t* qfull = bars + 2;    // [2]
   uint64_t* qempty = bars + 4;   // [2]
-  uint64_t* bar_sdp = bars + 6;
-  uint64_t* bar_pds = bars + 7;
-  uint64_t* bar_dq = bars + 8;
-  uint64_t* bar_dkv_full = bars + 9;
-  uint64_t* bar_dkv_free = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_sdp = bars + 6;       // [2] S/dP of a 64-key sub-block complete
+  uint64_t* bar_cons = bars + 8;      // [2] ... and loaded into registers by every row thread
+  uint64_t* bar_pds = bars + 10;
+  uint64_t* bar_free = bars + 11;     // dV/dK/dQ MMAs of a step retired: P/dS smem free, dQ (and dK/dV) readable
+  uint64_t* bar_dkv_free = bars + 12; // dK/dV accumulators of a key block have been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y;
   const float c1 = p.scale * LOG2E;
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 320, COL_DV = 384;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ0 = 256, COL_DK = 320, COL_DV = 384, COL_DQ1 = 448;
+  const bool dq_resident = p.nqt <= 2;   // uniform over the grid
+  const int total_steps = p.nkb * p.nqt;
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // ---------------------------------------------------------------------- TMA producer
+    // initialises the barriers and starts the K/V and first Q/dO loads BEFORE the block-wide sync, so the loads
+    // run under the delta / lse prologue of the row threads
     if (lane == 0) {
       tma_prefetch_desc(&tmQKV);
       if (p.P > 0) tma_prefetch_desc(&tmPKV);
@@ -424,16 +430,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_init(&qfull[i], 1);
         mbar_init(&qempty[i], 1);
       }
-      mbar_init(bar_sdp, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_sdp[i], 1);
+        mbar_init(&bar_cons[i], 256);
+      }
       mbar_init(bar_pds, 256);
-      mbar_init(bar_dq, 1);
-      mbar_init(bar_dkv_full, 1);
+      mbar_init(bar_free, 1);
       mbar_init(bar_dkv_free, 256);
       fence_barrier_init();
+      load_kv(sK, sV, &tmQKV, &tmPKV, bar_k, bar_v, p, n, h);
+      for (int step = 0; step < 2 && step < total_steps; ++step) {   // both ring stages are free at start
+        const int qt = step % p.nqt;
+        mbar_expect_tx(&qfull[step], 32768);
+        tma_load_3d(sQ + step * 16384, &tmQKV, &qfull[step], h * 64, qt * 128, n);
+        tma_load_3d(sQ + step * 16384 + 8192, &tmQKV, &qfull[step], h * 64, qt * 128 + 64, n);
+        tma_load_3d(sDO + step * 16384, &tmDO, &qfull[step], h * 64, qt * 128, n);
+        tma_load_3d(sDO + step * 16384 + 8192, &tmDO, &qfull[step], h * 64, qt * 128 + 64, n);
+      }
     }
-    __syncwarp();
+  } else if (warp == 8) {
     tmem_alloc<512>(tmem_slot);
-  } else if (warp < 8) {
+  } else {
     stage_bias(sBias, p.nkb * 128, p, n, tid, 256);
     // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q] (log2 domain, +inf for dead rows)
     for (int r = tid; r < p.nqt * 128; r += 256) {
@@ -441,10 +458,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (r < p.S) {
         const uint4* po = reinterpret_cast<const uint4*>(p.ctx + ((size_t)n * p.S + r) * p.H + h * 64);
         const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + ((size_t)n * p.S + r) * p.H + h * 64);
+        uint4 a[8], b[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint4 a = __ldg(po + j), b = __ldg(pd + j);
-          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+          a[j] = __ldg(po + j);
+          b[j] = __ldg(pd + j);
+        }
+        l = __ldg(p.lse + ((size_t)n * p.heads + h) * p.S + r) * LOG2E;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aw[4] = {a[j].x, a[j].y, a[j].z, a[j].w}, bw[4] = {b[j].x, b[j].y, b[j].z, b[j].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 fa = unpack_bf16(aw[e]), fb = unpack_bf16(bw[e]);
@@ -457,7 +480,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           const float* da = p.dalign + ((size_t)n * p.T + r) * p.R;
           for (int j = 0; j < p.R; ++j) d = fmaf(__ldg(pi + j), __ldg(da + j), d);
         }
-        l = __ldg(p.lse + ((size_t)n * p.heads + h) * p.S + r) * LOG2E;
       }
       sDelta[r] = d;
       sLse[r] = l;
@@ -469,21 +491,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 9) {
-    // -------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      load_kv(sK, sV, &tmQKV, &tmPKV, bar_k, bar_v, p, n, h);
-      int step = 0;
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        for (int qt = 0; qt < p.nqt; ++qt, ++step) {
-          const int s = step & 1;
-          const uint32_t ph = (step >> 1) & 1;
-          mbar_wait(&qempty[s], ph ^ 1);
-          mbar_expect_tx(&qfull[s], 32768);
-          tma_load_3d(sQ + s * 16384, &tmQKV, &qfull[s], h * 64, qt * 128, n);
-          tma_load_3d(sQ + s * 16384 + 8192, &tmQKV, &qfull[s], h * 64, qt * 128 + 64, n);
-          tma_load_3d(sDO + s * 16384, &tmDO, &qfull[s], h * 64, qt * 128, n);
-          tma_load_3d(sDO + s * 16384 + 8192, &tmDO, &qfull[s], h * 64, qt * 128 + 64, n);
-        }
+      for (int step = 2; step < total_steps; ++step) {
+        const int qt = step % p.nqt;
+        const int s = step & 1;
+        const uint32_t ph = (step >> 1) & 1;
+        mbar_wait(&qempty[s], ph ^ 1);
+        mbar_expect_tx(&qfull[s], 32768);
+        tma_load_3d(sQ + s * 16384, &tmQKV, &qfull[s], h * 64, qt * 128, n);
+        tma_load_3d(sQ + s * 16384 + 8192, &tmQKV, &qfull[s], h * 64, qt * 128 + 64, n);
+        tma_load_3d(sDO + s * 16384, &tmDO, &qfull[s], h * 64, qt * 128, n);
+        tma_load_3d(sDO + s * 16384 + 8192, &tmDO, &qfull[s], h * 64, qt * 128 + 64, n);
       }
     }
   } else if (warp == 8) {
@@ -492,28 +510,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
       const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
+      // S = Q K^T and dP = dO V^T of step `step`, 64-key sub-block `c`
+      auto issue_sdp = [&](int step, int c) {
+        const int kb = step / p.nqt;
+        const int nb = min(128, p.Kp - kb * 128) - c * 64;   // keys left in this sub-block
+        if (nb > 0) {
+          const uint32_t idesc_s = make_idesc_bf16(128, min(nb, 64), 0, 0);
+          const int s = step & 1;
+          const uint32_t q_addr = smem_u32(sQ + s * 16384), do_addr = smem_u32(sDO + s * 16384);
+          if (c == 0) {
+            mbar_wait(&qfull[s], (step >> 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t kv_off = kb * 16384 + c * 8192;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + COL_S + c * 64, make_smem_desc(q_addr + k * 32, 0, 1024),
+                      make_smem_desc(k_addr + kv_off + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + COL_DP + c * 64, make_smem_desc(do_addr + k * 32, 0, 1024),
+                      make_smem_desc(v_addr + kv_off + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_sdp[c]);
+      };
       mbar_wait(bar_k, 0);
       mbar_wait(bar_v, 0);
+      issue_sdp(0, 0);
+      issue_sdp(0, 1);
       int step = 0;
       for (int kb = 0; kb < p.nkb; ++kb) {
         const int nb = min(128, p.Kp - kb * 128);
-        const uint32_t idesc_s = make_idesc_bf16(128, nb, 0, 0);
         for (int qt = 0; qt < p.nqt; ++qt, ++step) {
           const int s = step & 1;
-          const uint32_t ph = (step >> 1) & 1;
           const uint32_t q_addr = smem_u32(sQ + s * 16384), do_addr = smem_u32(sDO + s * 16384);
-          mbar_wait(&qfull[s], ph);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + COL_S, make_smem_desc(q_addr + k * 32, 0, 1024),
-                      make_smem_desc(k_addr + kb * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + COL_DP, make_smem_desc(do_addr + k * 32, 0, 1024),
-                      make_smem_desc(v_addr + kb * 16384 + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-          umma_commit(bar_sdp);
-          mbar_wait(bar_pds, step & 1);
+          for (int c = 0; c < 2; ++c) {
+            mbar_wait(&bar_cons[c], step & 1);   // S/dP(step, c) are in registers: the columns can be overwritten
+            tc_fence_after();
+            if (step + 1 < total_steps) issue_sdp(step + 1, c);
+          }
+          mbar_wait(bar_pds, step & 1);   // P/dS(step) in smem
           if (qt == 0 && kb > 0) mbar_wait(bar_dkv_free, (kb - 1) & 1);
           tc_fence_after();
           const uint32_t acc0 = qt > 0 ? 1u : 0u;
@@ -525,13 +561,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
             umma_bf16(tmem_base + COL_DK, make_smem_desc(ds_addr + ks * 2048, 16384, 1024),
                       make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : acc0);
+          const uint32_t col_dq = (dq_resident && qt == 1) ? COL_DQ1 : COL_DQ0;
+          const uint32_t accq = (dq_resident && kb > 0) ? 1u : 0u;
           const int ksteps = nb >> 4;
-          for (int ks = 0; ks < ksteps; ++ks)  // dQ = dS K_kb
-            umma_bf16(tmem_base + COL_DQ, make_smem_desc(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
-                      make_smem_desc(k_addr + kb * 16384 + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < ksteps; ++ks)  // dQ (+)= dS K_kb
+            umma_bf16(tmem_base + col_dq, make_smem_desc(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                      make_smem_desc(k_addr + kb * 16384 + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : accq);
           umma_commit(&qempty[s]);
-          umma_commit(bar_dq);
-          if (qt == p.nqt - 1) umma_commit(bar_dkv_full);
+          umma_commit(bar_free);
         }
       }
     }
@@ -541,59 +578,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int half = tid >> 7;   // key-column half of every 128-key block
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t H3 = (size_t)3 * p.H;
-    int step = 0;
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int nb = min(128, p.Kp - kb * 128);
-      for (int qt = 0; qt < p.nqt; ++qt, ++step) {
-        const int q = qt * 128 + row;
-        const bool alive = q < p.S;
-        const bool q_txt = q < p.T;
-        const float lse2 = sLse[q], delta = sDelta[q];
-        const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
-        const float* darow =
-            (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
-        mbar_wait(bar_sdp, step & 1);
-        tc_fence_after();
-        // this thread's two 32-column chunks of the 128-key block are interleaved with the other half's
-        // (c0 = 32*half and 32*half + 64) so that a partial last block stays balanced between the two warps
-        const bool warp_alive = (qt * 128 + (warp & 3) * 32) < p.S;
-#pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = half * 32 + i * 64;
-          const int kk0 = kb * 128 + c0;
-          uint8_t* pblk = sP + (c0 >> 6) * 16384;
-          uint8_t* dblk = sDS + (c0 >> 6) * 16384;
-          if (!warp_alive || c0 >= nb) {
-            // dead q rows (rows >= S) or key columns beyond this block: P = dS = 0, no TMEM traffic, no math
-            const int piece0 = (c0 & 63) >> 3;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(pblk + sw128_offset(row, piece0 + j)) = z;
-              *reinterpret_cast<uint4*>(dblk + sw128_offset(row, piece0 + j)) = z;
-            }
-            continue;
-          }
-          const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
-          if (c0 + 32 <= nb)
-            bwd_chunk<MODE, false>(p, c1, taddr + COL_S, taddr + COL_DP, sBias, pblk, dblk, c0, kk0, nb, row, q, q_txt, w,
-                                   lse2, delta, darow);
-          else
-            bwd_chunk<MODE, true>(p, c1, taddr + COL_S, taddr + COL_DP, sBias, pblk, dblk, c0, kk0, nb, row, q, q_txt, w,
-                                  lse2, delta, darow);
-        }
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_pds);
 
-        // ---- dQ partial of this (key block, q tile): this thread owns 32 of the 64 columns
-        mbar_wait(bar_dq, step & 1);
-        tc_fence_after();
-        {
-          float dq[32];
-          tmem_ld_32x32(taddr + COL_DQ + half * 32, reinterpret_cast<uint32_t*>(dq));
-          tmem_ld_wait();
-          if (alive) {
+    // everything a finished step leaves behind in TMEM: dQ of its q tile (when due) and, after the last q tile of a
+    // key block, that block's dK (column half 0) / dV (half 1)
+    auto read_out = [&](int kb, int qt) {
+      const int q = qt * 128 + row;
+      const bool alive = q < p.S;
+      const bool dq_due = dq_resident ? (kb == p.nkb - 1) : true;
+      if (dq_due) {
+        float dq[32];
+        const uint32_t col_dq = (dq_resident && qt == 1) ? COL_DQ1 : COL_DQ0;
+        tmem_ld_32x32(taddr + col_dq + half * 32, reinterpret_cast<uint32_t*>(dq));
+        tmem_ld_wait();
+        if (alive) {
+          bool final = true;
+          if (!dq_resident) {
             float4* ws = reinterpret_cast<float4*>(p.dq_ws + (((size_t)n * p.heads + h) * p.S + q) * 64 + half * 32);
             if (kb > 0) {
 #pragma unroll
@@ -605,55 +604,143 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 dq[4 * j + 3] += f.w;
               }
             }
-            if (kb == p.nkb - 1) {
-              uint4* out = reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.S + q) * H3 + h * 64 + half * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 pk;
-                pk.x = pack_bf16(dq[8 * j + 0], dq[8 * j + 1]);
-                pk.y = pack_bf16(dq[8 * j + 2], dq[8 * j + 3]);
-                pk.z = pack_bf16(dq[8 * j + 4], dq[8 * j + 5]);
-                pk.w = pack_bf16(dq[8 * j + 6], dq[8 * j + 7]);
-                out[j] = pk;
-              }
-            } else {
+            if (kb != p.nkb - 1) {
+              final = false;
 #pragma unroll
               for (int j = 0; j < 8; ++j) ws[j] = make_float4(dq[4 * j], dq[4 * j + 1], dq[4 * j + 2], dq[4 * j + 3]);
             }
           }
-        }
-        // ---- dK (half 0) / dV (half 1) of this key block once the last q tile has been accumulated
-        if (qt == p.nqt - 1) {
-          mbar_wait(bar_dkv_full, kb & 1);
-          tc_fence_after();
-          const int kk = kb * 128 + row;
-          bf16* dst = nullptr;
-          if (kk < p.P)
-            dst = p.dpkv + ((size_t)n * p.P + kk) * (2 * p.H) + h * 64 + half * p.H;
-          else if (kk >= p.Ppad && kk - p.Ppad < p.S)
-            dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64 + half * p.H;
-          float acc[64];
-          const uint32_t col = half == 0 ? COL_DK : COL_DV;
-          tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
-          tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
-          tmem_ld_wait();
-          if (dst != nullptr) {
-            uint4* out = reinterpret_cast<uint4*>(dst);
+          if (final) {
+            uint4* out = reinterpret_cast<uint4*>(p.dqkv + ((size_t)n * p.S + q) * H3 + h * 64 + half * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               uint4 pk;
-              pk.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]);
-              pk.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
-              pk.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]);
-              pk.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
+              pk.x = pack_bf16(dq[8 * j + 0], dq[8 * j + 1]);
+              pk.y = pack_bf16(dq[8 * j + 2], dq[8 * j + 3]);
+              pk.z = pack_bf16(dq[8 * j + 4], dq[8 * j + 5]);
+              pk.w = pack_bf16(dq[8 * j + 6], dq[8 * j + 7]);
               out[j] = pk;
             }
           }
-          tc_fence_before();
-          mbar_arrive(bar_dkv_free);
         }
       }
+      if (qt == p.nqt - 1) {
+        const int kk = kb * 128 + row;
+        bf16* dst = nullptr;
+        if (kk < p.P)
+          dst = p.dpkv + ((size_t)n * p.P + kk) * (2 * p.H) + h * 64 + half * p.H;
+        else if (kk >= p.Ppad && kk - p.Ppad < p.S)
+          dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64 + half * p.H;
+        float acc[64];
+        const uint32_t col = half == 0 ? COL_DK : COL_DV;
+        tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
+        tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_dkv_free);
+        if (dst != nullptr) {
+          uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 pk;
+            pk.x = pack_bf16(acc[8 * j + 0], acc[8 * j + 1]);
+            pk.y = pack_bf16(acc[8 * j + 2], acc[8 * j + 3]);
+            pk.z = pack_bf16(acc[8 * j + 4], acc[8 * j + 5]);
+            pk.w = pack_bf16(acc[8 * j + 6], acc[8 * j + 7]);
+            out[j] = pk;
+          }
+        }
+      }
+    };
+
+    int step = 0;
+    int prev_kb = 0, prev_qt = 0;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int nb = min(128, p.Kp - kb * 128);
+      for (int qt = 0; qt < p.nqt; ++qt, ++step) {
+        const int q = qt * 128 + row;
+        const bool alive = q < p.S;
+        const bool q_txt = q < p.T;
+        const float lse2 = sLse[q], delta = sDelta[q];
+        const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
+        const float* darow =
+            (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
+        // this thread's two 32-column chunks of the 128-key block are interleaved with the other half's
+        // (c0 = 32*half and 32*half + 64) so that a partial last block stays balanced between the two warps
+        const bool warp_alive = (qt * 128 + (warp & 3) * 32) < p.S;
+        const float delta_s = delta * p.scale;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c0 = half * 32 + i * 64;
+          const int kk0 = kb * 128 + c0;
+          const bool live = warp_alive && c0 < nb;
+          float sv[32], dp[32];
+          uint32_t pp[16], dd[16];
+          mbar_wait(&bar_sdp[i], step & 1);
+          tc_fence_after();
+          if (live) {
+            tmem_ld_32x32(taddr + COL_S + c0, reinterpret_cast<uint32_t*>(sv));
+            tmem_ld_32x32(taddr + COL_DP + c0, reinterpret_cast<uint32_t*>(dp));
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          mbar_arrive(&bar_cons[i]);
+          if (!live) {
+            // dead q rows (rows >= S) or key columns beyond this block: P = dS = 0, no TMEM traffic, no math
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              pp[j] = 0u;
+              dd[j] = 0u;
+            }
+          } else {
+            const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
+            const bool img = darow != nullptr && kk0 + 32 > p.T && kk0 < p.S;
+            const bool safe = c0 + 32 > nb;
+            if (img) {
+              if (safe)
+                bwd_chunk_math<MODE, true, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
+                                                 pp, dd);
+              else
+                bwd_chunk_math<MODE, false, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
+                                                  pp, dd);
+            } else {
+              if (safe)
+                bwd_chunk_math<MODE, true, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
+                                                  pp, dd);
+              else
+                bwd_chunk_math<MODE, false, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s,
+                                                   darow, pp, dd);
+            }
+          }
+          if (i == 0 && step > 0) {
+            // the MMAs of the previous step have retired (they ran under the math above): its P/dS tiles are free
+            // and its accumulators readable
+            mbar_wait(bar_free, (step - 1) & 1);
+            tc_fence_after();
+            // flush mode re-uses the single dQ accumulator every step: drain it before this step's MMAs may start
+            if (!dq_resident) read_out(prev_kb, prev_qt);
+          }
+          const uint32_t pb = smem_u32(sP + (c0 >> 6) * 16384), db = smem_u32(sDS + (c0 >> 6) * 16384);
+          const int piece0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sts128(pb + sw128_offset(row, piece0 + j), pp[4 * j], pp[4 * j + 1], pp[4 * j + 2], pp[4 * j + 3]);
+            sts128(db + sw128_offset(row, piece0 + j), dd[4 * j], dd[4 * j + 1], dd[4 * j + 2], dd[4 * j + 3]);
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_pds);
+        // resident mode: nothing this step's MMAs write is still unread (dK/dV of a new key block wait for
+        // bar_dkv_free), so the read-out runs after the hand-off, when the P/dS registers are dead
+        if (step > 0 && dq_resident) read_out(prev_kb, prev_qt);
+        prev_kb = kb;
+        prev_qt = qt;
+      }
     }
+    mbar_wait(bar_free, (step - 1) & 1);
+    tc_fence_after();
+    read_out(prev_kb, prev_qt);
   }
   tc_fence_before();
   __syncthreads();
@@ -703,8 +790,8 @@ static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
       set_error("prefix_attn_bwd: null gradient pointer");
       return MODCR_ERR_SHAPE;
     }
-    if (p.nkb > 1 && a.dq_ws == nullptr) {
-      set_error("prefix_attn_bwd: workspace required when P+S > 128");
+    if (p.nkb > 1 && p.nqt > 2 && a.dq_ws == nullptr) {
+      set_error("prefix_attn_bwd: workspace required when S > 256 and P+S > 128");
       return MODCR_ERR_WORKSPACE;
     }
   }
