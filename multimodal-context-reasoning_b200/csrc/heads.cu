@@ -293,70 +293,62 @@ DEVINL float ld1(const void* base, size_t i) {
   return F32 ? reinterpret_cast<const float*>(base)[i] : __bfloat162float(reinterpret_cast<const bf16*>(base)[i]);
 }
 
-// smem: qs[H] | sc[L] | part[8][H]
+constexpr int CP_WARPS = 16;   // one CTA per sequence: 512 threads keep enough 128-bit loads in flight
+
+// Single pass over k (key == value, v10:818-819): every warp walks its rows with a running max / sum / pooled
+// accumulator (online softmax), the 16 partial states are merged at the end; the raw scores stay in shared memory
+// for the normalised weights `w`.   smem: qs[H] | sc[L] | wm[CP_WARPS] | wsum[CP_WARPS] | part[CP_WARPS][H]
 template <bool F32>
-__global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const void* __restrict__ q, const void* __restrict__ k,
-                                                           const float* __restrict__ mask, float* __restrict__ w,
-                                                           bf16* __restrict__ pooled, int L, int H) {
+__global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_fwd_kernel(const void* __restrict__ q, const void* __restrict__ k,
+                                                                     const float* __restrict__ mask, float* __restrict__ w,
+                                                                     bf16* __restrict__ pooled, int L, int H) {
   extern __shared__ float sm[];
-  __shared__ float sh[8];
   float* qs = sm;
   float* sc = qs + H;
-  float* part = sc + ((L + 3) & ~3);
+  float* wm = sc + ((L + 3) & ~3);
+  float* wsm = wm + CP_WARPS;
+  float* part = wsm + CP_WARPS;
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = H >> 8;
   constexpr int ES = F32 ? 4 : 2;
-  for (int c = threadIdx.x; c < H; c += 256) qs[c] = ld1<F32>(q, (size_t)n * H + c);
+  for (int c = threadIdx.x; c < H; c += CP_WARPS * 32) qs[c] = ld1<F32>(q, (size_t)n * H + c);
   __syncthreads();
   const char* kn = reinterpret_cast<const char*>(k) + (size_t)n * L * H * ES;
-  for (int l = warp; l < L; l += 8) {
-    float d = 0.f;
-#pragma unroll
-    for (int i = 0; i < CP_MAXV; ++i)
-      if (i < nv) {
-        float f[8];
-        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
-        const float* qq = qs + (lane + 32 * i) * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d = fmaf(f[j], qq[j], d);
-      }
-    d = wsum(d);
-    if (lane == 0) sc[l] = d + (mask ? __ldg(mask + (size_t)n * L + l) : 0.f);
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int l = threadIdx.x; l < L; l += 256) mx = fmaxf(mx, sc[l]);
-  mx = block_max(mx, sh);
-  float se = 0.f;
-  for (int l = threadIdx.x; l < L; l += 256) {
-    const float e = expf(sc[l] - mx);
-    sc[l] = e;
-    se += e;
-  }
-  se = block_sum(se, sh);
-  const float inv = 1.f / se;
-  for (int l = threadIdx.x; l < L; l += 256) {
-    const float p = sc[l] * inv;
-    sc[l] = p;
-    w[(size_t)n * L + l] = p;
-  }
-  __syncthreads();
+  float m = -INFINITY, se = 0.f;
   float acc[CP_MAXV][8];
 #pragma unroll
   for (int i = 0; i < CP_MAXV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int l = warp; l < L; l += 8) {
-    const float p = sc[l];
+  for (int l = warp; l < L; l += CP_WARPS) {
+    float f[CP_MAXV][8];
+    float d = 0.f;
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
-        float f[8];
-        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f);
+        ld8<F32>(kn + (size_t)l * H * ES, lane + 32 * i, f[i]);
+        const float* qq = qs + (lane + 32 * i) * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(p, f[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) d = fmaf(f[i][j], qq[j], d);
       }
+    d = wsum(d) + (mask ? __ldg(mask + (size_t)n * L + l) : 0.f);
+    if (lane == 0) sc[l] = d;
+    const float mn = fmaxf(m, d);
+    const float resc = expf(m - mn);     // 0 on the first row (m = -inf)
+    const float pe = expf(d - mn);
+    se = fmaf(se, resc, pe);
+    m = mn;
+#pragma unroll
+    for (int i = 0; i < CP_MAXV; ++i)
+      if (i < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(acc[i][j], resc, pe * f[i][j]);
+      }
+  }
+  if (lane == 0) {
+    wm[warp] = m;
+    wsm[warp] = se;
   }
 #pragma unroll
   for (int i = 0; i < CP_MAXV; ++i)
@@ -365,21 +357,33 @@ __global__ void __launch_bounds__(256) cls_pool_fwd_kernel(const void* __restric
       for (int j = 0; j < 8; ++j) part[warp * H + (lane + 32 * i) * 8 + j] = acc[i][j];
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < H; c += 256) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int ww = 0; ww < CP_WARPS; ++ww) mx = fmaxf(mx, wm[ww]);
+  float tot = 0.f;
+  float wscale[CP_WARPS];
+#pragma unroll
+  for (int ww = 0; ww < CP_WARPS; ++ww) {
+    wscale[ww] = wm[ww] == -INFINITY ? 0.f : expf(wm[ww] - mx);   // warps without rows (L < CP_WARPS)
+    tot = fmaf(wsm[ww], wscale[ww], tot);
+  }
+  const float inv = 1.f / tot;
+  for (int l = threadIdx.x; l < L; l += CP_WARPS * 32) w[(size_t)n * L + l] = expf(sc[l] - mx) * inv;
+  for (int c = threadIdx.x; c < H; c += CP_WARPS * 32) {
     float s = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) s += part[ww * H + c];
-    pooled[(size_t)n * H + c] = __float2bfloat16(s);
+    for (int ww = 0; ww < CP_WARPS; ++ww) s = fmaf(part[ww * H + c], wscale[ww], s);
+    pooled[(size_t)n * H + c] = __float2bfloat16(s * inv);
   }
 }
 
-// smem: qs[H] | dps[H] | wv[L] | dsv[L] | part[8][H]
+// smem: qs[H] | dps[H] | wv[L] | dsv[L] | part[CP_WARPS][H]
 template <bool F32>
-__global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const void* __restrict__ q,
+__global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const void* __restrict__ q,
                                                            const void* __restrict__ k, const float* __restrict__ w,
                                                            bf16* __restrict__ dq, bf16* __restrict__ dk, int L, int H) {
   extern __shared__ float sm[];
-  __shared__ float sh[8];
+  __shared__ float sh[CP_WARPS];
   const int Lp = (L + 3) & ~3;
   float* qs = sm;
   float* dps = qs + H;
@@ -390,15 +394,15 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = H >> 8;
   constexpr int ES = F32 ? 4 : 2;
-  for (int c = threadIdx.x; c < H; c += 256) {
+  for (int c = threadIdx.x; c < H; c += CP_WARPS * 32) {
     qs[c] = ld1<F32>(q, (size_t)n * H + c);
     dps[c] = __bfloat162float(dpooled[(size_t)n * H + c]);
   }
-  for (int l = threadIdx.x; l < L; l += 256) wv[l] = w[(size_t)n * L + l];
+  for (int l = threadIdx.x; l < L; l += CP_WARPS * 32) wv[l] = w[(size_t)n * L + l];
   __syncthreads();
   const char* kn = reinterpret_cast<const char*>(k) + (size_t)n * L * H * ES;
   bf16* dkn = dk + (size_t)n * L * H;
-  for (int l = warp; l < L; l += 8) {  // dw[l] = dpooled . k[l]
+  for (int l = warp; l < L; l += CP_WARPS) {  // dw[l] = dpooled . k[l]
     float d = 0.f;
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
@@ -414,16 +418,16 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
   }
   __syncthreads();
   float dot = 0.f;
-  for (int l = threadIdx.x; l < L; l += 256) dot += wv[l] * dsv[l];
+  for (int l = threadIdx.x; l < L; l += CP_WARPS * 32) dot += wv[l] * dsv[l];
   dot = block_sum(dot, sh);
-  for (int l = threadIdx.x; l < L; l += 256) dsv[l] = wv[l] * (dsv[l] - dot);
+  for (int l = threadIdx.x; l < L; l += CP_WARPS * 32) dsv[l] = wv[l] * (dsv[l] - dot);
   __syncthreads();
   float acc[CP_MAXV][8];
 #pragma unroll
   for (int i = 0; i < CP_MAXV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int l = warp; l < L; l += 8) {
+  for (int l = warp; l < L; l += CP_WARPS) {
     const float p = wv[l], ds = dsv[l];
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
@@ -447,10 +451,10 @@ __global__ void __launch_bounds__(256) cls_pool_bwd_kernel(const bf16* __restric
       for (int j = 0; j < 8; ++j) part[warp * H + (lane + 32 * i) * 8 + j] = acc[i][j];
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < H; c += 256) {
+  for (int c = threadIdx.x; c < H; c += CP_WARPS * 32) {
     float s = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) s += part[ww * H + c];
+    for (int ww = 0; ww < CP_WARPS; ++ww) s += part[ww * H + c];
     dq[(size_t)n * H + c] = __float2bfloat16(s);
   }
 }
@@ -469,7 +473,7 @@ static int cls_pool_check(int N, int L, int H, size_t smem, const char* what) {
 
 int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
                       int H, cudaStream_t st) {
-  const size_t smem = ((size_t)H + ((L + 3) & ~3) + 8 * (size_t)H) * 4;
+  const size_t smem = ((size_t)H + ((L + 3) & ~3) + 2 * CP_WARPS + CP_WARPS * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_fwd")) return rc;
   static size_t attr = 0;
   if (smem > attr && smem > 48 * 1024) {
@@ -478,15 +482,15 @@ int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mas
     attr = smem;
   }
   if (qk_f32)
-    cls_pool_fwd_kernel<true><<<N, 256, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
+    cls_pool_fwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
   else
-    cls_pool_fwd_kernel<false><<<N, 256, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
+    cls_pool_fwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
   return check_launch("cls_pool_attn_fwd");
 }
 
 int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,
                       int N, int L, int H, cudaStream_t st) {
-  const size_t smem = (2 * (size_t)H + 2 * ((L + 3) & ~3) + 8 * (size_t)H) * 4;
+  const size_t smem = (2 * (size_t)H + 2 * ((L + 3) & ~3) + CP_WARPS * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_bwd")) return rc;
   static size_t attr = 0;
   if (smem > attr && smem > 48 * 1024) {
@@ -495,9 +499,9 @@ int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_
     attr = smem;
   }
   if (qk_f32)
-    cls_pool_bwd_kernel<true><<<N, 256, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
+    cls_pool_bwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
   else
-    cls_pool_bwd_kernel<false><<<N, 256, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
+    cls_pool_bwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
   return check_launch("cls_pool_attn_bwd");
 }
 

@@ -399,11 +399,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   const int c = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < N) {
-    for (int r = blockIdx.y * 8 + wib; r < M; r += gridDim.y * 8) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (int64_t)r * ld + c)), f);
+    // four independent 128-bit loads in flight per thread (the loop is otherwise latency-bound)
+    const int stride = gridDim.y * 8;
+    for (int r = blockIdx.y * 8 + wib; r < M; r += 4 * stride) {
+      uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      for (int i = 0; i < 4; ++i) {
+        const int rr = r + i * stride;
+        u[i] = rr < M ? __ldg(reinterpret_cast<const uint4*>(x + (int64_t)rr * ld + c)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+        unpack8(u[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
     }
   }
 #pragma unroll
@@ -492,32 +503,51 @@ __global__ void chunk_bits_kernel(const float* __restrict__ cmask, uint32_t* __r
 // ---------------------------------------------------------------------------- chunk-mean queries
 // In place on the Q columns of the fused QKV buffer (row stride ld): for tokens t in [1, 1+len[n]),
 // Q[n,t,:] <- mean over tokens of the same chunk id (v10:66-78).  The operator is self-adjoint, so
-// the backward pass applies the same kernel to dQ.  One CTA per (sequence, 128-column slab); chunk
-// sums are accumulated in token order in fp32 shared memory.
-__global__ void __launch_bounds__(128) chunk_mean_kernel(bf16* __restrict__ q, int64_t ld, int S, const int32_t* __restrict__ chunk_id,
-                                                         int T, int max_chunks) {
-  extern __shared__ float csm[];
-  float* sums = csm;                                            // [max_chunks][128]
-  int* cnt = reinterpret_cast<int*>(csm + (size_t)max_chunks * 128);  // [max_chunks]
+// the backward pass applies the same kernel to dQ.
+// One CTA per (sequence, 64-column slab): the [T x 64] slab is staged in shared memory with 128-bit row loads,
+// chunk sums are formed in token order in fp32 (each chunk belongs to one quarter of the CTA, so the order of
+// the additions is fixed), then every token row is rewritten with its chunk mean.
+__global__ void __launch_bounds__(256) chunk_mean_kernel(bf16* __restrict__ q, int64_t ld, int S,
+                                                         const int32_t* __restrict__ chunk_id, int T, int max_chunks) {
+  extern __shared__ __align__(16) float csm[];
+  float* sums = csm;                                                    // [max_chunks][64]
+  int* cnt = reinterpret_cast<int*>(sums + (size_t)max_chunks * 64);    // [max_chunks rounded up to 4]
+  int* cid = cnt + ((max_chunks + 3) & ~3);                             // [T rounded up to 4]
+  bf16* tile = reinterpret_cast<bf16*>(cid + ((T + 3) & ~3));           // [T][64] (16-byte aligned)
   const int n = blockIdx.y;
-  const int col = blockIdx.x * 128 + threadIdx.x;
-  const int32_t* cid = chunk_id + (size_t)n * T;
-  for (int i = threadIdx.x; i < max_chunks; i += 128) cnt[i] = 0;
-  for (int i = threadIdx.x; i < max_chunks * 128; i += 128) sums[i] = 0.f;
-  __syncthreads();
-  for (int t = threadIdx.x; t < T; t += 128) {
-    const int c = cid[t];
-    if (c >= 0 && c < max_chunks) atomicAdd(&cnt[c], 1);
+  const int tid = threadIdx.x;
+  const int cg = tid & 7, rl = tid >> 3;
+  for (int i = tid; i < max_chunks; i += 256) cnt[i] = 0;
+  for (int i = tid; i < max_chunks * 64; i += 256) sums[i] = 0.f;
+  for (int t = tid; t < T; t += 256) {
+    const int c = chunk_id[(size_t)n * T + t];
+    cid[t] = (c >= 0 && c < max_chunks) ? c : -1;
   }
-  bf16* base = q + (size_t)n * S * ld + col;
-  for (int t = 0; t < T; ++t) {
-    const int c = cid[t];
-    if (c >= 0 && c < max_chunks) sums[c * 128 + threadIdx.x] += __bfloat162float(base[(size_t)t * ld]);
+  bf16* base = q + (size_t)n * S * ld + blockIdx.x * 64 + cg * 8;
+  for (int t = rl; t < T; t += 32)
+    *reinterpret_cast<uint4*>(tile + t * 64 + cg * 8) = *reinterpret_cast<const uint4*>(base + (size_t)t * ld);
+  __syncthreads();
+  for (int t = tid; t < T; t += 256)
+    if (cid[t] >= 0) atomicAdd(&cnt[cid[t]], 1);
+  {
+    const int col = tid & 63, part = tid >> 6;
+    for (int t = 0; t < T; ++t) {
+      const int c = cid[t];
+      if (c >= 0 && (c & 3) == part) sums[c * 64 + col] += __bfloat162float(tile[t * 64 + col]);
+    }
   }
   __syncthreads();
-  for (int t = 0; t < T; ++t) {
+  for (int t = rl; t < T; t += 32) {
     const int c = cid[t];
-    if (c >= 0 && c < max_chunks) base[(size_t)t * ld] = __float2bfloat16(sums[c * 128 + threadIdx.x] / (float)cnt[c]);
+    if (c < 0) continue;
+    const float k = (float)cnt[c];
+    const float* sc = sums + c * 64 + cg * 8;
+    uint4 pk;
+    pk.x = pack_bf16(sc[0] / k, sc[1] / k);
+    pk.y = pack_bf16(sc[2] / k, sc[3] / k);
+    pk.z = pack_bf16(sc[4] / k, sc[5] / k);
+    pk.w = pack_bf16(sc[6] / k, sc[7] / k);
+    *reinterpret_cast<uint4*>(base + (size_t)t * ld) = pk;
   }
 }
 
@@ -681,11 +711,13 @@ int chunk_bits(const float* cmask, uint32_t* bits, int N, int T, int cwords, cud
 
 int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_id, int T, int max_chunks,
                  cudaStream_t st) {
-  if (H % 128 != 0 || T > S || max_chunks <= 0) {
-    set_error("chunk_mean_q: bad shape H=%d T=%d S=%d max_chunks=%d", H, T, S, max_chunks);
+  if (H % 64 != 0 || ld % 8 != 0 || (reinterpret_cast<uintptr_t>(q) & 15) != 0 || T > S || max_chunks <= 0) {
+    set_error("chunk_mean_q: bad shape H=%d ld=%lld T=%d S=%d max_chunks=%d (H %% 64, ld %% 8, 16-byte base)", H,
+              (long long)ld, T, S, max_chunks);
     return MODCR_ERR_SHAPE;
   }
-  const size_t smem = (size_t)max_chunks * 128 * 4 + (size_t)max_chunks * 4;
+  const size_t smem = (size_t)max_chunks * 64 * 4 + (size_t)((max_chunks + 3) & ~3) * 4 + (size_t)((T + 3) & ~3) * 4 +
+                      (size_t)T * 64 * 2;
   if (smem > 200 * 1024) {
     set_error("chunk_mean_q: %d chunks need %zu B of shared memory", max_chunks, smem);
     return MODCR_ERR_UNSUPPORTED;
@@ -699,8 +731,8 @@ int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_
     }
     attr = smem;
   }
-  dim3 grid(H / 128, N);
-  chunk_mean_kernel<<<grid, 128, smem, st>>>((bf16*)q, ld, S, chunk_id, T, max_chunks);
+  dim3 grid(H / 64, N);
+  chunk_mean_kernel<<<grid, 256, smem, st>>>((bf16*)q, ld, S, chunk_id, T, max_chunks);
   return check_launch("chunk_mean_q");
 }
 

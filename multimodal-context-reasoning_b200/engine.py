@@ -31,6 +31,15 @@ def _zeros(shape, dtype, dev):
     return torch.zeros(shape, dtype=dtype, device=dev)
 
 
+def _zeros_many(shapes, dev):
+    """fp32 tensors that must start at zero (atomically reduced bias / LayerNorm gradients, split-K wgrad outputs),
+    cleared by ONE multi-tensor fill instead of one fill kernel each.  They stay separate allocations so that
+    autograd can adopt them as ``.grad`` without a copy."""
+    ts = [torch.empty(sh, dtype=F32, device=dev) for sh in shapes]
+    torch._foreach_zero_(ts)
+    return ts
+
+
 # --------------------------------------------------------------------------------------------
 class ParamStore:
     """fp32 master parameters (the module's ``nn.Parameter`` objects, reference state_dict names)
@@ -93,10 +102,12 @@ def _split_k(M, N, K):
     return max(1, min(NUM_SMS // tiles, kb // 4))
 
 
-def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None):
+def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None):
     """dW[out_f, in_f] = dY^T X  (fp32; split-K through TMA reduce-add when the tile grid is small).
-    With ``out`` given the product is accumulated into it."""
+    With ``out`` given the product is accumulated into it; ``zeroed`` is a pre-cleared destination."""
     dev = dY.device
+    if zeroed is not None:
+        out = zeroed
     if out is not None:
         ops.gemm(dY, X, out, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1,
                  split_k=_split_k(out_f, in_f, rows))
@@ -131,23 +142,24 @@ def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save):
     return y, y32
 
 
-def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads):
-    """Returns d(a) given d(y)."""
+def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None):
+    """Returns d(a) given d(y).  ``z``: pre-zeroed (dgam, dbet, db2, db1, dW2, dW1) from ``_zeros_many``."""
     dev = dy.device
     W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
     g2 = _empty((M, H), BF16, dev)
-    dgam, dbet, db2 = _zeros((H,), F32, dev), _zeros((H,), F32, dev), _zeros((H,), F32, dev)
+    if z is None:
+        z = _zeros_many([(H,), (H,), (H,), (I,), (H, I), (I, H)], dev)
+    dgam, dbet, db2, db1, dW2, dW1 = z
     ops.layernorm_bwd(dy, sv["pre2"], sv["mean2"], sv["rstd2"], ps.f32(pfx + "output.LayerNorm.weight"), g2, dgam, dbet,
                       db2, M, H)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = db2
-    grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M)
+    grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M, zeroed=dW2)
     du = _empty((M, I), BF16, dev)
     ops.gemm(g2, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)           # (g2 W2) * GELU'(u)
-    db1 = _zeros((I,), F32, dev)
     ops.colsum(du, I, M, I, db1)
     grads[pfx + "intermediate.dense.bias"] = db1
-    grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M)
+    grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M, zeroed=dW1)
     da = _empty((M, H), BF16, dev)
     ops.gemm(du, W1, da, M, H, I, b_mn=1, epi_in=g2, in_op=1)                # + residual branch
     return da
@@ -195,19 +207,21 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     return a, a32
 
 
-def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None):
-    """Returns (dx, dhist)."""
+def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None):
+    """Returns (dx, dhist).  ``z``: pre-zeroed (dgam, dbet, dbo, dbqkv, dWo, dWqkv) from ``_zeros_many``."""
     dev = da.device
     N, S, H, heads, P = ac.N, ac.S, ac.H, ac.heads, ac.P
     M = N * S
     Wqkv, _ = ps.qkv(pfx + "self.")
     g1 = _empty((M, H), BF16, dev)
-    dgam, dbet, dbo = _zeros((H,), F32, dev), _zeros((H,), F32, dev), _zeros((H,), F32, dev)
+    if z is None:
+        z = _zeros_many([(H,), (H,), (H,), (3 * H,), (H, H), (3 * H, H)], dev)
+    dgam, dbet, dbo, dbqkv, dWo, dWqkv = z
     ops.layernorm_bwd(da, sv["pre1"], sv["mean1"], sv["rstd1"], ps.f32(pfx + "output.LayerNorm.weight"), g1, dgam, dbet,
                       dbo, M, H)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = dbo
-    grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M)
+    grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M, zeroed=dWo)
     dctx = _empty((M, H), BF16, dev)
     ops.gemm(g1, ps.bf16(pfx + "output.dense.weight"), dctx, M, H, H, b_mn=1)
     dqkv = _empty((M, 3 * H), BF16, dev)
@@ -219,9 +233,8 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None):
                         sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws)
     if sv["chunk"]:
         ops.chunk_mean_q(dqkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)   # self-adjoint operator
-    dbqkv = _zeros((3 * H,), F32, dev)
     ops.colsum(dqkv, 3 * H, M, 3 * H, dbqkv)
-    dWqkv = wgrad(dqkv, sv["x"], 3 * H, H, M)
+    wgrad(dqkv, sv["x"], 3 * H, H, M, zeroed=dWqkv)
     dhist = None
     if P > 0:
         ops.colsum(dpkv, 2 * H, N * P, 2 * H, dbqkv[H:])
@@ -243,8 +256,10 @@ def layer_fwd(ps, pfx, x, x32, hist, ac, I, eps, save, do_chunk_cross=False, pro
 
 
 def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None):
-    da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, ac.H, I, grads)
-    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws)
+    H = ac.H
+    z = _zeros_many([(H,), (H,), (H,), (I,), (H, I), (I, H), (H,), (H,), (H,), (3 * H,), (H, H), (3 * H, H)], dy.device)
+    da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, H, I, grads, z[:6])
+    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws, z[6:])
 
 
 # -------------------------------------------------------------------------------------------- embeddings
