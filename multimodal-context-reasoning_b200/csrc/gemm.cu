@@ -12,9 +12,9 @@
 //   warp 0  TMA producer for the A/B smem ring            (1 elected thread)
 //   warp 1  tcgen05.mma issuer, accumulators in TMEM      (1 elected thread)
 //   warp 2  TMEM allocator + TMA loader of the optional epilogue input tile
-//   warps 4-11 epilogue in two groups of four warps (group g takes column chunks g, g+2, ...):
-//           tcgen05.ld -> bias / activation / residual-add / GELU' -> 128B-swizzled smem ->
-//           TMA store (or TMA reduce-add for split-K fp32); each group owns one out / aux / in buffer
+//   warps 4-11 epilogue in two groups of four warps (group g takes the 32-column chunks g, g+2, ...):
+//           tcgen05.ld -> bias / activation / residual-add / GELU' -> swizzled smem -> TMA store (or TMA
+//           reduce-add for split-K fp32); bf16 chunks ping-pong between two buffers per group
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // NCTA = 2 runs the same roles on CTA pairs (cluster of 2, tcgen05 cta_group::2): the pair owns a 256 x BN
@@ -52,12 +52,20 @@ struct Cfg {
   static constexpr int BN_LOAD = BN / NCTA;          // B rows this CTA loads
   static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CHUNK_BYTES = 128 * 128;  // 128 rows x 128 B
-  static constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
+  // Epilogue chunks are 128 rows x 32 columns: 128-byte rows (SWIZZLE_128B) for fp32, 64-byte rows (SWIZZLE_64B)
+  // for bf16.  bf16 outputs (and the aux copy) are double-buffered per epilogue group, so a chunk is written while
+  // the TMA store of the previous one still reads its buffer and one block barrier per chunk suffices.
+  static constexpr int ES = OUT_F32 ? 4 : 2;
+  static constexpr int CHUNK_COLS = 32;
+  static constexpr int ROW_BYTES = CHUNK_COLS * ES;
+  static constexpr int CHUNK_BYTES = 128 * ROW_BYTES;
   static constexpr int NCHUNK = BN / CHUNK_COLS;
-  static constexpr int OUT_BUFS = HAS_AUX ? 4 : 2;
-  static constexpr int IN_BUFS = HAS_IN ? 2 : 0;
-  static constexpr int EPI_BYTES = (OUT_BUFS + IN_BUFS) * CHUNK_BYTES;
+  static constexpr int NBUF = OUT_F32 ? 1 : 2;        // out (and aux) buffers per group
+  static constexpr int IN_DEPTH = OUT_F32 ? 1 : 2;    // epilogue-input buffers per group
+  static constexpr int OUT_BUFS = 2 * NBUF * (HAS_AUX ? 2 : 1);
+  static constexpr int IN_BUFS = HAS_IN ? 2 * IN_DEPTH : 0;
+  static constexpr int BIAS_BYTES = 2 * 128 * 4;      // per group: the 128 bias values of its chunks of one tile
+  static constexpr int EPI_BYTES = (OUT_BUFS + IN_BUFS) * CHUNK_BYTES + BIAS_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_MAX = 232448;  // 227 KB
   static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
@@ -100,14 +108,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sB = sA + STAGES * C::A_BYTES;
   uint8_t* sOut = sB + STAGES * C::B_BYTES;
   uint8_t* sIn = sOut + C::OUT_BUFS * C::CHUNK_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + C::IN_BUFS * C::CHUNK_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + C::IN_BUFS * C::CHUNK_BYTES + C::BIAS_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* infull = tempty + 2;
-  uint64_t* inempty = infull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inempty + 2);
+  uint64_t* infull = tempty + 2;     // [group][slot]
+  uint64_t* inempty = infull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inempty + 4);
+  float* sBiasG = reinterpret_cast<float*>(sIn + C::IN_BUFS * C::CHUNK_BYTES);   // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,6 +143,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], EPI_ARRIVALS);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&infull[i], 1);
       mbar_init(&inempty[i], 128);
     }
@@ -245,7 +256,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ epilogue-input loader
-    // chunk c of a tile belongs to epilogue group (c & 1); each group owns one input buffer
+    // chunk c of a tile belongs to epilogue group (c & 1); each group owns IN_DEPTH input buffers
     if (HAS_IN && lane == 0) {
       uint32_t cntg[2] = {0, 0};
       for (int t = group; t < total_tiles; t += ngroups) {
@@ -253,9 +264,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = (tc.m * NCTA + rank) * 128;
         for (int c = 0; c < C::NCHUNK; ++c) {
           const int g = c & 1;
-          mbar_wait(&inempty[g], (cntg[g] & 1) ^ 1);
-          mbar_expect_tx(&infull[g], C::CHUNK_BYTES);
-          tma_load_2d(sIn + g * C::CHUNK_BYTES, &tmIn, &infull[g], tc.n * BN + c * C::CHUNK_COLS, m0);
+          const uint32_t slot = cntg[g] % C::IN_DEPTH;
+          const uint32_t ph = (cntg[g] / C::IN_DEPTH) & 1;
+          const int bi = g * C::IN_DEPTH + slot;
+          mbar_wait(&inempty[bi], ph ^ 1);
+          mbar_expect_tx(&infull[bi], C::CHUNK_BYTES);
+          tma_load_2d(sIn + bi * C::CHUNK_BYTES, &tmIn, &infull[bi], tc.n * BN + c * C::CHUNK_COLS, m0);
           ++cntg[g];
         }
       }
@@ -266,38 +280,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int g = (warp - 4) >> 2;
     const int q = warp & 3;          // TMEM lane quarter == warp % 4
     const int row = q * 32 + lane;   // row inside the 128-row tile
+    const int gt = row;              // thread index inside the group
     const bool issuer = (q == 0 && lane == 0);
     const uint32_t bar_id = 1 + g;
-    uint8_t* out_buf = sOut + g * C::CHUNK_BYTES;
-    uint8_t* aux_buf = sOut + (2 + g) * C::CHUNK_BYTES;
-    const uint32_t out_s = smem_u32(out_buf), aux_s = smem_u32(aux_buf), in_s = smem_u32(sIn + g * C::CHUNK_BYTES);
-    int it = 0;
-    uint32_t cnt = 0;  // chunks handled by this group
+    uint8_t* out_base = sOut + g * C::NBUF * C::CHUNK_BYTES;
+    uint8_t* aux_base = sOut + (2 * C::NBUF + g * C::NBUF) * C::CHUNK_BYTES;
+    float* sBias = sBiasG + g * 128;
     const uint32_t tempty_r0 = NCTA == 2 ? mapa_rank(smem_u32(&tempty[0]), 0) : 0u;
     const uint32_t tempty_r1 = NCTA == 2 ? mapa_rank(smem_u32(&tempty[1]), 0) : 0u;
+    int it = 0;
+    uint32_t cnt = 0;  // chunks handled by this group
     for (int t = group; t < total_tiles; t += ngroups, ++it) {
       const TileCoord tc = decode_tile(p, t);
       const int m0 = (tc.m * NCTA + rank) * 128;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
+      if (add_bias) {
+        // stage this tile's bias values of the group's chunks (thread i: chunk g + 2 (i / 32), column i % 32); every
+        // thread of the group is past its last bias read of the previous tile (it passed that chunk's barrier)
+        const int col = tc.n * BN + (g + 2 * (gt >> 5)) * C::CHUNK_COLS + (gt & 31);
+        sBias[gt] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        named_bar_sync(bar_id, 128);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
 #pragma unroll 1
-      for (int c = g; c < C::NCHUNK; c += 2, ++cnt) {
+      for (int c = g, k = 0; c < C::NCHUNK; c += 2, ++k, ++cnt) {
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * C::CHUNK_COLS;
-        float v[C::CHUNK_COLS];
-        {
-          uint32_t* r = reinterpret_cast<uint32_t*>(v);
-          tmem_ld_32x32(taddr, r);
-          if (!OUT_F32) tmem_ld_32x32(taddr + 32, r + 32);
-          tmem_ld_wait();
-        }
+        float v[32];
+        tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+        tmem_ld_wait();
         if (c + 2 >= C::NCHUNK) {  // this group's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
           if constexpr (NCTA == 2) {   // to the leader's barrier, one arrive per warp
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(as ? tempty_r1 : tempty_r0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(as ? tempty_r1 : tempty_r0);
           } else {
             mbar_arrive(&tempty[as]);
           }
@@ -305,47 +323,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = tc.n * BN + c * C::CHUNK_COLS;
         if (p.alpha != 1.0f) {
 #pragma unroll
-          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] *= p.alpha;
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
         }
-        if (add_bias) {
-          if (n0 + C::CHUNK_COLS <= p.N) {
-#pragma unroll
-            for (int j = 0; j < C::CHUNK_COLS / 4; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-              v[4 * j + 0] += b4.x;
-              v[4 * j + 1] += b4.y;
-              v[4 * j + 2] += b4.z;
-              v[4 * j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < C::CHUNK_COLS; ++j)
-              if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-          }
-        }
-        // the TMA stores that last used this group's buffers must have finished reading them
-        if (issuer) tma_store_wait_read<0>();
-        named_bar_sync(bar_id, 128);
-        if (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
+        if (add_bias) {   // broadcast LDS: every lane reads the same address
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            uint4 pk;
-            pk.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            sts128(aux_s + sw128_offset(row, j), pk.x, pk.y, pk.z, pk.w);
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + k * 32 + 4 * j);
+            v[4 * j + 0] += b4.x;
+            v[4 * j + 1] += b4.y;
+            v[4 * j + 2] += b4.z;
+            v[4 * j + 3] += b4.w;
           }
+        }
+        const uint32_t buf = C::NBUF == 2 ? (cnt & 1u) : 0u;
+        uint8_t* out_buf = out_base + buf * C::CHUNK_BYTES;
+        uint8_t* aux_buf = aux_base + buf * C::CHUNK_BYTES;
+        const uint32_t out_s = smem_u32(out_buf), aux_s = smem_u32(aux_buf);
+        if (C::NBUF == 1) {
+          // single buffer: the TMA store that last used it must have finished reading it
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, 128);
+        }
+        if (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(aux_s + sw64_offset(row, j), pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         } else if (p.act == 2) {
 #pragma unroll
-          for (int j = 0; j < C::CHUNK_COLS; ++j) v[j] = tanhf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
         }
         if (HAS_IN) {
-          mbar_wait(&infull[g], cnt & 1);
+          const uint32_t slot = cnt % C::IN_DEPTH;
+          const int bi = g * C::IN_DEPTH + slot;
+          const uint32_t in_s = smem_u32(sIn + bi * C::CHUNK_BYTES);
+          mbar_wait(&infull[bi], (cnt / C::IN_DEPTH) & 1);
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -357,8 +373,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 pk = lds128(in_s + sw128_offset(row, j));
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = lds128(in_s + sw64_offset(row, j));
               const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -373,25 +389,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          mbar_arrive(&inempty[g]);
+          mbar_arrive(&inempty[bi]);
         }
         if (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; ++j)
             sts128f(out_s + sw128_offset(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 pk;
-            pk.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            pk.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            pk.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            pk.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            sts128(out_s + sw128_offset(row, j), pk.x, pk.y, pk.z, pk.w);
-          }
+          for (int j = 0; j < 4; ++j)
+            sts128(out_s + sw64_offset(row, j), pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
         fence_async_smem();
+        // double-buffered: the store issued one chunk ago (other buffer) must have been read before anyone passes
+        // this barrier and starts the next chunk, which overwrites that buffer; it had a whole chunk to drain
+        if (C::NBUF == 2 && issuer) tma_store_wait_read<0>();
         named_bar_sync(bar_id, 128);
         if (issuer) {
           if (n0 < p.N) {
@@ -467,7 +480,7 @@ static int launch_n(const GemmDesc& g, cudaStream_t stream) {
   tmAux = tmC;
   tmIn = tmC;
   if (HAS_AUX) {
-    rc = make_tmap_2d(&tmAux, g.aux, 2, g.M, g.N, g.ldaux, 128, 64);
+    rc = make_tmap_2d(&tmAux, g.aux, 2, g.M, g.N, g.ldaux, 128, C::CHUNK_COLS);
     if (rc) return rc;
   }
   if (HAS_IN) {

@@ -180,6 +180,11 @@ DEVINL uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
 DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without memory-ordering side effects (the release form costs a MEMBAR.ALL.GPU per arrive).  For hand-offs
+// that only order tcgen05 traffic, which tcgen05.fence::before_thread_sync / tcgen05.wait::ld already cover.
+DEVINL void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load into this CTA's shared memory whose completion bytes are signalled on a barrier of the pair's
 // leader CTA (`bar_cluster_addr` = mapa_rank(barrier, 0))
 DEVINL void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -328,5 +333,7 @@ DEVINL float4 lds128f(uint32_t addr) {
 // byte offset of 16-byte piece `piece` (0..7) of row `row` inside a 128B-swizzled
 // [rows x 128 B] tile whose base is 1024 B aligned
 DEVINL uint32_t sw128_offset(uint32_t row, uint32_t piece) { return row * 128u + ((piece ^ (row & 7u)) << 4); }
+// same for a 64B-swizzled [rows x 64 B] tile (4 pieces per row; address bits [4,6) ^= bits [7,9)), base 512 B aligned
+DEVINL uint32_t sw64_offset(uint32_t row, uint32_t piece) { return row * 64u + ((piece ^ ((row >> 1) & 3u)) << 4); }
 
 }  // namespace modcr

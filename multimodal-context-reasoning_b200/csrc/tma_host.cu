@@ -67,6 +67,7 @@ struct KeyHash {
 static std::mutex g_mu;
 static std::unordered_map<Key, CUtensorMap, KeyHash> g_cache;
 
+// The swizzle mode follows the inner box width: 128-byte rows -> SWIZZLE_128B, 64-byte rows -> SWIZZLE_64B.
 static int encode(CUtensorMap* out, const void* ptr, int elem_bytes, int rank, const cuuint64_t* dims,
                   const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
@@ -100,8 +101,9 @@ static int encode(CUtensorMap* out, const void* ptr, int elem_bytes, int rank, c
   }
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = box[0] * (cuuint32_t)elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
@@ -118,7 +120,7 @@ static int encode(CUtensorMap* out, const void* ptr, int elem_bytes, int rank, c
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols) {
-  if (box_cols * elem_bytes != 128 || box_rows > 256 || box_rows == 0) {
+  if ((box_cols * elem_bytes != 128 && box_cols * elem_bytes != 64) || box_rows > 256 || box_rows == 0) {
     set_error("bad TMA box %u x %u (elem %d B)", box_rows, box_cols, elem_bytes);
     return MODCR_ERR_SHAPE;
   }

@@ -8,7 +8,7 @@
 namespace modcr {
 
 // Row-major 2-D view [rows, cols] with leading dimension `ld` (elements).
-// The box is [box_rows, box_cols]; box_cols * elem_bytes must be 128 (SWIZZLE_128B).
+// The box is [box_rows, box_cols]; box_cols * elem_bytes must be 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
 // Returns 0 on success, negative error code otherwise (error text via set_error()).
 int make_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols);
