@@ -28,6 +28,7 @@
 #include "attn.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -331,6 +332,312 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ============================================================================ forward, persistent
+// For S <= 192 and P+S <= 192 (the PMR / VCR-base shapes).  One CTA per SM loops over (sequence, head) items; both
+// 128-row q tiles of an item are in flight at once on two softmax groups that share the item's K/V tiles:
+//   warps 0-3  group A: q rows [0,128)          warps 4-5  group B: q rows [128,192) (<= 64 rows, PV still M=128)
+//   warp 6     tcgen05.mma issuer + TMEM owner  warp 7     TMA producer (2-stage ring of Q_A | Q_B | K | V)
+// TMEM: group g owns columns [256 g, 256 g + 256): S in [0,192), O in [192,256), so S of the next item is issued the
+// moment the group has finished reading S of the current one, ahead of P V.  The row threads run
+//   pass 1 (max) of item i  ->  epilogue of item i-1 (O / sum -> bf16 -> TMA store)  ->  pass 2 (exp, P) of item i
+// which hides the P V latency of item i-1 behind pass 1 of item i.  P of group A overlays the dead Q_A | Q_B | K
+// tiles of its stage; group B (64 rows) has its own half-height P blocks whose upper halves are only ever read as
+// don't-care rows by the M=128 MMA.
+// Key rows in shared memory are [sequence rows ; prefix rows] with NO padding in between (exact-height TMA boxes for
+// the sequence tail and the prefix; the swizzle is a function of the shared-memory address, so a box may start on
+// any 128-byte row), which keeps P + S = 188 of the PMR shape inside 192 MMA columns; rows [S+P, Kp) are zeroed once.
+struct PersistLayout {
+  int stage_bytes, off_qb, off_k, off_v;   // per stage: Q_A at 0
+  int off_pb, off_oa, off_bias, off_bars;  // P blocks of group B (+ its O staging at +24 KB), O staging of group A
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmTail,
+                        const __grid_constant__ CUtensorMap tmPKV, const __grid_constant__ CUtensorMap tmCTXA,
+                        const __grid_constant__ CUtensorMap tmCTXB, const AttnParams p, const PersistLayout lay) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sPB = smem + lay.off_pb;
+  uint8_t* sOA = smem + lay.off_oa;
+  uint8_t* sOB = sPB + 24576;
+  float* sBiasAll = reinterpret_cast<float*>(smem + lay.off_bias);   // [2 groups][2 item parities][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.off_bars);
+  uint64_t* qk_full = bars + 0;      // [2] stage: Q_A, Q_B, K landed
+  uint64_t* v_full = bars + 2;       // [2] stage: V landed
+  uint64_t* stage_free = bars + 4;   // [2] every MMA reading the stage has retired
+  uint64_t* s_full = bars + 6;       // [2] group: S = Q K^T complete
+  uint64_t* p_ready = bars + 8;      // [2] group: P written (and S consumed)
+  uint64_t* o_full = bars + 10;      // [2] group: O = P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const float c1 = p.scale * LOG2E;
+  const int nblk = (p.Kp + 63) >> 6;
+  const bool two = p.nqt > 1;        // group B has rows
+  const int total = p.N * p.heads;
+  const int n_items = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 7) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      if (p.P > 0) tma_prefetch_desc(&tmPKV);
+      tma_prefetch_desc(&tmCTXA);
+      tma_prefetch_desc(&tmCTXB);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qk_full[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&stage_free[i], 1);
+        mbar_init(&s_full[i], 1);
+        mbar_init(&o_full[i], 1);
+      }
+      mbar_init(&p_ready[0], 128);
+      mbar_init(&p_ready[1], 64);
+      fence_barrier_init();
+    }
+  } else if (warp == 6) {
+    tmem_alloc<512>(tmem_slot);
+  } else {
+    // key rows [S+P, Kp) are never written by TMA: clear them once in both stages (K: finite scores under the -inf
+    // bias; V: 0 x 0 instead of 0 x garbage)
+    const int pad0 = (p.S + p.P) * 128, pad1 = p.Kp * 128;
+    for (int st = 0; st < 2; ++st) {
+      uint8_t* sK = smem + st * lay.stage_bytes + lay.off_k;
+      uint8_t* sV = smem + st * lay.stage_bytes + lay.off_v;
+      for (int b = pad0 + tid * 16; b < pad1; b += 192 * 16) {
+        *reinterpret_cast<uint4*>(sK + b) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sV + b) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 7) {
+    // ---------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int nfull = p.S >> 6;          // full 64-row boxes of the sequence
+      const int tail = p.S & 63;           // rows of the exact-height tail box
+      const uint32_t kv_bytes = (uint32_t)((p.S + p.P) * 128);
+      const uint32_t q_bytes = two ? 24576u : 16384u;   // group B: rows [128,192) only
+      for (int i = 0; i < n_items; ++i) {
+        const int w = blockIdx.x + i * gridDim.x;
+        const int n = w / p.heads, h = w - n * p.heads;
+        const int st = i & 1;
+        uint8_t* sQ = smem + st * lay.stage_bytes;
+        uint8_t* sK = sQ + lay.off_k;
+        uint8_t* sV = sQ + lay.off_v;
+        if (i >= 2) mbar_wait(&stage_free[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qk_full[st], q_bytes + kv_bytes);
+        tma_load_3d(sQ, &tmQKV, &qk_full[st], h * 64, 0, n);
+        tma_load_3d(sQ + 8192, &tmQKV, &qk_full[st], h * 64, 64, n);
+        if (two) tma_load_3d(sQ + lay.off_qb, &tmQKV, &qk_full[st], h * 64, 128, n);
+        for (int j = 0; j < nfull; ++j) tma_load_3d(sK + j * 8192, &tmQKV, &qk_full[st], p.H + h * 64, j * 64, n);
+        if (tail) tma_load_3d(sK + nfull * 8192, &tmTail, &qk_full[st], p.H + h * 64, nfull * 64, n);
+        if (p.P > 0) tma_load_3d(sK + p.S * 128, &tmPKV, &qk_full[st], h * 64, 0, n);
+        mbar_expect_tx(&v_full[st], kv_bytes);
+        for (int j = 0; j < nfull; ++j) tma_load_3d(sV + j * 8192, &tmQKV, &v_full[st], 2 * p.H + h * 64, j * 64, n);
+        if (tail) tma_load_3d(sV + nfull * 8192, &tmTail, &v_full[st], 2 * p.H + h * 64, nfull * 64, n);
+        if (p.P > 0) tma_load_3d(sV + p.S * 128, &tmPKV, &v_full[st], p.H + h * 64, 0, n);
+      }
+    }
+  } else if (warp == 6) {
+    // ---------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, p.Kp, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      const int ksteps = p.Kp >> 4;
+      auto issue_s = [&](int i, int g) {   // S_g(i) = Q_g K^T
+        const int st = i & 1;
+        const uint32_t q_addr = smem_u32(smem + st * lay.stage_bytes + (g ? lay.off_qb : 0));
+        const uint32_t k_addr = smem_u32(smem + st * lay.stage_bytes + lay.off_k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + g * 256, make_smem_desc(q_addr + k * 32, 0, 1024),
+                    make_smem_desc(k_addr + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int i, int g) {  // O_g(i) = P_g V
+        const int st = i & 1;
+        const uint32_t base = smem_u32(smem + st * lay.stage_bytes);
+        const uint32_t v_addr = base + lay.off_v;
+        const uint32_t pa[3] = {base, base + (uint32_t)lay.off_qb, base + (uint32_t)lay.off_k};
+        const uint32_t pb = smem_u32(sPB);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t blk = g ? pb + (ks >> 2) * 8192 : pa[ks >> 2];
+          umma_bf16(tmem_base + g * 256 + 192, make_smem_desc(blk + (ks & 3) * 32, 0, 1024),
+                    make_smem_desc(v_addr + ks * 2048, 8192, 1024), idesc_pv, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[g]);
+      };
+      if (n_items > 0) {
+        mbar_wait(&qk_full[0], 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        if (two) issue_s(0, 1);
+      }
+      for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1;
+        const bool more = i + 1 < n_items;
+        for (int g = 0; g < (two ? 2 : 1); ++g) {
+          mbar_wait(&p_ready[g], i & 1);      // P_g(i) written, S_g columns consumed
+          tc_fence_after();
+          if (more) {
+            if (g == 0) {
+              mbar_wait(&qk_full[st ^ 1], ((i + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(i + 1, g);
+          }
+          if (g == 0) {
+            mbar_wait(&v_full[st], (i >> 1) & 1);
+            tc_fence_after();
+          }
+          issue_pv(i, g);
+        }
+        umma_commit(&stage_free[st]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------- softmax rows
+    const int g = warp >> 2;                 // 0: rows [0,128), 1: rows [128,192)
+    const int gthreads = g ? 64 : 128;
+    const int gt = tid - g * 128;            // thread index inside the group == row inside the q tile
+    const int row = gt;
+    const int q = g * 128 + row;
+    const bool alive = q < p.S;
+    const bool warp_alive = (g * 128 + (warp & 3) * 32) < p.S;
+    const bool q_txt = q < p.T;
+    const bool active = g == 0 || two;       // group B without rows only idles
+    const uint32_t bar_id = 1 + g;
+    const bool issuer = gt == 0;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * 256;
+    uint8_t* sO = g ? sOB : sOA;
+    const CUtensorMap* tmO = g ? &tmCTXB : &tmCTXA;
+    const int full = p.Kp & ~31;
+
+    float inv_prev = 0.f;
+    int n_prev = 0, h_prev = 0;
+    auto epilogue = [&](int j) {   // O of item j -> ctx
+      mbar_wait(&o_full[g], j & 1);
+      tc_fence_after();
+      float o[64];
+      if (warp_alive) {
+        tmem_ld_32x32(taddr + 192, reinterpret_cast<uint32_t*>(o));
+        tmem_ld_32x32(taddr + 224, reinterpret_cast<uint32_t*>(o) + 32);
+        tmem_ld_wait();
+      }
+      if (issuer) tma_store_wait_read<0>();   // the previous store has finished reading the staging tile
+      named_bar_sync(bar_id, gthreads);
+      if (warp_alive) {
+        const uint32_t so = smem_u32(sO);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          sts128(so + sw128_offset(row, jj), pack_bf16(o[8 * jj + 0] * inv_prev, o[8 * jj + 1] * inv_prev),
+                 pack_bf16(o[8 * jj + 2] * inv_prev, o[8 * jj + 3] * inv_prev),
+                 pack_bf16(o[8 * jj + 4] * inv_prev, o[8 * jj + 5] * inv_prev),
+                 pack_bf16(o[8 * jj + 6] * inv_prev, o[8 * jj + 7] * inv_prev));
+      }
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_sync(bar_id, gthreads);
+      if (issuer) {
+        tma_store_3d(tmO, sO, h_prev * 64, g * 128, n_prev);
+        tma_store_commit();
+      }
+    };
+
+    if (active) {
+      for (int i = 0; i < n_items; ++i) {
+        const int w = blockIdx.x + i * gridDim.x;
+        const int n = w / p.heads, h = w - n * p.heads;
+        const int st = i & 1;
+        uint8_t* stage = smem + st * lay.stage_bytes;
+        // ---- per-key bias of this sequence, double-buffered by item parity: a slower thread of the group may still
+        // be reading the previous item's values, but everyone is past the ones of two items ago (barrier below)
+        float* sBias = sBiasAll + (g * 2 + (i & 1)) * 256;
+        for (int kk = gt; kk < nblk * 64; kk += gthreads) {   // smem key row kk: sequence rows first, then the prefix
+          float b = -INFINITY;
+          if (kk < p.S)
+            b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + p.P + kk) * LOG2E;
+          else if (kk < p.S + p.P)
+            b = __ldg(p.kbias + (size_t)n * (p.P + p.S) + (kk - p.S)) * LOG2E;
+          sBias[kk] = b;
+        }
+        named_bar_sync(bar_id, gthreads);
+        const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
+        float* pimg_row = nullptr;
+        if (p.probs_img != nullptr && alive && q_txt)
+          pimg_row = p.probs_img + (((size_t)n * p.heads + h) * p.T + q) * p.R;
+
+        // ---- pass 1: row maximum
+        mbar_wait(&s_full[g], i & 1);
+        tc_fence_after();
+        float m = -INFINITY, sum = 0.f, inv = 0.f;
+        if (warp_alive) {
+          for (int c0 = 0; c0 < full; c0 += 32) {
+            const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+            fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
+          }
+          if (full < p.Kp) {
+            const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+            fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+          }
+        }
+        // ---- epilogue of the previous item (its P V ran under pass 1)
+        if (i > 0) epilogue(i - 1);
+        // ---- pass 2: exp, row sum, P (bf16, swizzled) for the P V MMA
+        if (g == 0 && two) {   // P blocks 1, 2 overlay Q_B and K: group B's S = Q_B K^T must have retired too
+          mbar_wait(&s_full[1], i & 1);
+        }
+        if (warp_alive) {
+          for (int c0 = 0; c0 < full; c0 += 32) {
+            const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+            const int b = c0 >> 6;
+            uint8_t* blk = g ? sPB + b * 8192 : stage + (b == 0 ? 0 : (b == 1 ? lay.off_qb : lay.off_k));
+            fwd_chunk<MODE, 32, 2>(p, c1, taddr, sBias, blk, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
+          }
+          if (full < p.Kp) {
+            const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+            const int b = full >> 6;
+            uint8_t* blk = g ? sPB + b * 8192 : stage + (b == 0 ? 0 : (b == 1 ? lay.off_qb : lay.off_k));
+            fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, blk, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+          }
+          inv = sum > 0.f ? 1.0f / sum : 0.f;
+          if (p.probs_img != nullptr) {  // uniform over the CTA
+            const int first = (p.T >> 5) << 5;
+            for (int c0 = first; c0 < full; c0 += 32) {
+              const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+              fwd_chunk<MODE, 32, 3>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            }
+            if (full < p.Kp && full + 16 > first) {
+              const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
+              fwd_chunk<MODE, 16, 3>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            }
+          }
+          if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_ready[g]);
+        inv_prev = inv;
+        n_prev = n;
+        h_prev = h;
+      }
+      if (n_items > 0) epilogue(n_items - 1);
+      if (issuer) tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) tmem_dealloc<512>(tmem_base);
 }
 
 // ============================================================================ backward
@@ -818,10 +1125,87 @@ static int launch_fwd(const AttnDesc& a, const AttnParams& p, const CUtensorMap&
   return check_launch("prefix_attn_fwd");
 }
 
+template <int MODE>
+static int launch_fwd_persist(const AttnParams& p, const CUtensorMap& tmQKV, const CUtensorMap& tmTail,
+                              const CUtensorMap& tmPKV, const CUtensorMap& tmA, const CUtensorMap& tmB, size_t smem,
+                              const PersistLayout& lay, cudaStream_t stream) {
+  auto kern = attn_fwd_persist_kernel<MODE>;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("prefix_attn_fwd: cudaFuncSetAttribute(%zu B) failed: %s", smem, cudaGetErrorString(e));
+      return MODCR_ERR_CUDA;
+    }
+    attr = smem;
+  }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int total = p.N * p.heads;
+  const int grid = total < sms ? total : sms;
+  kern<<<grid, 256, smem, stream>>>(tmQKV, tmTail, tmPKV, tmA, tmB, p, lay);
+  return check_launch("prefix_attn_fwd");
+}
+
+// MODCR_ATTN_FWD_TILE=1 forces the one-CTA-per-q-tile kernel (A/B comparison; default: persistent where it applies)
+static bool attn_fwd_force_tile() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MODCR_ATTN_FWD_TILE");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
   AttnParams p;
   int rc = fill_params(a, p, false);
   if (rc) return rc;
+  const int kp2 = (p.S + p.P + 15) & ~15;   // [sequence ; prefix] without inner padding
+  if (p.S <= 192 && kp2 <= 192 && !attn_fwd_force_tile()) {
+    PersistLayout lay;
+    const int kbytes = (kp2 * 128 + 1023) & ~1023;
+    lay.off_qb = 16384;
+    lay.off_k = 32768;
+    lay.off_v = 32768 + (kbytes < 16384 ? 16384 : kbytes);   // P block 2 of group A needs 16 KB behind off_k
+    lay.stage_bytes = lay.off_v + kbytes;
+    lay.off_pb = 2 * lay.stage_bytes;
+    lay.off_oa = lay.off_pb + 32768;
+    lay.off_bias = lay.off_oa + 16384;
+    lay.off_bars = lay.off_bias + 2 * 2 * 256 * 4;
+    const size_t smem = 1024 + (size_t)lay.off_bars + 128;
+    if (smem <= 232448) {
+      AttnParams pp = p;
+      pp.Kp = kp2;
+      CUtensorMap tmQKV, tmTail, tmPKV, tmA, tmB;
+      rc = make_tmap_3d(&tmQKV, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, 64, 64);
+      if (rc) return rc;
+      tmTail = tmQKV;
+      if (p.S & 63) {
+        rc = make_tmap_3d(&tmTail, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, p.S & 63, 64);
+        if (rc) return rc;
+      }
+      tmPKV = tmQKV;
+      if (p.P > 0) {
+        rc = make_tmap_3d(&tmPKV, a.pkv, 2, p.N, p.P, 2 * p.H, 2 * p.H, (uint64_t)p.P * 2 * p.H, p.P, 64);
+        if (rc) return rc;
+      }
+      rc = make_tmap_3d(&tmA, a.ctx, 2, p.N, p.S, p.H, p.H, (uint64_t)p.S * p.H, 128, 64);
+      if (rc) return rc;
+      rc = make_tmap_3d(&tmB, a.ctx, 2, p.N, p.S, p.H, p.H, (uint64_t)p.S * p.H, 64, 64);
+      if (rc) return rc;
+      switch (p.mode) {
+        case 0: return launch_fwd_persist<0>(pp, tmQKV, tmTail, tmPKV, tmA, tmB, smem, lay, stream);
+        case 1: return launch_fwd_persist<1>(pp, tmQKV, tmTail, tmPKV, tmA, tmB, smem, lay, stream);
+        default: return launch_fwd_persist<2>(pp, tmQKV, tmTail, tmPKV, tmA, tmB, smem, lay, stream);
+      }
+    }
+  }
   const int nblk = (p.Kp + 63) / 64;
   // shared-memory plan: Q tile | K | V | extra P blocks | bias | barriers.  P block 0 overlays the Q tile and
   // P block 1 the K tile (both dead once S = QK^T has completed), which keeps cfg-2 under 113 KB -> 2 CTAs / SM.

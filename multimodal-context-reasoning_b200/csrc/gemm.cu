@@ -531,14 +531,25 @@ static int launch(const GemmDesc& g, cudaStream_t stream) {
   return launch_n<1, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>(g, stream);
 }
 
+// Same cost model as engine.py::_split_k: waves of (tile, split) units over the CTA pairs x (k-blocks per unit + a fixed
+// epilogue cost of ~8 k-blocks).
 int gemm_split_k_heuristic(int M, int N, int K, int bn) {
-  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int groups = num_sms() / gemm_ncta();
+  const int bm = 128 * gemm_ncta();
+  const int tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
   const int kb = (K + 63) / 64;
-  const int sms = num_sms();
-  if (tiles >= sms) return 1;
-  int s = sms / tiles;
-  if (s > kb / 4) s = kb / 4;  // keep >= 4 k-blocks per split
-  return s < 1 ? 1 : s;
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= 16; ++s) {
+    if (s > 1 && kb / s < 4) break;
+    const long waves = ((long)tiles * s + groups - 1) / groups;
+    const long cost = waves * ((kb + s - 1) / s + 8);
+    if (best_cost < 0 || cost < best_cost) {
+      best = s;
+      best_cost = cost;
+    }
+  }
+  return best;
 }
 
 int gemm_launch(const GemmDesc& g, cudaStream_t stream) {

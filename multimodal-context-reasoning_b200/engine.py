@@ -95,11 +95,21 @@ class ParamStore:
 
 
 def _split_k(M, N, K):
-    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    """Split-K factor of the wgrad GEMM: the tile grid (256 x 256 tiles on CTA pairs) of a weight gradient is much
+    smaller than the machine, so K (= rows of the activations) is split until the pairs are busy.  Cost model: waves of
+    work units over the pairs x (k-blocks per unit + a fixed epilogue / reduce-add cost in k-block units)."""
+    pairs = NUM_SMS // 2
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
     kb = (K + 63) // 64
-    if tiles >= NUM_SMS:
-        return 1
-    return max(1, min(NUM_SMS // tiles, kb // 4))
+    best, best_cost = 1, None
+    for s in range(1, 17):
+        if s > 1 and kb // s < 4:
+            break
+        waves = (tiles * s + pairs - 1) // pairs
+        cost = waves * ((kb + s - 1) // s + 8)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
 
 
 def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None):
