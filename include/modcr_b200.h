@@ -162,6 +162,12 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
                                void* stream);
 
+/* cross_attention_lyx with a single query per sequence (ClsLayer_lyx, modeling/modeling_vcr_chunkalign_v10.py:692-797,
+ * 856-857): out[n] = concat_h softmax_l(q_h[n] . k_h[n,l] / sqrt(d_h)) v_h[n,l].  q, out [N,H]; k, v [N,L,H]; all bf16.
+ * No mask (the reference never forwards word_mask), tau = 1, dropout p = 0. */
+int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int32_t N, int32_t L, int32_t H,
+                            int32_t heads, void* stream);
+
 /* ClsLayer2 attention pooling (v10:816-829). q [N,H], k [N,L,H] bf16 (qk_f32=0) or fp32 (qk_f32=1: the unscaled
  * 768-dim scores are the most rounding-sensitive spot of the path), mask fp32 [N,L] additive. */
 int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,

@@ -505,6 +505,106 @@ int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_
   return check_launch("cls_pool_attn_bwd");
 }
 
+// ============================================================================ cross_attention_lyx (one query)
+// ClsLayer_lyx (v10:856-870) attends with ONE query per sequence (the CLS vector) over L key/value rows with 8 heads
+// (cross_attention_lyx, v10:692-797: q scaled by head_dim^-0.5, no mask is ever passed, tau = 1, dropout p = 0).
+// One CTA per sequence; every lane owns H/32 contiguous channels, i.e. a fixed head (head_dim / (H/32) lanes per head),
+// so a head's score is a short shuffle reduction inside its lane group and the value row is weighted lane-locally.
+// Single pass with online softmax per head; the XA_WARPS partial states are merged through shared memory.
+// smem: qs[H] | wm[XA_WARPS][32] | ws[XA_WARPS][32] | part[XA_WARPS][H]
+constexpr int XA_WARPS = 16;
+
+template <int VEC>   // 16-byte vectors per lane: H = 32 * 8 * VEC
+__global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+                                                                          const bf16* __restrict__ v, bf16* __restrict__ out,
+                                                                          int L, int H, int lanes_per_head, float scaling) {
+  extern __shared__ float sm[];
+  float* qs = sm;
+  float* wm = qs + H;
+  float* wsm = wm + XA_WARPS * 32;
+  float* part = wsm + XA_WARPS * 32;
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int E = 8 * VEC;
+  for (int c = threadIdx.x; c < H; c += XA_WARPS * 32) qs[c] = __bfloat162float(q[(size_t)n * H + c]) * scaling;
+  __syncthreads();
+  float ql[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) ql[j] = qs[lane * E + j];
+  const bf16* kn = k + (size_t)n * L * H + lane * E;
+  const bf16* vn = v + (size_t)n * L * H + lane * E;
+  float m = -INFINITY, se = 0.f;
+  float acc[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) acc[j] = 0.f;
+  for (int l = warp; l < L; l += XA_WARPS) {
+    float kf[E], vf[E];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(kn + (size_t)l * H) + i), kf + 8 * i);
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(vn + (size_t)l * H) + i), vf + 8 * i);
+    }
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) d = fmaf(kf[j], ql[j], d);
+    for (int o = 1; o < lanes_per_head; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);   // head score
+    const float mn = fmaxf(m, d);
+    const float resc = expf(m - mn);     // 0 on the first row (m = -inf)
+    const float pe = expf(d - mn);
+    se = fmaf(se, resc, pe);
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < E; ++j) acc[j] = fmaf(acc[j], resc, pe * vf[j]);
+  }
+  wm[warp * 32 + lane] = m;
+  wsm[warp * 32 + lane] = se;
+#pragma unroll
+  for (int j = 0; j < E; ++j) part[warp * H + lane * E + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += XA_WARPS * 32) {
+    const int ln = c / E;   // the lane (hence head) that owns channel c
+    float mx = -INFINITY;
+#pragma unroll
+    for (int ww = 0; ww < XA_WARPS; ++ww) mx = fmaxf(mx, wm[ww * 32 + ln]);
+    float tot = 0.f, s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < XA_WARPS; ++ww) {
+      const float mw = wm[ww * 32 + ln];
+      const float sc = mw == -INFINITY ? 0.f : expf(mw - mx);   // warps without rows (L < XA_WARPS)
+      tot = fmaf(wsm[ww * 32 + ln], sc, tot);
+      s = fmaf(part[ww * H + c], sc, s);
+    }
+    out[(size_t)n * H + c] = __float2bfloat16(s / tot);
+  }
+}
+
+int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int N, int L, int H, int heads,
+                      cudaStream_t st) {
+  const int E = H / 32;
+  const int hd = heads > 0 ? H / heads : 0;
+  if (N <= 0 || L <= 0 || heads <= 0 || H % (32 * 8) != 0 || H % heads != 0 || (E != 24 && E != 32) || hd % E != 0 ||
+      ((hd / E) & (hd / E - 1)) != 0) {
+    set_error("cross_attn_q1_fwd: bad shape N=%d L=%d H=%d heads=%d (H in {768, 1024}, head_dim a power-of-two multiple of H/32)",
+              N, L, H, heads);
+    return MODCR_ERR_SHAPE;
+  }
+  const size_t smem = ((size_t)H + 2 * XA_WARPS * 32 + (size_t)XA_WARPS * H) * 4;
+  const float scaling = 1.0f / sqrtf((float)hd);
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(cross_attn_q1_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cross_attn_q1_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  if (E == 24)
+    cross_attn_q1_fwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, L,
+                                                               H, hd / E, scaling);
+  else
+    cross_attn_q1_fwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, L,
+                                                               H, hd / E, scaling);
+  return check_launch("cross_attn_q1_fwd");
+}
+
 // ============================================================================ classifier + CE
 constexpr int SC_MAXC = 8;
 

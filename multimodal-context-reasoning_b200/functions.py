@@ -253,6 +253,46 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         return (None, None, outs[0], outs[1], outs[2], dgp, dsp, *out_p)
 
 
+def cls_lyx_head_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers=2, heads=8):
+    """``cls_ensemble_1`` + ``n_layers`` x ``ClsLayer_lyx`` of ChunkAlign_CLS_enc4_align_ensemble (v10:925-975,
+    856-870), forward only (the encoders run under ``no_grad`` in the reference and the backward of this head is the
+    frozen-encoder training regime).  Inputs are bf16 ``[N,S,H]`` / ``[N,H]``; returns CLS ``[N,H]``
+    bf16.  ``word_len`` = T - 1 token rows taken from each of the three sources."""
+    N, S, H = g_out.shape
+    I = cfg["I"]
+    dev = g_out.device
+    L3 = 3 * word_len
+    cat = E._empty((N, 2 * H), BF16, dev)
+    ops.copy_rows(g_pool.contiguous(), 1, 0, cat, 2, 0, N, 1, H)          # [global_CLS | chunk_CLS]
+    ops.copy_rows(s_pool.contiguous(), 1, 0, cat, 2, 1, N, 1, H)
+    cls = E._empty((N, H), BF16, dev)
+    ops.gemm(cat, ps.bf16("cls_ensemble_1.weight"), cls, N, H, 2 * H, bias=ps.f32("cls_ensemble_1.bias"))
+    cls32 = E._empty((N, H), F32, dev)
+    ops.bf16_to_f32(cls, cls32)
+    X = E._empty((N, L3, H), BF16, dev)
+    for j, src in enumerate((g_out, s_out, c_hid)):
+        ops.copy_rows(src.contiguous(), S, 1, X, L3, j * word_len, N, word_len, H)
+    for i in range(n_layers):
+        pfx = "cls_layer_lyx.%d." % i
+        xa = pfx + "cross_attention."
+        q = E._empty((N, H), BF16, dev)
+        ops.gemm(cls, ps.bf16(xa + "q_proj.weight"), q, N, H, H, bias=ps.f32(xa + "q_proj.bias"))
+        k, v = E._empty((N, L3, H), BF16, dev), E._empty((N, L3, H), BF16, dev)
+        ops.gemm(X, ps.bf16(xa + "k_proj.weight"), k, N * L3, H, H, bias=ps.f32(xa + "k_proj.bias"))
+        ops.gemm(X, ps.bf16(xa + "v_proj.weight"), v, N * L3, H, H, bias=ps.f32(xa + "v_proj.bias"))
+        att = E._empty((N, H), BF16, dev)
+        ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads)             # word_mask is never forwarded (v10:856-857)
+        pre = E._empty((N, H), F32, dev)
+        ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
+                 in_op=1)                                                # + cls (residual of the LayerNorm)
+        c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
+        mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
+        ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
+                          cfg["eps"], y32=c32)
+        cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], None)
+    return cls
+
+
 class ScorerFn(torch.autograd.Function):
     """Linear(K -> C) + cross-entropy (+ binary_to_mp/argmax/matched) in one kernel (v10:1063-1069)."""
 

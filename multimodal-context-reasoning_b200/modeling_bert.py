@@ -250,3 +250,38 @@ class ImageBertForMultipleChoice(CaptionPreTrainedModel):
         if labels is not None:
             out = (loss,) + out
         return out
+
+
+class OscarForMultipleChoice(CaptionPreTrainedModel):
+    """modeling/modeling_bert.py:574-712: every (question, choice) pair is scored on its own --
+    ``[B,C,T]`` / ``[B,C,R,D]`` inputs flattened to ``[B*C,...]`` (:676-681), ``BertImgModel`` pooled output ->
+    ``Linear(H -> 2)`` -> cross-entropy over the flattened rows (``loss_type`` 'bxe' and the default; :699-710),
+    classifier + CE fused in one kernel.  Returns ``(loss), logits [B*C,2]``."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.loss_type = cfg_get(config, "loss_type", "bxe")
+        self.bert = BertImgModel(config)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        kind = cfg_get(config, "classifier", None)
+        if kind not in (None, "linear"):
+            raise NotImplementedError("only the linear classifier of OscarForMultipleChoice is implemented")
+        self.classifier = nn.Linear(config.hidden_size, 2 if kind == "linear" else config.num_labels)
+        self.apply(self._init_weights)
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, labels=None, position_ids=None,
+                head_mask=None, img_feats=None):
+        flat = lambda t: None if t is None else t.reshape(-1, *t.shape[2:])  # noqa: E731
+        outputs = self.bert(flat(input_ids), position_ids=flat(position_ids), token_type_ids=flat(token_type_ids),
+                            attention_mask=flat(attention_mask), head_mask=head_mask, img_feats=flat(img_feats))
+        pooled = outputs[1]
+        rows, C = pooled.shape[0], self.classifier.weight.shape[0]
+        if self.loss_type == "bce" and labels is not None:
+            raise NotImplementedError("loss_type 'bce' of OscarForMultipleChoice is not on the ModCR path")
+        labels_ = (torch.zeros((rows,), dtype=torch.int64, device=pooled.device) if labels is None
+                   else labels.reshape(-1).long().contiguous())
+        loss, logits = ScorerFn.apply(pooled, self.classifier.weight, self.classifier.bias, labels_, None, C, 1, False)
+        out = (logits,) + outputs[2:]
+        if labels is not None:
+            out = (loss,) + out
+        return out

@@ -9,7 +9,8 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .functions import AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, EncoderFn, EncoderRun, ScorerFn
+from .functions import (AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, EncoderFn, EncoderRun, ScorerFn,
+                        cls_lyx_head_forward)
 from .modeling_bert import (AttentionsNotMaterialised, BertIntermediate, BertOutput, CaptionBertAttention,
                             _EncoderModelBase)
 from .modeling_utils import cfg_get, check_no_dropout, engine_cfg
@@ -173,3 +174,99 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         _, logits, mp, pred, matched_0 = ScorerFn.apply(cls, self.classifier.weight, self.classifier.bias, lab, None, 2,
                                                         self.num_labels, True)
         return matched_0, pred, mp
+
+
+class cross_attention_lyx(nn.Module):
+    """Parameter container of the reference's 8-head cross-attention (v10:692-797): ``k_proj``, ``v_proj``,
+    ``q_proj``, ``out_proj``.  The one configuration the path uses (a single CLS query, no mask, ``tau=1``,
+    ``neg_type=False``, no ``prior_score``) runs in ``cross_attn_q1_fwd`` (csrc/heads.cu)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0, is_decoder=False, bias=True):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout, self.is_decoder = embed_dim, num_heads, dropout, is_decoder
+        self.head_dim = embed_dim // num_heads
+        if self.head_dim * num_heads != embed_dim:
+            raise ValueError("embed_dim must be divisible by num_heads (got %d and %d)" % (embed_dim, num_heads))
+        self.scaling = self.head_dim ** -0.5
+        self.k_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.v_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.q_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+
+class ClsLayer_lyx(nn.Module):
+    """v10:838-870 (a BertLayer subclass: the inherited ``attention`` block, ``ensemble`` and ``dense`` exist in the
+    state_dict but are never called).  Parameter container; executed by ``functions.cls_lyx_head_forward``."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.attention = CaptionBertAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+        self.ensemble = nn.Linear(config.hidden_size * 2, 1)
+        self.cross_attention = cross_attention_lyx(config.hidden_size, 8, dropout=0.1, is_decoder=True)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+
+class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
+    """Frozen-encoder alignment model used inside ``Abstract_Specific`` (v10:873-997): both encoders run without
+    gradients, ``cls_ensemble_1`` + 2 x ``ClsLayer_lyx`` fuse [global tokens ; chunk tokens ; chunk hidden states]
+    into ``CLS_ensem``; returns ``(CLS_ensem, align_loss, ([], None))``.  ``cls_layer``, ``classifier``,
+    ``fusion_align`` and ``prior`` are part of the reference's state_dict but never called.
+
+    Forward / scoring only in this round: the backward of the ``ClsLayer_lyx`` head (training with frozen encoders,
+    SURVEY.md 8 f3) is not implemented, and asking for it raises instead of silently returning a constant."""
+
+    def __init__(self, global_enc, seq_enc, num_labels):
+        super().__init__()
+        self.global_enc = global_enc
+        self.seq_enc = seq_enc
+        H = self.global_enc.config.hidden_size
+        self.cls_ensemble_1 = nn.Linear(H + self.seq_enc.config.hidden_size, H)
+        self.num_labels = num_labels
+        self.cls_layer_num = 2
+        self.cls_layer = nn.ModuleList([ClsLayer2(self.global_enc.config) for _ in range(self.cls_layer_num)])
+        self.cls_layer_lyx = nn.ModuleList([ClsLayer_lyx(self.global_enc.config) for _ in range(self.cls_layer_num)])
+        self.classifier = nn.Linear(H, 2)
+        self.fusion_align = nn.Linear(H * 2, 1024)
+        self.prior = nn.Linear(H, 1)
+        self.cls_loss_fct = nn.CrossEntropyLoss()
+        self._head_store = None
+
+    def _head_params(self):
+        named = {k: p for k, p in self.named_parameters()
+                 if k.startswith("cls_ensemble_1.") or k.startswith("cls_layer_lyx.")}
+        ps = self._head_store
+        if ps is None or ps.named.keys() != named.keys() or any(ps.named[k] is not named[k] for k in named):
+            ps = E.ParamStore(named)
+            self._head_store = ps
+        return ps, named
+
+    def forward(self, input_ids, img_feat, input_mask=None, label=None, token_type_ids=None, position_ids=None,
+                head_mask=None, encoder_history_states=None, offsets=None, chunk_attention_mask=None,
+                gather_index=None, align_pos=None, total_label=None, abstract_hidden_states=None):
+        ps, named = self._head_params()
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in named.values()):
+            raise NotImplementedError(
+                "modcr_b200: the backward of the ClsLayer_lyx head (frozen-encoder training) is not implemented; "
+                "call under torch.no_grad() / .eval() for scoring")
+        check_no_dropout(self, self.global_enc.config)
+        N, T = input_ids.shape
+        want_block = total_label is not None
+        with torch.no_grad():
+            g = self.global_enc(input_ids, img_feats=img_feat, attention_mask=input_mask, position_ids=position_ids,
+                                token_type_ids=token_type_ids, head_mask=None,
+                                encoder_history_states=encoder_history_states)
+            (s_out, s_pool, att), chunk_hidden = self.seq_enc(
+                input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
+                attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
+                head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
+            cfg = engine_cfg(self.global_enc.config)
+            CLS_ensem = cls_lyx_head_forward(ps, cfg, T - 1, g[0], s_out, chunk_hidden, g[1], s_pool,
+                                             n_layers=self.cls_layer_num, heads=8)
+            align_loss = None
+            if want_block:
+                align_loss, _ = AlignLossFn.apply(att.align_block, align_pos, total_label)
+        return CLS_ensem, align_loss, ([], None)

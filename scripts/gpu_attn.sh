@@ -8,5 +8,5 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; e
 grep -v Warning gpurun_out/bench.log | tail -2 | cut -c1-300
 export WARM=1 STEPS=1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv python scripts/quick_bench.py > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_persist -s 12 -c 1 -o gpurun_out/prof_attn_fwdp -f python scripts/quick_bench.py > gpurun_out/ncu_attn_fwdp.log 2>&1
+
 fi

@@ -408,6 +408,22 @@ def test_cls_pool_attn_fwd_bwd(L, H, dt):
     assert nerr(dq, qr.grad) < 1.5e-2 and nerr(dk, kr.grad) < 1.5e-2
 
 
+@pytest.mark.parametrize("L,H,heads", [(381, 768, 8), (69, 768, 8), (7, 768, 8), (130, 1024, 8)])
+def test_cross_attn_q1_matches_cross_attention_lyx(L, H, heads):
+    """cross_attention_lyx with a single query (v10:692-797): q scaled by head_dim^-0.5, softmax over L per head."""
+    N = 5
+    q, k, v = rnd(N, H, seed=21), rnd(N, L, H, seed=22), rnd(N, L, H, seed=23)
+    out = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    ops.cross_attn_q1_fwd(q, k, v, out, N, L, H, heads)
+    hd = H // heads
+    qf = (q.float() * hd ** -0.5).view(N, heads, 1, hd)
+    kf = k.float().view(N, L, heads, hd).permute(0, 2, 1, 3)
+    vf = v.float().view(N, L, heads, hd).permute(0, 2, 1, 3)
+    w = torch.softmax(qf @ kf.transpose(-1, -2), dim=-1)
+    ref = (w @ vf).permute(0, 2, 1, 3).reshape(N, H)
+    assert nerr(out, ref) < 1e-2
+
+
 def test_mc_scorer_ce_hard_labels_binary_to_mp():
     B, nc, H = 8, 4, 768
     rows = B * nc

@@ -175,3 +175,70 @@ def test_eval_no_grad_and_prefix_invariants():
                                         token_type_ids=bd["token_type_ids"], offsets=b["offsets"],
                                         chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"])
         assert expl.shape == (meta["B"], 4) and pre.shape == (meta["B"],)
+
+
+def test_ensemble_head_forward_matches_oracle():
+    """ChunkAlign_CLS_enc4_align_ensemble (v10:873-997): frozen encoders + cls_ensemble_1 +
+    2 x ClsLayer_lyx (8-head single-query cross-attention), against the fp32 CPU restatement that
+    tests/test_oracle.py pins bit-for-bit to the live reference class."""
+    from modcr_b200.modeling_vcr_chunkalign_v10 import ChunkAlign_CLS_enc4_align_ensemble
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = ChunkAlign_CLS_enc4_align_ensemble(BertImgModel(cfg), SeqBertImgModel(cfg), 4)
+    keys = statedict.chunkalign_ensemble_keys(CFG)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == dict(keys)
+    sd = params.fill_params(statedict.materialise(keys), 4)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    for (B, T, R, seed) in ((2, 24, 7, 3), (1, 40, 12, 5)):
+        b = synth.make_batch(B=B, T=T, R=R, seed=seed)
+        bd = synth.to_device(b, DEV)
+        with torch.no_grad():
+            cls, al, extra = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                               token_type_ids=bd["token_type_ids"], offsets=b["offsets"],
+                               chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"],
+                               align_pos=bd["align_pos"], total_label=bd["total_label"])
+            c_ref, al_ref = restate.chunkalign_ensemble_forward({k: v.clone() for k, v in sd.items()}, CFG, b, None)
+        assert extra == ([], None) and tuple(cls.shape) == (4 * B, 768)
+        err = float((cls.float().cpu() - c_ref).abs().max())
+        print("ensemble B=%d T=%d: max|dCLS| %.4f (|CLS| max %.2f)  align_loss %.5f vs %.5f" % (
+            B, T, err, float(c_ref.abs().max()), float(al), float(al_ref)))
+        assert err < 5e-2 and nerr(cls, c_ref) < 2e-2
+        assert abs(float(al) - float(al_ref)) < 1e-2
+    # the head has no backward yet: asking for one must fail loudly, not return a constant
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], token_type_ids=bd["token_type_ids"],
+          offsets=b["offsets"], chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"])
+
+
+def test_oscar_for_multiple_choice_matches_restated_scorer():
+    """OscarForMultipleChoice (modeling/modeling_bert.py:574-712): [B,C,...] inputs flattened to
+    [B*C,...], pooled -> Linear(H->2) -> CE over the flattened rows; forward and gradient of the head."""
+    import torch.nn.functional as F
+    from modcr_b200.modeling_bert import OscarForMultipleChoice
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg.loss_type, cfg.classifier, cfg.num_labels = "bxe", "linear", 2
+    torch.manual_seed(0)
+    m = OscarForMultipleChoice(cfg).to(DEV).train()
+    B, C, T, R = 2, 4, 24, 7
+    b = synth.make_batch(B=B, T=T, R=R, seed=11)
+    bd = synth.to_device(b, DEV)
+    shp = lambda t: t.reshape(B, C, *t.shape[1:])  # noqa: E731
+    labels = bd["label"].reshape(B, C)
+    loss, logits = m(shp(bd["input_ids"]), token_type_ids=shp(bd["token_type_ids"]), attention_mask=shp(bd["input_mask"]),
+                     labels=labels, img_feats=shp(bd["img_feat"]))[:2]
+    assert tuple(logits.shape) == (B * C, 2)
+    loss.backward()
+    # reference arithmetic of the head on the pooled output of the same encoder (CE over flattened rows)
+    with torch.no_grad():
+        pooled = m.bert(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=bd["input_mask"],
+                        img_feats=bd["img_feat"])[1].float()
+    W = m.classifier.weight.detach().float().clone().requires_grad_(True)
+    bb = m.classifier.bias.detach().float().clone().requires_grad_(True)
+    ref_logits = pooled @ W.t() + bb
+    ref_loss = F.cross_entropy(ref_logits, bd["label"].reshape(-1))
+    ref_loss.backward()
+    assert float((logits - ref_logits).abs().max()) < 2e-2
+    assert abs(float(loss) - float(ref_loss)) < 1e-2
+    assert nerr(m.classifier.weight.grad, W.grad) < 3e-2 and nerr(m.classifier.bias.grad, bb.grad) < 3e-2
+    assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
