@@ -59,6 +59,9 @@ size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
  *   a_mn = 0: A stored [M,K];  a_mn = 1: A stored [K,M]      (same for B with N)
  *   act: 0 none, 1 GELU(erf), 2 tanh;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in)
  *   aux: optional bf16 copy of the pre-activation;  c_fp32 + accumulate / split_k: wgrad
+ *   a_colsum (a_mn = 1 only): a_colsum[m] += sum_k A[k,m], fp32 -- the bias gradient dY^T 1 of the Linear whose weight
+ *   gradient dW = dY^T X this call computes, summed from the dY tiles the kernel stages anyway (replaces the reference's
+ *   autograd bias reduction, a separate pass over dY)
  */
 typedef struct modcr_gemm_desc {
   const void* A;
@@ -75,6 +78,7 @@ typedef struct modcr_gemm_desc {
   const void* epi_in;
   int64_t ld_in;
   int32_t in_op;
+  float* a_colsum;
 } modcr_gemm_desc;
 int modcr_gemm(const modcr_gemm_desc* d, void* stream);
 

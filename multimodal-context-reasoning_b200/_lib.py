@@ -18,7 +18,8 @@ class GemmDesc(C.Structure):
                 ("a_mn", c_i32), ("b_mn", c_i32), ("c_fp32", c_i32), ("accumulate", c_i32), ("split_k", c_i32),
                 ("M", c_i32), ("N", c_i32), ("K", c_i32),
                 ("alpha", c_float), ("bias", c_void_p), ("act", c_i32),
-                ("aux", c_void_p), ("ldaux", c_i64), ("epi_in", c_void_p), ("ld_in", c_i64), ("in_op", c_i32)]
+                ("aux", c_void_p), ("ldaux", c_i64), ("epi_in", c_void_p), ("ld_in", c_i64), ("in_op", c_i32),
+                ("a_colsum", c_void_p)]
 
 
 class RowMap(C.Structure):

@@ -74,6 +74,7 @@ int modcr_gemm(const modcr_gemm_desc* d, void* stream) {
   g.M = d->M; g.N = d->N; g.K = d->K;
   g.alpha = d->alpha; g.bias = d->bias; g.act = d->act;
   g.aux = d->aux; g.ldaux = d->ldaux; g.epi_in = d->epi_in; g.ld_in = d->ld_in; g.in_op = d->in_op;
+  g.a_colsum = d->a_colsum;
   return modcr::gemm_launch(g, S(stream));
 }
 

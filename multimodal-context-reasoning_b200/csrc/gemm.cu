@@ -12,6 +12,8 @@
 //   warp 0  TMA producer for the A/B smem ring            (1 elected thread)
 //   warp 1  tcgen05.mma issuer, accumulators in TMEM      (1 elected thread)
 //   warp 2  TMEM allocator + TMA loader of the optional epilogue input tile
+//   warps 2-3  (wgrad with a bias gradient) column sums of the staged A tiles: dW = dY^T X stages dY anyway, so
+//           db = dY^T 1 is accumulated from shared memory by the two otherwise idle warps of the n == 0 tiles
 //   warps 4-11 epilogue in two groups of four warps (group g takes the 32-column chunks g, g+2, ...):
 //           tcgen05.ld -> bias / activation / residual-add / GELU' -> swizzled smem -> TMA store (or TMA
 //           reduce-add for split-K fp32); bf16 chunks ping-pong between two buffers per group
@@ -43,6 +45,7 @@ struct GemmParams {
   int act;        // 0 none, 1 gelu(erf), 2 tanh
   int in_op;      // 0 none, 1 add, 2 multiply by gelu'(in)
   int reduce_add; // output through TMA reduce-add (fp32 accumulate in place)
+  float* a_colsum; // A MN-major only: a_colsum[m] += sum_k A[k,m] from the staged A tiles of the n == 0 tiles
 };
 
 template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
@@ -66,7 +69,7 @@ struct Cfg {
   static constexpr int IN_BUFS = HAS_IN ? 2 * IN_DEPTH : 0;
   static constexpr int BIAS_BYTES = 2 * 128 * 4;      // per group: the 128 bias values of its chunks of one tile
   static constexpr int EPI_BYTES = (OUT_BUFS + IN_BUFS) * CHUNK_BYTES + BIAS_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 320;
   static constexpr int SMEM_MAX = 232448;  // 227 KB
   static constexpr int STAGES_RAW = (SMEM_MAX - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -115,7 +118,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty = tfull + 2;
   uint64_t* infull = tempty + 2;     // [group][slot]
   uint64_t* inempty = infull + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inempty + 4);
+  uint64_t* consumed = inempty + 4;   // [STAGES] (column-sum warps) the MMAs reading the stage have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(consumed + C::STAGES);
   float* sBiasG = reinterpret_cast<float*>(sIn + C::IN_BUFS * C::CHUNK_BYTES);   // [2][128]
 
   const int warp = threadIdx.x >> 5;
@@ -126,6 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int group = blockIdx.x / NCTA;
   const int ngroups = gridDim.x / NCTA;
   const bool leader = rank == 0;
+  const bool do_colsum = A_MN && !HAS_IN && p.a_colsum != nullptr;   // uniform over the grid
   constexpr int EPI_ARRIVALS = NCTA == 2 ? 16 : 256;   // pairs: one (remote) arrive per epilogue warp
 
   if (warp == 0 && lane == 0) {
@@ -138,7 +143,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], do_colsum ? 2 : 1);   // MMA commit, or the two column-sum warps (which follow the MMAs)
+      mbar_init(&consumed[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -241,9 +247,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (NCTA == 2) umma_bf16_pair(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
           }
-          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (NCTA == 2) umma_commit_pair(&empty[stage], 3);
-          else umma_commit(&empty[stage]);
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire; with a bias gradient the slot goes to
+          // the column-sum warps first, which release it
+          uint64_t* rel = do_colsum ? &consumed[stage] : &empty[stage];
+          if (NCTA == 2) umma_commit_pair(rel, 3);
+          else umma_commit(rel);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -274,7 +282,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  if ((warp == 2 || warp == 3) && do_colsum) {
+    // ------------------------------------------------------------ column sums of the staged A tiles
+    // A stage is two [64 k-rows x 64 m] 128B-swizzled boxes.  Lane l owns m-columns 64 (l >> 4) + 4 (l & 15) .. + 4
+    // (half a 16-byte piece); warp 2 sums k-rows [0,32), warp 3 rows [32,64) of every stage.  Every tile's stages
+    // are released by these warps as well (the empty barrier counts them), but only n == 0 tiles are summed.
+    const int r0 = (warp - 2) * 32;
+    const int box = lane >> 4, piece = (lane & 15) >> 1, halfp = lane & 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = group; t < total_tiles; t += ngroups) {
+      const TileCoord tc = decode_tile(p, t);
+      const bool mine = tc.n == 0;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+        mbar_wait(&consumed[stage], phase);   // the tile landed and the MMAs are done with it
+        if (mine) {
+          const uint32_t base = smem_u32(sA + stage * C::A_BYTES) + box * 8192 + halfp * 8;
+          // k-rows beyond K were zero-filled by TMA
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const uint32_t rr = r0 + r;
+            uint32_t lo, hi;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];"
+                         : "=r"(lo), "=r"(hi)
+                         : "r"(base + rr * 128 + ((piece ^ (rr & 7)) << 4)));
+            const float2 a = unpack_bf16(lo), b = unpack_bf16(hi);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (mine) {
+        const int m = (tc.m * NCTA + rank) * 128 + box * 64 + piece * 8 + halfp * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (m + j < p.M) atomicAdd(p.a_colsum + m + j, acc[j]);
+      }
+    }
+  }
+  if (warp >= 4) {
     // ------------------------------------------------------------ epilogue (2 groups x 4 warps)
     // group g handles chunks c = g, g+2, ... of every tile; both groups read the same TMEM stage.
     const int g = (warp - 4) >> 2;
@@ -502,6 +555,11 @@ static int launch_n(const GemmDesc& g, cudaStream_t stream) {
   p.act = g.act;
   p.in_op = g.in_op;
   p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
+  p.a_colsum = g.a_colsum;
+  if (g.a_colsum != nullptr && (!A_MN || HAS_IN)) {
+    set_error("gemm: a_colsum needs A stored [K,M] (a_mn = 1) and no epilogue input");
+    return MODCR_ERR_UNSUPPORTED;
+  }
   const int total = p.m_tiles * p.n_tiles * p.split_k;
   const int groups_max = num_sms() / NCTA;
   const int groups = total < groups_max ? total : groups_max;

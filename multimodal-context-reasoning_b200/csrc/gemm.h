@@ -24,6 +24,7 @@ struct GemmDesc {
   const void* epi_in = nullptr;  // optional bf16 [M,N] epilogue input tile
   int64_t ld_in = 0;
   int in_op = 0;             // 1: C = f(acc) + in ; 2: C = f(acc) * gelu'(in)
+  float* a_colsum = nullptr; // optional fp32 [M]: += sum_k A[k,m] (A MN-major only; the bias gradient of a wgrad)
 };
 
 int gemm_launch(const GemmDesc& g, cudaStream_t stream);

@@ -112,23 +112,26 @@ def _split_k(M, N, K):
     return best
 
 
-def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None):
+def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None, bias_out=None):
     """dW[out_f, in_f] = dY^T X  (fp32; split-K through TMA reduce-add when the tile grid is small).
-    With ``out`` given the product is accumulated into it; ``zeroed`` is a pre-cleared destination."""
+    With ``out`` given the product is accumulated into it; ``zeroed`` is a pre-cleared destination.
+    ``bias_out`` (fp32 [out_f], pre-zeroed or accumulating) receives += dY^T 1, the bias gradient, summed inside
+    the same kernel from the dY tiles it stages (no separate pass over dY)."""
     dev = dY.device
     if zeroed is not None:
         out = zeroed
     if out is not None:
         ops.gemm(dY, X, out, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1,
-                 split_k=_split_k(out_f, in_f, rows))
+                 split_k=_split_k(out_f, in_f, rows), a_colsum=bias_out)
         return out
     sk = _split_k(out_f, in_f, rows)
     if sk > 1:
         dW = _zeros((out_f, in_f), F32, dev)
-        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1, split_k=sk)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, accumulate=1, split_k=sk,
+                 a_colsum=bias_out)
     else:
         dW = _empty((out_f, in_f), F32, dev)
-        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, lda=ldy, ldb=ldx, a_mn=1, b_mn=1, a_colsum=bias_out)
     return dW
 
 
@@ -167,9 +170,8 @@ def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None):
     grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M, zeroed=dW2)
     du = _empty((M, I), BF16, dev)
     ops.gemm(g2, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)           # (g2 W2) * GELU'(u)
-    ops.colsum(du, I, M, I, db1)
     grads[pfx + "intermediate.dense.bias"] = db1
-    grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M, zeroed=dW1)
+    grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M, zeroed=dW1, bias_out=db1)
     da = _empty((M, H), BF16, dev)
     ops.gemm(du, W1, da, M, H, I, b_mn=1, epi_in=g2, in_op=1)                # + residual branch
     return da
@@ -243,12 +245,10 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None):
                         sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws)
     if sv["chunk"]:
         ops.chunk_mean_q(dqkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)   # self-adjoint operator
-    ops.colsum(dqkv, 3 * H, M, 3 * H, dbqkv)
-    wgrad(dqkv, sv["x"], 3 * H, H, M, zeroed=dWqkv)
+    wgrad(dqkv, sv["x"], 3 * H, H, M, zeroed=dWqkv, bias_out=dbqkv)
     dhist = None
     if P > 0:
-        ops.colsum(dpkv, 2 * H, N * P, 2 * H, dbqkv[H:])
-        wgrad(dpkv, sv["hist"], 2 * H, H, N * P, out=dWqkv[H:])
+        wgrad(dpkv, sv["hist"], 2 * H, H, N * P, out=dWqkv[H:], bias_out=dbqkv[H:])
         dhist = _empty((N * P, H), BF16, dev)
         ops.gemm(dpkv, Wqkv[H:], dhist, N * P, H, 2 * H, b_mn=1)
     for i, n in enumerate(("query", "key", "value")):

@@ -219,9 +219,8 @@ class ClsLayer2HeadFn(torch.autograd.Function):
             dk = E._empty((N, L3, H), BF16, dev)
             ops.cls_pool_attn_bwd(dpool, sv["q"], sv["k"], sv["w"], dq, dk, N, L3, H)
             dbk = E._zeros((H,), F32, dev)
-            ops.colsum(dk, H, N * L3, H, dbk)
             grads[pfx + "align_k_proj.bias"] = dbk
-            grads[pfx + "align_k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3)
+            grads[pfx + "align_k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3, bias_out=dbk)
             dXn = E._empty((N, L3, H), BF16, dev)
             ops.gemm(dk, ps.bf16(pfx + "align_k_proj.weight"), dXn, N * L3, H, H, b_mn=1,
                      epi_in=dX, in_op=1)                                   # accumulate over the 3 layers

@@ -39,8 +39,9 @@ def rowmap(rows_per_seq=0, seq_stride=0, row0=0):
 
 # --------------------------------------------------------------------------- GEMM
 def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=None, act=0, aux=None,
-         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None):
-    """C[M,N] = epi(alpha * A B^T); operands are raw 2-D views described by (ptr, ld)."""
+         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None, a_colsum=None):
+    """C[M,N] = epi(alpha * A B^T); operands are raw 2-D views described by (ptr, ld).
+    ``a_colsum`` (a_mn=1): fp32 [M] that receives += sum_k A[k,m] (the bias gradient of a wgrad)."""
     d = GemmDesc()
     d.A, d.B, d.C = A.data_ptr(), B.data_ptr(), C_.data_ptr()
     d.lda = lda if lda is not None else (M if a_mn else K)
@@ -58,6 +59,7 @@ def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=N
     d.epi_in = _p(epi_in)
     d.ld_in = ld_in if ld_in is not None else N
     d.in_op = in_op if epi_in is not None else 0
+    d.a_colsum = _p(a_colsum)
     _lib.check(_lib.load().modcr_gemm(C.byref(d), _stream()), "gemm")
     return C_
 

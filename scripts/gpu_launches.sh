@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+export WARM=1 STEPS=1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv python scripts/quick_bench.py > gpurun_out/ncu_launch.log 2>&1
+tail -2 gpurun_out/ncu_launch.log

@@ -64,6 +64,20 @@ def test_gemm_backward_variants():
     assert nerr(dW, 2 * (dY.float().t() @ X.float())) < 1e-3
 
 
+def test_gemm_wgrad_fused_bias_gradient():
+    """a_colsum: the bias gradient dY^T 1 summed inside the wgrad kernel from the staged dY tiles (all splits, ragged
+    K and M), against a separate column sum."""
+    for (rows, out_f, in_f, sk) in ((1424, 768, 768, 4), (3048, 2304, 768, 3), (400, 2056, 768, 1), (128 * 9 + 5, 3072, 768, 2)):
+        dY, X = rnd(rows, out_f, seed=rows), rnd(rows, in_f, seed=rows + 1)
+        dW = torch.zeros(out_f, in_f, device=DEV)
+        db = torch.zeros(out_f, device=DEV)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, a_mn=1, b_mn=1, accumulate=1, split_k=sk, a_colsum=db)
+        assert nerr(dW, dY.float().t() @ X.float()) < 1e-4
+        assert nerr(db, dY.float().sum(0)) < 1e-5, (rows, out_f, sk)
+        ops.gemm(dY, X, dW, out_f, in_f, rows, a_mn=1, b_mn=1, accumulate=1, split_k=sk, a_colsum=db)   # accumulates
+        assert nerr(db, 2 * dY.float().sum(0)) < 1e-5
+
+
 def test_gemm_fp32_residual_stream():
     M, N, K = 712, 768, 3072
     A, B = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
