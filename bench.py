@@ -370,19 +370,42 @@ def run_ours(args):
     loss_val = float(loss)
 
     # ---- end to end through the public call with host buffers (`e2e`)
+    # Every step's inputs travel pinned host -> HBM inside the timed region; the copy of step i+1 is issued on a copy
+    # stream while step i computes (double-buffered staging tensors), then moved into the graph's static input buffers
+    # by a device-to-device copy at the start of its step.  The step's result (loss) is read back to the host each step.
     h2d = sum(v.numel() * v.element_size() for v in hb.values())
-    def e2e_step():
-        for k, v in hb.items():
-            static[k].copy_(v, non_blocking=True)   # pinned host -> HBM, on the compute stream
+    copy_stream = torch.cuda.Stream()
+    stage = [{k: torch.empty_like(v) for k, v in static.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(slot):
+        copy_stream.wait_event(consumed[slot])          # the step that used this staging slot has taken its inputs
+        with torch.cuda.stream(copy_stream):
+            for k, v in hb.items():
+                stage[slot][k].copy_(v, non_blocking=True)   # pinned host -> HBM
+            ready[slot].record(copy_stream)
+
+    def e2e_step(i):
+        slot = i & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[slot])
+        for k in hb:
+            static[k].copy_(stage[slot][k], non_blocking=True)
+        consumed[slot].record(cur)
+        prefetch(slot ^ 1)                               # next step's inputs, under this step's compute
         ls = run_step(static)
-        return ls.item()                     # D2H read of the step's result
-    for _ in range(2):
-        e2e_step()
+        return ls.item()                                 # D2H read of the step's result
+    for sl in range(2):
+        consumed[sl].record(torch.cuda.current_stream())
+    prefetch(0)
+    for i in range(2):
+        e2e_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        e2e_step(i)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps

@@ -78,11 +78,17 @@ constexpr float NEG2 = NEG_BIAS * LOG2E;  // the additive -10000 in the log2 dom
 // additive -10000 underflows to exactly 0 like in the fp32 reference.
 template <int MODE>
 DEVINL float masked_s2(float acc, float c1, float b2, int kk, int q, bool q_txt, int T, uint32_t w) {
-  if (MODE != 0) {
-    if (kk < T)
-      b2 = q_txt ? (((w >> (kk & 31)) & 1u) ? 0.f : NEG2) : NEG2;
-    else if (MODE == 2 && !q_txt)
-      b2 = (b2 == -INFINITY) ? b2 : ((kk == q) ? 0.f : NEG2);
+  if (MODE == 1) {
+    if (kk < T) b2 = q_txt ? (((w >> (kk & 31)) & 1u) ? 0.f : NEG2) : NEG2;
+  } else if (MODE == 2) {
+    // branch-free: every alternative is a value select (the if / else-if form compiled to real branches inside the
+    // unrolled column loops and made the layers 9-11 kernels branch-resolution bound, ncu: profiles/)
+    const float bit = ((w >> (kk & 31)) & 1u) ? 0.f : NEG2;
+    const float tval = q_txt ? bit : NEG2;                       // text key: own chunk (text row) / nothing (image row)
+    const float diag = (kk == q) ? 0.f : NEG2;                   // image key, image row: identity only
+    const float iv2 = (b2 == -INFINITY) ? b2 : diag;
+    const float ival = q_txt ? b2 : iv2;                         // image key, text row: the key bias
+    b2 = (kk < T) ? tval : ival;
   }
   return fmaf(acc, c1, b2);
 }
@@ -611,18 +617,46 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, blk, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
           }
           inv = sum > 0.f ? 1.0f / sum : 0.f;
-          if (p.probs_img != nullptr) {  // uniform over the CTA
+          if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
+        }
+        if (p.probs_img != nullptr) {  // uniform over the CTA
+          // Normalised text->region probabilities of this head (v10:982 consumes their sum over heads and layers).
+          // A thread owns a ROW, global memory wants a row's columns side by side: each warp transposes its
+          // 32 x 32 block through its 4 KB slice of the group's O staging tile (XOR-swizzled, conflict-free) and
+          // writes 128-byte row segments.
+          if (issuer) tma_store_wait_read<0>();   // the previous item's ctx store has finished reading the tile
+          named_bar_sync(bar_id, gthreads);
+          if (warp_alive) {
+            const uint32_t tile = smem_u32(sO) + (uint32_t)(warp & 3) * 4096u;
+            const int q0 = g * 128 + (warp & 3) * 32;          // first q row of this warp
+            float* pbase = p.probs_img + (((size_t)n * p.heads + h) * p.T) * p.R;
             const int first = (p.T >> 5) << 5;
-            for (int c0 = first; c0 < full; c0 += 32) {
+            for (int c0 = first; c0 < p.Kp; c0 += 32) {
+              const int wcols = min(32, p.Kp - c0);             // 32, or 16 for the last chunk
+              float v[32];
+              if (wcols == 32) tmem_ld_32x32(taddr + c0, reinterpret_cast<uint32_t*>(v));
+              else tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t*>(v));
+              tmem_ld_wait();
               const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-              fwd_chunk<MODE, 32, 3>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
-            }
-            if (full < p.Kp && full + 16 > first) {
-              const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-              fwd_chunk<MODE, 16, 3>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float pr = 0.f;
+                if (j < wcols)
+                  pr = fast_ex2(masked_s2<MODE>(v[j], c1, sBias[c0 + j], c0 + j, q, q_txt, p.T, wd) - m) * inv;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile + lane * 128 + ((j ^ lane) << 2)), "f"(pr) : "memory");
+              }
+              __syncwarp();
+              const int col = c0 + lane;                        // this lane's key column
+              const bool col_ok = col >= p.T && col < p.S;
+              for (int r = 0; r < 32; ++r) {
+                float pr;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pr) : "r"(tile + r * 128 + ((lane ^ r) << 2)));
+                const int qr = q0 + r;
+                if (col_ok && qr < p.T && qr < p.S) pbase[(size_t)qr * p.R + (col - p.T)] = pr;
+              }
+              __syncwarp();
             }
           }
-          if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
         }
         fence_async_smem();
         tc_fence_before();

@@ -724,8 +724,9 @@ __global__ void __launch_bounds__(256) scorer_bwd_kernel(const ScorerParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // every CTA recomputes the (tiny) dlogits above; the rows of dx and the elements of dW are split over the grid
   if (p.dx) {
-    for (int r = warp; r < p.rows; r += nw) {
+    for (int r = blockIdx.x * nw + warp; r < p.rows; r += gridDim.x * nw) {
       for (int v = lane; v < (p.K >> 3); v += 32) {
         float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < p.C; ++c) {
@@ -739,14 +740,14 @@ __global__ void __launch_bounds__(256) scorer_bwd_kernel(const ScorerParams p) {
     }
   }
   if (p.dW) {
-    for (int i = threadIdx.x; i < p.C * p.K; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.C * p.K; i += gridDim.x * blockDim.x) {
       const int c = i / p.K, kk = i - c * p.K;
       float s = 0.f;
       for (int r = 0; r < p.rows; ++r) s = fmaf(dl[(size_t)r * p.C + c], __bfloat162float(p.x[(size_t)r * p.K + kk]), s);
       p.dW[i] += s;
     }
   }
-  if (p.db) {
+  if (p.db && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
       float s = 0.f;
       for (int r = 0; r < p.rows; ++r) s += dl[(size_t)r * p.C + c];
@@ -790,7 +791,10 @@ int mc_scorer_ce_bwd(const ScorerDesc& d, cudaStream_t st) {
     set_error("mc_scorer_ce_bwd: rows*C=%d too large", d.rows * d.C);
     return MODCR_ERR_UNSUPPORTED;
   }
-  scorer_bwd_kernel<<<1, 256, smem, st>>>(p);
+  int grid = (d.rows + 7) / 8;
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  scorer_bwd_kernel<<<grid, 256, smem, st>>>(p);
   return check_launch("mc_scorer_ce_bwd");
 }
 
