@@ -242,3 +242,54 @@ def test_oscar_for_multiple_choice_matches_restated_scorer():
     assert abs(float(loss) - float(ref_loss)) < 1e-2
     assert nerr(m.classifier.weight.grad, W.grad) < 3e-2 and nerr(m.classifier.bias.grad, bb.grad) < 3e-2
     assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
+
+
+def test_full_size_cfg2_invariants():
+    """BASELINE.json configs[1] (32 questions x 4 choices, 128 tokens + 50 regions, prefix 10) is too large for the CPU
+    oracle, so the full-size step is checked through size-independent properties of the path:
+    determinism of the forward, choice-permutation equivariance of the scorer, duplicated questions scoring alike,
+    loss / alignment-loss ranges, and every trainable tensor receiving a finite gradient."""
+    B, T, R, P = 32, 128, 50, 10
+    torch.manual_seed(0)
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), 4).to(DEV).train()
+    b = synth.make_batch(B=B, T=T, R=R, seed=88)
+    # question 1 := question 0 (all four choices), so their logits must agree bit for bit
+    for k in ("input_ids", "token_type_ids", "input_mask", "img_feat", "chunk_attention_mask", "total_label", "align_pos",
+              "label"):
+        b[k][4:8] = b[k][0:4]
+    for k in ("offsets", "gather_index"):
+        b[k][4:8] = b[k][0:4]
+    bd = synth.to_device(b, DEV)
+    N = 4 * B
+    prefix = synth.make_prefix(12, P, 768, seed=89).to(DEV).requires_grad_(True)
+
+    def run(batch, lists):
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(12)]
+        out = m(batch["input_ids"], batch["img_feat"], input_mask=batch["input_mask"], label=batch["label"],
+                token_type_ids=batch["token_type_ids"], encoder_history_states=hist, offsets=lists["offsets"],
+                chunk_attention_mask=batch["chunk_attention_mask"], gather_index=lists["gather_index"],
+                align_pos=batch["align_pos"], total_label=batch["total_label"])
+        return out, m.last_logits.clone(), m.last_logit_expl.clone()
+
+    out, logits, expl = run(bd, b)
+    loss = out[0] + out[2]
+    loss.backward()
+    assert torch.isfinite(loss) and 0.3 < float(out[0]) < 1.5            # 2-way CE of an untrained scorer ~ ln 2
+    assert abs(float(out[2]) - float(torch.log(torch.tensor(float(R))))) < 0.3   # CE over softmaxed probabilities ~ ln R
+    assert torch.equal(logits[0:4], logits[4:8])                          # duplicated question
+    out2, logits2, _ = run(bd, b)
+    assert torch.equal(logits, logits2) and torch.equal(out[0], out2[0])  # deterministic forward
+    # permute the choices inside every question: per-sequence logits follow the permutation exactly
+    perm = torch.tensor([2, 0, 3, 1])
+    idx = (torch.arange(B).repeat_interleave(4) * 4 + perm.repeat(B))
+    bp = {k: (v[idx] if torch.is_tensor(v) and v.shape[0] == N else v) for k, v in b.items()}
+    lp = {k: [b[k][int(i)] for i in idx] for k in ("offsets", "gather_index")}
+    outp, logits_p, expl_p = run(synth.to_device(bp, DEV), lp)
+    assert torch.equal(logits_p, logits[idx.to(DEV)])
+    assert torch.equal(expl_p, expl[:, perm.to(DEV)])
+    assert abs(float(outp[0]) - float(out[0])) < 1e-5
+    bad = [k for k, p_ in m.named_parameters() if p_.grad is not None and not bool(torch.isfinite(p_.grad).all())]
+    assert not bad, bad
+    with_grad = sum(p_.grad is not None for p_ in m.parameters())
+    assert with_grad >= 400 and prefix.grad is not None and bool(torch.isfinite(prefix.grad).all())
