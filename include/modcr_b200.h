@@ -168,8 +168,13 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
 
 /* cross_attention_lyx with a single query per sequence (ClsLayer_lyx, modeling/modeling_vcr_chunkalign_v10.py:692-797,
  * 856-857): out[n] = concat_h softmax_l(q_h[n] . k_h[n,l] / sqrt(d_h)) v_h[n,l].  q, out [N,H]; k, v [N,L,H]; all bf16.
- * No mask (the reference never forwards word_mask), tau = 1, dropout p = 0. */
-int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int32_t N, int32_t L, int32_t H,
+ * No mask (the reference never forwards word_mask), tau = 1, dropout p = 0.  lse (optional, fp32 [N,heads]) is the
+ * per-head log-sum-exp the backward pass needs; the backward (autograd of v10:710-797) returns dq [N,H], dk, dv
+ * [N,L,H] in bf16. */
+int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t N, int32_t L,
+                            int32_t H, int32_t heads, void* stream);
+int modcr_cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse,
+                            const void* dout, void* dq, void* dk, void* dv, int32_t N, int32_t L, int32_t H,
                             int32_t heads, void* stream);
 
 /* ClsLayer2 attention pooling (v10:816-829). q [N,H], k [N,L,H] bf16 (qk_f32=0) or fp32 (qk_f32=1: the unscaled

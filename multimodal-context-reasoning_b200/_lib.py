@@ -69,7 +69,9 @@ SIGNATURES = {
                                    c_i32, c_i32, c_void_p],
     "modcr_align_softmax_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i32, c_i32, c_i32,
                                    c_void_p],
-    "modcr_cross_attn_q1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p],
+    "modcr_cross_attn_q1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p],
+    "modcr_cross_attn_q1_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_i32, c_i32, c_i32, c_i32, c_void_p],
     "modcr_cls_pool_attn_fwd": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p],
     "modcr_cls_pool_attn_bwd": [c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
                                 c_void_p],

@@ -209,10 +209,16 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
   return modcr::align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T, R, S(stream));
 }
 
-int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int32_t N, int32_t L, int32_t H,
+int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t N, int32_t L,
+                            int32_t H, int32_t heads, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::cross_attn_q1_fwd(q, k, v, out, lse, N, L, H, heads, S(stream));
+}
+int modcr_cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse,
+                            const void* dout, void* dq, void* dk, void* dv, int32_t N, int32_t L, int32_t H,
                             int32_t heads, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cross_attn_q1_fwd(q, k, v, out, N, L, H, heads, S(stream));
+  return modcr::cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads, S(stream));
 }
 
 int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,

@@ -517,7 +517,8 @@ constexpr int XA_WARPS = 16;
 template <int VEC>   // 16-byte vectors per lane: H = 32 * 8 * VEC
 __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
                                                                           const bf16* __restrict__ v, bf16* __restrict__ out,
-                                                                          int L, int H, int lanes_per_head, float scaling) {
+                                                                          float* __restrict__ lse, int L, int H,
+                                                                          int lanes_per_head, float scaling) {
   extern __shared__ float sm[];
   float* qs = sm;
   float* wm = qs + H;
@@ -575,10 +576,123 @@ __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_fwd_kernel(const 
       s = fmaf(part[ww * H + c], sc, s);
     }
     out[(size_t)n * H + c] = __float2bfloat16(s / tot);
+    // log-sum-exp of the head's (scaled) scores, one value per lane group, for the backward pass
+    if (lse != nullptr && (c % (E * lanes_per_head)) == 0) lse[(size_t)n * (32 / lanes_per_head) + ln / lanes_per_head] = mx + logf(tot);
   }
 }
 
-int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int N, int L, int H, int heads,
+// Backward of the above in one pass over the rows: with p_l = exp(s_l - lse), delta = dout . out (per head),
+//   dv_l = p_l dout,  ds_l = p_l (dout . v_l - delta),  dk_l = ds_l (scaling q),  dq = scaling sum_l ds_l k_l.
+// smem: part[XA_WARPS][H]
+template <int VEC>
+__global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+                                                                          const bf16* __restrict__ v, const bf16* __restrict__ out,
+                                                                          const float* __restrict__ lse, const bf16* __restrict__ dout,
+                                                                          bf16* __restrict__ dq, bf16* __restrict__ dk,
+                                                                          bf16* __restrict__ dv, int L, int H, int lanes_per_head,
+                                                                          float scaling) {
+  extern __shared__ float sm[];
+  float* part = sm;
+  const int n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int E = 8 * VEC;
+  float ql[E], dol[E];
+  float delta = 0.f;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    ql[j] = __bfloat162float(q[(size_t)n * H + lane * E + j]) * scaling;
+    dol[j] = __bfloat162float(dout[(size_t)n * H + lane * E + j]);
+    delta = fmaf(dol[j], __bfloat162float(out[(size_t)n * H + lane * E + j]), delta);
+  }
+  for (int o = 1; o < lanes_per_head; o <<= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+  const float lse_h = lse[(size_t)n * (32 / lanes_per_head) + lane / lanes_per_head];
+  const size_t rowbase = (size_t)n * L * H + lane * E;
+  float acc[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) acc[j] = 0.f;
+  for (int l = warp; l < L; l += XA_WARPS) {
+    float kf[E], vf[E];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(k + rowbase + (size_t)l * H) + i), kf + 8 * i);
+      unpack8h(__ldg(reinterpret_cast<const uint4*>(v + rowbase + (size_t)l * H) + i), vf + 8 * i);
+    }
+    float sdot = 0.f, dp = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      sdot = fmaf(kf[j], ql[j], sdot);
+      dp = fmaf(vf[j], dol[j], dp);
+    }
+    for (int o = 1; o < lanes_per_head; o <<= 1) {
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+      dp += __shfl_xor_sync(0xffffffffu, dp, o);
+    }
+    const float pr = expf(sdot - lse_h);
+    const float ds = pr * (dp - delta);
+    float okk[E], ov[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      okk[j] = ds * ql[j];
+      ov[j] = pr * dol[j];
+      acc[j] = fmaf(ds, kf[j], acc[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      reinterpret_cast<uint4*>(dk + rowbase + (size_t)l * H)[i] = pack8h(okk + 8 * i);
+      reinterpret_cast<uint4*>(dv + rowbase + (size_t)l * H)[i] = pack8h(ov + 8 * i);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < E; ++j) part[warp * H + lane * E + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += XA_WARPS * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < XA_WARPS; ++ww) s += part[ww * H + c];
+    dq[(size_t)n * H + c] = __float2bfloat16(s * scaling);
+  }
+}
+
+static int xa_check(int N, int L, int H, int heads, const char* what) {
+  const int E = H / 32;
+  const int hd = heads > 0 ? H / heads : 0;
+  if (N <= 0 || L <= 0 || heads <= 0 || H % (32 * 8) != 0 || H % heads != 0 || (E != 24 && E != 32) || hd % E != 0 ||
+      ((hd / E) & (hd / E - 1)) != 0) {
+    set_error("%s: bad shape N=%d L=%d H=%d heads=%d (H in {768, 1024}, head_dim a power-of-two multiple of H/32)", what,
+              N, L, H, heads);
+    return MODCR_ERR_SHAPE;
+  }
+  return MODCR_OK;
+}
+
+int cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
+                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, cudaStream_t st) {
+  if (int rc = xa_check(N, L, H, heads, "cross_attn_q1_bwd")) return rc;
+  if (lse == nullptr) {
+    set_error("cross_attn_q1_bwd: the forward pass must have written lse");
+    return MODCR_ERR_SHAPE;
+  }
+  const int E = H / 32, hd = H / heads;
+  const size_t smem = (size_t)XA_WARPS * H * 4;
+  const float scaling = 1.0f / sqrtf((float)hd);
+  static size_t attr = 0;
+  if (smem > attr && smem > 48 * 1024) {
+    cudaFuncSetAttribute(cross_attn_q1_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(cross_attn_q1_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  if (E == 24)
+    cross_attn_q1_bwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)out,
+                                                               lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, L, H,
+                                                               hd / E, scaling);
+  else
+    cross_attn_q1_bwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)out,
+                                                               lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, L, H,
+                                                               hd / E, scaling);
+  return check_launch("cross_attn_q1_bwd");
+}
+
+int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int N, int L, int H, int heads,
                       cudaStream_t st) {
   const int E = H / 32;
   const int hd = heads > 0 ? H / heads : 0;
@@ -597,11 +711,11 @@ int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, in
     attr = smem;
   }
   if (E == 24)
-    cross_attn_q1_fwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, L,
-                                                               H, hd / E, scaling);
+    cross_attn_q1_fwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, lse,
+                                                               L, H, hd / E, scaling);
   else
-    cross_attn_q1_fwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, L,
-                                                               H, hd / E, scaling);
+    cross_attn_q1_fwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, lse,
+                                                               L, H, hd / E, scaling);
   return check_launch("cross_attn_q1_fwd");
 }
 

@@ -53,8 +53,10 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
 // ClsLayer2 attention pooling (v10:816-829): w = softmax(q k^T + mask) (no 1/sqrt(d)), pooled = w k
 // q [N,H] and k [N,L,H] are bf16 (qk_f32 = 0) or fp32 (qk_f32 = 1)
 // multi-head attention of one query per sequence over L key/value rows (cross_attention_lyx, v10:692-797)
-int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, int N, int L, int H, int heads,
+int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int N, int L, int H, int heads,
                       cudaStream_t st);
+int cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
+                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, cudaStream_t st);
 int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
                       int H, cudaStream_t st);
 int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,

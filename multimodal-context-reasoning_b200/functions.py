@@ -252,11 +252,9 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         return (None, None, outs[0], outs[1], outs[2], dgp, dsp, *out_p)
 
 
-def cls_lyx_head_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers=2, heads=8):
-    """``cls_ensemble_1`` + ``n_layers`` x ``ClsLayer_lyx`` of ChunkAlign_CLS_enc4_align_ensemble (v10:925-975,
-    856-870), forward only (the encoders run under ``no_grad`` in the reference and the backward of this head is the
-    frozen-encoder training regime).  Inputs are bf16 ``[N,S,H]`` / ``[N,H]``; returns CLS ``[N,H]``
-    bf16.  ``word_len`` = T - 1 token rows taken from each of the three sources."""
+def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers, heads, want_saves):
+    """``cls_ensemble_1`` + ``n_layers`` x ``ClsLayer_lyx`` (v10:925-975, 856-870).  Inputs are bf16 ``[N,S,H]`` /
+    ``[N,H]``; returns (CLS ``[N,H]`` bf16, saves).  ``word_len`` = T - 1 token rows taken from each source."""
     N, S, H = g_out.shape
     I = cfg["I"]
     dev = g_out.device
@@ -271,16 +269,19 @@ def cls_lyx_head_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool,
     X = E._empty((N, L3, H), BF16, dev)
     for j, src in enumerate((g_out, s_out, c_hid)):
         ops.copy_rows(src.contiguous(), S, 1, X, L3, j * word_len, N, word_len, H)
+    saves = []
     for i in range(n_layers):
         pfx = "cls_layer_lyx.%d." % i
         xa = pfx + "cross_attention."
+        sv = {} if want_saves else None
         q = E._empty((N, H), BF16, dev)
         ops.gemm(cls, ps.bf16(xa + "q_proj.weight"), q, N, H, H, bias=ps.f32(xa + "q_proj.bias"))
         k, v = E._empty((N, L3, H), BF16, dev), E._empty((N, L3, H), BF16, dev)
         ops.gemm(X, ps.bf16(xa + "k_proj.weight"), k, N * L3, H, H, bias=ps.f32(xa + "k_proj.bias"))
         ops.gemm(X, ps.bf16(xa + "v_proj.weight"), v, N * L3, H, H, bias=ps.f32(xa + "v_proj.bias"))
         att = E._empty((N, H), BF16, dev)
-        ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads)             # word_mask is never forwarded (v10:856-857)
+        lse = E._empty((N, heads), F32, dev) if want_saves else None
+        ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads, lse)         # word_mask is never forwarded (v10:856-857)
         pre = E._empty((N, H), F32, dev)
         ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
                  in_op=1)                                                # + cls (residual of the LayerNorm)
@@ -288,8 +289,73 @@ def cls_lyx_head_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool,
         mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
         ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
                           cfg["eps"], y32=c32)
-        cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], None)
-    return cls
+        if sv is not None:
+            sv.update(cls_in=cls, q=q, k=k, v=v, att=att, lse=lse, pre=pre, mean=mean, rstd=rstd)
+        cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv)
+        saves.append(sv)
+    return cls, (saves, cat, X)
+
+
+def cls_lyx_head_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers=2, heads=8):
+    """Forward-only (scoring) form of the head."""
+    return _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers, heads, False)[0]
+
+
+class ClsLyxHeadFn(torch.autograd.Function):
+    """``cls_ensemble_1`` + 2 x ``ClsLayer_lyx`` with gradients for the head's parameters -- the frozen-encoder
+    training regime of ChunkAlign_CLS_enc4_align_ensemble (v10:891-975: the encoders run under ``no_grad``, so the
+    three token sources and the pooled vectors are constants here).
+
+    inputs : run (ClsHeadRun; ``run.heads``, ``run.n_layers``), word_len, g_out, s_out, c_hid, g_pool, s_pool, then
+             the parameters in ``run.names`` order
+    output : CLS_ensem [N,H] bf16"""
+
+    @staticmethod
+    def forward(ctx, run, word_len, g_out, s_out, c_hid, g_pool, s_pool, *params):
+        cls, (saves, cat, X) = _cls_lyx_forward(run.ps, run.cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool,
+                                                run.n_layers, run.heads, True)
+        ctx.run, ctx.saves, ctx.cat, ctx.X, ctx.word_len = run, saves, cat, X, word_len
+        return cls
+
+    @staticmethod
+    def backward(ctx, dcls):
+        run, ps, cfg = ctx.run, ctx.run.ps, ctx.run.cfg
+        H, I, heads = cfg["H"], cfg["I"], run.heads
+        N = ctx.cat.shape[0]
+        L3 = 3 * ctx.word_len
+        dev = dcls.device
+        grads = {}
+        d = dcls.to(BF16).contiguous()
+        for i in range(run.n_layers - 1, -1, -1):
+            pfx = "cls_layer_lyx.%d." % i
+            xa = pfx + "cross_attention."
+            sv = ctx.saves[i]
+            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads)
+            g = E._empty((N, H), BF16, dev)
+            dgam, dbet, dbo, dbq, dbk, dbv = E._zeros_many([(H,)] * 6, dev)
+            ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbo,
+                              N, H)
+            grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"] = dgam, dbet
+            grads[xa + "out_proj.bias"] = dbo
+            grads[xa + "out_proj.weight"] = E.wgrad(g, sv["att"], H, H, N)
+            datt = E._empty((N, H), BF16, dev)
+            ops.gemm(g, ps.bf16(xa + "out_proj.weight"), datt, N, H, H, b_mn=1)
+            dq = E._empty((N, H), BF16, dev)
+            dk, dv = E._empty((N, L3, H), BF16, dev), E._empty((N, L3, H), BF16, dev)
+            ops.cross_attn_q1_bwd(sv["q"], sv["k"], sv["v"], sv["att"], sv["lse"], datt, dq, dk, dv, N, L3, H, heads)
+            grads[xa + "k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3, bias_out=dbk)
+            grads[xa + "v_proj.weight"] = E.wgrad(dv, ctx.X, H, H, N * L3, bias_out=dbv)
+            grads[xa + "q_proj.weight"] = E.wgrad(dq, sv["cls_in"], H, H, N, bias_out=dbq)
+            grads[xa + "k_proj.bias"], grads[xa + "v_proj.bias"], grads[xa + "q_proj.bias"] = dbk, dbv, dbq
+            dnew = E._empty((N, H), BF16, dev)
+            ops.gemm(dq, ps.bf16(xa + "q_proj.weight"), dnew, N, H, H, b_mn=1, epi_in=g, in_op=1)   # + residual branch
+            d = dnew
+            ctx.saves[i] = None
+        dbe = E._zeros((H,), F32, dev)
+        grads["cls_ensemble_1.bias"] = dbe
+        grads["cls_ensemble_1.weight"] = E.wgrad(d, ctx.cat, H, 2 * H, N, bias_out=dbe)
+        out_p = [grads.get(n) for n in run.names]
+        return (None, None, None, None, None, None, None, *out_p)
 
 
 class ScorerFn(torch.autograd.Function):

@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .functions import (AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, EncoderFn, EncoderRun, ScorerFn,
+from .functions import (AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, ClsLyxHeadFn, EncoderFn, EncoderRun, ScorerFn,
                         cls_lyx_head_forward)
 from .modeling_bert import (AttentionsNotMaterialised, BertIntermediate, BertOutput, CaptionBertAttention,
                             _EncoderModelBase)
@@ -216,8 +216,9 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
     into ``CLS_ensem``; returns ``(CLS_ensem, align_loss, ([], None))``.  ``cls_layer``, ``classifier``,
     ``fusion_align`` and ``prior`` are part of the reference's state_dict but never called.
 
-    Forward / scoring only in this round: the backward of the ``ClsLayer_lyx`` head (training with frozen encoders,
-    SURVEY.md 8 f3) is not implemented, and asking for it raises instead of silently returning a constant."""
+    The encoders are frozen (``no_grad``, like the reference); ``CLS_ensem`` carries gradients to ``cls_ensemble_1``
+    and the ``ClsLayer_lyx`` stack (``functions.ClsLyxHeadFn``), which is what the mapping networks of
+    ``Abstract_Specific`` train through (modeling/modeling_ensemble.py:466-490)."""
 
     def __init__(self, global_enc, seq_enc, num_labels):
         super().__init__()
@@ -248,10 +249,6 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
                 head_mask=None, encoder_history_states=None, offsets=None, chunk_attention_mask=None,
                 gather_index=None, align_pos=None, total_label=None, abstract_hidden_states=None):
         ps, named = self._head_params()
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in named.values()):
-            raise NotImplementedError(
-                "modcr_b200: the backward of the ClsLayer_lyx head (frozen-encoder training) is not implemented; "
-                "call under torch.no_grad() / .eval() for scoring")
         check_no_dropout(self, self.global_enc.config)
         N, T = input_ids.shape
         want_block = total_label is not None
@@ -263,10 +260,16 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
                 input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
                 attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
                 head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
-            cfg = engine_cfg(self.global_enc.config)
-            CLS_ensem = cls_lyx_head_forward(ps, cfg, T - 1, g[0], s_out, chunk_hidden, g[1], s_pool,
-                                             n_layers=self.cls_layer_num, heads=8)
             align_loss = None
             if want_block:
                 align_loss, _ = AlignLossFn.apply(att.align_block, align_pos, total_label)
+        cfg = engine_cfg(self.global_enc.config)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in named.values()):
+            run = ClsHeadRun(ps, list(named.keys()), cfg, N, T, g[0].shape[1])
+            run.heads, run.n_layers = 8, self.cls_layer_num
+            CLS_ensem = ClsLyxHeadFn.apply(run, T - 1, g[0], s_out, chunk_hidden, g[1], s_pool, *named.values())
+        else:
+            with torch.no_grad():
+                CLS_ensem = cls_lyx_head_forward(ps, cfg, T - 1, g[0], s_out, chunk_hidden, g[1], s_pool,
+                                                 n_layers=self.cls_layer_num, heads=8)
         return CLS_ensem, align_loss, ([], None)

@@ -159,10 +159,16 @@ def align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T,
                                                       _p(dblock), N, T, R, _stream()), "align_softmax_ce_bwd")
 
 
-def cross_attn_q1_fwd(q, k, v, out, N, L, H, heads):
-    """cross_attention_lyx with one query per sequence (v10:692-797): bf16 q/out [N,H], k/v [N,L,H]."""
-    _lib.check(_lib.load().modcr_cross_attn_q1_fwd(_p(q), _p(k), _p(v), _p(out), N, L, H, heads, _stream()),
+def cross_attn_q1_fwd(q, k, v, out, N, L, H, heads, lse=None):
+    """cross_attention_lyx with one query per sequence (v10:692-797): bf16 q/out [N,H], k/v [N,L,H];
+    ``lse`` fp32 [N,heads] (optional) feeds the backward pass."""
+    _lib.check(_lib.load().modcr_cross_attn_q1_fwd(_p(q), _p(k), _p(v), _p(out), _p(lse), N, L, H, heads, _stream()),
                "cross_attn_q1_fwd")
+
+
+def cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads):
+    _lib.check(_lib.load().modcr_cross_attn_q1_bwd(_p(q), _p(k), _p(v), _p(out), _p(lse), _p(dout), _p(dq), _p(dk), _p(dv),
+                                                   N, L, H, heads, _stream()), "cross_attn_q1_bwd")
 
 
 def cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H):

@@ -204,11 +204,43 @@ def test_ensemble_head_forward_matches_oracle():
             B, T, err, float(c_ref.abs().max()), float(al), float(al_ref)))
         assert err < 5e-2 and nerr(cls, c_ref) < 2e-2
         assert abs(float(al) - float(al_ref)) < 1e-2
-    # the head has no backward yet: asking for one must fail loudly, not return a constant
+    # frozen-encoder training regime: gradients of the head's parameters against autograd of the oracle
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], token_type_ids=bd["token_type_ids"],
-          offsets=b["offsets"], chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"])
+    b = synth.make_batch(B=2, T=24, R=7, seed=3)
+    bd = synth.to_device(b, DEV)
+    proj = torch.randn(8, 768, generator=torch.Generator().manual_seed(5))
+    cls = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], token_type_ids=bd["token_type_ids"],
+            offsets=b["offsets"], chunk_attention_mask=bd["chunk_attention_mask"], gather_index=b["gather_index"])[0]
+    assert cls.requires_grad
+    (cls.float() * proj.to(DEV)).sum().backward()
+    sdr = {k: v.clone() for k, v in sd.items()}
+    head = [k for k in sdr if (k.startswith("cls_ensemble_1.") or k.startswith("cls_layer_lyx."))
+            and torch.is_floating_point(sdr[k])]
+    for k in head:
+        sdr[k].requires_grad_(True)
+    bb = dict(b)
+    bb["total_label"] = None
+    c_ref, _ = restate.chunkalign_ensemble_forward(sdr, CFG, bb, None)
+    (c_ref * proj).sum().backward()
+    named = dict(m.named_parameters())
+    errs = {}
+    for k in head:
+        gr = sdr[k].grad
+        if gr is None:                       # never-called parameters (inherited attention.*, ensemble, dense)
+            assert named[k].grad is None, k
+            continue
+        assert named[k].grad is not None, k
+        if k.endswith("cross_attention.k_proj.bias"):
+            # softmax is invariant to a shift of every score, so the exact gradient of the key bias is 0: compare
+            # against the scale of the value-bias gradient instead of the reference's rounding noise
+            vb = sdr[k.replace("k_proj", "v_proj")].grad.norm()
+            assert float(named[k].grad.float().cpu().norm()) < 2e-2 * float(vb), k
+            continue
+        errs[k] = l2err(named[k].grad, gr)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("ensemble head grad rel-L2 err (worst):", {k: round(v, 4) for k, v in worst})
+    assert len(errs) >= 28 and max(errs.values()) < 0.1, worst
+    assert all(p_.grad is None for k, p_ in named.items() if k.startswith("global_enc.") or k.startswith("seq_enc."))
 
 
 def test_oscar_for_multiple_choice_matches_restated_scorer():
