@@ -149,6 +149,12 @@ typedef struct modcr_attn_desc {
   void* dqkv;             /* backward: bf16 [N,S,3H] */
   void* dpkv;             /* backward: bf16 [N,P,2H] */
   float* dq_ws;           /* backward workspace, modcr_workspace_bytes(1, {N,S,heads}) */
+  /* training-mode dropout of the attention probabilities (modeling_bert.py:62, v10:94): softmax -> dropout -> P V, the
+   * returned text->region probabilities are post-dropout.  mask = hash(*drop_seed, drop_site, (n, head, q, key));
+   * drop_p = 0 disables it.  The backward pass must be given the same (seed, site, p). */
+  const uint32_t* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 } modcr_attn_desc;
 int modcr_prefix_attn_fwd(const modcr_attn_desc* d, void* stream);
 int modcr_prefix_attn_bwd(const modcr_attn_desc* d, void* stream);
@@ -166,23 +172,35 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
                                void* stream);
 
+/* Training-mode dropout of the hidden-state sites (a_transformers/modeling_bert.py:209, 371, 449;
+ * modeling_transfomres.py:681; v10:343, 832, 866): out16 = in16 * m (bf16, may alias), io32 = io32 * m (+ res32),
+ * m = keep / (1 - p) with keep(seed, site, element index) a counter-based hash -- the backward pass regenerates the mask
+ * from the same (seed, site).  `seed` points to one uint32 in device memory (so a replayed CUDA graph can advance it). */
+int modcr_dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed,
+                  uint32_t site, float p, void* stream);
+
 /* cross_attention_lyx with a single query per sequence (ClsLayer_lyx, modeling/modeling_vcr_chunkalign_v10.py:692-797,
  * 856-857): out[n] = concat_h softmax_l(q_h[n] . k_h[n,l] / sqrt(d_h)) v_h[n,l].  q, out [N,H]; k, v [N,L,H]; all bf16.
  * No mask (the reference never forwards word_mask), tau = 1, dropout p = 0.  lse (optional, fp32 [N,heads]) is the
  * per-head log-sum-exp the backward pass needs; the backward (autograd of v10:710-797) returns dq [N,H], dk, dv
  * [N,L,H] in bf16. */
 int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t N, int32_t L,
-                            int32_t H, int32_t heads, void* stream);
+                            int32_t H, int32_t heads, const uint32_t* drop_seed, uint32_t drop_site, float drop_p,
+                            void* stream);
 int modcr_cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse,
                             const void* dout, void* dq, void* dk, void* dv, int32_t N, int32_t L, int32_t H,
-                            int32_t heads, void* stream);
+                            int32_t heads, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
 
 /* ClsLayer2 attention pooling (v10:816-829). q [N,H], k [N,L,H] bf16 (qk_f32=0) or fp32 (qk_f32=1: the unscaled
- * 768-dim scores are the most rounding-sensitive spot of the path), mask fp32 [N,L] additive. */
+ * 768-dim scores are the most rounding-sensitive spot of the path), mask fp32 [N,L] additive.  drop_*: training-mode
+ * dropout of the attention weights (v10:828; drop_p = 0 disables it; w is returned undropped, the pooled vector uses
+ * the dropped weights). */
 int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,
-                            int32_t N, int32_t L, int32_t H, void* stream);
+                            int32_t N, int32_t L, int32_t H, const uint32_t* drop_seed, uint32_t drop_site, float drop_p,
+                            void* stream);
 int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int32_t qk_f32, const float* w, void* dq,
-                            void* dk, int32_t N, int32_t L, int32_t H, void* stream);
+                            void* dk, int32_t N, int32_t L, int32_t H, const uint32_t* drop_seed, uint32_t drop_site,
+                            float drop_p, void* stream);
 
 /* Fused multiple-choice classifier + cross-entropy (v10:1063-1069, 363-373;
  * modeling/modeling_ensemble.py:511-536; modeling/modeling_bert.py:553-567, 690-710). */

@@ -31,7 +31,8 @@ class AttnDesc(C.Structure):
                 ("scale", c_float),
                 ("qkv", c_void_p), ("pkv", c_void_p), ("kbias", c_void_p), ("cbits", c_void_p), ("cwords", c_i32),
                 ("ctx", c_void_p), ("lse", c_void_p), ("probs_img", c_void_p),
-                ("dctx", c_void_p), ("dalign", c_void_p), ("dqkv", c_void_p), ("dpkv", c_void_p), ("dq_ws", c_void_p)]
+                ("dctx", c_void_p), ("dalign", c_void_p), ("dqkv", c_void_p), ("dpkv", c_void_p), ("dq_ws", c_void_p),
+                ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float)]
 
 
 class ScorerDesc(C.Structure):
@@ -69,12 +70,15 @@ SIGNATURES = {
                                    c_i32, c_i32, c_void_p],
     "modcr_align_softmax_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i32, c_i32, c_i32,
                                    c_void_p],
-    "modcr_cross_attn_q1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p],
+    "modcr_dropout": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, C.c_uint32, c_float, c_void_p],
+    "modcr_cross_attn_q1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p,
+                                C.c_uint32, c_float, c_void_p],
     "modcr_cross_attn_q1_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_i32, c_i32, c_i32, c_i32, c_void_p],
-    "modcr_cls_pool_attn_fwd": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p],
+                                c_i32, c_i32, c_i32, c_i32, c_void_p, C.c_uint32, c_float, c_void_p],
+    "modcr_cls_pool_attn_fwd": [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p,
+                                C.c_uint32, c_float, c_void_p],
     "modcr_cls_pool_attn_bwd": [c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
-                                c_void_p],
+                                c_void_p, C.c_uint32, c_float, c_void_p],
     "modcr_mc_scorer_ce_fwd": [C.POINTER(ScorerDesc), c_void_p],
     "modcr_mc_scorer_ce_bwd": [C.POINTER(ScorerDesc), c_void_p],
     "modcr_cast_pad": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i32, c_i64, c_void_p],

@@ -57,7 +57,19 @@ struct AttnParams {
   bf16* dqkv;
   bf16* dpkv;
   float* dq_ws;
+  // training-mode dropout of the attention probabilities (modeling_bert.py:62, v10:94): keep(seed, site, element)
+  const uint32_t* drop_seed;   // device pointer to the step's seed; nullptr / drop_thr == 0: no dropout
+  uint32_t drop_site, drop_thr;
+  float drop_inv;              // 1 / (1 - p)
+  int seq_first;               // shared-memory key rows are [sequence ; prefix] (persistent forward) instead of [prefix ; sequence]
 };
+
+// logical key id of shared-memory key row kk (same in every kernel, whatever its row order): sequence key j -> j,
+// prefix key j -> S + j
+DEVINL uint32_t drop_key_id(const AttnParams& p, int kk) {
+  if (p.seq_first) return (uint32_t)kk;
+  return kk < p.Ppad ? (uint32_t)(p.S + kk) : (uint32_t)(kk - p.Ppad);
+}
 
 template <int W>
 DEVINL void tmem_ld_cols(uint32_t taddr, float* v) {
@@ -126,9 +138,11 @@ struct FwdLayout {
   int off_p[8];                          // P blocks (16 KB each); block 0 overlays Q, block 1 overlays K when it fits
 };
 
+// `drow` = ((n * heads + h) * S + q) * (S + P): the row's base index into the dropout mask; `dseed` the step's seed
 template <int MODE, int W, int PASS>
 DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float* sBias, uint8_t* blk, int c0, int row,
-                      int q, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row) {
+                      int q, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row, uint32_t drow = 0,
+                      uint32_t dseed = 0) {
   float v[W];
   tmem_ld_cols<W>(taddr + c0, v);
   float bb[W];
@@ -148,6 +162,11 @@ DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float
       sum += e;
       v[j] = e;
     }
+    if (p.drop_thr != 0) {   // uniform: P V uses the dropped probabilities, the row sum the undropped ones
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        v[j] = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, c0 + j), p.drop_thr) ? v[j] * p.drop_inv : 0.f;
+    }
     const int piece0 = (c0 & 63) >> 3;
 #pragma unroll
     for (int j = 0; j < W / 8; ++j) {
@@ -163,8 +182,11 @@ DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const int kk = c0 + j;
-        if (kk >= p.T && kk < p.S)
-          pimg_row[kk - p.T] = fast_ex2(masked_s2<MODE>(v[j], c1, bb[j], kk, q, q_txt, p.T, w) - m) * inv;
+        if (kk >= p.T && kk < p.S) {
+          float pr = fast_ex2(masked_s2<MODE>(v[j], c1, bb[j], kk, q, q_txt, p.T, w) - m) * inv;
+          if (p.drop_thr != 0) pr = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, kk), p.drop_thr) ? pr * p.drop_inv : 0.f;
+          pimg_row[kk - p.T] = pr;
+        }
       }
     }
   }
@@ -263,6 +285,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool alive = q < p.S;
     const bool warp_alive = (qt * 128 + warp * 32) < p.S;
     const bool q_txt = q < p.T;
+    const uint32_t dseed = p.drop_thr != 0 ? __ldg(p.drop_seed) : 0u;
+    const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
     float* pimg_row = nullptr;
@@ -276,32 +300,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const int full = p.Kp & ~31;
       for (int c0 = 0; c0 < full; c0 += 32) {
         const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-        fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row, drow, dseed);
       }
       if (full < p.Kp) {
         const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-        fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row);
+        fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row, drow, dseed);
       }
       for (int c0 = 0; c0 < full; c0 += 32) {
         const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
         fwd_chunk<MODE, 32, 2>(p, c1, taddr, sBias, smem + lay.off_p[c0 >> 6], c0, row, q, q_txt, w, m, sum, inv,
-                               pimg_row);
+                               pimg_row, drow, dseed);
       }
       if (full < p.Kp) {
         const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
         fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, smem + lay.off_p[full >> 6], full, row, q, q_txt, w, m, sum, inv,
-                               pimg_row);
+                               pimg_row, drow, dseed);
       }
       inv = sum > 0.f ? 1.0f / sum : 0.f;
       if (p.probs_img != nullptr) {  // uniform over the CTA
         const int first = (p.T >> 5) << 5;
         for (int c0 = first; c0 < full; c0 += 32) {
           const uint32_t w = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-          fwd_chunk<MODE, 32, 3>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row);
+          fwd_chunk<MODE, 32, 3>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, w, m, sum, inv, pimg_row, drow, dseed);
         }
         if (full < p.Kp && full + 16 > first) {
           const uint32_t w = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-          fwd_chunk<MODE, 16, 3>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row);
+          fwd_chunk<MODE, 16, 3>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, w, m, sum, inv, pimg_row, drow, dseed);
         }
       }
       if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
@@ -521,6 +545,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const bool alive = q < p.S;
     const bool warp_alive = (g * 128 + (warp & 3) * 32) < p.S;
     const bool q_txt = q < p.T;
+    const uint32_t dseed = p.drop_thr != 0 ? __ldg(p.drop_seed) : 0u;
     const bool active = g == 0 || two;       // group B without rows only idles
     const uint32_t bar_id = 1 + g;
     const bool issuer = gt == 0;
@@ -566,6 +591,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const int n = w / p.heads, h = w - n * p.heads;
         const int st = i & 1;
         uint8_t* stage = smem + st * lay.stage_bytes;
+        const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
         // ---- per-key bias of this sequence, double-buffered by item parity: a slower thread of the group may still
         // be reading the previous item's values, but everyone is past the ones of two items ago (barrier below)
         float* sBias = sBiasAll + (g * 2 + (i & 1)) * 256;
@@ -590,11 +616,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         if (warp_alive) {
           for (int c0 = 0; c0 < full; c0 += 32) {
             const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
-            fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            fwd_chunk<MODE, 32, 1>(p, c1, taddr, sBias, nullptr, c0, row, q, q_txt, wd, m, sum, inv, pimg_row, drow, dseed);
           }
           if (full < p.Kp) {
             const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
-            fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            fwd_chunk<MODE, 16, 1>(p, c1, taddr, sBias, nullptr, full, row, q, q_txt, wd, m, sum, inv, pimg_row, drow, dseed);
           }
         }
         // ---- epilogue of the previous item (its P V ran under pass 1)
@@ -608,13 +634,13 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
             const int b = c0 >> 6;
             uint8_t* blk = g ? sPB + b * 8192 : stage + (b == 0 ? 0 : (b == 1 ? lay.off_qb : lay.off_k));
-            fwd_chunk<MODE, 32, 2>(p, c1, taddr, sBias, blk, c0, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            fwd_chunk<MODE, 32, 2>(p, c1, taddr, sBias, blk, c0, row, q, q_txt, wd, m, sum, inv, pimg_row, drow, dseed);
           }
           if (full < p.Kp) {
             const uint32_t wd = (crow != nullptr && (full >> 5) < p.cwords) ? __ldg(crow + (full >> 5)) : 0u;
             const int b = full >> 6;
             uint8_t* blk = g ? sPB + b * 8192 : stage + (b == 0 ? 0 : (b == 1 ? lay.off_qb : lay.off_k));
-            fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, blk, full, row, q, q_txt, wd, m, sum, inv, pimg_row);
+            fwd_chunk<MODE, 16, 2>(p, c1, taddr, sBias, blk, full, row, q, q_txt, wd, m, sum, inv, pimg_row, drow, dseed);
           }
           inv = sum > 0.f ? 1.0f / sum : 0.f;
           if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
@@ -641,8 +667,11 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float pr = 0.f;
-                if (j < wcols)
+                if (j < wcols) {
                   pr = fast_ex2(masked_s2<MODE>(v[j], c1, sBias[c0 + j], c0 + j, q, q_txt, p.T, wd) - m) * inv;
+                  if (p.drop_thr != 0)   // the alignment head consumes the post-dropout probabilities (v10:982)
+                    pr = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, c0 + j), p.drop_thr) ? pr * p.drop_inv : 0.f;
+                }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile + lane * 128 + ((j ^ lane) << 2)), "f"(pr) : "memory");
               }
               __syncwarp();
@@ -693,7 +722,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 template <int MODE, bool SAFE, bool DALIGN>
 DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, const float* sBias, int c0, int kk0,
                            int nb, int q, bool q_txt, uint32_t w, float lse2, float delta_s, const float* darow,
-                           uint32_t* pp, uint32_t* dd) {
+                           uint32_t* pp, uint32_t* dd, uint32_t drow = 0, uint32_t dseed = 0) {
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {   // 4 columns at a time keeps the live register set small
     const float4 b4 = *reinterpret_cast<const float4*>(sBias + kk0 + 4 * g4);
@@ -712,7 +741,14 @@ DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, 
       if (DALIGN) {
         if (kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
       }
+      float pd = pr[e];
+      if (p.drop_thr != 0) {   // uniform: dV uses D o P, dS uses D o dP (D = keep / (1 - p)); delta is unchanged
+        const float dm = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, kk), p.drop_thr) ? p.drop_inv : 0.f;
+        pd *= dm;
+        g *= dm;
+      }
       ds[e] = pr[e] * fmaf(g, p.scale, -delta_s);   // dS = P (dP - delta) scale
+      pr[e] = pd;
     }
     pp[2 * g4] = pack_bf16(pr[0], pr[1]);
     pp[2 * g4 + 1] = pack_bf16(pr[2], pr[3]);
@@ -919,6 +955,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int half = tid >> 7;   // key-column half of every 128-key block
     const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const size_t H3 = (size_t)3 * p.H;
+    const uint32_t dseed = p.drop_thr != 0 ? __ldg(p.drop_seed) : 0u;
 
     // everything a finished step leaves behind in TMEM: dQ of its q tile (when due) and, after the last q tile of a
     // key block, that block's dK (column half 0) / dV (half 1)
@@ -1002,6 +1039,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q = qt * 128 + row;
         const bool alive = q < p.S;
         const bool q_txt = q < p.T;
+        const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
         const float lse2 = sLse[q], delta = sDelta[q];
         const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
         const float* darow =
@@ -1040,17 +1078,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             if (img) {
               if (safe)
                 bwd_chunk_math<MODE, true, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                 pp, dd);
+                                                 pp, dd, drow, dseed);
               else
                 bwd_chunk_math<MODE, false, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                  pp, dd);
+                                                  pp, dd, drow, dseed);
             } else {
               if (safe)
                 bwd_chunk_math<MODE, true, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                  pp, dd);
+                                                  pp, dd, drow, dseed);
               else
                 bwd_chunk_math<MODE, false, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s,
-                                                   darow, pp, dd);
+                                                   darow, pp, dd, drow, dseed);
             }
           }
           if (i == 0 && step > 0) {
@@ -1122,6 +1160,21 @@ static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
   p.lse = a.lse; p.probs_img = a.probs_img;
   p.ctx = (const bf16*)a.ctx; p.dctx = (const bf16*)a.dctx; p.dalign = a.dalign;
   p.dqkv = (bf16*)a.dqkv; p.dpkv = (bf16*)a.dpkv; p.dq_ws = a.dq_ws;
+  p.seq_first = 0;
+  p.drop_seed = a.drop_seed; p.drop_site = a.drop_site; p.drop_thr = 0; p.drop_inv = 1.f;
+  if (a.drop_p > 0.f) {
+    if (!(a.drop_p < 1.f) || a.drop_seed == nullptr) {
+      set_error("prefix_attn: dropout needs 0 <= p < 1 and a device seed pointer");
+      return MODCR_ERR_SHAPE;
+    }
+    if ((double)a.N * a.heads * a.S * (a.S + a.P) >= 4294967296.0) {
+      set_error("prefix_attn: dropout mask index exceeds 32 bits");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    p.drop_thr = (uint32_t)fmin(4294967295.0, (double)a.drop_p * 4294967296.0);
+    if (p.drop_thr == 0) p.drop_thr = 1;
+    p.drop_inv = 1.0f / (1.0f - a.drop_p);
+  }
   if (a.lse == nullptr || a.ctx == nullptr) {
     set_error("prefix_attn: null ctx / lse pointer");
     return MODCR_ERR_SHAPE;
@@ -1216,6 +1269,7 @@ int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
     if (smem <= 232448) {
       AttnParams pp = p;
       pp.Kp = kp2;
+      pp.seq_first = 1;
       CUtensorMap tmQKV, tmTail, tmPKV, tmA, tmB;
       rc = make_tmap_3d(&tmQKV, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, 64, 64);
       if (rc) return rc;

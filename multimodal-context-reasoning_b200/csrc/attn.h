@@ -29,6 +29,10 @@ struct AttnDesc {
   void* dqkv = nullptr;                 // bf16 [N,S,3H]
   void* dpkv = nullptr;                 // bf16 [N,P,2H]
   float* dq_ws = nullptr;               // fp32 [N*heads, S, 64] workspace (only touched when Kp > 128)
+  // training-mode dropout of the attention probabilities: mask = f(*drop_seed, drop_site, (n, head, q, key))
+  const uint32_t* drop_seed = nullptr;  // device pointer to the step's seed
+  uint32_t drop_site = 0;
+  float drop_p = 0.f;
 };
 
 int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream);

@@ -168,6 +168,7 @@ static void to_attn(const modcr_attn_desc* d, modcr::AttnDesc& a) {
   a.qkv = d->qkv; a.pkv = d->pkv; a.kbias = d->kbias; a.cbits = d->cbits; a.cwords = d->cwords;
   a.ctx = d->ctx; a.lse = d->lse; a.probs_img = d->probs_img;
   a.dctx = d->dctx; a.dalign = d->dalign; a.dqkv = d->dqkv; a.dpkv = d->dpkv; a.dq_ws = d->dq_ws;
+  a.drop_seed = d->drop_seed; a.drop_site = d->drop_site; a.drop_p = d->drop_p;
 }
 int modcr_prefix_attn_fwd(const modcr_attn_desc* d, void* stream) {
   ARCH_OR_RETURN();
@@ -209,27 +210,37 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
   return modcr::align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T, R, S(stream));
 }
 
-int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t N, int32_t L,
-                            int32_t H, int32_t heads, void* stream) {
+int modcr_dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed,
+                  uint32_t site, float p, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cross_attn_q1_fwd(q, k, v, out, lse, N, L, H, heads, S(stream));
+  return modcr::dropout(in16, out16, io32, res32, n, seed, site, p, S(stream));
+}
+
+int modcr_cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t N, int32_t L,
+                            int32_t H, int32_t heads, const uint32_t* drop_seed, uint32_t drop_site, float drop_p,
+                            void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::cross_attn_q1_fwd(q, k, v, out, lse, N, L, H, heads, drop_seed, drop_site, drop_p, S(stream));
 }
 int modcr_cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse,
                             const void* dout, void* dq, void* dk, void* dv, int32_t N, int32_t L, int32_t H,
-                            int32_t heads, void* stream) {
+                            int32_t heads, const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads, S(stream));
+  return modcr::cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads, drop_seed, drop_site, drop_p,
+                                  S(stream));
 }
 
 int modcr_cls_pool_attn_fwd(const void* q, const void* k, int32_t qk_f32, const float* mask, float* w, void* pooled,
-                            int32_t N, int32_t L, int32_t H, void* stream) {
+                            int32_t N, int32_t L, int32_t H, const uint32_t* drop_seed, uint32_t drop_site, float drop_p,
+                            void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cls_pool_attn_fwd(q, k, qk_f32, mask, w, pooled, N, L, H, S(stream));
+  return modcr::cls_pool_attn_fwd(q, k, qk_f32, mask, w, pooled, N, L, H, drop_seed, drop_site, drop_p, S(stream));
 }
 int modcr_cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int32_t qk_f32, const float* w, void* dq,
-                            void* dk, int32_t N, int32_t L, int32_t H, void* stream) {
+                            void* dk, int32_t N, int32_t L, int32_t H, const uint32_t* drop_seed, uint32_t drop_site,
+                            float drop_p, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::cls_pool_attn_bwd(dpooled, q, k, qk_f32, w, dq, dk, N, L, H, S(stream));
+  return modcr::cls_pool_attn_bwd(dpooled, q, k, qk_f32, w, dq, dk, N, L, H, drop_seed, drop_site, drop_p, S(stream));
 }
 
 static void to_scorer(const modcr_scorer_desc* d, modcr::ScorerDesc& s) {

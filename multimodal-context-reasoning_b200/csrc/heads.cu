@@ -301,11 +301,14 @@ constexpr int CP_WARPS = 16;   // one CTA per sequence: 512 threads keep enough 
 template <bool F32>
 __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_fwd_kernel(const void* __restrict__ q, const void* __restrict__ k,
                                                                      const float* __restrict__ mask, float* __restrict__ w,
-                                                                     bf16* __restrict__ pooled, int L, int H) {
+                                                                     bf16* __restrict__ pooled, int L, int H,
+                                                                     const uint32_t* __restrict__ dseed_ptr, uint32_t dsite,
+                                                                     uint32_t dthr, float dinv) {
   extern __shared__ float sm[];
   float* qs = sm;
   float* sc = qs + H;
   float* wm = sc + ((L + 3) & ~3);
+  const uint32_t dseed = dthr != 0 ? __ldg(dseed_ptr) : 0u;   // dropout of the attention weights (v10:828)
   float* wsm = wm + CP_WARPS;
   float* part = wsm + CP_WARPS;
   const int n = blockIdx.x;
@@ -339,11 +342,13 @@ __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_fwd_kernel(const void*
     const float pe = expf(d - mn);
     se = fmaf(se, resc, pe);
     m = mn;
+    // the pooled vector uses the dropped weight, the normaliser the undropped one
+    const float ped = (dthr != 0 && !drop_keep(dseed, dsite, (uint32_t)(n * L + l), dthr)) ? 0.f : pe * dinv;
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(acc[i][j], resc, pe * f[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(acc[i][j], resc, ped * f[i][j]);
       }
   }
   if (lane == 0) {
@@ -381,9 +386,12 @@ __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_fwd_kernel(const void*
 template <bool F32>
 __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_bwd_kernel(const bf16* __restrict__ dpooled, const void* __restrict__ q,
                                                            const void* __restrict__ k, const float* __restrict__ w,
-                                                           bf16* __restrict__ dq, bf16* __restrict__ dk, int L, int H) {
+                                                           bf16* __restrict__ dq, bf16* __restrict__ dk, int L, int H,
+                                                           const uint32_t* __restrict__ dseed_ptr, uint32_t dsite, uint32_t dthr,
+                                                           float dinv) {
   extern __shared__ float sm[];
   __shared__ float sh[CP_WARPS];
+  const uint32_t dseed = dthr != 0 ? __ldg(dseed_ptr) : 0u;
   const int Lp = (L + 3) & ~3;
   float* qs = sm;
   float* dps = qs + H;
@@ -414,6 +422,8 @@ __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_bwd_kernel(const bf16*
         for (int j = 0; j < 8; ++j) d = fmaf(f[j], dd[j], d);
       }
     d = wsum(d);
+    // dropout: pooled = sum_l D_l w_l k_l  =>  d w_l = D_l (dpooled . k_l)
+    if (dthr != 0) d = drop_keep(dseed, dsite, (uint32_t)(n * L + l), dthr) ? d * dinv : 0.f;
     if (lane == 0) dsv[l] = d;
   }
   __syncthreads();
@@ -428,7 +438,9 @@ __global__ void __launch_bounds__(CP_WARPS * 32) cls_pool_bwd_kernel(const bf16*
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   for (int l = warp; l < L; l += CP_WARPS) {
-    const float p = wv[l], ds = dsv[l];
+    float p = wv[l];
+    const float ds = dsv[l];
+    if (dthr != 0) p = drop_keep(dseed, dsite, (uint32_t)(n * L + l), dthr) ? p * dinv : 0.f;   // value path: D_l w_l
 #pragma unroll
     for (int i = 0; i < CP_MAXV; ++i)
       if (i < nv) {
@@ -471,8 +483,20 @@ static int cls_pool_check(int N, int L, int H, size_t smem, const char* what) {
   return MODCR_OK;
 }
 
+static uint32_t drop_threshold(float p) {
+  if (!(p > 0.f)) return 0u;
+  const uint32_t t = (uint32_t)fmin(4294967295.0, (double)p * 4294967296.0);
+  return t == 0 ? 1u : t;
+}
+
 int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
-                      int H, cudaStream_t st) {
+                      int H, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st) {
+  const uint32_t dthr = drop_threshold(dp);
+  const float dinv = dthr ? 1.0f / (1.0f - dp) : 1.0f;
+  if (dthr && (dseed == nullptr || !(dp < 1.f))) {
+    set_error("cls_pool_attn_fwd: dropout needs a device seed pointer and p < 1");
+    return MODCR_ERR_SHAPE;
+  }
   const size_t smem = ((size_t)H + ((L + 3) & ~3) + 2 * CP_WARPS + CP_WARPS * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_fwd")) return rc;
   static size_t attr = 0;
@@ -482,14 +506,20 @@ int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mas
     attr = smem;
   }
   if (qk_f32)
-    cls_pool_fwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
+    cls_pool_fwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H, dseed, dsite, dthr, dinv);
   else
-    cls_pool_fwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H);
+    cls_pool_fwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>(q, k, mask, w, (bf16*)pooled, L, H, dseed, dsite, dthr, dinv);
   return check_launch("cls_pool_attn_fwd");
 }
 
 int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,
-                      int N, int L, int H, cudaStream_t st) {
+                      int N, int L, int H, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st) {
+  const uint32_t dthr = drop_threshold(dp);
+  const float dinv = dthr ? 1.0f / (1.0f - dp) : 1.0f;
+  if (dthr && (dseed == nullptr || !(dp < 1.f))) {
+    set_error("cls_pool_attn_bwd: dropout needs a device seed pointer and p < 1");
+    return MODCR_ERR_SHAPE;
+  }
   const size_t smem = (2 * (size_t)H + 2 * ((L + 3) & ~3) + CP_WARPS * (size_t)H) * 4;
   if (int rc = cls_pool_check(N, L, H, smem, "cls_pool_attn_bwd")) return rc;
   static size_t attr = 0;
@@ -499,9 +529,11 @@ int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_
     attr = smem;
   }
   if (qk_f32)
-    cls_pool_bwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
+    cls_pool_bwd_kernel<true><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H, dseed,
+                                                             dsite, dthr, dinv);
   else
-    cls_pool_bwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H);
+    cls_pool_bwd_kernel<false><<<N, CP_WARPS * 32, smem, st>>>((const bf16*)dpooled, q, k, w, (bf16*)dq, (bf16*)dk, L, H, dseed,
+                                                              dsite, dthr, dinv);
   return check_launch("cls_pool_attn_bwd");
 }
 
@@ -518,9 +550,13 @@ template <int VEC>   // 16-byte vectors per lane: H = 32 * 8 * VEC
 __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
                                                                           const bf16* __restrict__ v, bf16* __restrict__ out,
                                                                           float* __restrict__ lse, int L, int H,
-                                                                          int lanes_per_head, float scaling) {
+                                                                          int lanes_per_head, float scaling,
+                                                                          const uint32_t* __restrict__ dseed_ptr, uint32_t dsite,
+                                                                          uint32_t dthr, float dinv) {
   extern __shared__ float sm[];
   float* qs = sm;
+  const uint32_t dseed = dthr != 0 ? __ldg(dseed_ptr) : 0u;   // attention-probability dropout (v10:785, p = 0.1)
+  const int nheads = 32 / lanes_per_head;
   float* wm = qs + H;
   float* wsm = wm + XA_WARPS * 32;
   float* part = wsm + XA_WARPS * 32;
@@ -554,8 +590,10 @@ __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_fwd_kernel(const 
     const float pe = expf(d - mn);
     se = fmaf(se, resc, pe);
     m = mn;
+    const float ped = (dthr != 0 && !drop_keep(dseed, dsite, (uint32_t)((n * nheads + lane / lanes_per_head) * L + l), dthr))
+                          ? 0.f : pe * dinv;
 #pragma unroll
-    for (int j = 0; j < E; ++j) acc[j] = fmaf(acc[j], resc, pe * vf[j]);
+    for (int j = 0; j < E; ++j) acc[j] = fmaf(acc[j], resc, ped * vf[j]);
   }
   wm[warp * 32 + lane] = m;
   wsm[warp * 32 + lane] = se;
@@ -590,9 +628,12 @@ __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_bwd_kernel(const 
                                                                           const float* __restrict__ lse, const bf16* __restrict__ dout,
                                                                           bf16* __restrict__ dq, bf16* __restrict__ dk,
                                                                           bf16* __restrict__ dv, int L, int H, int lanes_per_head,
-                                                                          float scaling) {
+                                                                          float scaling, const uint32_t* __restrict__ dseed_ptr,
+                                                                          uint32_t dsite, uint32_t dthr, float dinv) {
   extern __shared__ float sm[];
   float* part = sm;
+  const uint32_t dseed = dthr != 0 ? __ldg(dseed_ptr) : 0u;
+  const int nheads = 32 / lanes_per_head;
   const int n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int E = 8 * VEC;
@@ -628,12 +669,18 @@ __global__ void __launch_bounds__(XA_WARPS * 32) cross_attn_q1_bwd_kernel(const 
       dp += __shfl_xor_sync(0xffffffffu, dp, o);
     }
     const float pr = expf(sdot - lse_h);
+    float prd = pr;            // value path uses D o P, the score gradient D o dP (delta = dout . out is unchanged)
+    if (dthr != 0) {
+      const float dm = drop_keep(dseed, dsite, (uint32_t)((n * nheads + lane / lanes_per_head) * L + l), dthr) ? dinv : 0.f;
+      prd *= dm;
+      dp *= dm;
+    }
     const float ds = pr * (dp - delta);
     float okk[E], ov[E];
 #pragma unroll
     for (int j = 0; j < E; ++j) {
       okk[j] = ds * ql[j];
-      ov[j] = pr * dol[j];
+      ov[j] = prd * dol[j];
       acc[j] = fmaf(ds, kf[j], acc[j]);
     }
 #pragma unroll
@@ -666,8 +713,15 @@ static int xa_check(int N, int L, int H, int heads, const char* what) {
 }
 
 int cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
-                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, cudaStream_t st) {
+                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, const uint32_t* dseed, uint32_t dsite,
+                      float dp, cudaStream_t st) {
   if (int rc = xa_check(N, L, H, heads, "cross_attn_q1_bwd")) return rc;
+  const uint32_t dthr = drop_threshold(dp);
+  const float dinv = dthr ? 1.0f / (1.0f - dp) : 1.0f;
+  if (dthr && (dseed == nullptr || !(dp < 1.f))) {
+    set_error("cross_attn_q1_bwd: dropout needs a device seed pointer and p < 1");
+    return MODCR_ERR_SHAPE;
+  }
   if (lse == nullptr) {
     set_error("cross_attn_q1_bwd: the forward pass must have written lse");
     return MODCR_ERR_SHAPE;
@@ -684,16 +738,22 @@ int cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* o
   if (E == 24)
     cross_attn_q1_bwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)out,
                                                                lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, L, H,
-                                                               hd / E, scaling);
+                                                               hd / E, scaling, dseed, dsite, dthr, dinv);
   else
     cross_attn_q1_bwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)out,
                                                                lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, L, H,
-                                                               hd / E, scaling);
+                                                               hd / E, scaling, dseed, dsite, dthr, dinv);
   return check_launch("cross_attn_q1_bwd");
 }
 
 int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int N, int L, int H, int heads,
-                      cudaStream_t st) {
+                      const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st) {
+  const uint32_t dthr = drop_threshold(dp);
+  const float dinv = dthr ? 1.0f / (1.0f - dp) : 1.0f;
+  if (dthr && (dseed == nullptr || !(dp < 1.f))) {
+    set_error("cross_attn_q1_fwd: dropout needs a device seed pointer and p < 1");
+    return MODCR_ERR_SHAPE;
+  }
   const int E = H / 32;
   const int hd = heads > 0 ? H / heads : 0;
   if (N <= 0 || L <= 0 || heads <= 0 || H % (32 * 8) != 0 || H % heads != 0 || (E != 24 && E != 32) || hd % E != 0 ||
@@ -712,10 +772,10 @@ int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, fl
   }
   if (E == 24)
     cross_attn_q1_fwd_kernel<3><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, lse,
-                                                               L, H, hd / E, scaling);
+                                                               L, H, hd / E, scaling, dseed, dsite, dthr, dinv);
   else
     cross_attn_q1_fwd_kernel<4><<<N, XA_WARPS * 32, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, lse,
-                                                               L, H, hd / E, scaling);
+                                                               L, H, hd / E, scaling, dseed, dsite, dthr, dinv);
   return check_launch("cross_attn_q1_fwd");
 }
 

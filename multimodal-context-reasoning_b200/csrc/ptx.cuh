@@ -330,6 +330,23 @@ DEVINL float4 lds128f(uint32_t addr) {
   return v;
 }
 
+// ------------------------------------------------------------------ dropout masks
+// Counter-based: keep(seed, site, idx) is a pure function of the step's seed (read from device memory so that a
+// replayed CUDA graph draws fresh masks), the call site and the element's logical index, so the backward pass
+// regenerates the mask of its forward instead of storing it.  32-bit integer hash ("lowbias32" finaliser).
+DEVINL uint32_t drop_hash(uint32_t seed, uint32_t site, uint32_t idx) {
+  uint32_t x = (idx ^ seed) * 0x9E3779B1u;
+  x ^= site * 0x85EBCA77u;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+// keep probability 1 - p  <=>  hash >= p * 2^32
+DEVINL bool drop_keep(uint32_t seed, uint32_t site, uint32_t idx, uint32_t thr) { return drop_hash(seed, site, idx) >= thr; }
+
 // byte offset of 16-byte piece `piece` (0..7) of row `row` inside a 128B-swizzled
 // [rows x 128 B] tile whose base is 1024 B aligned
 DEVINL uint32_t sw128_offset(uint32_t row, uint32_t piece) { return row * 128u + ((piece ^ (row & 7u)) << 4); }

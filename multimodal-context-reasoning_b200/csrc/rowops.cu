@@ -551,6 +551,42 @@ __global__ void __launch_bounds__(256) chunk_mean_kernel(bf16* __restrict__ q, i
   }
 }
 
+// ---------------------------------------------------------------------------- dropout (training mode)
+// Reference sites: BertEmbeddings / img_embedding dropout (a_transformers 209, transfomres 681), BertSelfOutput and
+// BertOutput (a_transformers 371, 449: LayerNorm(dropout(dense(x)) + residual)), the heads' hidden dropouts.
+//   out16 = in16 * m          (bf16, may alias)      io32 = io32 * m (+ res32)     m = keep / (1 - p), same mask for both
+__global__ void __launch_bounds__(256) dropout_kernel(const bf16* __restrict__ in16, bf16* __restrict__ out16,
+                                                      float* __restrict__ io32, const float* __restrict__ res32, int64_t nvec,
+                                                      const uint32_t* __restrict__ seed_ptr, uint32_t site, uint32_t thr,
+                                                      float inv_keep) {
+  const uint32_t seed = __ldg(seed_ptr);
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * blockDim.x) {
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = drop_keep(seed, site, (uint32_t)(v * 8 + j), thr) ? inv_keep : 0.f;
+    if (in16 != nullptr) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in16) + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= m[j];
+      reinterpret_cast<uint4*>(out16)[v] = pack8(f);
+    }
+    if (io32 != nullptr) {
+      float4 a = reinterpret_cast<float4*>(io32)[2 * v], b = reinterpret_cast<float4*>(io32)[2 * v + 1];
+      a.x *= m[0]; a.y *= m[1]; a.z *= m[2]; a.w *= m[3];
+      b.x *= m[4]; b.y *= m[5]; b.z *= m[6]; b.w *= m[7];
+      if (res32 != nullptr) {
+        const float4 ra = __ldg(reinterpret_cast<const float4*>(res32) + 2 * v);
+        const float4 rb = __ldg(reinterpret_cast<const float4*>(res32) + 2 * v + 1);
+        a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
+        b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
+      }
+      reinterpret_cast<float4*>(io32)[2 * v] = a;
+      reinterpret_cast<float4*>(io32)[2 * v + 1] = b;
+    }
+  }
+}
+
 // ============================================================================ host launchers
 static inline int blocks_for(int64_t work, int per_block, int cap = 148 * 16) {
   int64_t b = (work + per_block - 1) / per_block;
@@ -734,6 +770,21 @@ int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_
   dim3 grid(H / 64, N);
   chunk_mean_kernel<<<grid, 256, smem, st>>>((bf16*)q, ld, S, chunk_id, T, max_chunks);
   return check_launch("chunk_mean_q");
+}
+
+int dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed, uint32_t site,
+            float p, cudaStream_t st) {
+  if (n % 8 != 0 || seed == nullptr || !(p >= 0.f && p < 1.f) || (in16 == nullptr) != (out16 == nullptr) ||
+      (in16 == nullptr && io32 == nullptr)) {
+    set_error("dropout: n=%lld must be a multiple of 8, 0 <= p < 1, a seed pointer and at least one tensor are required",
+              (long long)n);
+    return MODCR_ERR_SHAPE;
+  }
+  if (n == 0) return MODCR_OK;
+  const uint32_t thr = (uint32_t)fmin(4294967295.0, (double)p * 4294967296.0);
+  dropout_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)in16, (bf16*)out16, io32, res32, n / 8, seed, site, thr,
+                                                         1.0f / (1.0f - p));
+  return check_launch("dropout");
 }
 
 }  // namespace modcr

@@ -52,15 +52,19 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
 
 // ClsLayer2 attention pooling (v10:816-829): w = softmax(q k^T + mask) (no 1/sqrt(d)), pooled = w k
 // q [N,H] and k [N,L,H] are bf16 (qk_f32 = 0) or fp32 (qk_f32 = 1)
+// training-mode dropout with a counter-based mask (seed read from device memory): out16 = in16 * m, io32 = io32 * m (+ res32)
+int dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed, uint32_t site,
+            float p, cudaStream_t st);
 // multi-head attention of one query per sequence over L key/value rows (cross_attention_lyx, v10:692-797)
 int cross_attn_q1_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int N, int L, int H, int heads,
-                      cudaStream_t st);
+                      const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st);
 int cross_attn_q1_bwd(const void* q, const void* k, const void* v, const void* out, const float* lse, const void* dout,
-                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, cudaStream_t st);
+                      void* dq, void* dk, void* dv, int N, int L, int H, int heads, const uint32_t* dseed, uint32_t dsite,
+                      float dp, cudaStream_t st);
 int cls_pool_attn_fwd(const void* q, const void* k, int qk_f32, const float* mask, float* w, void* pooled, int N, int L,
-                      int H, cudaStream_t st);
+                      int H, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st);
 int cls_pool_attn_bwd(const void* dpooled, const void* q, const void* k, int qk_f32, const float* w, void* dq, void* dk,
-                      int N, int L, int H, cudaStream_t st);
+                      int N, int L, int H, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st);
 
 // Fused small classifier + cross-entropy (+ binary_to_mp / argmax / matched):
 //   logits[r, c] = x[r,:] . W[c,:] + b[c]            x bf16 [rows,K], W fp32 [C,K], C <= 8

@@ -31,6 +31,48 @@ def _zeros(shape, dtype, dev):
     return torch.zeros(shape, dtype=dtype, device=dev)
 
 
+# -------------------------------------------------------------------------------------------- dropout state
+class Drop:
+    """Training-mode dropout of one forward/backward pair: probabilities, the step's seed (a device int32 tensor the
+    kernels read, so a replayed CUDA graph draws fresh masks) and the site-id base of the module.  Masks are a pure
+    function of (seed, site, element index) and are regenerated in the backward pass."""
+    __slots__ = ("p_hidden", "p_attn", "seed", "base")
+
+    def __init__(self, p_hidden, p_attn, seed, base):
+        self.p_hidden, self.p_attn, self.seed, self.base = float(p_hidden), float(p_attn), seed, int(base)
+
+    def site(self, layer, k):
+        return (self.base + layer * 8 + k) & 0x7FFFFFFF
+
+
+_RNG_STATE = {}
+
+
+def manual_seed(seed):
+    """Seed the dropout masks of every device (the state advances by an LCG step per encoder / head forward)."""
+    _RNG_STATE.clear()
+    _RNG_STATE["seed"] = int(seed) & 0x7FFFFFFF
+
+
+def next_seed(dev):
+    """Advance the per-device dropout state (on the device: capturable) and return a private copy for this pass."""
+    key = str(dev)
+    st = _RNG_STATE.get(key)
+    if st is None:
+        st = torch.full((1,), _RNG_STATE.get("seed", 0x2545F491), dtype=torch.int32, device=dev)
+        _RNG_STATE[key] = st
+    st.mul_(1664525).add_(1013904223)      # int32 wrap-around LCG
+    return st.clone()
+
+
+def make_drop(module_training, config_hidden_p, config_attn_p, dev, base):
+    """``None`` (no dropout arithmetic at all) unless the module is training with a non-zero probability."""
+    ph, pa = float(config_hidden_p or 0.0), float(config_attn_p or 0.0)
+    if not module_training or (ph <= 0.0 and pa <= 0.0):
+        return None
+    return Drop(ph, pa, next_seed(dev), base)
+
+
 def _zeros_many(shapes, dev):
     """fp32 tensors that must start at zero (atomically reduced bias / LayerNorm gradients, split-K wgrad outputs),
     cleared by ONE multi-tensor fill instead of one fill kernel each.  They stay separate allocations so that
@@ -136,7 +178,7 @@ def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None, b
 
 
 # -------------------------------------------------------------------------------------------- FFN block
-def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save):
+def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save, drop=None, site=0):
     """BertIntermediate + BertOutput (a_transformers/modeling_bert.py:434-437, 447-451).
     ``a`` is the bf16 tensor-core operand, ``a32`` the fp32 residual; returns ``(y, y32)``."""
     dev = a.device
@@ -145,7 +187,12 @@ def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save):
     u = _empty((M, I), BF16, dev) if save is not None else None
     ops.gemm(a, W1, gact, M, I, H, bias=ps.f32(pfx + "intermediate.dense.bias"), act=1, aux=u)
     pre2 = _empty((M, H), F32, dev)                                         # fp32 residual stream
-    ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1)
+    if drop is not None and drop.p_hidden > 0.0:
+        # BertOutput: LayerNorm(dropout(dense(y)) + x)  (a_transformers/modeling_bert.py:447-451)
+        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"))
+        ops.dropout(None, None, pre2, a32, M * H, drop.seed, site, drop.p_hidden)
+    else:
+        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1)
     y, y32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
     mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
     ops.layernorm_fwd(pre2, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), y, mean2,
@@ -155,7 +202,7 @@ def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save):
     return y, y32
 
 
-def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None):
+def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None, drop=None, site=0):
     """Returns d(a) given d(y).  ``z``: pre-zeroed (dgam, dbet, db2, db1, dW2, dW1) from ``_zeros_many``."""
     dev = dy.device
     W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
@@ -167,9 +214,16 @@ def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None):
                       db2, M, H)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = db2
-    grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M, zeroed=dW2)
+    g2d = g2                                 # gradient w.r.t. the dense output (masked under dropout)
+    if drop is not None and drop.p_hidden > 0.0:
+        g2d = _empty((M, H), BF16, dev)
+        ops.dropout(g2, g2d, None, None, M * H, drop.seed, site, drop.p_hidden)
+        db2.zero_()                          # the LayerNorm kernel summed the unmasked gradient
+        grads[pfx + "output.dense.weight"] = wgrad(g2d, sv["gact"], H, I, M, zeroed=dW2, bias_out=db2)
+    else:
+        grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M, zeroed=dW2)
     du = _empty((M, I), BF16, dev)
-    ops.gemm(g2, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)           # (g2 W2) * GELU'(u)
+    ops.gemm(g2d, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)          # (g2 W2) * GELU'(u)
     grads[pfx + "intermediate.dense.bias"] = db1
     grads[pfx + "intermediate.dense.weight"] = wgrad(du, sv["a"], I, H, M, zeroed=dW1, bias_out=db1)
     da = _empty((M, H), BF16, dev)
@@ -188,7 +242,7 @@ class AttnCfg:
         self.kbias, self.cbits, self.cwords, self.chunk_id, self.max_chunks = kbias, cbits, cwords, chunk_id, max_chunks
 
 
-def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, probs_img=None):
+def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, probs_img=None, drop=None, site=0):
     """CaptionBertAttention: self-attention with prefix (modeling/modeling_bert.py:34-93, v10:55-129)
     followed by BertSelfOutput.  ``x`` [N*S,H]; ``hist`` [N*P,H] or None."""
     dev = x.device
@@ -205,10 +259,17 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
         ops.chunk_mean_q(qkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)
     ctx = _empty((M, H), BF16, dev)
     lse = _empty((N, heads, S), F32, dev)
-    ops.prefix_attn_fwd(N, S, P, heads, ac.T, ac.mode, qkv, pkv, ac.kbias, ac.cbits, ac.cwords, ctx, lse, probs_img)
+    adrop = (drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None
+    ops.prefix_attn_fwd(N, S, P, heads, ac.T, ac.mode, qkv, pkv, ac.kbias, ac.cbits, ac.cwords, ctx, lse, probs_img,
+                        drop=adrop)
     pre1 = _empty((M, H), F32, dev)                                         # fp32 residual stream
-    ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
-             epi_in=x32, in_op=1)
+    if drop is not None and drop.p_hidden > 0.0:
+        # BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)  (a_transformers/modeling_bert.py:369-373)
+        ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"))
+        ops.dropout(None, None, pre1, x32, M * H, drop.seed, site + 1, drop.p_hidden)
+    else:
+        ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
+                 epi_in=x32, in_op=1)
     a, a32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
     mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
     ops.layernorm_fwd(pre1, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), a, mean1,
@@ -219,7 +280,7 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     return a, a32
 
 
-def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None):
+def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop=None, site=0):
     """Returns (dx, dhist).  ``z``: pre-zeroed (dgam, dbet, dbo, dbqkv, dWo, dWqkv) from ``_zeros_many``."""
     dev = da.device
     N, S, H, heads, P = ac.N, ac.S, ac.H, ac.heads, ac.P
@@ -233,16 +294,24 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None):
                       dbo, M, H)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = dbo
-    grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M, zeroed=dWo)
+    g1d = g1                                 # gradient w.r.t. the dense output (masked under dropout)
+    if drop is not None and drop.p_hidden > 0.0:
+        g1d = _empty((M, H), BF16, dev)
+        ops.dropout(g1, g1d, None, None, M * H, drop.seed, site + 1, drop.p_hidden)
+        dbo.zero_()                          # the LayerNorm kernel summed the unmasked gradient
+        grads[pfx + "output.dense.weight"] = wgrad(g1d, sv["ctx"], H, H, M, zeroed=dWo, bias_out=dbo)
+    else:
+        grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M, zeroed=dWo)
     dctx = _empty((M, H), BF16, dev)
-    ops.gemm(g1, ps.bf16(pfx + "output.dense.weight"), dctx, M, H, H, b_mn=1)
+    ops.gemm(g1d, ps.bf16(pfx + "output.dense.weight"), dctx, M, H, H, b_mn=1)
     dqkv = _empty((M, 3 * H), BF16, dev)
     dpkv = _empty((N * P, 2 * H), BF16, dev) if P > 0 else None
     if ws is None:
         ws = _empty((ops.attn_bwd_workspace_bytes(N, S, heads) // 4,), F32, dev)
     use_align = dalign if sv["probs_img"] is not None else None
     ops.prefix_attn_bwd(N, S, P, heads, ac.T, ac.mode, sv["qkv"], sv["pkv"], ac.kbias, ac.cbits, ac.cwords, sv["ctx"],
-                        sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws)
+                        sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws,
+                        drop=(drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None)
     if sv["chunk"]:
         ops.chunk_mean_q(dqkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)   # self-adjoint operator
     wgrad(dqkv, sv["x"], 3 * H, H, M, zeroed=dWqkv, bias_out=dbqkv)
@@ -259,17 +328,20 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None):
     return dx, dhist
 
 
-def layer_fwd(ps, pfx, x, x32, hist, ac, I, eps, save, do_chunk_cross=False, probs_img=None):
-    """CaptionBertLayer.forward (modeling/modeling_transfomres.py:481-489, v10:140-150); returns (y, y32)."""
-    a, a32 = attention_fwd(ps, pfx + "attention.", x, x32, hist, ac, eps, save, do_chunk_cross, probs_img)
-    return ffn_fwd(ps, pfx, a, a32, ac.N * ac.S, ac.H, I, eps, save)
+def layer_fwd(ps, pfx, x, x32, hist, ac, I, eps, save, do_chunk_cross=False, probs_img=None, drop=None, layer=0):
+    """CaptionBertLayer.forward (modeling/modeling_transfomres.py:481-489, v10:140-150); returns (y, y32).
+    Dropout sites of layer ``layer``: +0 attention probabilities, +1 attention output, +2 FFN output."""
+    site = drop.site(layer + 1, 0) if drop is not None else 0
+    a, a32 = attention_fwd(ps, pfx + "attention.", x, x32, hist, ac, eps, save, do_chunk_cross, probs_img, drop, site)
+    return ffn_fwd(ps, pfx, a, a32, ac.N * ac.S, ac.H, I, eps, save, drop, site + 2)
 
 
-def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None):
+def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None, drop=None, layer=0):
     H = ac.H
     z = _zeros_many([(H,), (H,), (H,), (I,), (H, I), (I, H), (H,), (H,), (H,), (3 * H,), (H, H), (3 * H, H)], dy.device)
-    da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, H, I, grads, z[:6])
-    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws, z[6:])
+    site = drop.site(layer + 1, 0) if drop is not None else 0
+    da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, H, I, grads, z[:6], drop, site + 2)
+    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws, z[6:], drop, site)
 
 
 # -------------------------------------------------------------------------------------------- embeddings

@@ -34,6 +34,7 @@ class EncoderRun:
         self.kbias, self.P, self.is_seq = kbias, P, is_seq
         self.cbits, self.cwords, self.chunk_id, self.max_chunks = cbits, cwords, chunk_id, max_chunks
         self.want_block = want_block
+        self.drop = None                      # engine.Drop in training mode with dropout
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
         self.S = self.T + self.R
@@ -70,6 +71,10 @@ class EncoderFn(torch.autograd.Function):
         emb_save = {} if need_grad else None
         x, x32 = E.embeddings_fwd(ps, cfg, run.input_ids, run.token_type_ids, run.position_ids, run.img_feats,
                                   emb_save)
+        drop = run.drop
+        if drop is not None and drop.p_hidden > 0.0:
+            # BertEmbeddings.dropout and the img_embedding dropout (a_transformers 209; transfomres 681, v10:343)
+            ops.dropout(x, x, x32, None, N * S * H, drop.seed, drop.site(0, 0), drop.p_hidden)
         x, x32 = x.view(N * S, H), x32.view(N * S, H)
         saves = []
         chunk_hidden = None
@@ -82,7 +87,7 @@ class EncoderFn(torch.autograd.Function):
                 chunk_hidden = x
             pi = probs[i - (L - nprob)] if (nprob and i >= L - nprob) else None
             x, x32 = E.layer_fwd(ps, "encoder.layer.%d." % i, x, x32, hist[i] if hist else None, ac, I, cfg["eps"], sv,
-                                 cross, pi)
+                                 cross, pi, drop, i)
             saves.append(sv)
         pooled = E.pooler_fwd(ps, x, N, S, H)
         seq_out = x.view(N, S, H)
@@ -120,12 +125,14 @@ class EncoderFn(torch.autograd.Function):
         for i in range(L - 1, -1, -1):
             ac, _ = run.layer_cfg(i)
             da = dalign if (ctx.nprob and i >= L - ctx.nprob) else None
-            dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws)
+            dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws, run.drop, i)
             ctx.saves[i] = None  # free this layer's activations
             if ctx.n_hist:
                 dhists[i] = dh
             if run.is_seq and i == CROSS_MODAL_START and d_chunk is not None and d_chunk.numel():
                 ops.add_bf16(dy, d_chunk.to(BF16).contiguous(), dy)
+        if run.drop is not None and run.drop.p_hidden > 0.0:
+            ops.dropout(dy, dy, None, None, N * S * H, run.drop.seed, run.drop.site(0, 0), run.drop.p_hidden)
         E.embeddings_bwd(ps, cfg, ctx.emb_save, dy.view(N, S, H), grads)
         out_h = []
         for i in range(ctx.n_hist):
@@ -142,6 +149,7 @@ class EncoderFn(torch.autograd.Function):
 class ClsHeadRun:
     def __init__(self, ps, names, cfg, N, T, S):
         self.ps, self.names, self.cfg, self.N, self.T, self.S = ps, names, cfg, N, T, S
+        self.drop = None                      # engine.Drop in training mode with dropout
 
 
 class ClsLayer2HeadFn(torch.autograd.Function):
@@ -179,17 +187,24 @@ class ClsLayer2HeadFn(torch.autograd.Function):
             ops.gemm(X, ps.bf16(pfx + "align_k_proj.weight"), k, N * L3, H, H, bias=ps.f32(pfx + "align_k_proj.bias"))
             w = E._empty((N, L3), F32, dev)
             pooled = E._empty((N, H), BF16, dev)
-            ops.cls_pool_attn_fwd(q, k, word_mask, w, pooled, N, L3, H)
+            drop = run.drop
+            hdrop = drop is not None and drop.p_hidden > 0.0
+            wdrop = (drop.seed, drop.site(i, 0), drop.p_hidden) if hdrop else None   # v10:828
+            ops.cls_pool_attn_fwd(q, k, word_mask, w, pooled, N, L3, H, drop=wdrop)
             pre = E._empty((N, H), F32, dev)
-            ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"), epi_in=cls32,
-                     in_op=1)
+            if hdrop:                                                      # LayerNorm(dropout(dense(.)) + cls), v10:831-833
+                ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"))
+                ops.dropout(None, None, pre, cls32, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+            else:
+                ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"),
+                         epi_in=cls32, in_op=1)
             c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
             mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
             ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
                               cfg["eps"], y32=c32)
             if sv is not None:
                 sv.update(cls_in=cls, q=q, k=k, w=w, pooled=pooled, pre=pre, mean=mean, rstd=rstd)
-            cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv)
+            cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv, drop, drop.site(i, 2) if drop else 0)
             saves.append(sv)
         ctx.run, ctx.saves, ctx.cat, ctx.X = run, saves, cat, X
         return cls
@@ -206,18 +221,28 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         for i in range(cfg["n_cls_layers"] - 1, -1, -1):
             pfx = "cls_layer.%d." % i
             sv = ctx.saves[i]
-            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads)
+            drop = run.drop
+            hdrop = drop is not None and drop.p_hidden > 0.0
+            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads, None, drop, drop.site(i, 2) if drop else 0)
             g = E._empty((N, H), BF16, dev)
             dgam, dbet, dbd = E._zeros((H,), F32, dev), E._zeros((H,), F32, dev), E._zeros((H,), F32, dev)
             ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbd,
                               N, H)
             grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"], grads[pfx + "dense.bias"] = dgam, dbet, dbd
-            grads[pfx + "dense.weight"] = E.wgrad(g, sv["pooled"], H, H, N)
+            gd = g                               # gradient w.r.t. the dense output (masked under dropout)
+            if hdrop:
+                gd = E._empty((N, H), BF16, dev)
+                ops.dropout(g, gd, None, None, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+                dbd.zero_()
+                grads[pfx + "dense.weight"] = E.wgrad(gd, sv["pooled"], H, H, N, bias_out=dbd)
+            else:
+                grads[pfx + "dense.weight"] = E.wgrad(g, sv["pooled"], H, H, N)
             dpool = E._empty((N, H), BF16, dev)
-            ops.gemm(g, ps.bf16(pfx + "dense.weight"), dpool, N, H, H, b_mn=1)
+            ops.gemm(gd, ps.bf16(pfx + "dense.weight"), dpool, N, H, H, b_mn=1)
             dq = E._empty((N, H), BF16, dev)
             dk = E._empty((N, L3, H), BF16, dev)
-            ops.cls_pool_attn_bwd(dpool, sv["q"], sv["k"], sv["w"], dq, dk, N, L3, H)
+            ops.cls_pool_attn_bwd(dpool, sv["q"], sv["k"], sv["w"], dq, dk, N, L3, H,
+                                  drop=(drop.seed, drop.site(i, 0), drop.p_hidden) if hdrop else None)
             dbk = E._zeros((H,), F32, dev)
             grads[pfx + "align_k_proj.bias"] = dbk
             grads[pfx + "align_k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3, bias_out=dbk)
@@ -252,7 +277,7 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         return (None, None, outs[0], outs[1], outs[2], dgp, dsp, *out_p)
 
 
-def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers, heads, want_saves):
+def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_layers, heads, want_saves, drop=None):
     """``cls_ensemble_1`` + ``n_layers`` x ``ClsLayer_lyx`` (v10:925-975, 856-870).  Inputs are bf16 ``[N,S,H]`` /
     ``[N,H]``; returns (CLS ``[N,H]`` bf16, saves).  ``word_len`` = T - 1 token rows taken from each source."""
     N, S, H = g_out.shape
@@ -281,17 +306,22 @@ def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_l
         ops.gemm(X, ps.bf16(xa + "v_proj.weight"), v, N * L3, H, H, bias=ps.f32(xa + "v_proj.bias"))
         att = E._empty((N, H), BF16, dev)
         lse = E._empty((N, heads), F32, dev) if want_saves else None
-        ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads, lse)         # word_mask is never forwarded (v10:856-857)
+        adrop = (drop.seed, drop.site(i, 0), drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None
+        ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads, lse, drop=adrop)   # word_mask is never forwarded (v10:856-857)
         pre = E._empty((N, H), F32, dev)
-        ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
-                 in_op=1)                                                # + cls (residual of the LayerNorm)
+        if drop is not None and drop.p_hidden > 0.0:                     # LayerNorm(dropout(CLS_ensem_1) + cls), v10:866-867
+            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"))
+            ops.dropout(None, None, pre, cls32, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+        else:
+            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
+                     in_op=1)                                            # + cls (residual of the LayerNorm)
         c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
         mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
         ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
                           cfg["eps"], y32=c32)
         if sv is not None:
             sv.update(cls_in=cls, q=q, k=k, v=v, att=att, lse=lse, pre=pre, mean=mean, rstd=rstd)
-        cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv)
+        cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv, drop, drop.site(i, 2) if drop else 0)
         saves.append(sv)
     return cls, (saves, cat, X)
 
@@ -313,7 +343,7 @@ class ClsLyxHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, run, word_len, g_out, s_out, c_hid, g_pool, s_pool, *params):
         cls, (saves, cat, X) = _cls_lyx_forward(run.ps, run.cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool,
-                                                run.n_layers, run.heads, True)
+                                                run.n_layers, run.heads, True, run.drop)
         ctx.run, ctx.saves, ctx.cat, ctx.X, ctx.word_len = run, saves, cat, X, word_len
         return cls
 
@@ -330,19 +360,29 @@ class ClsLyxHeadFn(torch.autograd.Function):
             pfx = "cls_layer_lyx.%d." % i
             xa = pfx + "cross_attention."
             sv = ctx.saves[i]
-            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads)
+            drop = run.drop
+            dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads, None, drop, drop.site(i, 2) if drop else 0)
             g = E._empty((N, H), BF16, dev)
             dgam, dbet, dbo, dbq, dbk, dbv = E._zeros_many([(H,)] * 6, dev)
             ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbo,
                               N, H)
             grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"] = dgam, dbet
             grads[xa + "out_proj.bias"] = dbo
-            grads[xa + "out_proj.weight"] = E.wgrad(g, sv["att"], H, H, N)
+            gd = g                               # gradient w.r.t. the out_proj output (masked under dropout)
+            if drop is not None and drop.p_hidden > 0.0:
+                gd = E._empty((N, H), BF16, dev)
+                ops.dropout(g, gd, None, None, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+                dbo.zero_()
+                grads[xa + "out_proj.weight"] = E.wgrad(gd, sv["att"], H, H, N, bias_out=dbo)
+            else:
+                grads[xa + "out_proj.weight"] = E.wgrad(g, sv["att"], H, H, N)
             datt = E._empty((N, H), BF16, dev)
-            ops.gemm(g, ps.bf16(xa + "out_proj.weight"), datt, N, H, H, b_mn=1)
+            ops.gemm(gd, ps.bf16(xa + "out_proj.weight"), datt, N, H, H, b_mn=1)
             dq = E._empty((N, H), BF16, dev)
             dk, dv = E._empty((N, L3, H), BF16, dev), E._empty((N, L3, H), BF16, dev)
-            ops.cross_attn_q1_bwd(sv["q"], sv["k"], sv["v"], sv["att"], sv["lse"], datt, dq, dk, dv, N, L3, H, heads)
+            adrop = (drop.seed, drop.site(i, 0), drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None
+            ops.cross_attn_q1_bwd(sv["q"], sv["k"], sv["v"], sv["att"], sv["lse"], datt, dq, dk, dv, N, L3, H, heads,
+                                  drop=adrop)
             grads[xa + "k_proj.weight"] = E.wgrad(dk, ctx.X, H, H, N * L3, bias_out=dbk)
             grads[xa + "v_proj.weight"] = E.wgrad(dv, ctx.X, H, H, N * L3, bias_out=dbv)
             grads[xa + "q_proj.weight"] = E.wgrad(dq, sv["cls_in"], H, H, N, bias_out=dbq)
@@ -356,6 +396,29 @@ class ClsLyxHeadFn(torch.autograd.Function):
         grads["cls_ensemble_1.weight"] = E.wgrad(d, ctx.cat, H, 2 * H, N, bias_out=dbe)
         out_p = [grads.get(n) for n in run.names]
         return (None, None, None, None, None, None, None, *out_p)
+
+
+class DropoutFn(torch.autograd.Function):
+    """Training-mode dropout of a bf16 tensor with the counter-based mask of ``modcr_dropout`` (pooled-output
+    dropout of the *ForMultipleChoice heads, modeling/modeling_bert.py:553, 697)."""
+
+    @staticmethod
+    def forward(ctx, x, seed, site, p):
+        xb = _as_bf16(x).contiguous()
+        if xb.numel() % 8 != 0:
+            raise RuntimeError("modcr_b200: dropout needs a multiple of 8 elements")
+        out = torch.empty_like(xb)
+        ops.dropout(xb, out, None, None, xb.numel(), seed, site, p)
+        ctx.sv = (seed, site, p, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        seed, site, p, dt = ctx.sv
+        db = _as_bf16(dout).contiguous()
+        dx = torch.empty_like(db)
+        ops.dropout(db, dx, None, None, db.numel(), seed, site, p)
+        return dx.to(dt), None, None, None
 
 
 class ScorerFn(torch.autograd.Function):

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .functions import EncoderFn, EncoderRun, ScorerFn
+from .functions import DropoutFn, EncoderFn, EncoderRun, ScorerFn
 from .modeling_utils import (BertConfig, CaptionPreTrainedModel, ImgPreTrainedModel, cfg_get, check_no_dropout,  # noqa: F401
                              engine_cfg)
 
@@ -174,7 +174,6 @@ class BertImgModel(_EncoderModelBase):
         which case the prefix keys are always visible."""
         if head_mask is not None:
             raise NotImplementedError("head_mask is always None on the ModCR path (modeling_transfomres.py:656-657)")
-        check_no_dropout(self, self.config)
         N, T = input_ids.shape
         R = 0 if img_feats is None else img_feats.shape[1]
         S = T + R
@@ -195,6 +194,8 @@ class BertImgModel(_EncoderModelBase):
         kbias = E.make_key_bias(attention_mask)
         ps, names, params = self._store()
         run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P)
+        run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
+                               cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 1 << 20)
         seq_out, pooled, _, _ = EncoderFn.apply(run, len(hist), *hist, *params)
         outputs = (seq_out, pooled)
         if cfg_get(self.config, "output_attentions", False):
@@ -229,13 +230,20 @@ class ImageBertForMultipleChoice(CaptionPreTrainedModel):
         self.classifier = nn.Linear(self.num_choice * config.hidden_size, config.num_labels)
         # NB the reference forgets the call parentheses on init_weights (:531): the head keeps torch's default init
 
+    def _pooled_dropout(self, pooled):
+        """``self.dropout(pooled_output)`` (modeling/modeling_bert.py:553, 697) in training mode."""
+        p = float(self.dropout.p)
+        if not self.training or p <= 0.0:
+            return pooled
+        return DropoutFn.apply(pooled, E.next_seed(pooled.device), 5 << 20, p)
+
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, labels=None, position_ids=None,
                 head_mask=None, img_feats=None):
         nc = self.num_choice
         flat = lambda t: None if t is None else t.reshape(-1, *t.shape[2:])  # noqa: E731
         outputs = self.bert(flat(input_ids), position_ids=flat(position_ids), token_type_ids=flat(token_type_ids),
                             attention_mask=flat(attention_mask), head_mask=head_mask, img_feats=flat(img_feats))
-        pooled = outputs[1]
+        pooled = self._pooled_dropout(outputs[1])
         B = pooled.shape[0] // nc
         x = pooled.reshape(B, nc * pooled.shape[1])
         if labels is None:
@@ -274,7 +282,7 @@ class OscarForMultipleChoice(CaptionPreTrainedModel):
         flat = lambda t: None if t is None else t.reshape(-1, *t.shape[2:])  # noqa: E731
         outputs = self.bert(flat(input_ids), position_ids=flat(position_ids), token_type_ids=flat(token_type_ids),
                             attention_mask=flat(attention_mask), head_mask=head_mask, img_feats=flat(img_feats))
-        pooled = outputs[1]
+        pooled = ImageBertForMultipleChoice._pooled_dropout(self, outputs[1])
         rows, C = pooled.shape[0], self.classifier.weight.shape[0]
         if self.loss_type == "bce" and labels is not None:
             raise NotImplementedError("loss_type 'bce' of OscarForMultipleChoice is not on the ModCR path")

@@ -78,14 +78,12 @@ def engine_cfg(config):
 
 
 def check_no_dropout(module, config):
-    """The kernels implement the p = 0 / eval path (the parity and benchmark configuration,
-    SURVEY.md 8(d)); training-mode dropout is not silently dropped."""
+    """Kept for callers that want the deterministic (parity / benchmark) arithmetic guaranteed: raises when the module
+    would apply training-mode dropout.  The kernels implement dropout (counter-based masks, ``engine.Drop``)."""
     if module.training and (float(cfg_get(config, "hidden_dropout_prob", 0.0)) > 0.0 or
                             float(cfg_get(config, "attention_probs_dropout_prob", 0.0)) > 0.0):
-        raise NotImplementedError(
-            "modcr_b200: training-mode dropout (hidden %.2f / attention %.2f) is not implemented in the CUDA path; "
-            "set both probabilities to 0 or call .eval()" % (config.hidden_dropout_prob,
-                                                               config.attention_probs_dropout_prob))
+        raise RuntimeError("modcr_b200: module is in training mode with dropout (hidden %.2f / attention %.2f)" % (
+            config.hidden_dropout_prob, config.attention_probs_dropout_prob))
 
 
 class CaptionPreTrainedModel(nn.Module):

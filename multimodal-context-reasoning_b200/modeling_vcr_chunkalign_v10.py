@@ -49,7 +49,6 @@ class SeqBertImgModel(_EncoderModelBase):
             raise NotImplementedError("seq_enc never receives history states on the ModCR path (v10:1042-1046)")
         if img_feats is None or attention_mask is None or input_mask is None or gather_index is None:
             raise ValueError("SeqBertImgModel needs img_feats, the chunk attention_mask, input_mask and gather_index")
-        check_no_dropout(self, self.config)
         N, T = input_ids.shape
         dev = input_ids.device
         kbias = E.make_key_bias(input_mask)
@@ -63,6 +62,8 @@ class SeqBertImgModel(_EncoderModelBase):
         run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, 0,
                          is_seq=True, cbits=cbits, cwords=cwords, chunk_id=chunk_id, max_chunks=max_chunks,
                          want_block=_want_align_block)
+        run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
+                               cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 2 << 20)
         seq_out, pooled, chunk_hidden, block = EncoderFn.apply(run, 0, *params)
         att = AttentionsNotMaterialised(block if block.numel() else None)
         return (seq_out, pooled, att), (chunk_hidden if chunk_hidden.numel() else None)
@@ -127,7 +128,6 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
             input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
             attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
             head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
-        check_no_dropout(self, self.global_enc.config)
         ps, names, params = self._head_params()
         cfg = engine_cfg(self.global_enc.config)
         cfg["n_cls_layers"] = self.cls_layer_num
@@ -136,6 +136,8 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         wm = (1.0 - input_mask[:, 1:T].to(torch.float32)) * NEG
         wm = torch.cat((wm, wm, wm), -1).contiguous()
         run = ClsHeadRun(ps, names, cfg, N, T, S)
+        run.drop = E.make_drop(self.training, cfg_get(self.global_enc.config, "hidden_dropout_prob", 0.0), 0.0,
+                               input_ids.device, 3 << 20)
         cls = ClsLayer2HeadFn.apply(run, wm, g[0], s_out, chunk_hidden, g[1], s_pool, *params)
         # detached debug views (never keep the autograd graph of a finished step alive)
         self.last_intermediates = dict(global_output=g[0].detach(), global_CLS=g[1].detach(), seq_output=s_out.detach(),
@@ -249,7 +251,6 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
                 head_mask=None, encoder_history_states=None, offsets=None, chunk_attention_mask=None,
                 gather_index=None, align_pos=None, total_label=None, abstract_hidden_states=None):
         ps, named = self._head_params()
-        check_no_dropout(self, self.global_enc.config)
         N, T = input_ids.shape
         want_block = total_label is not None
         with torch.no_grad():
@@ -267,6 +268,9 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in named.values()):
             run = ClsHeadRun(ps, list(named.keys()), cfg, N, T, g[0].shape[1])
             run.heads, run.n_layers = 8, self.cls_layer_num
+            # hidden dropout of ClsLayer_lyx / BertOutput + the 0.1 probability dropout of cross_attention_lyx (v10:848)
+            run.drop = E.make_drop(self.training, cfg_get(self.global_enc.config, "hidden_dropout_prob", 0.0),
+                                   self.cls_layer_lyx[0].cross_attention.dropout, input_ids.device, 4 << 20)
             CLS_ensem = ClsLyxHeadFn.apply(run, T - 1, g[0], s_out, chunk_hidden, g[1], s_pool, *named.values())
         else:
             with torch.no_grad():

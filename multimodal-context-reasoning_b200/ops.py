@@ -112,25 +112,27 @@ def img_embed_ln_bwd(dy, dymap, packed, pre, mean, rstd, gamma, use_ln, dpre, dW
 
 # --------------------------------------------------------------------------- attention
 def _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, dctx=None,
-               dalign=None, dqkv=None, dpkv=None, dq_ws=None):
+               dalign=None, dqkv=None, dpkv=None, dq_ws=None, drop=None):
     d = AttnDesc()
     d.N, d.S, d.P, d.heads, d.T, d.mode = N, S, P, heads, T, mode
     d.scale = 0.125
     d.qkv, d.pkv, d.kbias, d.cbits, d.cwords = _p(qkv), _p(pkv), _p(kbias), _p(cbits), cwords
     d.ctx, d.lse, d.probs_img = _p(ctx), _p(lse), _p(probs_img)
     d.dctx, d.dalign, d.dqkv, d.dpkv, d.dq_ws = _p(dctx), _p(dalign), _p(dqkv), _p(dpkv), _p(dq_ws)
+    if drop is not None:                      # (seed tensor, site, p): attention-probability dropout
+        d.drop_seed, d.drop_site, d.drop_p = _p(drop[0]), int(drop[1]), float(drop[2])
     return d
 
 
-def prefix_attn_fwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None):
-    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img)
+def prefix_attn_fwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, drop=None):
+    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, drop=drop)
     _lib.check(_lib.load().modcr_prefix_attn_fwd(C.byref(d), _stream()), "prefix_attn_fwd")
 
 
 def prefix_attn_bwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
-                    dpkv, dq_ws):
+                    dpkv, dq_ws, drop=None):
     d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
-                   dpkv, dq_ws)
+                   dpkv, dq_ws, drop)
     _lib.check(_lib.load().modcr_prefix_attn_bwd(C.byref(d), _stream()), "prefix_attn_bwd")
 
 
@@ -159,28 +161,45 @@ def align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T,
                                                       _p(dblock), N, T, R, _stream()), "align_softmax_ce_bwd")
 
 
-def cross_attn_q1_fwd(q, k, v, out, N, L, H, heads, lse=None):
+def dropout(in16, out16, io32, res32, n, seed, site, p):
+    """out16 = in16 * m (bf16), io32 = io32 * m (+ res32) (fp32, in place); m = keep / (1 - p), mask = f(seed, site, i)."""
+    _lib.check(_lib.load().modcr_dropout(_p(in16), _p(out16), _p(io32), _p(res32), n, _p(seed), site, float(p), _stream()),
+               "dropout")
+
+
+def _drop3(drop):
+    """(seed tensor, site, p) -> ctypes arguments; ``None`` disables dropout."""
+    if drop is None:
+        return None, 0, 0.0
+    return _p(drop[0]), int(drop[1]), float(drop[2])
+
+
+def cross_attn_q1_fwd(q, k, v, out, N, L, H, heads, lse=None, drop=None):
     """cross_attention_lyx with one query per sequence (v10:692-797): bf16 q/out [N,H], k/v [N,L,H];
-    ``lse`` fp32 [N,heads] (optional) feeds the backward pass."""
-    _lib.check(_lib.load().modcr_cross_attn_q1_fwd(_p(q), _p(k), _p(v), _p(out), _p(lse), N, L, H, heads, _stream()),
-               "cross_attn_q1_fwd")
+    ``lse`` fp32 [N,heads] (optional) feeds the backward pass; ``drop`` = (seed, site, p) of the probability dropout."""
+    ds, dsite, dp = _drop3(drop)
+    _lib.check(_lib.load().modcr_cross_attn_q1_fwd(_p(q), _p(k), _p(v), _p(out), _p(lse), N, L, H, heads, ds, dsite, dp,
+                                                   _stream()), "cross_attn_q1_fwd")
 
 
-def cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads):
+def cross_attn_q1_bwd(q, k, v, out, lse, dout, dq, dk, dv, N, L, H, heads, drop=None):
+    ds, dsite, dp = _drop3(drop)
     _lib.check(_lib.load().modcr_cross_attn_q1_bwd(_p(q), _p(k), _p(v), _p(out), _p(lse), _p(dout), _p(dq), _p(dk), _p(dv),
-                                                   N, L, H, heads, _stream()), "cross_attn_q1_bwd")
+                                                   N, L, H, heads, ds, dsite, dp, _stream()), "cross_attn_q1_bwd")
 
 
-def cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H):
+def cls_pool_attn_fwd(q, k, mask, w, pooled, N, L, H, drop=None):
     if q.dtype != k.dtype:
         raise RuntimeError("modcr_b200: cls_pool q and k must share a dtype")
+    ds, dsite, dp = _drop3(drop)
     _lib.check(_lib.load().modcr_cls_pool_attn_fwd(_p(q), _p(k), int(k.dtype == F32), _p(mask), _p(w), _p(pooled), N, L,
-                                                   H, _stream()), "cls_pool_attn_fwd")
+                                                   H, ds, dsite, dp, _stream()), "cls_pool_attn_fwd")
 
 
-def cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H):
+def cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H, drop=None):
+    ds, dsite, dp = _drop3(drop)
     _lib.check(_lib.load().modcr_cls_pool_attn_bwd(_p(dpooled), _p(q), _p(k), int(k.dtype == F32), _p(w), _p(dq),
-                                                   _p(dk), N, L, H, _stream()), "cls_pool_attn_bwd")
+                                                   _p(dk), N, L, H, ds, dsite, dp, _stream()), "cls_pool_attn_bwd")
 
 
 def _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None, num_choice=4,

@@ -72,10 +72,24 @@ def test_cpu_tensors_are_rejected_loudly():
         g(ids, img_feats=torch.randn(2, 3, 24), attention_mask=torch.ones(2, 9))
 
 
-def test_training_dropout_is_not_silently_dropped():
+def test_dropout_state_host_logic():
+    """Training-mode dropout is driven by ``engine.Drop``: absent in eval / p = 0 (so the deterministic kernels are
+    untouched), otherwise a per-pass device seed that advances every pass and distinct site ids per layer and role."""
+    engine.manual_seed(7)
+    assert engine.make_drop(False, 0.3, 0.1, "cpu", 1 << 20) is None
+    assert engine.make_drop(True, 0.0, 0.0, "cpu", 1 << 20) is None
+    d1 = engine.make_drop(True, 0.3, 0.1, "cpu", 1 << 20)
+    d2 = engine.make_drop(True, 0.3, 0.1, "cpu", 2 << 20)
+    assert d1.p_hidden == pytest.approx(0.3) and d1.p_attn == pytest.approx(0.1)
+    assert d1.seed.dtype == torch.int32 and int(d1.seed) != int(d2.seed)          # the state advanced
+    sites = {d.site(layer, k) for d in (d1, d2) for layer in range(13) for k in range(3)}
+    assert len(sites) == 2 * 13 * 3                                              # no two call sites share a mask stream
+    engine.manual_seed(7)
+    assert int(engine.make_drop(True, 0.3, 0.1, "cpu", 1 << 20).seed) == int(d1.seed)   # reproducible
+    # the product path still has no CPU fallback, dropout or not
     g = BertImgModel(small_cfg(hidden_dropout_prob=0.3))
     g.train()
-    with pytest.raises(NotImplementedError, match="dropout"):
+    with pytest.raises(RuntimeError):
         g(torch.randint(1, 60, (2, 6)), img_feats=torch.randn(2, 3, 24), attention_mask=torch.ones(2, 9))
 
 

@@ -531,3 +531,165 @@ def test_errors_are_reported_not_swallowed():
         ops.layernorm_fwd(x, x, x, x, None, None, 8, 100, 1e-12)
     with pytest.raises(RuntimeError):
         ops.prefix_attn_fwd(1, 600, 0, 2, 0, 0, x, None, x, None, 0, x, x)
+
+
+# ------------------------------------------------------------------------------- dropout (training mode)
+def host_keep(seed, site, idx, p):
+    """Host restatement of the counter-based dropout mask (csrc/ptx.cuh drop_hash / drop_keep), exact."""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFF)
+    x = ((idx.astype(np.uint64) ^ np.uint64(seed & 0xFFFFFFFF)) * np.uint64(0x9E3779B1)) & M
+    x ^= np.uint64((site * 0x85EBCA77) & 0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    thr = max(1, min(0xFFFFFFFF, int(float(np.float32(p)) * 4294967296.0)))
+    return torch.from_numpy((x >= np.uint64(thr)))
+
+
+def _seed_tensor(v):
+    return torch.tensor([v], dtype=torch.int32, device=DEV)
+
+
+def test_dropout_kernel_matches_host_mask():
+    import numpy as np
+    n, p, site, seedv = 64 * 768, 0.3, 12345, 987654321
+    x16 = rnd(n, seed=31)
+    x32 = torch.randn(n, generator=torch.Generator().manual_seed(32)).to(DEV)
+    res = torch.randn(n, generator=torch.Generator().manual_seed(33)).to(DEV)
+    keep = host_keep(seedv, site, np.arange(n), p).to(DEV)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.01
+    out16 = torch.empty_like(x16)
+    io32 = x32.clone()
+    ops.dropout(x16, out16, io32, res, n, _seed_tensor(seedv), site, p)
+    scale = 1.0 / (1.0 - p)
+    assert torch.equal(out16 == 0, ~keep | (x16 == 0))
+    assert nerr(out16, x16.float() * keep * scale) < 1e-2
+    torch.testing.assert_close(io32, x32 * keep * scale + res, atol=1e-5, rtol=1e-5)
+    other = torch.empty_like(x16)
+    ops.dropout(x16, other, None, None, n, _seed_tensor(seedv), site + 1, p)      # another site: another mask
+    assert float(((other == 0) != (out16 == 0)).float().mean()) > 0.2
+    again = torch.empty_like(x16)
+    ops.dropout(x16, again, None, None, n, _seed_tensor(seedv), site, p)          # same (seed, site): same mask
+    assert torch.equal(again, out16)
+
+
+@pytest.mark.parametrize("mode,P,S,T", [(0, 10, 178, 128), (2, 0, 178, 128), (0, 0, 300, 200), (0, 3, 130, 0)])
+def test_prefix_attention_dropout_fwd_bwd(mode, P, S, T):
+    """softmax -> dropout -> P V with the host-restated mask (persistent and tiled kernels use different key-row
+    orders in shared memory but the same logical mask), forward and backward."""
+    import numpy as np
+    N, heads, p, site, seedv = 2, 4, 0.1, 777, 13579
+    H = heads * 64
+    qkv = rnd(N, S, 3 * H, seed=41 + mode)
+    pkv = rnd(N, P, 2 * H, seed=42) if P > 0 else None
+    key_mask = torch.ones(N, P + S)
+    lens = [S] * N
+    if T > 0:
+        lens = [T, max(T // 2, 3)]
+        for n in range(N):
+            key_mask[n, P + lens[n]:P + T] = 0.0
+    key_mask = key_mask.to(DEV)
+    cm = _chunk_mask(N, T, lens, 5).to(DEV) if mode != 0 else None
+    cwords = (T + 31) // 32 if mode != 0 else 0
+    kbias = torch.empty(N, P + S, device=DEV)
+    ops.key_bias(key_mask, kbias)
+    cbits = None
+    if mode != 0:
+        cbits = torch.zeros(N, T, cwords, dtype=torch.int32, device=DEV)
+        ops.chunk_bits(cm, cbits, N, T, cwords)
+    want_align = mode == 2
+    R = S - T
+    seed = _seed_tensor(seedv)
+    ctx = torch.empty(N, S, H, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(N, heads, S, device=DEV)
+    probs_img = torch.zeros(N, heads, T, R, device=DEV) if want_align else None
+    Tk = T if (mode != 0 or want_align) else 0
+    ops.prefix_attn_fwd(N, S, P, heads, Tk, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, drop=(seed, site, p))
+    # host mask in the reference's key order [prefix ; sequence]: logical id of prefix key j is S + j, of sequence key j is j
+    K = P + S
+    kid = torch.cat([S + torch.arange(P), torch.arange(S)])
+    rows = (torch.arange(N * heads * S) * K).view(N, heads, S, 1)
+    idx = (rows + kid.view(1, 1, 1, K)).numpy().astype(np.uint64)
+    keep = host_keep(seedv, site, idx, p).to(DEV).float() / (1.0 - p)
+    qkv_r = qkv.float().requires_grad_(True)
+    pkv_r = pkv.float().requires_grad_(True) if P > 0 else None
+    am = _dense_mask(mode, N, S, T, P, key_mask, cm)
+    q, k, v = qkv_r.split(H, -1)
+    if P > 0:
+        pk, pv = pkv_r.split(H, -1)
+        k, v = torch.cat([pk, k], 1), torch.cat([pv, v], 1)
+    hsplit = lambda t: t.view(N, -1, heads, 64).permute(0, 2, 1, 3)  # noqa: E731
+    scores = hsplit(q) @ hsplit(k).transpose(-1, -2) * 0.125 + am
+    probs = torch.softmax(scores, -1) * keep
+    ctx_r = (probs @ hsplit(v)).permute(0, 2, 1, 3).reshape(N, S, H)
+    assert nerr(ctx, ctx_r) < 1.5e-2
+    if want_align:
+        torch.testing.assert_close(probs_img, probs[:, :, :T, T:].detach(), atol=3e-5, rtol=2e-3)
+    dctx = rnd(N, S, H, seed=43)
+    g = torch.Generator().manual_seed(5)
+    dalign = (torch.randn(N, T, R, generator=g) * 0.5).to(DEV) if want_align else None
+    loss = (ctx_r * dctx.float()).sum()
+    if dalign is not None:
+        loss = loss + (probs[:, :, :T, T:].sum(1) * dalign).sum()
+    loss.backward()
+    dqkv = torch.zeros(N, S, 3 * H, dtype=torch.bfloat16, device=DEV)
+    dpkv = torch.zeros(N, P, 2 * H, dtype=torch.bfloat16, device=DEV) if P > 0 else None
+    ws = torch.empty(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, device=DEV)
+    ops.prefix_attn_bwd(N, S, P, heads, Tk, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
+                        dpkv, ws, drop=(seed, site, p))
+    gq, gk, gv = qkv_r.grad.split(H, -1)
+    dq, dk, dv = dqkv.split(H, -1)
+    assert nerr(dv, gv) < 2e-2, "dV"
+    assert nerr(dk, gk) < 2e-2, "dK"
+    assert nerr(dq, gq) < 2e-2, "dQ"
+    if P > 0:
+        assert nerr(dpkv, pkv_r.grad) < 2e-2, "dprefix"
+
+
+def test_head_attention_dropout_fwd_bwd():
+    """ClsLayer2 pooling (weights dropout, v10:828) and cross_attention_lyx (probability dropout, v10:785) with the
+    host-restated masks, forward and backward."""
+    import numpy as np
+    N, L, H, heads, p, site, seedv = 3, 69, 768, 8, 0.3, 4242, 2468
+    seed = _seed_tensor(seedv)
+    # ---- cls_pool
+    q = torch.randn(N, H, generator=torch.Generator().manual_seed(1)).mul(0.05).to(DEV).requires_grad_(True)
+    k = torch.randn(N, L, H, generator=torch.Generator().manual_seed(2)).to(DEV).requires_grad_(True)
+    mask = torch.zeros(N, L, device=DEV)
+    mask[1, L - 9:] = NEG
+    w = torch.empty(N, L, device=DEV)
+    pooled = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    ops.cls_pool_attn_fwd(q.detach(), k.detach(), mask, w, pooled, N, L, H, drop=(seed, site, p))
+    keep = host_keep(seedv, site, np.arange(N * L), p).view(N, L).to(DEV).float() / (1 - p)
+    w_r = torch.softmax((q.unsqueeze(1) @ k.transpose(1, 2)).squeeze(1) + mask, -1)
+    pooled_r = ((w_r * keep).unsqueeze(1) @ k).squeeze(1)
+    torch.testing.assert_close(w, w_r.detach(), atol=1e-5, rtol=1e-4)          # returned weights are undropped
+    assert nerr(pooled, pooled_r) < 1e-2
+    dpool = rnd(N, H, seed=3)
+    (pooled_r * dpool.float()).sum().backward()
+    dq = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    dk = torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV)
+    ops.cls_pool_attn_bwd(dpool, q.detach(), k.detach(), w, dq, dk, N, L, H, drop=(seed, site, p))
+    assert nerr(dq, q.grad) < 2e-2 and nerr(dk, k.grad) < 2e-2
+    # ---- cross attention
+    q2, k2, v2 = rnd(N, H, seed=21), rnd(N, L, H, seed=22), rnd(N, L, H, seed=23)
+    out = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(N, heads, device=DEV)
+    ops.cross_attn_q1_fwd(q2, k2, v2, out, N, L, H, heads, lse, drop=(seed, site + 1, 0.1))
+    hd = H // heads
+    keep2 = host_keep(seedv, site + 1, np.arange(N * heads * L), 0.1).view(N, heads, 1, L).to(DEV).float() / 0.9
+    qf = q2.float().requires_grad_(True)
+    kf, vf = k2.float().requires_grad_(True), v2.float().requires_grad_(True)
+    sc = (qf * hd ** -0.5).view(N, heads, 1, hd) @ kf.view(N, L, heads, hd).permute(0, 2, 3, 1)
+    pr = torch.softmax(sc, -1) * keep2
+    ref = (pr @ vf.view(N, L, heads, hd).permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(N, H)
+    assert nerr(out, ref) < 1e-2
+    dout = rnd(N, H, seed=24)
+    (ref * dout.float()).sum().backward()
+    dq2 = torch.empty(N, H, dtype=torch.bfloat16, device=DEV)
+    dk2, dv2 = torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV), torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV)
+    ops.cross_attn_q1_bwd(q2, k2, v2, out, lse, dout, dq2, dk2, dv2, N, L, H, heads, drop=(seed, site + 1, 0.1))
+    assert nerr(dq2, qf.grad) < 2e-2 and nerr(dk2, kf.grad) < 2e-2 and nerr(dv2, vf.grad) < 2e-2
