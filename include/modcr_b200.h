@@ -172,6 +172,30 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
                                void* stream);
 
+/* Training driver (run_PMR_ModCR.py:127-145, 211-227): torch.nn.utils.clip_grad_norm_ over all parameters followed by
+ * transformers.AdamW.step() with two learning-rate groups (seq_enc x 0.1), eps 1e-5, bias correction, fused into two
+ * launches over a block table (one block per 8192-element chunk of one tensor: blk_tensor / blk_chunk, int32 [nblocks]).
+ *   meta  : device array, one entry per parameter tensor (fp32 master weight, AdamW moments, length, LR multiplier, wd)
+ *   grads : device array of fp32 gradient pointers in the same order; NULL = no gradient this step (tensor skipped)
+ *   hyper : device fp32[4] = {lr, 1 - beta1^t, 1 - beta2^t, max_grad_norm (<= 0: no clipping)}  (device memory, so the
+ *           step can be replayed inside a CUDA graph while the schedule advances)
+ * modcr_grad_sqnorm adds the sum of squares of every gradient to *out_sq (zeroed by the caller); modcr_adamw_step
+ * scales the gradients by min(1, max_norm / (sqrt(*grad_sq) + 1e-6)) on the fly (grad_sq NULL: no clipping) and applies
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps) ; p -= lr wd p. */
+typedef struct modcr_optim_tensor {
+  float* p;
+  float* m;
+  float* v;
+  int64_t n;
+  float lr_mul;
+  float wd;
+} modcr_optim_tensor;
+int modcr_grad_sqnorm(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
+                       const int32_t* blk_chunk, int32_t nblocks, float* out_sq, void* stream);
+int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
+                     const int32_t* blk_chunk, int32_t nblocks, const float* hyper, const float* grad_sq, float beta1,
+                     float beta2, float eps, void* stream);
+
 /* Training-mode dropout of the hidden-state sites (a_transformers/modeling_bert.py:209, 371, 449;
  * modeling_transfomres.py:681; v10:343, 832, 866): out16 = in16 * m (bf16, may alias), io32 = io32 * m (+ res32),
  * m = keep / (1 - p) with keep(seed, site, element index) a counter-based hash -- the backward pass regenerates the mask

@@ -210,6 +210,18 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
   return modcr::align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T, R, S(stream));
 }
 
+int modcr_grad_sqnorm(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
+                       const int32_t* blk_chunk, int32_t nblocks, float* out_sq, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::grad_sqnorm(meta, grads, blk_tensor, blk_chunk, nblocks, out_sq, S(stream));
+}
+int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
+                     const int32_t* blk_chunk, int32_t nblocks, const float* hyper, const float* grad_sq, float beta1,
+                     float beta2, float eps, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta1, beta2, eps, S(stream));
+}
+
 int modcr_dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed,
                   uint32_t site, float p, void* stream) {
   ARCH_OR_RETURN();

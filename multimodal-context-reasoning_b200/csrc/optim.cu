@@ -1,0 +1,130 @@
+// Fused multi-tensor gradient-norm clip + AdamW for the training driver.
+//
+// Replaces, per optimisation step of run_PMR_ModCR.py:211-227 / run_vcr_ModCR.py,
+//     torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)      (one reduction + one scale per tensor)
+//     transformers.AdamW.step()   (two LR groups: seq_enc x 0.1; eps 1e-5; bias correction; weight_decay 0)
+// -- ~485 tensors x ~10 tiny launches in the reference -- by two launches over a (tensor, chunk) block table:
+//   1. grad_sqnorm_kernel : sum of squares of every gradient -> one fp32 scalar
+//   2. adamw_kernel       : g' = g * min(1, max_norm / (norm + 1e-6)),  m, v, p update in one pass (7 x 4 B / element)
+// The update is the HuggingFace AdamW of the reference (eps added to sqrt(v) before the bias correction):
+//     m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ; p -= lr_t * m / (sqrt(v) + eps) ; p -= lr * wd * p
+//     lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
+// Step-dependent scalars (lr, the two bias corrections, max_norm) are read from device memory so that the step can
+// sit inside a replayed CUDA graph.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rowops.h"
+#include "tma_host.h"
+
+namespace modcr {
+
+constexpr int OPT_CHUNK = 8192;   // elements per block
+constexpr int OPT_THREADS = 256;
+
+struct OptTensor {   // mirrors modcr_optim_tensor (include/modcr_b200.h)
+  float* p;
+  float* m;
+  float* v;
+  int64_t n;
+  float lr_mul;
+  float wd;
+};
+
+__global__ void __launch_bounds__(OPT_THREADS) grad_sqnorm_kernel(const OptTensor* __restrict__ meta, const float* const* __restrict__ grads,
+                                                                  const int32_t* __restrict__ blk_tensor,
+                                                                  const int32_t* __restrict__ blk_chunk, float* __restrict__ out) {
+  __shared__ float sh[OPT_THREADS / 32];
+  const int t = blk_tensor[blockIdx.x];
+  const float* g = grads[t];
+  float s = 0.f;
+  if (g != nullptr) {
+    const int64_t n = meta[t].n;
+    const int64_t base = (int64_t)blk_chunk[blockIdx.x] * OPT_CHUNK;
+    const int64_t end = min(base + OPT_CHUNK, n);
+    if ((n & 3) == 0) {
+      for (int64_t i = base + threadIdx.x * 4; i < end; i += OPT_THREADS * 4) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(g + i));
+        s = fmaf(x.x, x.x, s); s = fmaf(x.y, x.y, s); s = fmaf(x.z, x.z, s); s = fmaf(x.w, x.w, s);
+      }
+    } else {
+      for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) s = fmaf(g[i], g[i], s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < OPT_THREADS / 32; ++i) tot += sh[i];
+    atomicAdd(out, tot);
+  }
+}
+
+// hyper = {lr, 1 - b1^t, 1 - b2^t, max_grad_norm (<= 0: no clipping)}
+__global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const OptTensor* __restrict__ meta, const float* const* __restrict__ grads,
+                                                            const int32_t* __restrict__ blk_tensor,
+                                                            const int32_t* __restrict__ blk_chunk, const float* __restrict__ hyper,
+                                                            const float* __restrict__ grad_sq, float b1, float b2, float eps) {
+  const int t = blk_tensor[blockIdx.x];
+  const float* g = grads[t];
+  if (g == nullptr) return;   // parameter without a gradient this step: untouched, like torch optimizers
+  const OptTensor mt = meta[t];
+  const float lr = __ldg(hyper) * mt.lr_mul;
+  const float bc1 = __ldg(hyper + 1), bc2 = __ldg(hyper + 2), max_norm = __ldg(hyper + 3);
+  float clip = 1.f;
+  if (grad_sq != nullptr && max_norm > 0.f) clip = fminf(1.f, max_norm / (sqrtf(__ldg(grad_sq)) + 1e-6f));
+  const float step = lr * sqrtf(bc2) / bc1;
+  const float decay = 1.f - lr * mt.wd;
+  const int64_t base = (int64_t)blk_chunk[blockIdx.x] * OPT_CHUNK;
+  const int64_t end = min(base + OPT_CHUNK, mt.n);
+  auto upd = [&](float gi, float& m, float& v, float& p) {
+    gi *= clip;
+    m = fmaf(b1, m, (1.f - b1) * gi);
+    v = fmaf(b2, v, (1.f - b2) * gi * gi);
+    p = fmaf(-step, m / (sqrtf(v) + eps), p);
+    p *= decay;
+  };
+  if ((mt.n & 3) == 0) {
+    for (int64_t i = base + threadIdx.x * 4; i < end; i += OPT_THREADS * 4) {
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i));
+      float4 m = *reinterpret_cast<float4*>(mt.m + i), v = *reinterpret_cast<float4*>(mt.v + i);
+      float4 p = *reinterpret_cast<float4*>(mt.p + i);
+      upd(gg.x, m.x, v.x, p.x); upd(gg.y, m.y, v.y, p.y); upd(gg.z, m.z, v.z, p.z); upd(gg.w, m.w, v.w, p.w);
+      *reinterpret_cast<float4*>(mt.m + i) = m;
+      *reinterpret_cast<float4*>(mt.v + i) = v;
+      *reinterpret_cast<float4*>(mt.p + i) = p;
+    }
+  } else {
+    for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) upd(g[i], mt.m[i], mt.v[i], mt.p[i]);
+  }
+}
+
+int grad_sqnorm(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+                float* out, cudaStream_t st) {
+  if (nblocks <= 0) return MODCR_OK;
+  if (meta == nullptr || grads == nullptr || blk_tensor == nullptr || blk_chunk == nullptr || out == nullptr) {
+    set_error("grad_sqnorm: null table pointer");
+    return MODCR_ERR_SHAPE;
+  }
+  grad_sqnorm_kernel<<<nblocks, OPT_THREADS, 0, st>>>((const OptTensor*)meta, (const float* const*)grads, blk_tensor, blk_chunk,
+                                                     out);
+  return check_launch("grad_sqnorm");
+}
+
+int adamw_step(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+               const float* hyper, const float* grad_sq, float b1, float b2, float eps, cudaStream_t st) {
+  if (nblocks <= 0) return MODCR_OK;
+  if (meta == nullptr || grads == nullptr || blk_tensor == nullptr || blk_chunk == nullptr || hyper == nullptr) {
+    set_error("adamw_step: null table pointer");
+    return MODCR_ERR_SHAPE;
+  }
+  adamw_kernel<<<nblocks, OPT_THREADS, 0, st>>>((const OptTensor*)meta, (const float* const*)grads, blk_tensor, blk_chunk, hyper,
+                                               grad_sq, b1, b2, eps);
+  return check_launch("adamw_step");
+}
+
+}  // namespace modcr

@@ -52,6 +52,12 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
 
 // ClsLayer2 attention pooling (v10:816-829): w = softmax(q k^T + mask) (no 1/sqrt(d)), pooled = w k
 // q [N,H] and k [N,L,H] are bf16 (qk_f32 = 0) or fp32 (qk_f32 = 1)
+// fused multi-tensor gradient-norm + AdamW (csrc/optim.cu); `meta` = device array of OptTensor, `grads` = device array
+// of gradient pointers (NULL entries are skipped), one block per (tensor, 8192-element chunk) of the block table
+int grad_sqnorm(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+                float* out, cudaStream_t st);
+int adamw_step(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+               const float* hyper, const float* grad_sq, float b1, float b2, float eps, cudaStream_t st);
 // training-mode dropout with a counter-based mask (seed read from device memory): out16 = in16 * m, io32 = io32 * m (+ res32)
 int dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed, uint32_t site,
             float p, cudaStream_t st);

@@ -161,6 +161,16 @@ def align_softmax_ce_bwd(block, align_pos, total_label, out, gout, dblock, N, T,
                                                       _p(dblock), N, T, R, _stream()), "align_softmax_ce_bwd")
 
 
+def grad_sqnorm(meta, grads, blk_tensor, blk_chunk, nblocks, out_sq):
+    _lib.check(_lib.load().modcr_grad_sqnorm(_p(meta), _p(grads), _p(blk_tensor), _p(blk_chunk), nblocks, _p(out_sq),
+                                             _stream()), "grad_sqnorm")
+
+
+def adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta1, beta2, eps):
+    _lib.check(_lib.load().modcr_adamw_step(_p(meta), _p(grads), _p(blk_tensor), _p(blk_chunk), nblocks, _p(hyper),
+                                            _p(grad_sq), beta1, beta2, eps, _stream()), "adamw_step")
+
+
 def dropout(in16, out16, io32, res32, n, seed, site, p):
     """out16 = in16 * m (bf16), io32 = io32 * m (+ res32) (fp32, in place); m = keep / (1 - p), mask = f(seed, site, i)."""
     _lib.check(_lib.load().modcr_dropout(_p(in16), _p(out16), _p(io32), _p(res32), n, _p(seed), site, float(p), _stream()),

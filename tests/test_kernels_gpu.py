@@ -693,3 +693,42 @@ def test_head_attention_dropout_fwd_bwd():
     dk2, dv2 = torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV), torch.empty(N, L, H, dtype=torch.bfloat16, device=DEV)
     ops.cross_attn_q1_bwd(q2, k2, v2, out, lse, dout, dq2, dk2, dv2, N, L, H, heads, drop=(seed, site + 1, 0.1))
     assert nerr(dq2, qf.grad) < 2e-2 and nerr(dk2, kf.grad) < 2e-2 and nerr(dv2, vf.grad) < 2e-2
+
+
+def test_fused_adamw_with_clipping_matches_reference_update():
+    """Two launches (gradient norm, AdamW) against the per-tensor arithmetic of the reference driver:
+    clip_grad_norm_ + transformers.AdamW (eps inside the bias-corrected denominator), two LR groups, a tensor without
+    a gradient left untouched, odd-sized tensors, three steps."""
+    from modcr_b200.training import FusedAdamW
+    g = torch.Generator().manual_seed(0)
+    shapes = [(768, 768), (3072,), (13, 7), (2, 768), (5,)]
+    ps = [torch.randn(*sh, generator=g).to(DEV).requires_grad_(True) for sh in shapes]
+    ref = [p.detach().clone().double() for p in ps]
+    lr, b1, b2, eps, max_norm = 2e-3, 0.9, 0.999, 1e-5, 1.0
+    groups = [{"params": ps[:3], "lr": lr}, {"params": ps[3:], "lr": lr * 0.1}]
+    lrs = [lr, lr, lr, lr * 0.1, lr * 0.1]
+    opt = FusedAdamW(groups, lr=lr, betas=(b1, b2), eps=eps, max_grad_norm=max_norm)
+    m = [torch.zeros_like(r) for r in ref]
+    v = [torch.zeros_like(r) for r in ref]
+    for t in range(1, 4):
+        grads = [torch.randn(*sh, generator=g).to(DEV) * (3.0 if t == 2 else 0.01) for sh in shapes]
+        for i, p in enumerate(ps):
+            p.grad = None if (i == 4 and t == 2) else grads[i].clone()
+        versions = [p._version for p in ps]
+        norm = opt.step()
+        present = [grads[i].double() for i in range(5) if ps[i].grad is not None]
+        tot = torch.sqrt(sum((x * x).sum() for x in present))
+        assert abs(float(norm) - float(tot)) < 1e-3 * float(tot)
+        clip = min(1.0, max_norm / (float(tot) + 1e-6))
+        for i in range(5):
+            if ps[i].grad is None:
+                continue
+            gi = grads[i].double() * clip
+            m[i] = b1 * m[i] + (1 - b1) * gi
+            v[i] = b2 * v[i] + (1 - b2) * gi * gi
+            step = lrs[i] * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+            ref[i] = ref[i] - step * m[i] / (v[i].sqrt() + eps)
+        for i in range(5):
+            assert float((ps[i].detach().double() - ref[i]).abs().max()) < 2e-6, (t, i)
+            assert torch.equal(ps[i].grad, grads[i]) if ps[i].grad is not None else True    # .grad itself is not modified
+        assert all(p._version == vv + 1 for p, vv in zip(ps, versions))     # operand caches see the update
