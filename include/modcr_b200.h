@@ -79,6 +79,12 @@ typedef struct modcr_gemm_desc {
   int64_t ld_in;
   int32_t in_op;
   float* a_colsum;
+  /* training-mode dropout of the dense output inside the epilogue: C = dropout(f(acc + bias)) (+ in), i.e.
+   * LayerNorm(dropout(dense(x)) + residual) of BertSelfOutput / BertOutput without an extra pass; mask index m * N + n,
+   * drop_p = 0: off */
+  const uint32_t* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
 } modcr_gemm_desc;
 int modcr_gemm(const modcr_gemm_desc* d, void* stream);
 
@@ -97,10 +103,14 @@ typedef struct modcr_rowmap {
 int modcr_layernorm_fwd(const void* x, int32_t x_f32, modcr_rowmap xmap, const float* gamma, const float* beta,
                         void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd, int32_t M, int32_t H,
                         float eps, void* stream);
-/* dbias (optional) receives sum_rows dx = bias gradient of the Linear that produced x. fp32 outputs accumulate. */
+/* dbias (optional) receives sum_rows dx = bias gradient of the Linear that produced x. fp32 outputs accumulate.
+ * dx_masked (optional, training-mode dropout of that Linear's output: LayerNorm(dropout(dense(.)) + residual)): second
+ * bf16 [M,H] output dx * mask / (1 - p), the gradient w.r.t. the dense output, with the mask of the forward
+ * modcr_dropout call (same seed / site, element index m * H + column); dbias then sums the masked gradient. */
 int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, int32_t x_f32, modcr_rowmap xmap,
                         const float* mean, const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap,
-                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream);
+                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* dx_masked,
+                        const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream);
 
 /* BertEmbeddings.forward (a_transformers/modeling_bert.py:184-211): gather + sum + LayerNorm. */
 int modcr_txt_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,

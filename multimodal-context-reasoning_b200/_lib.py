@@ -19,7 +19,7 @@ class GemmDesc(C.Structure):
                 ("M", c_i32), ("N", c_i32), ("K", c_i32),
                 ("alpha", c_float), ("bias", c_void_p), ("act", c_i32),
                 ("aux", c_void_p), ("ldaux", c_i64), ("epi_in", c_void_p), ("ld_in", c_i64), ("in_op", c_i32),
-                ("a_colsum", c_void_p)]
+                ("a_colsum", c_void_p), ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float)]
 
 
 class RowMap(C.Structure):
@@ -53,7 +53,7 @@ SIGNATURES = {
     "modcr_layernorm_fwd": [c_void_p, c_i32, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p,
                             c_i32, c_i32, c_float, c_void_p],
     "modcr_layernorm_bwd": [c_void_p, RowMap, c_void_p, c_i32, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap,
-                            c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
+                            c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_void_p, C.c_uint32, c_float, c_void_p],
     "modcr_txt_embed_ln_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_float, c_void_p],
     "modcr_txt_embed_ln_bwd": [c_void_p, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -61,14 +61,13 @@ struct AttnParams {
   const uint32_t* drop_seed;   // device pointer to the step's seed; nullptr / drop_thr == 0: no dropout
   uint32_t drop_site, drop_thr;
   float drop_inv;              // 1 / (1 - p)
-  int seq_first;               // shared-memory key rows are [sequence ; prefix] (persistent forward) instead of [prefix ; sequence]
+  int kid_split, kid_sub;      // logical key id of shared-memory key row kk: kk < kid_split ? S + kk : kk - kid_sub
 };
 
 // logical key id of shared-memory key row kk (same in every kernel, whatever its row order): sequence key j -> j,
-// prefix key j -> S + j
+// prefix key j -> S + j.  [prefix(pad) ; sequence] rows: split = sub = Ppad; [sequence ; prefix] rows: split = sub = 0.
 DEVINL uint32_t drop_key_id(const AttnParams& p, int kk) {
-  if (p.seq_first) return (uint32_t)kk;
-  return kk < p.Ppad ? (uint32_t)(p.S + kk) : (uint32_t)(kk - p.Ppad);
+  return kk < p.kid_split ? (uint32_t)(p.S + kk) : (uint32_t)(kk - p.kid_sub);
 }
 
 template <int W>
@@ -138,7 +137,7 @@ struct FwdLayout {
   int off_p[8];                          // P blocks (16 KB each); block 0 overlays Q, block 1 overlays K when it fits
 };
 
-// `drow` = ((n * heads + h) * S + q) * (S + P): the row's base index into the dropout mask; `dseed` the step's seed
+// `drow` = drop_hash(seed, site, (n * heads + h) * S + q): the row part of the dropout mask hash
 template <int MODE, int W, int PASS>
 DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float* sBias, uint8_t* blk, int c0, int row,
                       int q, bool q_txt, uint32_t w, float& m, float& sum, float inv, float* pimg_row, uint32_t drow = 0,
@@ -165,7 +164,7 @@ DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float
     if (p.drop_thr != 0) {   // uniform: P V uses the dropped probabilities, the row sum the undropped ones
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        v[j] = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, c0 + j), p.drop_thr) ? v[j] * p.drop_inv : 0.f;
+        v[j] = drop_keep_row(drow, drop_key_id(p, c0 + j), p.drop_thr) ? v[j] * p.drop_inv : 0.f;
     }
     const int piece0 = (c0 & 63) >> 3;
 #pragma unroll
@@ -184,7 +183,7 @@ DEVINL void fwd_chunk(const AttnParams& p, float c1, uint32_t taddr, const float
         const int kk = c0 + j;
         if (kk >= p.T && kk < p.S) {
           float pr = fast_ex2(masked_s2<MODE>(v[j], c1, bb[j], kk, q, q_txt, p.T, w) - m) * inv;
-          if (p.drop_thr != 0) pr = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, kk), p.drop_thr) ? pr * p.drop_inv : 0.f;
+          if (p.drop_thr != 0) pr = drop_keep_row(drow, drop_key_id(p, kk), p.drop_thr) ? pr * p.drop_inv : 0.f;
           pimg_row[kk - p.T] = pr;
         }
       }
@@ -286,7 +285,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool warp_alive = (qt * 128 + warp * 32) < p.S;
     const bool q_txt = q < p.T;
     const uint32_t dseed = p.drop_thr != 0 ? __ldg(p.drop_seed) : 0u;
-    const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
+    const uint32_t drow = p.drop_thr != 0 ? drop_hash(dseed, p.drop_site, (uint32_t)((n * p.heads + h) * p.S + q)) : 0u;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
     float* pimg_row = nullptr;
@@ -591,7 +590,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const int n = w / p.heads, h = w - n * p.heads;
         const int st = i & 1;
         uint8_t* stage = smem + st * lay.stage_bytes;
-        const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
+        const uint32_t drow = p.drop_thr != 0 ? drop_hash(dseed, p.drop_site, (uint32_t)((n * p.heads + h) * p.S + q)) : 0u;
         // ---- per-key bias of this sequence, double-buffered by item parity: a slower thread of the group may still
         // be reading the previous item's values, but everyone is past the ones of two items ago (barrier below)
         float* sBias = sBiasAll + (g * 2 + (i & 1)) * 256;
@@ -670,7 +669,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 if (j < wcols) {
                   pr = fast_ex2(masked_s2<MODE>(v[j], c1, sBias[c0 + j], c0 + j, q, q_txt, p.T, wd) - m) * inv;
                   if (p.drop_thr != 0)   // the alignment head consumes the post-dropout probabilities (v10:982)
-                    pr = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, c0 + j), p.drop_thr) ? pr * p.drop_inv : 0.f;
+                    pr = drop_keep_row(drow, drop_key_id(p, c0 + j), p.drop_thr) ? pr * p.drop_inv : 0.f;
                 }
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile + lane * 128 + ((j ^ lane) << 2)), "f"(pr) : "memory");
               }
@@ -743,7 +742,7 @@ DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, 
       }
       float pd = pr[e];
       if (p.drop_thr != 0) {   // uniform: dV uses D o P, dS uses D o dP (D = keep / (1 - p)); delta is unchanged
-        const float dm = drop_keep(dseed, p.drop_site, drow + drop_key_id(p, kk), p.drop_thr) ? p.drop_inv : 0.f;
+        const float dm = drop_keep_row(drow, drop_key_id(p, kk), p.drop_thr) ? p.drop_inv : 0.f;
         pd *= dm;
         g *= dm;
       }
@@ -1039,7 +1038,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int q = qt * 128 + row;
         const bool alive = q < p.S;
         const bool q_txt = q < p.T;
-        const uint32_t drow = (uint32_t)(((n * p.heads + h) * p.S + q) * (p.S + p.P));
+        const uint32_t drow = p.drop_thr != 0 ? drop_hash(dseed, p.drop_site, (uint32_t)((n * p.heads + h) * p.S + q)) : 0u;
         const float lse2 = sLse[q], delta = sDelta[q];
         const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
         const float* darow =
@@ -1160,7 +1159,7 @@ static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
   p.lse = a.lse; p.probs_img = a.probs_img;
   p.ctx = (const bf16*)a.ctx; p.dctx = (const bf16*)a.dctx; p.dalign = a.dalign;
   p.dqkv = (bf16*)a.dqkv; p.dpkv = (bf16*)a.dpkv; p.dq_ws = a.dq_ws;
-  p.seq_first = 0;
+  p.kid_split = p.Ppad; p.kid_sub = p.Ppad;
   p.drop_seed = a.drop_seed; p.drop_site = a.drop_site; p.drop_thr = 0; p.drop_inv = 1.f;
   if (a.drop_p > 0.f) {
     if (!(a.drop_p < 1.f) || a.drop_seed == nullptr) {
@@ -1269,7 +1268,7 @@ int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream) {
     if (smem <= 232448) {
       AttnParams pp = p;
       pp.Kp = kp2;
-      pp.seq_first = 1;
+      pp.kid_split = 0; pp.kid_sub = 0;
       CUtensorMap tmQKV, tmTail, tmPKV, tmA, tmB;
       rc = make_tmap_3d(&tmQKV, a.qkv, 2, p.N, p.S, 3 * p.H, 3 * p.H, (uint64_t)p.S * 3 * p.H, 64, 64);
       if (rc) return rc;

@@ -75,6 +75,7 @@ int modcr_gemm(const modcr_gemm_desc* d, void* stream) {
   g.alpha = d->alpha; g.bias = d->bias; g.act = d->act;
   g.aux = d->aux; g.ldaux = d->ldaux; g.epi_in = d->epi_in; g.ld_in = d->ld_in; g.in_op = d->in_op;
   g.a_colsum = d->a_colsum;
+  g.drop_seed = d->drop_seed; g.drop_site = d->drop_site; g.drop_p = d->drop_p;
   return modcr::gemm_launch(g, S(stream));
 }
 
@@ -86,10 +87,11 @@ int modcr_layernorm_fwd(const void* x, int32_t x_f32, modcr_rowmap xmap, const f
 }
 int modcr_layernorm_bwd(const void* dy, modcr_rowmap dymap, const void* x, int32_t x_f32, modcr_rowmap xmap,
                         const float* mean, const float* rstd, const float* gamma, void* dx, modcr_rowmap dxmap,
-                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* stream) {
+                        float* dgamma, float* dbeta, float* dbias, int32_t M, int32_t H, void* dx_masked,
+                        const uint32_t* drop_seed, uint32_t drop_site, float drop_p, void* stream) {
   ARCH_OR_RETURN();
   return modcr::layernorm_bwd(dy, RM(dymap), x, x_f32, RM(xmap), mean, rstd, gamma, dx, RM(dxmap), dgamma, dbeta, dbias,
-                              M, H, S(stream));
+                              M, H, dx_masked, drop_seed, drop_site, drop_p, S(stream));
 }
 
 int modcr_txt_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
@@ -152,7 +154,7 @@ int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packe
   }
   modcr::RowMap id;
   int rc = modcr::layernorm_bwd(dy, RM(dymap), pre, 1, id, mean, rstd, gamma, dpre, id, dgamma, dbeta, dbias, (int)rows, H,
-                                S(stream));
+                                nullptr, nullptr, 0, 0.f, S(stream));
   if (rc) return rc;
   // dW[H, Dpad] = dpre^T packed      (A = dpre stored [K=rows, M=H], B = packed stored [K=rows, N=Dpad])
   modcr::GemmDesc g;

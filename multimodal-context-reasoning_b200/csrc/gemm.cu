@@ -26,6 +26,7 @@
 // 128 x 256 x 64 MACs, which is what lifts the kernel off the L2->SM bandwidth limit (ncu: profiles/).
 #include "gemm.h"
 
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -46,6 +47,11 @@ struct GemmParams {
   int in_op;      // 0 none, 1 add, 2 multiply by gelu'(in)
   int reduce_add; // output through TMA reduce-add (fp32 accumulate in place)
   float* a_colsum; // A MN-major only: a_colsum[m] += sum_k A[k,m] from the staged A tiles of the n == 0 tiles
+  // training-mode dropout of f(acc + bias) BEFORE the epilogue input is applied (LayerNorm(dropout(dense(x)) + residual)):
+  // keep = hash(*drop_seed, drop_site, m * N + n) >= drop_thr; drop_thr == 0: off
+  const uint32_t* drop_seed;
+  uint32_t drop_site, drop_thr;
+  float drop_inv;
 };
 
 template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
@@ -410,6 +416,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
         }
+        if (p.drop_thr != 0) {   // uniform
+          const uint32_t dseed = __ldg(p.drop_seed);
+          const uint32_t base = (uint32_t)(m0 + row) * (uint32_t)p.N + (uint32_t)n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_site, base + j, p.drop_thr) ? v[j] * p.drop_inv : 0.f;
+        }
         if (HAS_IN) {
           const uint32_t slot = cnt % C::IN_DEPTH;
           const int bi = g * C::IN_DEPTH + slot;
@@ -556,6 +568,16 @@ static int launch_n(const GemmDesc& g, cudaStream_t stream) {
   p.in_op = g.in_op;
   p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
   p.a_colsum = g.a_colsum;
+  p.drop_seed = g.drop_seed; p.drop_site = g.drop_site; p.drop_thr = 0; p.drop_inv = 1.f;
+  if (g.drop_p > 0.f) {
+    if (g.drop_seed == nullptr || !(g.drop_p < 1.f) || (double)g.M * g.N >= 4294967296.0 || g.split_k > 1 || g.accumulate) {
+      set_error("gemm: epilogue dropout needs a device seed pointer, p < 1, M*N < 2^32 and no split-K / accumulate");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    p.drop_thr = (uint32_t)fmin(4294967295.0, (double)g.drop_p * 4294967296.0);
+    if (p.drop_thr == 0) p.drop_thr = 1;
+    p.drop_inv = 1.0f / (1.0f - g.drop_p);
+  }
   if (g.a_colsum != nullptr && (!A_MN || HAS_IN)) {
     set_error("gemm: a_colsum needs A stored [K,M] (a_mn = 1) and no epilogue input");
     return MODCR_ERR_UNSUPPORTED;

@@ -25,6 +25,10 @@ struct GemmDesc {
   int64_t ld_in = 0;
   int in_op = 0;             // 1: C = f(acc) + in ; 2: C = f(acc) * gelu'(in)
   float* a_colsum = nullptr; // optional fp32 [M]: += sum_k A[k,m] (A MN-major only; the bias gradient of a wgrad)
+  // training-mode dropout of f(acc + bias) before the epilogue input: mask = hash(*drop_seed, drop_site, m * N + n)
+  const uint32_t* drop_seed = nullptr;
+  uint32_t drop_site = 0;
+  float drop_p = 0.f;
 };
 
 int gemm_launch(const GemmDesc& g, cudaStream_t stream);

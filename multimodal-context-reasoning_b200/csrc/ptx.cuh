@@ -346,6 +346,16 @@ DEVINL uint32_t drop_hash(uint32_t seed, uint32_t site, uint32_t idx) {
 }
 // keep probability 1 - p  <=>  hash >= p * 2^32
 DEVINL bool drop_keep(uint32_t seed, uint32_t site, uint32_t idx, uint32_t thr) { return drop_hash(seed, site, idx) >= thr; }
+// Two-level form for the attention kernels, where the per-element cost matters (they are issue-bound): the row part
+// rowh = drop_hash(seed, site, row) is computed once per thread and item, the element part is a Weyl step on the key id
+// followed by one multiply-xorshift round (5 integer ops per element instead of ~16).
+DEVINL bool drop_keep_row(uint32_t rowh, uint32_t kid, uint32_t thr) {
+  uint32_t x = rowh ^ (kid * 0x9E3779B1u);
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 13;
+  return x >= thr;
+}
 
 // byte offset of 16-byte piece `piece` (0..7) of row `row` inside a 128B-swizzled
 // [rows x 128 B] tile whose base is 1024 B aligned

@@ -127,8 +127,13 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const void* __restrict__ x, RowMap xmap,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               bf16* __restrict__ dx, RowMap dxmap, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dbias, int M, int H) {
+              float* __restrict__ dbias, int M, int H, bf16* __restrict__ dxm, const uint32_t* __restrict__ dseed_ptr,
+              uint32_t dsite, uint32_t dthr, float dinv) {
+  // dxm (training-mode dropout of the producing dense layer, LayerNorm(dropout(dense(.)) + residual)): second output
+  // dx * mask / (1 - p) -- the gradient w.r.t. the dense output -- and `dbias` then sums the masked gradient; `dx`
+  // stays the gradient of the residual branch.  Mask index = m * H + column, as in the forward modcr_dropout call.
   __shared__ float red[LNB_WARPS][32 * 8 + 1];
+  const uint32_t dseed = dthr != 0 ? __ldg(dseed_ptr) : 0u;
   const int wib = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int wstride = gridDim.x * LNB_WARPS;
@@ -169,11 +174,16 @@ ln_bwd_kernel(const bf16* __restrict__ dy, RowMap dymap, const void* __restrict_
     for (int i = 0; i < NV; ++i) {
       float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = rs * (d[i][j] * gm[i][j] - s1 - xh[i][j] * s2);
-        ax[i][j] += o[j];
-      }
+      for (int j = 0; j < 8; ++j) o[j] = rs * (d[i][j] * gm[i][j] - s1 - xh[i][j] * s2);
       reinterpret_cast<uint4*>(dxr)[lane + 32 * i] = pack8(o);
+      if (dthr != 0) {   // uniform
+        const uint32_t base = (uint32_t)m * (uint32_t)H + (uint32_t)(lane + 32 * i) * 8u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = drop_keep(dseed, dsite, base + j, dthr) ? o[j] * dinv : 0.f;
+        reinterpret_cast<uint4*>(dxm + (size_t)m * H)[lane + 32 * i] = pack8(o);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ax[i][j] += o[j];
     }
   }
   // cross-warp reduction of the three column accumulators, then one atomic per column per CTA
@@ -616,14 +626,25 @@ int layernorm_fwd(const void* x, int x_f32, RowMap xmap, const float* gamma, con
 
 int layernorm_bwd(const void* dy, RowMap dymap, const void* x, int x_f32, RowMap xmap, const float* mean,
                   const float* rstd, const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias,
-                  int M, int H, cudaStream_t st) {
+                  int M, int H, void* dxm, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st) {
   if (int rc = check_h(H, "layernorm_bwd")) return rc;
   if (M <= 0) return MODCR_OK;
+  uint32_t dthr = 0;
+  float dinv = 1.f;
+  if (dxm != nullptr) {
+    if (dseed == nullptr || !(dp > 0.f && dp < 1.f) || (double)M * H >= 4294967296.0) {
+      set_error("layernorm_bwd: the masked output needs a device seed pointer, 0 < p < 1 and M*H < 2^32");
+      return MODCR_ERR_SHAPE;
+    }
+    dthr = (uint32_t)fmin(4294967295.0, (double)dp * 4294967296.0);
+    if (dthr == 0) dthr = 1;
+    dinv = 1.0f / (1.0f - dp);
+  }
   const int grid = blocks_for(M, LNB_WARPS, 148);
   const int nv = H >> 8;
 #define LNB_LAUNCH(F32, NV)                                                                                          \
   ln_bwd_kernel<F32, NV><<<grid, LNB_WARPS * 32, 0, st>>>((const bf16*)dy, dymap, x, xmap, mean, rstd, gamma, (bf16*)dx, \
-                                                          dxmap, dgamma, dbeta, dbias, M, H)
+                                                          dxmap, dgamma, dbeta, dbias, M, H, (bf16*)dxm, dseed, dsite, dthr, dinv)
   if (x_f32) {
     if (nv == 1) LNB_LAUNCH(true, 1); else if (nv == 2) LNB_LAUNCH(true, 2); else if (nv == 3) LNB_LAUNCH(true, 3); else LNB_LAUNCH(true, 4);
   } else {

@@ -18,7 +18,7 @@ int layernorm_fwd(const void* x, int x_f32, RowMap xmap, const float* gamma, con
                   RowMap ymap, float* mean, float* rstd, int M, int H, float eps, cudaStream_t st);
 int layernorm_bwd(const void* dy, RowMap dymap, const void* x, int x_f32, RowMap xmap, const float* mean,
                   const float* rstd, const float* gamma, void* dx, RowMap dxmap, float* dgamma, float* dbeta, float* dbias,
-                  int M, int H, cudaStream_t st);
+                  int M, int H, void* dxm, const uint32_t* dseed, uint32_t dsite, float dp, cudaStream_t st);
 int txt_embed_ln_fwd(const int64_t* ids, const int64_t* tts, const int64_t* pos_ids, const float* word, const float* type,
                      const float* pos, const float* gamma, const float* beta, void* y, float* y32, RowMap ymap,
                      float* mean, float* rstd, int N, int T, int H, float eps, cudaStream_t st);

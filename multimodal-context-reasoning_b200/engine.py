@@ -189,8 +189,8 @@ def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save, drop=None, site=0):
     pre2 = _empty((M, H), F32, dev)                                         # fp32 residual stream
     if drop is not None and drop.p_hidden > 0.0:
         # BertOutput: LayerNorm(dropout(dense(y)) + x)  (a_transformers/modeling_bert.py:447-451)
-        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"))
-        ops.dropout(None, None, pre2, a32, M * H, drop.seed, site, drop.p_hidden)
+        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1,
+                 drop=(drop.seed, site, drop.p_hidden))
     else:
         ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1)
     y, y32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
@@ -210,18 +210,14 @@ def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None, drop=None, site=0):
     if z is None:
         z = _zeros_many([(H,), (H,), (H,), (I,), (H, I), (I, H)], dev)
     dgam, dbet, db2, db1, dW2, dW1 = z
+    hdrop = drop is not None and drop.p_hidden > 0.0
+    g2d = _empty((M, H), BF16, dev) if hdrop else g2      # gradient w.r.t. the dense output (masked under dropout)
     ops.layernorm_bwd(dy, sv["pre2"], sv["mean2"], sv["rstd2"], ps.f32(pfx + "output.LayerNorm.weight"), g2, dgam, dbet,
-                      db2, M, H)
+                      db2, M, H, dx_masked=g2d if hdrop else None,
+                      drop=(drop.seed, site, drop.p_hidden) if hdrop else None)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = db2
-    g2d = g2                                 # gradient w.r.t. the dense output (masked under dropout)
-    if drop is not None and drop.p_hidden > 0.0:
-        g2d = _empty((M, H), BF16, dev)
-        ops.dropout(g2, g2d, None, None, M * H, drop.seed, site, drop.p_hidden)
-        db2.zero_()                          # the LayerNorm kernel summed the unmasked gradient
-        grads[pfx + "output.dense.weight"] = wgrad(g2d, sv["gact"], H, I, M, zeroed=dW2, bias_out=db2)
-    else:
-        grads[pfx + "output.dense.weight"] = wgrad(g2, sv["gact"], H, I, M, zeroed=dW2)
+    grads[pfx + "output.dense.weight"] = wgrad(g2d, sv["gact"], H, I, M, zeroed=dW2)
     du = _empty((M, I), BF16, dev)
     ops.gemm(g2d, W2, du, M, I, H, b_mn=1, epi_in=sv["u"], in_op=2)          # (g2 W2) * GELU'(u)
     grads[pfx + "intermediate.dense.bias"] = db1
@@ -265,8 +261,8 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     pre1 = _empty((M, H), F32, dev)                                         # fp32 residual stream
     if drop is not None and drop.p_hidden > 0.0:
         # BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)  (a_transformers/modeling_bert.py:369-373)
-        ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"))
-        ops.dropout(None, None, pre1, x32, M * H, drop.seed, site + 1, drop.p_hidden)
+        ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
+                 epi_in=x32, in_op=1, drop=(drop.seed, site + 1, drop.p_hidden))
     else:
         ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
                  epi_in=x32, in_op=1)
@@ -290,18 +286,14 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop
     if z is None:
         z = _zeros_many([(H,), (H,), (H,), (3 * H,), (H, H), (3 * H, H)], dev)
     dgam, dbet, dbo, dbqkv, dWo, dWqkv = z
+    hdrop = drop is not None and drop.p_hidden > 0.0
+    g1d = _empty((M, H), BF16, dev) if hdrop else g1      # gradient w.r.t. the dense output (masked under dropout)
     ops.layernorm_bwd(da, sv["pre1"], sv["mean1"], sv["rstd1"], ps.f32(pfx + "output.LayerNorm.weight"), g1, dgam, dbet,
-                      dbo, M, H)
+                      dbo, M, H, dx_masked=g1d if hdrop else None,
+                      drop=(drop.seed, site + 1, drop.p_hidden) if hdrop else None)
     grads[pfx + "output.LayerNorm.weight"], grads[pfx + "output.LayerNorm.bias"] = dgam, dbet
     grads[pfx + "output.dense.bias"] = dbo
-    g1d = g1                                 # gradient w.r.t. the dense output (masked under dropout)
-    if drop is not None and drop.p_hidden > 0.0:
-        g1d = _empty((M, H), BF16, dev)
-        ops.dropout(g1, g1d, None, None, M * H, drop.seed, site + 1, drop.p_hidden)
-        dbo.zero_()                          # the LayerNorm kernel summed the unmasked gradient
-        grads[pfx + "output.dense.weight"] = wgrad(g1d, sv["ctx"], H, H, M, zeroed=dWo, bias_out=dbo)
-    else:
-        grads[pfx + "output.dense.weight"] = wgrad(g1, sv["ctx"], H, H, M, zeroed=dWo)
+    grads[pfx + "output.dense.weight"] = wgrad(g1d, sv["ctx"], H, H, M, zeroed=dWo)
     dctx = _empty((M, H), BF16, dev)
     ops.gemm(g1d, ps.bf16(pfx + "output.dense.weight"), dctx, M, H, H, b_mn=1)
     dqkv = _empty((M, 3 * H), BF16, dev)

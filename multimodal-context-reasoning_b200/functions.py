@@ -193,8 +193,8 @@ class ClsLayer2HeadFn(torch.autograd.Function):
             ops.cls_pool_attn_fwd(q, k, word_mask, w, pooled, N, L3, H, drop=wdrop)
             pre = E._empty((N, H), F32, dev)
             if hdrop:                                                      # LayerNorm(dropout(dense(.)) + cls), v10:831-833
-                ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"))
-                ops.dropout(None, None, pre, cls32, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+                ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"),
+                         epi_in=cls32, in_op=1, drop=(drop.seed, drop.site(i, 1), drop.p_hidden))
             else:
                 ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"),
                          epi_in=cls32, in_op=1)
@@ -226,17 +226,12 @@ class ClsLayer2HeadFn(torch.autograd.Function):
             dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads, None, drop, drop.site(i, 2) if drop else 0)
             g = E._empty((N, H), BF16, dev)
             dgam, dbet, dbd = E._zeros((H,), F32, dev), E._zeros((H,), F32, dev), E._zeros((H,), F32, dev)
+            gd = E._empty((N, H), BF16, dev) if hdrop else g    # gradient w.r.t. the dense output (masked under dropout)
             ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbd,
-                              N, H)
+                              N, H, dx_masked=gd if hdrop else None,
+                              drop=(drop.seed, drop.site(i, 1), drop.p_hidden) if hdrop else None)
             grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"], grads[pfx + "dense.bias"] = dgam, dbet, dbd
-            gd = g                               # gradient w.r.t. the dense output (masked under dropout)
-            if hdrop:
-                gd = E._empty((N, H), BF16, dev)
-                ops.dropout(g, gd, None, None, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
-                dbd.zero_()
-                grads[pfx + "dense.weight"] = E.wgrad(gd, sv["pooled"], H, H, N, bias_out=dbd)
-            else:
-                grads[pfx + "dense.weight"] = E.wgrad(g, sv["pooled"], H, H, N)
+            grads[pfx + "dense.weight"] = E.wgrad(gd, sv["pooled"], H, H, N)
             dpool = E._empty((N, H), BF16, dev)
             ops.gemm(gd, ps.bf16(pfx + "dense.weight"), dpool, N, H, H, b_mn=1)
             dq = E._empty((N, H), BF16, dev)
@@ -310,8 +305,8 @@ def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_l
         ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads, lse, drop=adrop)   # word_mask is never forwarded (v10:856-857)
         pre = E._empty((N, H), F32, dev)
         if drop is not None and drop.p_hidden > 0.0:                     # LayerNorm(dropout(CLS_ensem_1) + cls), v10:866-867
-            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"))
-            ops.dropout(None, None, pre, cls32, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
+            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
+                     in_op=1, drop=(drop.seed, drop.site(i, 1), drop.p_hidden))
         else:
             ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
                      in_op=1)                                            # + cls (residual of the LayerNorm)
@@ -364,18 +359,14 @@ class ClsLyxHeadFn(torch.autograd.Function):
             dc = E.ffn_bwd(ps, pfx, sv, d, N, H, I, grads, None, drop, drop.site(i, 2) if drop else 0)
             g = E._empty((N, H), BF16, dev)
             dgam, dbet, dbo, dbq, dbk, dbv = E._zeros_many([(H,)] * 6, dev)
+            hdrop = drop is not None and drop.p_hidden > 0.0
+            gd = E._empty((N, H), BF16, dev) if hdrop else g    # gradient w.r.t. the out_proj output (masked under dropout)
             ops.layernorm_bwd(dc, sv["pre"], sv["mean"], sv["rstd"], ps.f32(pfx + "LayerNorm.weight"), g, dgam, dbet, dbo,
-                              N, H)
+                              N, H, dx_masked=gd if hdrop else None,
+                              drop=(drop.seed, drop.site(i, 1), drop.p_hidden) if hdrop else None)
             grads[pfx + "LayerNorm.weight"], grads[pfx + "LayerNorm.bias"] = dgam, dbet
             grads[xa + "out_proj.bias"] = dbo
-            gd = g                               # gradient w.r.t. the out_proj output (masked under dropout)
-            if drop is not None and drop.p_hidden > 0.0:
-                gd = E._empty((N, H), BF16, dev)
-                ops.dropout(g, gd, None, None, N * H, drop.seed, drop.site(i, 1), drop.p_hidden)
-                dbo.zero_()
-                grads[xa + "out_proj.weight"] = E.wgrad(gd, sv["att"], H, H, N, bias_out=dbo)
-            else:
-                grads[xa + "out_proj.weight"] = E.wgrad(g, sv["att"], H, H, N)
+            grads[xa + "out_proj.weight"] = E.wgrad(gd, sv["att"], H, H, N)
             datt = E._empty((N, H), BF16, dev)
             ops.gemm(gd, ps.bf16(xa + "out_proj.weight"), datt, N, H, H, b_mn=1)
             dq = E._empty((N, H), BF16, dev)

@@ -39,7 +39,7 @@ def rowmap(rows_per_seq=0, seq_stride=0, row0=0):
 
 # --------------------------------------------------------------------------- GEMM
 def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=None, act=0, aux=None,
-         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None, a_colsum=None):
+         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None, a_colsum=None, drop=None):
     """C[M,N] = epi(alpha * A B^T); operands are raw 2-D views described by (ptr, ld).
     ``a_colsum`` (a_mn=1): fp32 [M] that receives += sum_k A[k,m] (the bias gradient of a wgrad)."""
     d = GemmDesc()
@@ -60,6 +60,8 @@ def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=N
     d.ld_in = ld_in if ld_in is not None else N
     d.in_op = in_op if epi_in is not None else 0
     d.a_colsum = _p(a_colsum)
+    if drop is not None:                      # (seed tensor, site, p): dropout of f(acc + bias) before `epi_in`
+        d.drop_seed, d.drop_site, d.drop_p = _p(drop[0]), int(drop[1]), float(drop[2])
     _lib.check(_lib.load().modcr_gemm(C.byref(d), _stream()), "gemm")
     return C_
 
@@ -71,10 +73,14 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, M, H, eps, xmap=IDENT, ymap=IDE
                                                ymap, _p(mean), _p(rstd), M, H, eps, _stream()), "layernorm_fwd")
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dbias, M, H, dymap=IDENT, xmap=IDENT, dxmap=IDENT):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dbias, M, H, dymap=IDENT, xmap=IDENT, dxmap=IDENT,
+                  dx_masked=None, drop=None):
+    """``dx_masked`` + ``drop`` = (seed, site, p): second output dx * mask / (1 - p) for the dense layer whose dropped
+    output fed this LayerNorm; ``dbias`` then sums the masked gradient."""
+    ds, dsite, dp = (None, 0, 0.0) if drop is None else (_p(drop[0]), int(drop[1]), float(drop[2]))
     _lib.check(_lib.load().modcr_layernorm_bwd(_p(dy), dymap, _p(x), int(x.dtype == F32), xmap, _p(mean), _p(rstd),
                                                _p(gamma), _p(dx), dxmap, _p(dgamma), _p(dbeta), _p(dbias), M, H,
-                                               _stream()), "layernorm_bwd")
+                                               _p(dx_masked), ds, dsite, dp, _stream()), "layernorm_bwd")
 
 
 def txt_embed_ln_fwd(ids, tts, pos_ids, word, type_, pos, gamma, beta, y, ymap, mean, rstd, N, T, H, eps, y32=None):

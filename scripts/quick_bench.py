@@ -12,7 +12,8 @@ B = int(os.environ.get("B", 32)); T = int(os.environ.get("T", 128)); R = int(os.
 steps = int(os.environ.get("STEPS", 5))
 dev = "cuda"
 torch.manual_seed(0)
-cfg = BertConfig(vocab_size=30567, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+cfg = BertConfig(vocab_size=30567, hidden_dropout_prob=float(os.environ.get("P_HIDDEN", 0.0)),
+                 attention_probs_dropout_prob=float(os.environ.get("P_ATTN", 0.0)))
 m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), 4).to(dev)
 m.train()
 b = synth.make_batch(B=B, T=T, R=R, seed=88)

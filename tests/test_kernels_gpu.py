@@ -549,6 +549,25 @@ def host_keep(seed, site, idx, p):
     return torch.from_numpy((x >= np.uint64(thr)))
 
 
+def host_keep_attn(seed, site, rows, kid, p):
+    """Two-level mask of the attention kernels (csrc/ptx.cuh drop_keep_row): row hash, then one round on the key id."""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFF)
+    x = ((rows.astype(np.uint64) ^ np.uint64(seed & 0xFFFFFFFF)) * np.uint64(0x9E3779B1)) & M
+    x ^= np.uint64((site * 0x85EBCA77) & 0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15)
+    x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    y = x ^ ((kid.astype(np.uint64) * np.uint64(0x9E3779B1)) & M)
+    y ^= y >> np.uint64(15)
+    y = (y * np.uint64(0x2C1B3C6D)) & M
+    y ^= y >> np.uint64(13)
+    thr = max(1, min(0xFFFFFFFF, int(float(np.float32(p)) * 4294967296.0)))
+    return torch.from_numpy((y >= np.uint64(thr)))
+
+
 def _seed_tensor(v):
     return torch.tensor([v], dtype=torch.int32, device=DEV)
 
@@ -611,9 +630,9 @@ def test_prefix_attention_dropout_fwd_bwd(mode, P, S, T):
     # host mask in the reference's key order [prefix ; sequence]: logical id of prefix key j is S + j, of sequence key j is j
     K = P + S
     kid = torch.cat([S + torch.arange(P), torch.arange(S)])
-    rows = (torch.arange(N * heads * S) * K).view(N, heads, S, 1)
-    idx = (rows + kid.view(1, 1, 1, K)).numpy().astype(np.uint64)
-    keep = host_keep(seedv, site, idx, p).to(DEV).float() / (1.0 - p)
+    rows = torch.arange(N * heads * S).view(N, heads, S, 1).expand(N, heads, S, K).numpy()
+    kids = kid.view(1, 1, 1, K).expand(N, heads, S, K).numpy()
+    keep = host_keep_attn(seedv, site, rows, kids, p).to(DEV).float() / (1.0 - p)
     qkv_r = qkv.float().requires_grad_(True)
     pkv_r = pkv.float().requires_grad_(True) if P > 0 else None
     am = _dense_mask(mode, N, S, T, P, key_mask, cm)
@@ -732,3 +751,35 @@ def test_fused_adamw_with_clipping_matches_reference_update():
             assert float((ps[i].detach().double() - ref[i]).abs().max()) < 2e-6, (t, i)
             assert torch.equal(ps[i].grad, grads[i]) if ps[i].grad is not None else True    # .grad itself is not modified
         assert all(p._version == vv + 1 for p, vv in zip(ps, versions))     # operand caches see the update
+
+
+def test_gemm_epilogue_dropout_and_layernorm_masked_gradient():
+    """Dense-output dropout fused into the GEMM epilogue (C = dropout(acc + bias) + residual) and its backward half
+    fused into the LayerNorm backward (second output dx * mask, bias gradient from the masked values), against the
+    host-restated mask."""
+    import numpy as np
+    M, H, K, p, site, seedv = 1424, 768, 768, 0.3, 31, 424242
+    seed = _seed_tensor(seedv)
+    A, W = rnd(M, K, seed=51), rnd(H, K, scale=0.05, seed=52)
+    bias = torch.randn(H, generator=torch.Generator().manual_seed(53)).to(DEV)
+    res = torch.randn(M, H, generator=torch.Generator().manual_seed(54)).to(DEV)
+    pre = torch.empty(M, H, device=DEV)
+    ops.gemm(A, W, pre, M, H, K, bias=bias, epi_in=res, in_op=1, drop=(seed, site, p))
+    keep = host_keep(seedv, site, np.arange(M * H), p).view(M, H).to(DEV).float() / (1 - p)
+    ref = (A.float() @ W.float().t() + bias) * keep + res
+    assert nerr(pre, ref) < 1e-4
+    # LayerNorm backward with the masked second output
+    gamma = (1 + 0.1 * torch.randn(H, generator=torch.Generator().manual_seed(55))).to(DEV)
+    x = pre.clone().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(x, (H,), gamma, torch.zeros(H, device=DEV), 1e-12)
+    dy = rnd(M, H, seed=56)
+    (y * dy.float()).sum().backward()
+    mean = pre.mean(-1)
+    rstd = (pre.var(-1, unbiased=False) + 1e-12).rsqrt()
+    dx = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    dxm = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    dgam, dbet, dbias = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.layernorm_bwd(dy, pre, mean, rstd, gamma, dx, dgam, dbet, dbias, M, H, dx_masked=dxm, drop=(seed, site, p))
+    assert nerr(dx, x.grad) < 1e-2
+    assert nerr(dxm, x.grad * keep) < 1e-2
+    assert nerr(dbias, (x.grad * keep).sum(0)) < 1e-2
