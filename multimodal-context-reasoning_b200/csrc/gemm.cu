@@ -61,16 +61,17 @@ struct Cfg {
   static constexpr int BN_LOAD = BN / NCTA;          // B rows this CTA loads
   static constexpr int B_BYTES = BN_LOAD * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // Epilogue chunks are 128 rows x 32 columns: 128-byte rows (SWIZZLE_128B) for fp32, 64-byte rows (SWIZZLE_64B)
-  // for bf16.  bf16 outputs (and the aux copy) are double-buffered per epilogue group, so a chunk is written while
-  // the TMA store of the previous one still reads its buffer and one block barrier per chunk suffices.
+  // Epilogue chunks are 128 rows x 64 bytes (SWIZZLE_64B): 32 bf16 or 16 fp32 columns.  Outputs (and the aux copy)
+  // and the epilogue-input tiles are double-buffered per epilogue group, so a chunk is written while the TMA store
+  // of the previous one still reads its buffer, the input of chunk k+1 is in flight while chunk k is processed, and
+  // one block barrier per chunk suffices.
   static constexpr int ES = OUT_F32 ? 4 : 2;
-  static constexpr int CHUNK_COLS = 32;
+  static constexpr int CHUNK_COLS = OUT_F32 ? 16 : 32;
   static constexpr int ROW_BYTES = CHUNK_COLS * ES;
   static constexpr int CHUNK_BYTES = 128 * ROW_BYTES;
   static constexpr int NCHUNK = BN / CHUNK_COLS;
-  static constexpr int NBUF = OUT_F32 ? 1 : 2;        // out (and aux) buffers per group
-  static constexpr int IN_DEPTH = OUT_F32 ? 1 : 2;    // epilogue-input buffers per group
+  static constexpr int NBUF = 2;                      // out (and aux) buffers per group
+  static constexpr int IN_DEPTH = 2;                  // epilogue-input buffers per group
   static constexpr int OUT_BUFS = 2 * NBUF * (HAS_AUX ? 2 : 1);
   static constexpr int IN_BUFS = HAS_IN ? 2 * IN_DEPTH : 0;
   static constexpr int BIAS_BYTES = 2 * 128 * 4;      // per group: the 128 bias values of its chunks of one tile
@@ -342,6 +343,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int gt = row;              // thread index inside the group
     const bool issuer = (q == 0 && lane == 0);
     const uint32_t bar_id = 1 + g;
+    constexpr int CC = C::CHUNK_COLS;
     uint8_t* out_base = sOut + g * C::NBUF * C::CHUNK_BYTES;
     uint8_t* aux_base = sOut + (2 * C::NBUF + g * C::NBUF) * C::CHUNK_BYTES;
     float* sBias = sBiasG + g * 128;
@@ -356,9 +358,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t aphase = (it >> 1) & 1;
       const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
       if (add_bias) {
-        // stage this tile's bias values of the group's chunks (thread i: chunk g + 2 (i / 32), column i % 32); every
+        // stage this tile's bias values of the group's chunks (thread i: chunk g + 2 (i / CC), column i % CC); every
         // thread of the group is past its last bias read of the previous tile (it passed that chunk's barrier)
-        const int col = tc.n * BN + (g + 2 * (gt >> 5)) * C::CHUNK_COLS + (gt & 31);
+        const int col = tc.n * BN + (g + 2 * (gt / CC)) * CC + (gt % CC);
         sBias[gt] = col < p.N ? __ldg(p.bias + col) : 0.f;
         named_bar_sync(bar_id, 128);
       }
@@ -367,8 +369,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
       for (int c = g, k = 0; c < C::NCHUNK; c += 2, ++k, ++cnt) {
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN + c * C::CHUNK_COLS;
-        float v[32];
-        tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+        float v[CC];
+        if constexpr (CC == 32) tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
+        else tmem_ld_32x16(taddr, reinterpret_cast<uint32_t*>(v));
         tmem_ld_wait();
         if (c + 2 >= C::NCHUNK) {  // this group's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
@@ -382,12 +385,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n0 = tc.n * BN + c * C::CHUNK_COLS;
         if (p.alpha != 1.0f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+          for (int j = 0; j < CC; ++j) v[j] *= p.alpha;
         }
         if (add_bias) {   // broadcast LDS: every lane reads the same address
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sBias + k * 32 + 4 * j);
+          for (int j = 0; j < CC / 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sBias + k * CC + 4 * j);
             v[4 * j + 0] += b4.x;
             v[4 * j + 1] += b4.y;
             v[4 * j + 2] += b4.z;
@@ -403,7 +406,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(bar_id, 128);
         }
-        if (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
+        if constexpr (HAS_AUX) {  // pre-activation copy (bf16) for the backward pass
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             sts128(aux_s + sw64_offset(row, j), pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
@@ -411,16 +414,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < CC; ++j) v[j] = gelu_fast(v[j]);
         } else if (p.act == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          for (int j = 0; j < CC; ++j) v[j] = tanhf(v[j]);
         }
         if (p.drop_thr != 0) {   // uniform
           const uint32_t dseed = __ldg(p.drop_seed);
           const uint32_t base = (uint32_t)(m0 + row) * (uint32_t)p.N + (uint32_t)n0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = drop_keep(dseed, p.drop_site, base + j, p.drop_thr) ? v[j] * p.drop_inv : 0.f;
+          for (int j = 0; j < CC; ++j) v[j] = drop_keep(dseed, p.drop_site, base + j, p.drop_thr) ? v[j] * p.drop_inv : 0.f;
         }
         if (HAS_IN) {
           const uint32_t slot = cnt % C::IN_DEPTH;
@@ -429,14 +432,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&infull[bi], (cnt / C::IN_DEPTH) & 1);
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 f = lds128f(in_s + sw128_offset(row, j));
+            for (int j = 0; j < 4; ++j) {
+              const float4 f = lds128f(in_s + sw64_offset(row, j));
               v[4 * j + 0] += f.x;
               v[4 * j + 1] += f.y;
               v[4 * j + 2] += f.z;
               v[4 * j + 3] += f.w;
             }
-          } else {
+          } else if constexpr (!OUT_F32) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 pk = lds128(in_s + sw64_offset(row, j));
@@ -456,10 +459,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           mbar_arrive(&inempty[bi]);
         }
-        if (OUT_F32) {
+        if constexpr (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128f(out_s + sw128_offset(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            sts128f(out_s + sw64_offset(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
