@@ -191,15 +191,24 @@ int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, con
  *           step can be replayed inside a CUDA graph while the schedule advances)
  * modcr_grad_sqnorm adds the sum of squares of every gradient to *out_sq (zeroed by the caller); modcr_adamw_step
  * scales the gradients by min(1, max_norm / (sqrt(*grad_sq) + 1e-6)) on the fly (grad_sq NULL: no clipping) and applies
- *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps) ; p -= lr wd p. */
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr sqrt(1-b2^t)/(1-b1^t) m / (sqrt(v) + eps) ; p -= lr wd p
+ * and, when `shadow` is set, rewrites the kernel-operand copy of the parameter in the same pass (shadow_kind 1: bf16,
+ * 2: fp32; same element order as p) so the next forward does not re-cast the weights.
+ * modcr_grad_clip is the in-place clip (g *= min(1, max_norm / (sqrt(*grad_sq) + 1e-6))) of the accumulation micro-steps
+ * that do not end in optimizer.step() (run_PMR_ModCR.py:215 clips after every backward). */
 typedef struct modcr_optim_tensor {
   float* p;
   float* m;
   float* v;
+  void* shadow;
   int64_t n;
   float lr_mul;
   float wd;
+  int32_t shadow_kind;
+  int32_t reserved;
 } modcr_optim_tensor;
+int modcr_grad_clip(const modcr_optim_tensor* meta, float* const* grads, const int32_t* blk_tensor,
+                    const int32_t* blk_chunk, int32_t nblocks, const float* grad_sq, float max_norm, void* stream);
 int modcr_grad_sqnorm(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
                        const int32_t* blk_chunk, int32_t nblocks, float* out_sq, void* stream);
 int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,

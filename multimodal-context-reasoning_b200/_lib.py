@@ -71,6 +71,7 @@ SIGNATURES = {
     "modcr_align_softmax_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i32, c_i32, c_i32,
                                    c_void_p],
     "modcr_grad_sqnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p],
+    "modcr_grad_clip": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_float, c_void_p],
     "modcr_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_float, c_float, c_float,
                          c_void_p],
     "modcr_dropout": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, C.c_uint32, c_float, c_void_p],

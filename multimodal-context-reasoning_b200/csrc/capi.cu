@@ -217,6 +217,11 @@ int modcr_grad_sqnorm(const modcr_optim_tensor* meta, const float* const* grads,
   ARCH_OR_RETURN();
   return modcr::grad_sqnorm(meta, grads, blk_tensor, blk_chunk, nblocks, out_sq, S(stream));
 }
+int modcr_grad_clip(const modcr_optim_tensor* meta, float* const* grads, const int32_t* blk_tensor,
+                    const int32_t* blk_chunk, int32_t nblocks, const float* grad_sq, float max_norm, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::grad_clip(meta, grads, blk_tensor, blk_chunk, nblocks, grad_sq, max_norm, S(stream));
+}
 int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, const int32_t* blk_tensor,
                      const int32_t* blk_chunk, int32_t nblocks, const float* hyper, const float* grad_sq, float beta1,
                      float beta2, float eps, void* stream) {

@@ -5,7 +5,11 @@
 //     transformers.AdamW.step()   (two LR groups: seq_enc x 0.1; eps 1e-5; bias correction; weight_decay 0)
 // -- ~485 tensors x ~10 tiny launches in the reference -- by two launches over a (tensor, chunk) block table:
 //   1. grad_sqnorm_kernel : sum of squares of every gradient -> one fp32 scalar
-//   2. adamw_kernel       : g' = g * min(1, max_norm / (norm + 1e-6)),  m, v, p update in one pass (7 x 4 B / element)
+//   2. adamw_kernel       : g' = g * min(1, max_norm / (norm + 1e-6)),  m, v, p update in one pass (7 x 4 B / element),
+//                           plus the refreshed kernel-operand copy of the parameter (bf16 weight / packed fp32 bias,
+//                           `shadow`), so the next forward pass does not re-cast ~100 weight matrices
+//   3. grad_clip_kernel   : the in-place clip of the micro-steps that do not end in optimizer.step()
+//                           (gradient accumulation, run_PMR_ModCR.py:215: clip_grad_norm_ after EVERY backward)
 // The update is the HuggingFace AdamW of the reference (eps added to sqrt(v) before the bias correction):
 //     m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ; p -= lr_t * m / (sqrt(v) + eps) ; p -= lr * wd * p
 //     lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
@@ -27,9 +31,12 @@ struct OptTensor {   // mirrors modcr_optim_tensor (include/modcr_b200.h)
   float* p;
   float* m;
   float* v;
+  void* shadow;          // optional operand copy refreshed with the update: bf16 (kind 1) or fp32 (kind 2), same layout
   int64_t n;
   float lr_mul;
   float wd;
+  int32_t shadow_kind;
+  int32_t reserved;
 };
 
 __global__ void __launch_bounds__(OPT_THREADS) grad_sqnorm_kernel(const OptTensor* __restrict__ meta, const float* const* __restrict__ grads,
@@ -97,9 +104,46 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const OptTensor* __r
       *reinterpret_cast<float4*>(mt.m + i) = m;
       *reinterpret_cast<float4*>(mt.v + i) = v;
       *reinterpret_cast<float4*>(mt.p + i) = p;
+      if (mt.shadow_kind == 1) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(mt.shadow) + i) = pk;
+      } else if (mt.shadow_kind == 2) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(mt.shadow) + i) = p;
+      }
     }
   } else {
-    for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) upd(g[i], mt.m[i], mt.v[i], mt.p[i]);
+    for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) {
+      upd(g[i], mt.m[i], mt.v[i], mt.p[i]);
+      if (mt.shadow_kind == 1) reinterpret_cast<__nv_bfloat16*>(mt.shadow)[i] = __float2bfloat16(mt.p[i]);
+      else if (mt.shadow_kind == 2) reinterpret_cast<float*>(mt.shadow)[i] = mt.p[i];
+    }
+  }
+}
+
+// in-place g *= min(1, max_norm / (sqrt(*grad_sq) + 1e-6)): torch.nn.utils.clip_grad_norm_ on an accumulating gradient
+__global__ void __launch_bounds__(OPT_THREADS) grad_clip_kernel(const OptTensor* __restrict__ meta, float* const* __restrict__ grads,
+                                                                const int32_t* __restrict__ blk_tensor,
+                                                                const int32_t* __restrict__ blk_chunk,
+                                                                const float* __restrict__ grad_sq, float max_norm) {
+  const float clip = max_norm / (sqrtf(__ldg(grad_sq)) + 1e-6f);
+  if (!(clip < 1.f)) return;   // torch clamps the coefficient to 1: nothing to do
+  const int t = blk_tensor[blockIdx.x];
+  float* g = grads[t];
+  if (g == nullptr) return;
+  const int64_t n = meta[t].n;
+  const int64_t base = (int64_t)blk_chunk[blockIdx.x] * OPT_CHUNK;
+  const int64_t end = min(base + OPT_CHUNK, n);
+  if ((n & 3) == 0) {
+    for (int64_t i = base + threadIdx.x * 4; i < end; i += OPT_THREADS * 4) {
+      float4 x = *reinterpret_cast<float4*>(g + i);
+      x.x *= clip; x.y *= clip; x.z *= clip; x.w *= clip;
+      *reinterpret_cast<float4*>(g + i) = x;
+    }
+  } else {
+    for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) g[i] *= clip;
   }
 }
 
@@ -113,6 +157,22 @@ int grad_sqnorm(const void* meta, const void* grads, const int32_t* blk_tensor, 
   grad_sqnorm_kernel<<<nblocks, OPT_THREADS, 0, st>>>((const OptTensor*)meta, (const float* const*)grads, blk_tensor, blk_chunk,
                                                      out);
   return check_launch("grad_sqnorm");
+}
+
+int grad_clip(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+              const float* grad_sq, float max_norm, cudaStream_t st) {
+  if (nblocks <= 0) return MODCR_OK;
+  if (meta == nullptr || grads == nullptr || blk_tensor == nullptr || blk_chunk == nullptr || grad_sq == nullptr) {
+    set_error("grad_clip: null table pointer");
+    return MODCR_ERR_SHAPE;
+  }
+  if (!(max_norm > 0.f)) {
+    set_error("grad_clip: max_norm must be positive");
+    return MODCR_ERR_SHAPE;
+  }
+  grad_clip_kernel<<<nblocks, OPT_THREADS, 0, st>>>((const OptTensor*)meta, (float* const*)grads, blk_tensor, blk_chunk, grad_sq,
+                                                   max_norm);
+  return check_launch("grad_clip");
 }
 
 int adamw_step(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,

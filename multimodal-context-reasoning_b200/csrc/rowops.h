@@ -56,6 +56,8 @@ int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int
 // of gradient pointers (NULL entries are skipped), one block per (tensor, 8192-element chunk) of the block table
 int grad_sqnorm(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
                 float* out, cudaStream_t st);
+int grad_clip(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
+              const float* grad_sq, float max_norm, cudaStream_t st);
 int adamw_step(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
                const float* hyper, const float* grad_sq, float b1, float b2, float eps, cudaStream_t st);
 // training-mode dropout with a counter-based mask (seed read from device memory): out16 = in16 * m, io32 = io32 * m (+ res32)

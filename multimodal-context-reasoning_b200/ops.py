@@ -172,6 +172,11 @@ def grad_sqnorm(meta, grads, blk_tensor, blk_chunk, nblocks, out_sq):
                                              _stream()), "grad_sqnorm")
 
 
+def grad_clip(meta, grads, blk_tensor, blk_chunk, nblocks, grad_sq, max_norm):
+    _lib.check(_lib.load().modcr_grad_clip(_p(meta), _p(grads), _p(blk_tensor), _p(blk_chunk), nblocks, _p(grad_sq),
+                                           float(max_norm), _stream()), "grad_clip")
+
+
 def adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta1, beta2, eps):
     _lib.check(_lib.load().modcr_adamw_step(_p(meta), _p(grads), _p(blk_tensor), _p(blk_chunk), nblocks, _p(hyper),
                                             _p(grad_sq), beta1, beta2, eps, _stream()), "adamw_step")

@@ -115,6 +115,31 @@ def load():
     return ns
 
 
+def load_ensemble():
+    """``modeling.modeling_ensemble`` of the reference (``Abstract_Specific``, ``PrefixMLP``).  Its RoBERTa import comes
+    from ``local_transformers.zip``, which the reference does not ship: that one name is stubbed (the tests pass their
+    own language-model stand-in to the constructor, the class never touches ``RobertaModel`` itself)."""
+    ns = load()
+    if getattr(ns, "ens", None) is not None:
+        return ns
+    import importlib
+    import transformers
+    chain = "local_transformers.adapter_transformers.models.roberta"
+    parts = chain.split(".")
+    for i in range(1, len(parts) + 1):
+        name = ".".join(parts[:i])
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules[chain].RobertaModel = type("RobertaModel", (), {})
+    for n in ("AutoTokenizer", "AutoModelForSeq2SeqLM", "LogitsProcessorList", "MinLengthLogitsProcessor"):
+        try:
+            getattr(transformers, n)
+        except Exception:
+            setattr(transformers, n, type(n, (), {}))
+    ns.ens = importlib.import_module("modeling.modeling_ensemble")
+    return ns
+
+
 def make_config(ns, **over):
     """BertConfig carrying the attributes the run scripts monkey-patch on
     (run_PMR_ModCR.py:717-726,736-748) plus transformers-5 gaps."""

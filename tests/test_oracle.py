@@ -176,3 +176,53 @@ def test_mc_scorers():
     w4, b4 = torch.randn(3, 64), torch.randn(3)
     loss4, lg4 = restate.choice_flattened_scorer(pooled, w4, b4, torch.tensor([2, 0]))
     assert lg4.shape == (2, 3) and float(loss4) > 0
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_abstract_specific_restatement_matches_live_reference():
+    """the REAL ``Abstract_Specific`` (modeling/modeling_ensemble.py:424-540) with the test stand-in for
+    its language model against ``restate.abstract_specific_forward`` -- forward values and the gradients that reach the
+    two mapping networks and the ClsLayer_lyx head -- plus the state_dict surface of this package's class."""
+    import standin_lm
+    from modcr_b200.modeling_bert import BertImgModel
+    from modcr_b200.modeling_ensemble import Abstract_Specific
+    from modcr_b200.modeling_utils import BertConfig
+    from modcr_b200.modeling_vcr_chunkalign_v10 import ChunkAlign_CLS_enc4_align_ensemble, SeqBertImgModel
+    ns = ref_shim.load_ensemble()
+    cfg = ref_shim.make_config(ns)
+    calec = ns.v10.ChunkAlign_CLS_enc4_align_ensemble(ns.tfm.BertImgModel(cfg), ns.v10.SeqBertImgModel(cfg), 4)
+    lm = standin_lm.StandInLM()
+    m = ns.ens.Abstract_Specific(roberta_model=lm, calec_model=calec, clip_model=None, num_labels=4)
+    lm_sd = {k: v.clone() for k, v in lm.state_dict().items()}
+    sd = params.fill_params(m.state_dict(), 6)   # fills in place (the state_dict aliases the parameters)
+    for k, v in lm_sd.items():
+        sd["roberta." + k] = v                   # keep the stand-in's own deterministic weights
+    m.load_state_dict(sd)
+    m.eval()
+    mine_cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    mine = Abstract_Specific(standin_lm.StandInLM(),
+                             ChunkAlign_CLS_enc4_align_ensemble(BertImgModel(mine_cfg), SeqBertImgModel(mine_cfg), 4))
+    assert {k: tuple(v.shape) for k, v in mine.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+
+    b = synth.make_batch(B=1, T=24, R=7, seed=3)
+    rb = standin_lm.make_inputs(4, seed=1)
+    out = m(None, None, rb["r_input_ids"], rb["r_token_type_ids"], rb["r_attention_mask"], b["input_ids"], b["img_feat"],
+            input_mask=b["input_mask"], token_type_ids=b["token_type_ids"], offsets=b["offsets"],
+            chunk_attention_mask=b["chunk_attention_mask"], gather_index=b["gather_index"], label=b["label_onehot"],
+            align_pos=b["align_pos"], total_label=b["total_label"])
+    out[0].backward()
+    sdr = {k: v.clone() for k, v in sd.items()}
+    watch = [k for k in sdr if k.startswith("mapping_network_") or k.startswith("abst_confidence_scorer.")
+             or k.startswith("calec.cls_ensemble_1.") or k.startswith("calec.cls_layer_lyx.0.cross_attention.v_proj.")]
+    for k in watch:
+        sdr[k].requires_grad_(True)
+    lm2 = standin_lm.StandInLM()
+    loss, logits, prefix_emb, cls = restate.abstract_specific_forward(sdr, CFG, b, lm2, rb)
+    loss.backward()
+    assert out[1][0] is None and out[1][1] is None and out[1][3] is None
+    assert float((out[0] - loss).detach().abs()) < 1e-6 and float((out[1][2] - loss).detach().abs()) < 1e-6
+    torch.testing.assert_close(out[2], logits, atol=1e-6, rtol=1e-5)
+    named = dict(m.named_parameters())
+    for k in watch:
+        torch.testing.assert_close(named[k].grad, sdr[k].grad, atol=1e-7, rtol=1e-4)
