@@ -57,7 +57,7 @@ size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
  *   img_embedding   modeling/modeling_transfomres.py:676-681
  * and their dgrad / wgrad in the backward pass (autograd of the reference).
  *   a_mn = 0: A stored [M,K];  a_mn = 1: A stored [K,M]      (same for B with N)
- *   act: 0 none, 1 GELU(erf), 2 tanh;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in)
+ *   act: 0 none, 1 GELU(erf), 2 tanh, 3 ReLU;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in)
  *   aux: optional bf16 copy of the pre-activation;  c_fp32 + accumulate / split_k: wgrad
  *   a_colsum (a_mn = 1 only): a_colsum[m] += sum_k A[k,m], fp32 -- the bias gradient dY^T 1 of the Linear whose weight
  *   gradient dW = dY^T X this call computes, summed from the dY tiles the kernel stages anyway (replaces the reference's
@@ -264,6 +264,8 @@ typedef struct modcr_scorer_desc {
   void* dx;               /* backward: bf16 [rows,K] */
   float* dW;              /* backward: fp32 [C,K], accumulates */
   float* db;              /* backward: fp32 [C], accumulates */
+  int32_t loss_kind;      /* 0: cross-entropy over [rows*C/G, G]; 1: instance_bce_with_logits (modeling/modeling_bert.py:416-421):
+                             mean over all elements of BCE-with-logits against `soft`, times G (= labels.size(1)) */
 } modcr_scorer_desc;
 int modcr_mc_scorer_ce_fwd(const modcr_scorer_desc* d, void* stream);
 int modcr_mc_scorer_ce_bwd(const modcr_scorer_desc* d, void* stream);
@@ -278,6 +280,15 @@ int modcr_copy_rows(const void* src, int64_t src_seq_stride, int32_t srow0, void
                     int32_t drow0, int32_t nseq, int32_t nrows, int32_t H, int32_t accumulate, void* stream);
 int modcr_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream);
 int modcr_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+/* 'mlp' classifier of ImageBertForMultipleChoice (modeling/modeling_bert.py:511-528: Linear -> ReLU [-> BertLayerNorm] ->
+ * Linear): the ReLU runs in the modcr_gemm epilogue (act = 3); relu_bwd is dx = dy * (y > 0) on the bf16 ReLU output;
+ * rowln_* is the LayerNorm over hidden*cls_hidden_scale columns of the few [questions] rows (any H % 8 == 0; bf16 in/out,
+ * fp32 statistics; dgamma / dbeta accumulate). */
+int modcr_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+int modcr_rowln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int32_t M,
+                    int32_t H, float eps, void* stream);
+int modcr_rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                    float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream);
 int modcr_key_bias(const float* mask, float* kbias, int64_t total, void* stream);
 int modcr_chunk_bits(const float* chunk_mask, uint32_t* bits, int32_t N, int32_t T, int32_t cwords, void* stream);
 int modcr_accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int32_t cols,

@@ -40,7 +40,8 @@ class ScorerDesc(C.Structure):
                 ("rows", c_i32), ("K", c_i32), ("C", c_i32), ("G", c_i32),
                 ("hard", c_void_p), ("soft", c_void_p), ("logits", c_void_p), ("loss", c_void_p),
                 ("mp", c_void_p), ("pred", c_void_p), ("matched", c_void_p), ("num_choice", c_i32),
-                ("gout", c_float), ("dx", c_void_p), ("dW", c_void_p), ("db", c_void_p)]
+                ("gout", c_float), ("dx", c_void_p), ("dW", c_void_p), ("db", c_void_p),
+                ("loss_kind", c_i32)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/modcr_b200.h
@@ -90,6 +91,10 @@ SIGNATURES = {
     "modcr_colsum": [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p],
     "modcr_copy_rows": [c_void_p, c_i64, c_i32, c_void_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_void_p],
     "modcr_add_bf16": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "modcr_relu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "modcr_rowln_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_float, c_void_p],
+    "modcr_rowln_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
+                        c_void_p],
     "modcr_tanh_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "modcr_key_bias": [c_void_p, c_void_p, c_i64, c_void_p],
     "modcr_chunk_bits": [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p],

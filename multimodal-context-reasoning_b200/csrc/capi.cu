@@ -266,6 +266,7 @@ static void to_scorer(const modcr_scorer_desc* d, modcr::ScorerDesc& s) {
   s.x = d->x; s.W = d->W; s.b = d->b; s.rows = d->rows; s.K = d->K; s.C = d->C; s.G = d->G;
   s.hard = d->hard; s.soft = d->soft; s.logits = d->logits; s.loss = d->loss; s.mp = d->mp; s.pred = d->pred;
   s.matched = d->matched; s.num_choice = d->num_choice; s.gout = d->gout; s.dx = d->dx; s.dW = d->dW; s.db = d->db;
+  s.loss_kind = d->loss_kind;
 }
 int modcr_mc_scorer_ce_fwd(const modcr_scorer_desc* d, void* stream) {
   ARCH_OR_RETURN();
@@ -309,6 +310,20 @@ int modcr_copy_rows(const void* src, int64_t src_seq_stride, int32_t srow0, void
 int modcr_add_bf16(const void* a, const void* b, void* y, int64_t n, void* stream) {
   ARCH_OR_RETURN();
   return modcr::add_bf16(a, b, y, n, S(stream));
+}
+int modcr_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::relu_bwd(dy, y, dx, n, S(stream));
+}
+int modcr_rowln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int32_t M,
+                    int32_t H, float eps, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::rowln_fwd(x, gamma, beta, y, mean, rstd, M, H, eps, S(stream));
+}
+int modcr_rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                    float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::rowln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, H, S(stream));
 }
 int modcr_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
   ARCH_OR_RETURN();

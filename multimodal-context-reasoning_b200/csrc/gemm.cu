@@ -43,7 +43,7 @@ struct GemmParams {
   int m_tiles, n_tiles;
   float alpha;
   const float* bias;
-  int act;        // 0 none, 1 gelu(erf), 2 tanh
+  int act;        // 0 none, 1 gelu(erf), 2 tanh, 3 relu
   int in_op;      // 0 none, 1 add, 2 multiply by gelu'(in)
   int reduce_add; // output through TMA reduce-add (fp32 accumulate in place)
   float* a_colsum; // A MN-major only: a_colsum[m] += sum_k A[k,m] from the staged A tiles of the n == 0 tiles
@@ -418,6 +418,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else if (p.act == 2) {
 #pragma unroll
           for (int j = 0; j < CC; ++j) v[j] = tanhf(v[j]);
+        } else if (p.act == 3) {
+#pragma unroll
+          for (int j = 0; j < CC; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.drop_thr != 0) {   // uniform
           const uint32_t dseed = __ldg(p.drop_seed);

@@ -799,6 +799,7 @@ struct ScorerParams {
   bf16* dx;
   float* dW;
   float* db;
+  int loss_kind;  // 0 cross-entropy over the view [V,G]; 1 instance_bce_with_logits (modeling_bert.py:416-421)
 };
 
 DEVINL void scorer_logits(const ScorerParams& p) {
@@ -834,6 +835,14 @@ __global__ void __launch_bounds__(256) scorer_fwd_kernel(const ScorerParams p) {
   float ls = 0.f;
   for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
     const float* lg = p.logits + (size_t)v * p.G;
+    if (p.loss_kind == 1) {
+      // mean over all V*G elements of softplus(l) - t*l, times labels.size(1) = G  ==  sum / V
+      for (int g = 0; g < p.G; ++g) {
+        const float l = lg[g], t = p.soft[(size_t)v * p.G + g];
+        ls += fmaxf(l, 0.f) - l * t + log1pf(expf(-fabsf(l)));
+      }
+      continue;
+    }
     float mx = -INFINITY;
     for (int g = 0; g < p.G; ++g) mx = fmaxf(mx, lg[g]);
     float se = 0.f;
@@ -881,6 +890,11 @@ __global__ void __launch_bounds__(256) scorer_bwd_kernel(const ScorerParams p) {
   const float scale = p.gout / (float)p.V;
   for (int v = threadIdx.x; v < p.V; v += blockDim.x) {
     const float* lg = p.logits + (size_t)v * p.G;
+    if (p.loss_kind == 1) {  // d/dl [softplus(l) - t*l] = sigmoid(l) - t
+      for (int g = 0; g < p.G; ++g)
+        dl[(size_t)v * p.G + g] = (1.f / (1.f + expf(-lg[g])) - p.soft[(size_t)v * p.G + g]) * scale;
+      continue;
+    }
     float mx = -INFINITY;
     for (int g = 0; g < p.G; ++g) mx = fmaxf(mx, lg[g]);
     float se = 0.f;
@@ -947,6 +961,11 @@ static int scorer_params(const ScorerDesc& d, ScorerParams& p, const char* what)
   p.V = d.rows * d.C / d.G; p.hard = d.hard; p.soft = d.soft; p.logits = d.logits; p.loss = d.loss; p.mp = d.mp;
   p.pred = d.pred; p.matched = d.matched; p.num_choice = d.num_choice; p.gout = d.gout; p.dx = (bf16*)d.dx; p.dW = d.dW;
   p.db = d.db;
+  p.loss_kind = d.loss_kind;
+  if (d.loss_kind != 0 && (d.loss_kind != 1 || d.soft == nullptr)) {
+    set_error("%s: loss_kind %d needs fp32 targets (1 = BCE with logits) or must be 0", what, d.loss_kind);
+    return MODCR_ERR_SHAPE;
+  }
   return MODCR_OK;
 }
 

@@ -488,6 +488,79 @@ __global__ void tanh_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
   }
 }
 
+// dx = dy * (y > 0)   (ReLU backward of the mlp classifier, modeling/modeling_bert.py:516-528; y = relu output)
+__global__ void relu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ dx, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy) + i), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(y) + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = b[j] > 0.f ? a[j] : 0.f;
+    reinterpret_cast<uint4*>(dx)[i] = pack8(a);
+  }
+}
+
+// LayerNorm of a few wide rows (the mlp classifier's BertLayerNorm over hidden*cls_hidden_scale columns,
+// modeling/modeling_bert.py:519): one CTA per row, any H that is a multiple of 8.  Not a hot kernel (rows = questions).
+DEVINL float cta_sum256(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sh[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) rowln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ y,
+                                                        float* __restrict__ mean, float* __restrict__ rstd, int H, float eps) {
+  __shared__ float sh[8];
+  const bf16* xr = x + (size_t)blockIdx.x * H;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < H; c += 256) s += __bfloat162float(xr[c]);
+  const float mu = cta_sum256(s, sh) / (float)H;
+  float q = 0.f;
+  for (int c = threadIdx.x; c < H; c += 256) {
+    const float d = __bfloat162float(xr[c]) - mu;
+    q += d * d;
+  }
+  const float rs = rsqrtf(cta_sum256(q, sh) / (float)H + eps);
+  for (int c = threadIdx.x; c < H; c += 256)
+    y[(size_t)blockIdx.x * H + c] = __float2bfloat16((__bfloat162float(xr[c]) - mu) * rs * gamma[c] + beta[c]);
+  if (threadIdx.x == 0) {
+    mean[blockIdx.x] = mu;
+    rstd[blockIdx.x] = rs;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy  (atomics over rows)
+__global__ void __launch_bounds__(256) rowln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, bf16* __restrict__ dx,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int H) {
+  __shared__ float sh[8];
+  const size_t base = (size_t)blockIdx.x * H;
+  const float mu = mean[blockIdx.x], rs = rstd[blockIdx.x];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < H; c += 256) {
+    const float g = __bfloat162float(dy[base + c]) * gamma[c];
+    const float xh = (__bfloat162float(x[base + c]) - mu) * rs;
+    s1 += g;
+    s2 += g * xh;
+  }
+  const float m1 = cta_sum256(s1, sh) / (float)H;
+  const float m2 = cta_sum256(s2, sh) / (float)H;
+  for (int c = threadIdx.x; c < H; c += 256) {
+    const float d = __bfloat162float(dy[base + c]);
+    const float xh = (__bfloat162float(x[base + c]) - mu) * rs;
+    dx[base + c] = __float2bfloat16(rs * (d * gamma[c] - m1 - xh * m2));
+    atomicAdd(dgamma + c, d * xh);
+    atomicAdd(dbeta + c, d);
+  }
+}
+
 // ---------------------------------------------------------------------------- masks
 // kbias[n, k] = (1 - mask[n, k]) * -10000   (modeling_transfomres.py:628-641, no dtype cast)
 __global__ void key_bias_kernel(const float* __restrict__ mask, float* __restrict__ kbias, int64_t total) {
@@ -738,6 +811,35 @@ int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st) 
   if (n == 0) return MODCR_OK;
   add_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n / 8);
   return check_launch("add_bf16");
+}
+
+int relu_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st) {
+  if (n <= 0 || n % 8 != 0) {
+    set_error("relu_bwd: n=%lld must be a positive multiple of 8", (long long)n);
+    return MODCR_ERR_SHAPE;
+  }
+  relu_bwd_kernel<<<blocks_for(n / 8, 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (bf16*)dx, n / 8);
+  return check_launch("relu_bwd");
+}
+
+int rowln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int H,
+              float eps, cudaStream_t st) {
+  if (M <= 0 || H <= 0 || H % 8 != 0) {
+    set_error("rowln_fwd: bad shape M=%d H=%d (H must be a multiple of 8)", M, H);
+    return MODCR_ERR_SHAPE;
+  }
+  rowln_fwd_kernel<<<M, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)y, mean, rstd, H, eps);
+  return check_launch("rowln_fwd");
+}
+
+int rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+              float* dgamma, float* dbeta, int M, int H, cudaStream_t st) {
+  if (M <= 0 || H <= 0 || H % 8 != 0) {
+    set_error("rowln_bwd: bad shape M=%d H=%d (H must be a multiple of 8)", M, H);
+    return MODCR_ERR_SHAPE;
+  }
+  rowln_bwd_kernel<<<M, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (bf16*)dx, dgamma, dbeta, H);
+  return check_launch("rowln_bwd");
 }
 
 int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st) {

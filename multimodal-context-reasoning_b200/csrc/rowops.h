@@ -36,6 +36,11 @@ int copy_rows(const void* src, int64_t src_seq_stride, int srow0, void* dst, int
               int nrows, int H, int accumulate, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st);
 int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
+int relu_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
+int rowln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int H,
+              float eps, cudaStream_t st);
+int rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+              float* dgamma, float* dbeta, int M, int H, cudaStream_t st);
 int key_bias(const float* mask, float* kbias, int64_t total, cudaStream_t st);
 int chunk_bits(const float* cmask, uint32_t* bits, int N, int T, int cwords, cudaStream_t st);
 int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_id, int T, int max_chunks,
@@ -95,6 +100,7 @@ struct ScorerDesc {
   void* dx = nullptr;          // bf16 [rows, K]
   float* dW = nullptr;         // fp32 [C, K] accumulate
   float* db = nullptr;         // fp32 [C] accumulate
+  int loss_kind = 0;           // 0 CE, 1 BCE-with-logits x G (instance_bce_with_logits)
 };
 int mc_scorer_ce_fwd(const ScorerDesc& d, cudaStream_t st);
 int mc_scorer_ce_bwd(const ScorerDesc& d, cudaStream_t st);

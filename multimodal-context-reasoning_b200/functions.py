@@ -416,7 +416,7 @@ class ScorerFn(torch.autograd.Function):
     """Linear(K -> C) + cross-entropy (+ binary_to_mp/argmax/matched) in one kernel (v10:1063-1069)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, hard, soft, G, num_choice, want_mp):
+    def forward(ctx, x, W, b, hard, soft, G, num_choice, want_mp, loss_kind=0):
         rows, K = x.shape
         Cc = W.shape[0]
         dev = x.device
@@ -429,8 +429,9 @@ class ScorerFn(torch.autograd.Function):
             pred = E._empty((rows // num_choice,), torch.int64, dev)
             matched = E._empty((rows // num_choice,), torch.uint8, dev)
         Wc, bc = W.detach().contiguous(), (None if b is None else b.detach().contiguous())
-        ops.mc_scorer_ce_fwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice)
-        ctx.sv = (xb, Wc, bc, hard, soft, logits, G, x.dtype, b is not None)
+        ops.mc_scorer_ce_fwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice,
+                             loss_kind=loss_kind)
+        ctx.sv = (xb, Wc, bc, hard, soft, logits, G, x.dtype, b is not None, loss_kind)
         outs = [loss.view(()), logits]
         if want_mp:
             outs += [mp, pred, matched.bool()]
@@ -440,7 +441,7 @@ class ScorerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss, *unused):
-        xb, Wc, bc, hard, soft, logits, G, xdtype, has_b = ctx.sv
+        xb, Wc, bc, hard, soft, logits, G, xdtype, has_b, loss_kind = ctx.sv
         rows, K = xb.shape
         Cc = Wc.shape[0]
         dev = xb.device
@@ -448,10 +449,57 @@ class ScorerFn(torch.autograd.Function):
         dW = E._zeros((Cc, K), F32, dev)
         db = E._zeros((Cc,), F32, dev) if has_b else None
         # the upstream gradient is a device scalar; fold it in afterwards to avoid a host sync
-        ops.mc_scorer_ce_bwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, 1.0, dx, dW, db)
+        ops.mc_scorer_ce_bwd(xb, Wc, bc, rows, K, Cc, G, hard, soft, logits, 1.0, dx, dW, db, loss_kind=loss_kind)
         g = dloss.to(F32)
         dxo = (dx.float() * g).to(xdtype) if xdtype != BF16 else (dx * g.to(BF16))
-        return dxo, dW * g, (db * g if has_b else None), None, None, None, None, None
+        return dxo, dW * g, (db * g if has_b else None), None, None, None, None, None, None
+
+
+class MlpHiddenFn(torch.autograd.Function):
+    """Hidden part of the 'mlp' classifier of ImageBertForMultipleChoice (modeling/modeling_bert.py:511-528):
+    ``z = [LayerNorm](relu(x W1^T + b1))`` -- tcgen05 GEMM with the bias + ReLU epilogue, row LayerNorm over
+    ``hidden*cls_hidden_scale`` columns when ``use_img_layernorm``; the final Linear + loss is ``ScorerFn``."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, gamma, beta, w1_16, eps):
+        rows, K = x.shape
+        Hm = W1.shape[0]
+        dev = x.device
+        xb = _as_bf16(x).contiguous()
+        h = E._empty((rows, Hm), BF16, dev)
+        ops.gemm(xb, w1_16, h, rows, Hm, K, bias=b1.detach(), act=3)
+        mean = rstd = None
+        z = h
+        if gamma is not None:
+            z = E._empty((rows, Hm), BF16, dev)
+            mean, rstd = E._empty((rows,), F32, dev), E._empty((rows,), F32, dev)
+            ops.rowln_fwd(h, gamma.detach(), beta.detach(), z, mean, rstd, rows, Hm, eps)
+        ctx.sv = (xb, h, mean, rstd, None if gamma is None else gamma.detach(), w1_16, x.dtype, x.requires_grad)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xb, h, mean, rstd, gamma, w1_16, xdtype, need_dx = ctx.sv
+        rows, K = xb.shape
+        Hm = h.shape[1]
+        dev = xb.device
+        dzb = _as_bf16(dz).contiguous()
+        dgamma = dbeta = None
+        dh = dzb
+        if gamma is not None:
+            dh = E._empty((rows, Hm), BF16, dev)
+            dgamma, dbeta = E._zeros((Hm,), F32, dev), E._zeros((Hm,), F32, dev)
+            ops.rowln_bwd(dzb, h, mean, rstd, gamma, dh, dgamma, dbeta, rows, Hm)
+        dpre = E._empty((rows, Hm), BF16, dev)
+        ops.relu_bwd(dh, h, dpre)
+        db1 = E._zeros((Hm,), F32, dev)
+        dW1 = E.wgrad(dpre, xb, Hm, K, rows, bias_out=db1)
+        dx = None
+        if need_dx:
+            dxb = E._empty((rows, K), BF16, dev)
+            ops.gemm(dpre, w1_16, dxb, rows, K, Hm, b_mn=1)
+            dx = dxb.to(xdtype)
+        return dx, dW1, db1, dgamma, dbeta, None, None
 
 
 class AlignLossFn(torch.autograd.Function):

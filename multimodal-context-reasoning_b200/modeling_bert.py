@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from . import engine as E
-from .functions import DropoutFn, EncoderFn, EncoderRun, ScorerFn
+from .functions import DropoutFn, EncoderFn, EncoderRun, MlpHiddenFn, ScorerFn
 from .modeling_utils import (BertConfig, CaptionPreTrainedModel, ImgPreTrainedModel, cfg_get, check_no_dropout,  # noqa: F401
                              engine_cfg)
 
@@ -214,6 +214,39 @@ def instance_bce_with_logits(logits, labels, reduction="mean"):
     return loss
 
 
+def _make_classifier(config, in_features, num_labels, kind, use_img_layernorm):
+    """Classifier variants of modeling/modeling_bert.py:511-530 (same nn.Sequential layout => same state_dict keys)."""
+    if kind == "linear":
+        return nn.Linear(in_features, num_labels)
+    if kind != "mlp":
+        raise ValueError("config.classifier must be 'linear' or 'mlp' (got %r)" % (kind,))
+    hid = config.hidden_size * cfg_get(config, "cls_hidden_scale", 2)
+    if use_img_layernorm:
+        return nn.Sequential(nn.Linear(in_features, hid), nn.ReLU(),
+                             BertLayerNorm(hid, eps=config.layer_norm_eps), nn.Linear(hid, num_labels))
+    return nn.Sequential(nn.Linear(in_features, hid), nn.ReLU(), nn.Linear(hid, num_labels))
+
+
+def _classifier_hidden(model, x):
+    """Runs everything of ``model.classifier`` but its last Linear (which the fused scorer kernel applies together
+    with the loss); returns ``(hidden, last_linear)``."""
+    cls = model.classifier
+    if isinstance(cls, nn.Linear):
+        return x, cls
+    lin0, last = cls[0], cls[-1]
+    ln = cls[2] if len(cls) == 4 else None
+    if lin0.weight.dtype != torch.float32 or not lin0.weight.is_cuda:
+        raise RuntimeError("modcr_b200: classifier weights must be float32 CUDA tensors (no CPU fallback)")
+    named = {"classifier.0.weight": lin0.weight}
+    ps = model._cls_store
+    if ps is None or ps.named["classifier.0.weight"] is not lin0.weight:
+        ps = E.ParamStore(named)
+        model._cls_store = ps
+    z = MlpHiddenFn.apply(x, lin0.weight, lin0.bias, None if ln is None else ln.weight, None if ln is None else ln.bias,
+                          ps.bf16("classifier.0.weight"), 0.0 if ln is None else float(ln.eps))
+    return z, last
+
+
 class ImageBertForMultipleChoice(CaptionPreTrainedModel):
     """modeling/modeling_bert.py:492-568: choice-flattened classifier
     ``pooled.view(-1, num_choice*H) -> Linear -> CE`` fused into one kernel."""
@@ -225,9 +258,10 @@ class ImageBertForMultipleChoice(CaptionPreTrainedModel):
         self.num_labels = config.num_labels
         self.bert = BertImgModel(config)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
-        if cfg_get(config, "classifier", "linear") != "linear":
-            raise NotImplementedError("only the linear classifier of ImageBertForMultipleChoice is implemented")
-        self.classifier = nn.Linear(self.num_choice * config.hidden_size, config.num_labels)
+        self.classifier = _make_classifier(config, self.num_choice * config.hidden_size, config.num_labels,
+                                           cfg_get(config, "classifier", "linear"),
+                                           cfg_get(config, "use_img_layernorm", None))
+        self._cls_store = None
         # NB the reference forgets the call parentheses on init_weights (:531): the head keeps torch's default init
 
     def _pooled_dropout(self, pooled):
@@ -250,10 +284,14 @@ class ImageBertForMultipleChoice(CaptionPreTrainedModel):
             labels_ = torch.zeros((B,), dtype=torch.int64, device=x.device)
         else:
             labels_ = labels.view(-1)
-        if self.loss_type == "bce":
-            raise NotImplementedError("loss_type 'bce' of ImageBertForMultipleChoice is not on the ModCR path")
-        loss, logits = ScorerFn.apply(x, self.classifier.weight, self.classifier.bias, labels_.contiguous(), None,
-                                      self.num_labels, nc, False)
+        x, last = _classifier_hidden(self, x)
+        if self.loss_type == "bce" and labels is not None:
+            # instance_bce_with_logits(logits, labels.view(-1, num_labels)) (:416-421, :562)
+            soft = labels.reshape(-1, self.num_labels).to(torch.float32).contiguous()
+            loss, logits = ScorerFn.apply(x, last.weight, last.bias, None, soft, self.num_labels, nc, False, 1)
+        else:
+            loss, logits = ScorerFn.apply(x, last.weight, last.bias, labels_.long().contiguous(), None,
+                                          self.num_labels, nc, False)
         out = (logits,) + outputs[2:]
         if labels is not None:
             out = (loss,) + out
@@ -272,9 +310,11 @@ class OscarForMultipleChoice(CaptionPreTrainedModel):
         self.bert = BertImgModel(config)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
         kind = cfg_get(config, "classifier", None)
-        if kind not in (None, "linear"):
-            raise NotImplementedError("only the linear classifier of OscarForMultipleChoice is implemented")
-        self.classifier = nn.Linear(config.hidden_size, 2 if kind == "linear" else config.num_labels)
+        if kind in (None, "linear"):
+            self.classifier = nn.Linear(config.hidden_size, 2 if kind == "linear" else config.num_labels)
+        else:   # 'mlp' (:646-660): Linear(H -> H*scale) -> ReLU [-> LayerNorm] -> Linear(-> 2)
+            self.classifier = _make_classifier(config, config.hidden_size, 2, kind, None)
+        self._cls_store = None
         self.apply(self._init_weights)
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, labels=None, position_ids=None,
@@ -283,12 +323,16 @@ class OscarForMultipleChoice(CaptionPreTrainedModel):
         outputs = self.bert(flat(input_ids), position_ids=flat(position_ids), token_type_ids=flat(token_type_ids),
                             attention_mask=flat(attention_mask), head_mask=head_mask, img_feats=flat(img_feats))
         pooled = ImageBertForMultipleChoice._pooled_dropout(self, outputs[1])
-        rows, C = pooled.shape[0], self.classifier.weight.shape[0]
+        pooled, last = _classifier_hidden(self, pooled)
+        rows, C = pooled.shape[0], last.weight.shape[0]
         if self.loss_type == "bce" and labels is not None:
-            raise NotImplementedError("loss_type 'bce' of OscarForMultipleChoice is not on the ModCR path")
-        labels_ = (torch.zeros((rows,), dtype=torch.int64, device=pooled.device) if labels is None
-                   else labels.reshape(-1).long().contiguous())
-        loss, logits = ScorerFn.apply(pooled, self.classifier.weight, self.classifier.bias, labels_, None, C, 1, False)
+            # instance_bce_with_logits(logits, labels.view(-1, num_labels)) (:700-701)
+            soft = labels.reshape(-1, C).to(torch.float32).contiguous()
+            loss, logits = ScorerFn.apply(pooled, last.weight, last.bias, None, soft, C, 1, False, 1)
+        else:   # 'bxe' and the default: CrossEntropyLoss over the flattened rows (:702-710)
+            labels_ = (torch.zeros((rows,), dtype=torch.int64, device=pooled.device) if labels is None
+                       else labels.reshape(-1).long().contiguous())
+            loss, logits = ScorerFn.apply(pooled, last.weight, last.bias, labels_, None, C, 1, False)
         out = (logits,) + outputs[2:]
         if labels is not None:
             out = (loss,) + out

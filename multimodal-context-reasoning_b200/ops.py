@@ -224,26 +224,30 @@ def cls_pool_attn_bwd(dpooled, q, k, w, dq, dk, N, L, H, drop=None):
 
 
 def _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None, num_choice=4,
-                 gout=1.0, dx=None, dW=None, db=None):
+                 gout=1.0, dx=None, dW=None, db=None, loss_kind=0):
     d = ScorerDesc()
     d.x, d.W, d.b = _p(x), _p(W), _p(b)
     d.rows, d.K, d.C, d.G = rows, K, Cc, G
     d.hard, d.soft, d.logits, d.loss = _p(hard), _p(soft), _p(logits), _p(loss)
     d.mp, d.pred, d.matched, d.num_choice = _p(mp), _p(pred), _p(matched), num_choice
     d.gout, d.dx, d.dW, d.db = gout, _p(dx), _p(dW), _p(db)
+    d.loss_kind = loss_kind
     return d
 
 
 def mc_scorer_ce_fwd(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp=None, pred=None, matched=None,
-                     num_choice=4):
+                     num_choice=4, loss_kind=0):
+    """``loss_kind`` 0: cross-entropy over the view [rows*C/G, G]; 1: ``instance_bce_with_logits`` against ``soft``."""
     _chk(hard, I64, "labels")
     _chk(soft, F32, "soft labels")
-    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice)
+    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, loss, mp, pred, matched, num_choice,
+                     loss_kind=loss_kind)
     _lib.check(_lib.load().modcr_mc_scorer_ce_fwd(C.byref(d), _stream()), "mc_scorer_ce_fwd")
 
 
-def mc_scorer_ce_bwd(x, W, b, rows, K, Cc, G, hard, soft, logits, gout, dx, dW, db):
-    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, None, gout=gout, dx=dx, dW=dW, db=db)
+def mc_scorer_ce_bwd(x, W, b, rows, K, Cc, G, hard, soft, logits, gout, dx, dW, db, loss_kind=0):
+    d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, None, gout=gout, dx=dx, dW=dW, db=db,
+                     loss_kind=loss_kind)
     _lib.check(_lib.load().modcr_mc_scorer_ce_bwd(C.byref(d), _stream()), "mc_scorer_ce_bwd")
 
 
@@ -287,6 +291,20 @@ def add_bf16(a, b, y):
 
 def tanh_bwd(dy, y, dx):
     _lib.check(_lib.load().modcr_tanh_bwd(_p(dy), _p(y), _p(dx), dy.numel(), _stream()), "tanh_bwd")
+
+
+def relu_bwd(dy, y, dx):
+    _lib.check(_lib.load().modcr_relu_bwd(_p(dy), _p(y), _p(dx), dy.numel(), _stream()), "relu_bwd")
+
+
+def rowln_fwd(x, gamma, beta, y, mean, rstd, M, H, eps):
+    _lib.check(_lib.load().modcr_rowln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, H, eps, _stream()),
+               "rowln_fwd")
+
+
+def rowln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, H):
+    _lib.check(_lib.load().modcr_rowln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma), _p(dbeta),
+                                           M, H, _stream()), "rowln_bwd")
 
 
 def key_bias(mask, kbias):

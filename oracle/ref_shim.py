@@ -91,7 +91,9 @@ def load():
         # a_transformers/file_utils etc. may want more 4.x names; surface the error
         raise
     # transformers-5 init_weights needs post_init state -> plain apply
-    a_bert.BertPreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    # (OscarForMultipleChoice calls the transformers-1.x form ``self.apply(self.init_weights)``, modeling_bert.py:671)
+    a_bert.BertPreTrainedModel.init_weights = (
+        lambda self, module=None: self.apply(self._init_weights) if module is None else self._init_weights(module))
 
     # CPU only: the chunk-mean loop calls .cuda(device) (v10:71,74)
     torch.Tensor.cuda = lambda self, *a, **k: self

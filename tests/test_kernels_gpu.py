@@ -503,6 +503,62 @@ def test_mc_scorer_ce_soft_labels_and_choice_flattened():
     torch.testing.assert_close(loss[0], torch.nn.functional.cross_entropy(lr4, lab), atol=1e-5, rtol=1e-5)
 
 
+def test_scorer_bce_relu_rowln():
+    """loss_type 'bce' (instance_bce_with_logits, modeling/modeling_bert.py:416-421) of the fused scorer, and the pieces of
+    the 'mlp' classifier (:511-528): ReLU in the GEMM epilogue, relu_bwd, row LayerNorm over hidden*cls_hidden_scale."""
+    F = torch.nn.functional
+    torch.manual_seed(3)
+    B, K, G = 6, 1536, 4
+    x = rnd(B, K, seed=1)
+    W = (0.03 * torch.randn(G, K)).to(DEV)
+    b = (0.05 * torch.randn(G)).to(DEV)
+    tgt = torch.rand(B, G).to(DEV)
+    logits, loss = torch.empty(B, G, device=DEV), torch.empty(1, device=DEV)
+    ops.mc_scorer_ce_fwd(x, W, b, B, K, G, G, None, tgt, logits, loss, loss_kind=1)
+    xr = x.float().requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    lr = xr @ Wr.t() + br
+    loss_r = F.binary_cross_entropy_with_logits(lr, tgt) * G
+    torch.testing.assert_close(logits, lr.detach(), atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(loss[0], loss_r.detach(), atol=1e-5, rtol=1e-5)
+    loss_r.backward()
+    dx = torch.empty(B, K, dtype=torch.bfloat16, device=DEV)
+    dW, db = torch.zeros(G, K, device=DEV), torch.zeros(G, device=DEV)
+    ops.mc_scorer_ce_bwd(x, W, b, B, K, G, G, None, tgt, logits, 1.0, dx, dW, db, loss_kind=1)
+    assert nerr(dx, xr.grad) < 1e-2 and nerr(dW, Wr.grad) < 1e-4 and nerr(db, br.grad) < 1e-4
+    with pytest.raises(RuntimeError, match="loss_kind"):
+        ops.mc_scorer_ce_fwd(x, W, b, B, K, G, G, torch.zeros(B, dtype=torch.int64, device=DEV), None, logits, loss,
+                             loss_kind=1)
+    # ReLU epilogue (few rows: M = 6 questions against a 128-row tile) + relu_bwd
+    Hin, Hm = 3072, 1536
+    xin, W1 = rnd(B, Hin, seed=4), rnd(Hm, Hin, scale=0.02, seed=5)
+    b1 = rnd(Hm, seed=6, dtype=torch.float32)
+    h = torch.empty(B, Hm, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(xin, W1, h, B, Hm, Hin, bias=b1, act=3)
+    href = torch.relu(xin.float() @ W1.float().t() + b1)
+    assert nerr(h, href) < 1e-2 and float(h.float().min()) >= 0.0
+    dy = rnd(B, Hm, seed=7)
+    dpre = torch.empty_like(dy)
+    ops.relu_bwd(dy, h, dpre)
+    assert torch.equal(dpre, torch.where(h.float() > 0, dy.float(), torch.zeros_like(dy.float())).to(torch.bfloat16))
+    # row LayerNorm forward / backward
+    gamma = (1.0 + 0.1 * torch.randn(Hm)).to(DEV)
+    beta = (0.1 * torch.randn(Hm)).to(DEV)
+    z = torch.empty_like(h)
+    mean, rstd = torch.empty(B, device=DEV), torch.empty(B, device=DEV)
+    ops.rowln_fwd(h, gamma, beta, z, mean, rstd, B, Hm, 1e-12)
+    hr = h.float().requires_grad_(True)
+    gr, ber = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    zr = F.layer_norm(hr, (Hm,), gr, ber, 1e-12)
+    assert nerr(z, zr) < 1e-2
+    torch.testing.assert_close(mean, hr.detach().mean(-1), atol=1e-5, rtol=1e-4)
+    (zr * dy.float()).sum().backward()
+    dh = torch.empty_like(h)
+    dg, dbt = torch.zeros(Hm, device=DEV), torch.zeros(Hm, device=DEV)
+    ops.rowln_bwd(dy, h, mean, rstd, gamma, dh, dg, dbt, B, Hm)
+    assert nerr(dh, hr.grad) < 1e-2 and nerr(dg, gr.grad) < 1e-3 and nerr(dbt, ber.grad) < 1e-3
+
+
 def test_copy_rows_colsum_add_tanh():
     N, S, T, H = 3, 9, 6, 256
     a, b = rnd(N, S, H, seed=1), rnd(N, S, H, seed=2)

@@ -279,6 +279,53 @@ def test_oscar_for_multiple_choice_matches_restated_scorer():
     assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
 
 
+@pytest.mark.parametrize("which,classifier,use_ln,loss_type", [
+    ("image", "mlp", 1, "bce"), ("image", "mlp", None, "sfmx"), ("image", "linear", 1, "bce"), ("oscar", "mlp", 1, "bce")])
+def test_mc_head_variants_match_restated_heads(which, classifier, use_ln, loss_type):
+    """'mlp' classifiers (Linear -> ReLU [-> LayerNorm] -> Linear) and the 'bce' loss
+    (instance_bce_with_logits) of ImageBertForMultipleChoice / OscarForMultipleChoice (modeling/modeling_bert.py:492-712),
+    forward and gradients of the head against the restated head (pinned to the live reference classes in
+    tests/test_oracle.py) evaluated on the pooled output of the same encoder."""
+    from modcr_b200.modeling_bert import ImageBertForMultipleChoice, OscarForMultipleChoice
+    B, C, T, R = 2, 4, 24, 7
+    num_labels = 4 if which == "image" else 2
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     num_hidden_layers=2)
+    cfg.loss_type, cfg.classifier, cfg.num_labels, cfg.num_choice, cfg.use_img_layernorm = \
+        loss_type, classifier, num_labels, C, use_ln
+    torch.manual_seed(0)
+    m = (ImageBertForMultipleChoice if which == "image" else OscarForMultipleChoice)(cfg).to(DEV).train()
+    bd = synth.to_device(synth.make_batch(B=B, T=T, R=R, seed=11), DEV)
+    shp = lambda t: t.reshape(B, C, *t.shape[1:])  # noqa: E731
+    g = torch.Generator().manual_seed(3)
+    if loss_type == "bce":
+        labels = (torch.rand(B, num_labels, generator=g) if which == "image"
+                  else torch.rand(B * C, num_labels, generator=g)).to(DEV)
+    else:
+        labels = torch.randint(0, num_labels, (B,), generator=g).to(DEV)
+    loss, logits = m(shp(bd["input_ids"]), token_type_ids=shp(bd["token_type_ids"]), attention_mask=shp(bd["input_mask"]),
+                     labels=labels, img_feats=shp(bd["img_feat"]))[:2]
+    loss.backward()
+    with torch.no_grad():
+        pooled = m.bert(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=bd["input_mask"],
+                        img_feats=bd["img_feat"])[1].float()
+    sd = {k: v.detach().float().clone().requires_grad_(True) for k, v in m.state_dict().items() if k.startswith("classifier.")}
+    pooled_r = pooled.clone().requires_grad_(True)
+    if which == "image":
+        ref_loss, ref_logits = restate.image_bert_mc_head(sd, pooled_r, labels, C, num_labels, loss_type, cfg.layer_norm_eps)
+    else:
+        ref_loss, ref_logits = restate.oscar_mc_head(sd, pooled_r, labels, num_labels, loss_type, cfg.layer_norm_eps)
+    ref_loss.backward()
+    assert float((logits - ref_logits).abs().max()) < 2e-2
+    assert abs(float(loss) - float(ref_loss)) < 1e-2
+    named = dict(m.named_parameters())
+    errs = {k: l2err(named[k].grad, v.grad) for k, v in sd.items()}
+    print("mc head grad rel-L2 err:", {k: round(e, 4) for k, e in errs.items()})
+    # same 10 % relative-L2 bar as the other gradient checks: the LayerNorm backward differences bf16 gradients
+    assert max(errs.values()) < 0.1, errs
+    assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
+
+
 def test_full_size_cfg2_invariants():
     """BASELINE.json configs[1] (32 questions x 4 choices, 128 tokens + 50 regions, prefix 10) is too large for the CPU
     oracle, so the full-size step is checked through size-independent properties of the path:

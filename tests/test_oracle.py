@@ -92,6 +92,53 @@ def test_restatement_matches_live_reference_and_state_dict_surface():
     assert float((r2[0] - c2).abs().max()) == 0.0 and float((r2[1] - al2).abs()) == 0.0
 
 
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+@pytest.mark.parametrize("which,classifier,use_ln,loss_type", [
+    ("image", "mlp", 1, "bce"), ("image", "mlp", None, "sfmx"), ("image", "linear", 1, "bce"),
+    ("oscar", "mlp", 1, "bce"), ("oscar", "linear", 1, "bxe")])
+def test_restated_mc_heads_match_live_reference(which, classifier, use_ln, loss_type):
+    """the restated classifier / loss variants of ImageBertForMultipleChoice and OscarForMultipleChoice
+    (modeling/modeling_bert.py:492-568, 574-712) against the live reference classes (2-layer encoder to stay fast)."""
+    ns = ref_shim.load()
+    B, C, T, R = 2, 4, 12, 5
+    num_labels = 4 if which == "image" else 2
+    cfg = ref_shim.make_config(ns, num_hidden_layers=2, classifier=classifier, use_img_layernorm=use_ln,
+                               loss_type=loss_type, num_labels=num_labels, num_choice=C, output_attentions=False)
+    torch.manual_seed(5)
+    cls = ns.mbert.ImageBertForMultipleChoice if which == "image" else ns.mbert.OscarForMultipleChoice
+    m = cls(cfg).eval()
+    b = synth.make_batch(B=B, T=T, R=R, seed=21)
+    shp = lambda t: t.reshape(B, C, *t.shape[1:])  # noqa: E731
+    g = torch.Generator().manual_seed(3)
+    if loss_type == "bce":
+        labels = torch.rand(B, num_labels, generator=g) if which == "image" else torch.rand(B * C, num_labels, generator=g)
+    elif which == "image":
+        labels = torch.randint(0, num_labels, (B,), generator=g)
+    else:
+        labels = b["label"].reshape(B, C)
+    with torch.no_grad():
+        ref_loss, ref_logits = m(shp(b["input_ids"]), token_type_ids=shp(b["token_type_ids"]),
+                                 attention_mask=shp(b["input_mask"]), labels=labels, img_feats=shp(b["img_feat"]))[:2]
+        pooled = m.bert(b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=b["input_mask"],
+                        img_feats=b["img_feat"])[1]
+        sd = m.state_dict()
+        if which == "image":
+            loss, logits = restate.image_bert_mc_head(sd, pooled, labels, C, num_labels, loss_type, cfg.layer_norm_eps)
+        else:
+            loss, logits = restate.oscar_mc_head(sd, pooled, labels, num_labels, loss_type, cfg.layer_norm_eps)
+    assert float((logits - ref_logits).abs().max()) == 0.0 and float((loss - ref_loss).abs()) == 0.0
+    # state_dict surface of our drop-in class
+    from modcr_b200.modeling_bert import ImageBertForMultipleChoice, OscarForMultipleChoice, BertConfig as OurCfg
+    ocfg = OurCfg(vocab_size=cfg.vocab_size, num_hidden_layers=2)
+    for k in ("classifier", "use_img_layernorm", "loss_type", "num_labels", "num_choice"):
+        setattr(ocfg, k, getattr(cfg, k))
+    ours = (ImageBertForMultipleChoice if which == "image" else OscarForMultipleChoice)(ocfg)
+    ours_keys = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    ref_keys = {k: tuple(v.shape) for k, v in sd.items()}
+    assert ours_keys == ref_keys
+
+
 # ---- known-answer invariants (SURVEY.md section 4), small shapes ----------------
 def _small():
     sd = _weights(11)
