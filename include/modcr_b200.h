@@ -271,6 +271,41 @@ int modcr_mc_scorer_ce_fwd(const modcr_scorer_desc* d, void* stream);
 int modcr_mc_scorer_ce_bwd(const modcr_scorer_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device-side batch packer.  Replaces the collate function SNLIGPT_gen_collate
+ * (Data/VCRChunkAlign.py:690-741) and the per-choice tensor building of the dataset's __getitem__ (:655-686): the host
+ * fills ONE pinned buffer, copies it once, and this call expands it into the padded batch of the reference's batch
+ * contract plus the packed forms the kernels read (chunk-bit mask, chunk ids).
+ *   header int32 [N,4]   : text length L, number of boxes, label (0/1), index of the question's feature block
+ *   tokens int32 [N,T,2] : word 0 = input id; word 1 = (chunk id + 1) | segment << 10 | align_pos << 11 | total_label << 12
+ *                          (chunk id of tokens 1..L-2 = position of the token's chunk in `offsets`, :667-670; 0 = none)
+ *   feats  fp32 [U,R,D]  : one block per QUESTION; the four choices share it (4x fewer bytes over PCIe)
+ * Outputs (caller-allocated; optional ones may be NULL): input_ids / token_type_ids / total_label / align_pos int64 [N,T]
+ * (pad value 0, :698-705), label int64 [N] and label_f fp32 [N] (:706-708), input_mask fp32 [N,T+R] = text mask || box
+ * mask (:709-714), chunk_id int32 [N,T] (-1 outside chunks), chunk_bits uint32 [N,T,cwords] with cwords = ceil(T/32),
+ * bit k of row q = chunk mask [q,k] of utils/GetChunk_v4_vcr.py:104-140 zero-padded to [T,T] (:716-723), chunk_mask the
+ * same as dense fp32 [N,T,T] (only for callers that want the reference tensor), img_feat fp32 [N,R,D] with rows beyond
+ * the question's box count zero.  T <= 512, D even; tokens / feats / img_feat 8-byte aligned. */
+typedef struct modcr_pack_desc {
+  const int32_t* header;
+  const int32_t* tokens;
+  const float* feats;
+  int32_t N, T, R, D;
+  int64_t* input_ids;
+  int64_t* token_type_ids;
+  int64_t* total_label;
+  int64_t* align_pos;
+  int64_t* label;
+  float* label_f;
+  float* input_mask;
+  int32_t* chunk_id;
+  uint32_t* chunk_bits;
+  int32_t cwords;
+  float* chunk_mask;
+  float* img_feat;
+} modcr_pack_desc;
+int modcr_pack_batch(const modcr_pack_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Small utilities of the path. */
 int modcr_cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int32_t cols,
                    int64_t row_step, void* stream);

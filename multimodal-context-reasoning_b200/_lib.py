@@ -44,6 +44,15 @@ class ScorerDesc(C.Structure):
                 ("loss_kind", c_i32)]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("header", c_void_p), ("tokens", c_void_p), ("feats", c_void_p),
+                ("N", c_i32), ("T", c_i32), ("R", c_i32), ("D", c_i32),
+                ("input_ids", c_void_p), ("token_type_ids", c_void_p), ("total_label", c_void_p),
+                ("align_pos", c_void_p), ("label", c_void_p), ("label_f", c_void_p), ("input_mask", c_void_p),
+                ("chunk_id", c_void_p), ("chunk_bits", c_void_p), ("cwords", c_i32), ("chunk_mask", c_void_p),
+                ("img_feat", c_void_p)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/modcr_b200.h
 SIGNATURES = {
     "modcr_version": [],
@@ -86,6 +95,7 @@ SIGNATURES = {
                                 c_void_p, C.c_uint32, c_float, c_void_p],
     "modcr_mc_scorer_ce_fwd": [C.POINTER(ScorerDesc), c_void_p],
     "modcr_mc_scorer_ce_bwd": [C.POINTER(ScorerDesc), c_void_p],
+    "modcr_pack_batch": [C.POINTER(PackDesc), c_void_p],
     "modcr_cast_pad": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i32, c_i64, c_void_p],
     "modcr_bf16_to_f32": [c_void_p, c_void_p, c_i64, c_i32, c_void_p],
     "modcr_colsum": [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p],

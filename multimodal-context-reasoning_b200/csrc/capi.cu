@@ -289,6 +289,21 @@ int modcr_mc_scorer_ce_bwd(const modcr_scorer_desc* d, void* stream) {
   return modcr::mc_scorer_ce_bwd(s, S(stream));
 }
 
+int modcr_pack_batch(const modcr_pack_desc* d, void* stream) {
+  ARCH_OR_RETURN();
+  if (d == nullptr) {
+    modcr::set_error("modcr_pack_batch: null descriptor");
+    return modcr::MODCR_ERR_SHAPE;
+  }
+  modcr::PackDesc s;
+  s.header = d->header; s.tokens = d->tokens; s.feats = d->feats; s.N = d->N; s.T = d->T; s.R = d->R; s.D = d->D;
+  s.input_ids = d->input_ids; s.token_type_ids = d->token_type_ids; s.total_label = d->total_label;
+  s.align_pos = d->align_pos; s.label = d->label; s.label_f = d->label_f; s.input_mask = d->input_mask;
+  s.chunk_id = d->chunk_id; s.chunk_bits = d->chunk_bits; s.cwords = d->cwords; s.chunk_mask = d->chunk_mask;
+  s.img_feat = d->img_feat;
+  return modcr::pack_batch(s, S(stream));
+}
+
 int modcr_cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int32_t cols,
                    int64_t row_step, void* stream) {
   ARCH_OR_RETURN();

@@ -19,6 +19,7 @@
 #include <cstdint>
 
 #include "rowops.h"
+#include "tma_host.h"
 
 namespace modcr {
 

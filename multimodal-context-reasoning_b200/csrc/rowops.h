@@ -105,4 +105,25 @@ struct ScorerDesc {
 int mc_scorer_ce_fwd(const ScorerDesc& d, cudaStream_t st);
 int mc_scorer_ce_bwd(const ScorerDesc& d, cudaStream_t st);
 
+// device-side batch packer (pack.cu; SURVEY 8 f2, Data/VCRChunkAlign.py:655-741)
+struct PackDesc {
+  const int32_t* header = nullptr;
+  const int32_t* tokens = nullptr;
+  const float* feats = nullptr;
+  int N = 0, T = 0, R = 0, D = 0;
+  int64_t* input_ids = nullptr;
+  int64_t* token_type_ids = nullptr;
+  int64_t* total_label = nullptr;
+  int64_t* align_pos = nullptr;
+  int64_t* label = nullptr;
+  float* label_f = nullptr;
+  float* input_mask = nullptr;
+  int32_t* chunk_id = nullptr;
+  uint32_t* chunk_bits = nullptr;
+  int cwords = 0;
+  float* chunk_mask = nullptr;
+  float* img_feat = nullptr;
+};
+int pack_batch(const PackDesc& d, cudaStream_t st);
+
 }  // namespace modcr

@@ -38,7 +38,8 @@ class SeqBertImgModel(_EncoderModelBase):
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, input_mask=None, position_ids=None,
                 head_mask=None, img_feats=None, img_mask=None, encoder_history_states=None, offsets=None,
                 gather_index=None, _want_align_block=True):
-        """``attention_mask`` is the 0/1 chunk mask ``[N,T,T]``; ``input_mask`` ``[N,T+R]`` the key padding
+        """``attention_mask`` is the 0/1 chunk mask ``[N,T,T]`` (or its int32 bit-packed form ``[N,T,ceil(T/32)]``
+        from ``packer.BatchPacker``); ``input_mask`` ``[N,T+R]`` the key padding
         mask; ``gather_index`` the ragged per-sequence chunk ids (or an already packed int32 ``[N,T]``
         tensor with -1 outside the chunked span).  Returns ``((sequence_output, pooled_output, attentions),
         chunk_hidden_states)`` like v10:360; ``attentions.align_block`` is the fp32 ``[N,T,R]`` sum over the
@@ -52,7 +53,13 @@ class SeqBertImgModel(_EncoderModelBase):
         N, T = input_ids.shape
         dev = input_ids.device
         kbias = E.make_key_bias(input_mask)
-        cbits, cwords = E.make_chunk_bits(attention_mask)
+        if attention_mask.dtype == torch.int32:     # already packed by the device-side collate (packer.BatchPacker)
+            cwords = (T + 31) // 32
+            if tuple(attention_mask.shape) != (N, T, cwords):
+                raise ValueError("packed chunk mask must be int32 [N,T,ceil(T/32)]")
+            cbits = attention_mask.contiguous()
+        else:
+            cbits, cwords = E.make_chunk_bits(attention_mask)
         if torch.is_tensor(gather_index):
             chunk_id = gather_index.to(device=dev, dtype=torch.int32).contiguous()
             max_chunks = T

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AttnDesc, GemmDesc, RowMap, ScorerDesc
+from ._lib import AttnDesc, GemmDesc, PackDesc, RowMap, ScorerDesc
 
 BF16, F32, I64 = torch.bfloat16, torch.float32, torch.int64
 IDENT = RowMap(0, 0, 0)
@@ -249,6 +249,24 @@ def mc_scorer_ce_bwd(x, W, b, rows, K, Cc, G, hard, soft, logits, gout, dx, dW, 
     d = _scorer_desc(x, W, b, rows, K, Cc, G, hard, soft, logits, None, gout=gout, dx=dx, dW=dW, db=db,
                      loss_kind=loss_kind)
     _lib.check(_lib.load().modcr_mc_scorer_ce_bwd(C.byref(d), _stream()), "mc_scorer_ce_bwd")
+
+
+def pack_batch(header, tokens, feats, N, T, R, D, input_ids, input_mask, token_type_ids=None, total_label=None,
+               align_pos=None, label=None, label_f=None, chunk_id=None, chunk_bits=None, chunk_mask=None, img_feat=None):
+    """Device-side collate (Data/VCRChunkAlign.py:690-741): expands the packed descriptors into the padded batch."""
+    for t, dt, nm in ((header, torch.int32, "header"), (tokens, torch.int32, "tokens"), (feats, F32, "feats"),
+                      (input_ids, I64, "input_ids"), (token_type_ids, I64, "token_type_ids"),
+                      (total_label, I64, "total_label"), (align_pos, I64, "align_pos"), (label, I64, "label"),
+                      (label_f, F32, "label_f"), (input_mask, F32, "input_mask"), (chunk_id, torch.int32, "chunk_id"),
+                      (chunk_bits, torch.int32, "chunk_bits"), (chunk_mask, F32, "chunk_mask"), (img_feat, F32, "img_feat")):
+        _chk(t, dt, nm)
+    d = PackDesc()
+    d.header, d.tokens, d.feats = _p(header), _p(tokens), _p(feats)
+    d.N, d.T, d.R, d.D = N, T, R, D
+    d.input_ids, d.token_type_ids, d.total_label, d.align_pos = _p(input_ids), _p(token_type_ids), _p(total_label), _p(align_pos)
+    d.label, d.label_f, d.input_mask, d.chunk_id = _p(label), _p(label_f), _p(input_mask), _p(chunk_id)
+    d.chunk_bits, d.cwords, d.chunk_mask, d.img_feat = _p(chunk_bits), (T + 31) // 32, _p(chunk_mask), _p(img_feat)
+    _lib.check(_lib.load().modcr_pack_batch(C.byref(d), _stream()), "pack_batch")
 
 
 # --------------------------------------------------------------------------- utilities

@@ -1,0 +1,138 @@
+"""Device-side batch packer -- host half.
+
+Stands where the reference's ``SNLIGPT_gen_collate`` (Data/VCRChunkAlign.py:690-741) and the tensor building of the
+dataset's ``__getitem__`` (:655-686) stand: takes the ragged per-(question, choice) samples, writes ONE pinned host
+buffer (int32 descriptors + one feature block per question), copies it to the device once and lets
+``modcr_pack_batch`` (csrc/pack.cu) expand it into the padded batch of the reference's batch contract.  The chunk mask
+travels as chunk ids (derived from ``offsets``, :667-670) and is expanded on the device straight into the bit mask the
+attention kernels read; the image features of the four choices of a question cross PCIe once, not four times.
+
+``unbatch`` turns a padded synthetic batch (``synth.make_batch``) back into ragged samples -- what a dataset would
+hand to the collate function -- for tests and for the end-to-end measurement.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+I32, I64, F32 = torch.int32, torch.int64, torch.float32
+
+
+def unbatch(batch, num_choices=4):
+    """Padded batch -> list of per-(question, choice) samples with the reference's field names (:683-686).
+    The four choices of a question share ONE ``img_feat`` tensor object, as in the reference's ``__getitem__``."""
+    N, T = batch["input_ids"].shape
+    R = batch["img_feat"].shape[1]
+    samples = []
+    for n in range(N):
+        L = int(batch["input_mask"][n, :T].sum().item())
+        q0 = (n // num_choices) * num_choices
+        if n == q0:
+            feat, fmask = batch["img_feat"][n].clone(), batch["input_mask"][n, T:T + R].clone()
+        samples.append(dict(
+            input_ids=batch["input_ids"][n, :L].clone(), segment_ids=batch["token_type_ids"][n, :L].clone(),
+            input_mask=torch.ones(L), img_feat=feat, img_mask=fmask, target=batch["label"][n].clone(),
+            chunk_mask=batch["chunk_attention_mask"][n, :L, :L].clone(), gather_index=batch["gather_index"][n],
+            offsets=batch["offsets"][n], total_label=batch["total_label"][n, :L].clone(),
+            align_pos=batch["align_pos"][n, :L].clone()))
+    return samples
+
+
+class PackedBatch(dict):
+    """The batch dict of the reference contract (device tensors) plus ``chunk_bits`` / ``chunk_id`` / ``max_chunks``.
+    ``chunk_attention_mask`` holds the int32 bit mask ``[N,T,ceil(T/32)]`` (``SeqBertImgModel`` accepts it in place of
+    the dense fp32 ``[N,T,T]`` tensor) and ``gather_index`` the int32 chunk ids ``[N,T]``."""
+
+
+class BatchPacker:
+    def __init__(self, device, feat_dim=2054, pad_T=None, pad_R=None, dense_chunk_mask=False):
+        """``pad_T`` / ``pad_R``: pad to fixed sizes (static shapes for CUDA-graph replay) instead of the batch maxima the
+        reference pads to (:699, :709-711).  ``dense_chunk_mask``: also emit the reference's fp32 ``[N,T,T]`` tensor."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("modcr_b200: BatchPacker needs a CUDA device (no CPU path)")
+        self.D, self.pad_T, self.pad_R, self.dense = feat_dim, pad_T, pad_R, dense_chunk_mask
+        self._pinned = None
+        self.h2d_bytes = 0
+
+    def _buffer(self, nbytes):
+        if self._pinned is None or self._pinned.numel() < nbytes:
+            self._pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return self._pinned
+
+    def pack(self, samples):
+        N, D = len(samples), self.D
+        lens = [int(s["input_ids"].numel()) for s in samples]
+        nbox = [int(s["img_mask"].sum().item()) for s in samples]
+        T = max(lens) if self.pad_T is None else self.pad_T
+        R = max(nbox) if self.pad_R is None else self.pad_R
+        if max(lens) > T or max(nbox) > R:
+            raise ValueError("sample longer than pad_T / pad_R")
+        # one feature block per distinct img_feat tensor (the choices of a question share theirs)
+        blocks, block_of = [], {}
+        for s in samples:
+            key = s["img_feat"].data_ptr()
+            if key not in block_of:
+                block_of[key] = len(blocks)
+                blocks.append(s["img_feat"])
+        U = len(blocks)
+        hdr_b, tok_b = N * 4 * 4, N * T * 2 * 4
+        feat_off = (hdr_b + tok_b + 15) & ~15
+        total = feat_off + U * R * D * 4
+        buf = self._buffer(total)
+        nb = buf.numpy()
+        header = nb[:hdr_b].view(np.int32).reshape(N, 4)
+        tokens = nb[hdr_b:hdr_b + tok_b].view(np.int32).reshape(N, T, 2)
+        feats = nb[feat_off:total].view(np.float32).reshape(U, R, D)
+        tokens[:] = 0
+        max_chunks = 1
+        for n, s in enumerate(samples):
+            L = lens[n]
+            header[n] = (L, nbox[n], int(s["target"]), block_of[s["img_feat"].data_ptr()])
+            cid = np.zeros(L, dtype=np.int64)
+            offs = s["offsets"]
+            k = 1
+            for idx, chunk in enumerate(offs):          # gather_index of :667-670, shifted by +1 (0 = no chunk)
+                c = len(chunk)
+                cid[k:k + c] = idx + 1
+                k += c
+            if len(offs) > 1023 - 1:
+                raise ValueError("more than 1022 chunks in one sequence")
+            max_chunks = max(max_chunks, len(offs))
+            tl = s["total_label"].numpy().astype(np.int64)
+            if tl.size and (tl.min() < 0 or tl.max() >= (1 << 19)):
+                raise ValueError("total_label outside [0, 2^19)")
+            tokens[n, :L, 0] = s["input_ids"].numpy()
+            tokens[n, :L, 1] = (cid | (s["segment_ids"].numpy().astype(np.int64) << 10)
+                                | ((s["align_pos"].numpy() != 0).astype(np.int64) << 11) | (tl << 12)).astype(np.int32)
+        for u, f in enumerate(blocks):
+            r = min(R, f.shape[0])
+            feats[u, :r] = f[:r].numpy()
+            feats[u, r:] = 0.0
+        dev = self.device
+        dbuf = torch.empty(total, dtype=torch.uint8, device=dev)
+        dbuf.copy_(buf[:total], non_blocking=True)              # the ONE host-to-device copy of the batch
+        self.h2d_bytes = total
+        d_header = dbuf[:hdr_b].view(I32)
+        d_tokens = dbuf[hdr_b:hdr_b + tok_b].view(I32)
+        d_feats = dbuf[feat_off:total].view(F32)
+        cw = (T + 31) // 32
+        out = PackedBatch(
+            input_ids=torch.empty((N, T), dtype=I64, device=dev), token_type_ids=torch.empty((N, T), dtype=I64, device=dev),
+            total_label=torch.empty((N, T), dtype=I64, device=dev), align_pos=torch.empty((N, T), dtype=I64, device=dev),
+            label=torch.empty((N,), dtype=F32, device=dev), label_long=torch.empty((N,), dtype=I64, device=dev),
+            input_mask=torch.empty((N, T + R), dtype=F32, device=dev),
+            gather_index=torch.empty((N, T), dtype=I32, device=dev),
+            chunk_attention_mask=torch.empty((N, T, cw), dtype=I32, device=dev),
+            img_feat=torch.empty((N, R, D), dtype=F32, device=dev))
+        dense = torch.empty((N, T, T), dtype=F32, device=dev) if self.dense else None
+        ops.pack_batch(d_header, d_tokens, d_feats, N, T, R, D, out["input_ids"], out["input_mask"],
+                       token_type_ids=out["token_type_ids"], total_label=out["total_label"], align_pos=out["align_pos"],
+                       label=out["label_long"], label_f=out["label"], chunk_id=out["gather_index"],
+                       chunk_bits=out["chunk_attention_mask"], chunk_mask=dense, img_feat=out["img_feat"])
+        dbuf.record_stream(torch.cuda.current_stream(dev))
+        out["offsets"] = [s["offsets"] for s in samples]
+        out["max_chunks"] = max_chunks
+        if dense is not None:
+            out["dense_chunk_mask"] = dense
+        return out

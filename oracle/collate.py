@@ -1,0 +1,60 @@
+"""ORACLE (test infrastructure, CPU): restatement of the reference's batch assembly for the ModCR path.
+
+* ``chunk_mask_from_offsets``  utils/GetChunk_v4_vcr.py:104-140 -- the dense [L,L] chunk mask the offline chunker stores
+  next to ``offsets`` (eye + full first / last row + one block per chunk).
+* ``gather_index_from_offsets``  Data/VCRChunkAlign.py:667-670.
+* ``snli_gpt_gen_collate``  Data/VCRChunkAlign.py:690-741 (``SNLIGPT_gen_collate``), the fields the hot path consumes
+  (the RoBERTa-side ``r_*`` fields are padded the same way and are left out here).
+
+The reference's data module cannot be imported (toolz / lmdb / clip ... are absent), so this is a
+line-by-line restatement; tests/test_oracle.py checks it against the synthetic batch generator, whose padded tensors
+were used to produce the reference golden vectors.
+"""
+import torch
+from torch.nn.utils.rnn import pad_sequence
+
+
+def chunk_mask_from_offsets(L, offsets):
+    m = torch.eye(L)                                   # :106
+    m[0, :L] = 1                                       # :108
+    for chunk in offsets:                              # :121-135 (symmetric links inside a chunk)
+        chunk = [chunk] if isinstance(chunk, int) else chunk
+        for a in chunk:
+            for b in chunk:
+                m[a][b] = 1
+    m[L - 1, :L] = 1                                   # :139
+    return m
+
+
+def gather_index_from_offsets(offsets):
+    gi = []
+    for idx, s in enumerate(offsets):                  # :667-669
+        gi.extend([idx] * len(s))
+    return torch.tensor(gi, dtype=torch.int64)
+
+
+def snli_gpt_gen_collate(samples):
+    """``samples``: list over (question, choice) of dicts with the names of the reference's per-choice tuple
+    (:683-686): input_ids [L], segment_ids [L], input_mask [L], img_feat [Rmax,D], img_mask [Rmax], target (0-d),
+    chunk_mask [L,L], gather_index, offsets, total_label [L], align_pos [L]."""
+    g = lambda k: [s[k] for s in samples]  # noqa: E731
+    input_mask = pad_sequence(g("input_mask"), batch_first=True, padding_value=0)      # :698
+    input_ids = pad_sequence(g("input_ids"), batch_first=True, padding_value=0)        # :699
+    total_label = pad_sequence(g("total_label"), batch_first=True, padding_value=0)    # :700
+    align_pos = pad_sequence(g("align_pos"), batch_first=True, padding_value=0)        # :701
+    segment_ids = pad_sequence(g("segment_ids"), batch_first=True, padding_value=0)    # :703
+    target = torch.stack(g("target"), dim=0).type(torch.FloatTensor)                   # :704-705
+    img_mask = torch.stack(g("img_mask"), dim=0)                                       # :707
+    img_feat = torch.stack(g("img_feat"), dim=0)                                       # :708
+    max_img = int(torch.max(torch.sum(img_mask, dim=-1)).item())                       # :709
+    img_mask, img_feat = img_mask[:, :max_img], img_feat[:, :max_img]                  # :710-711
+    input_mask = torch.cat((input_mask, img_mask), -1)                                 # :712
+    max_hypo = input_ids.size(1)
+    padded = []
+    for item in g("chunk_mask"):                                                       # :715-721
+        item = torch.cat((item, torch.zeros((max_hypo - item.size(0), item.size(1)))), 0)
+        item = torch.cat((item, torch.zeros((max_hypo, max_hypo - item.size(1)))), 1)
+        padded.append(item)
+    return {"input_ids": input_ids, "token_type_ids": segment_ids, "input_mask": input_mask, "img_feat": img_feat,
+            "label": target, "chunk_attention_mask": torch.stack(padded, 0), "gather_index": g("gather_index"),
+            "offsets": g("offsets"), "total_label": total_label, "align_pos": align_pos}

@@ -280,7 +280,8 @@ def test_oscar_for_multiple_choice_matches_restated_scorer():
 
 
 @pytest.mark.parametrize("which,classifier,use_ln,loss_type", [
-    ("image", "mlp", 1, "bce"), ("image", "mlp", None, "sfmx"), ("image", "linear", 1, "bce"), ("oscar", "mlp", 1, "bce")])
+    ("image", "mlp", 1, "bce"), ("image", "mlp", 1, "sfmx"), ("image", "linear", 1, "bce"), ("oscar", "mlp", 1, "bce"),
+    ("oscar", "mlp", 1, "bxe")])
 def test_mc_head_variants_match_restated_heads(which, classifier, use_ln, loss_type):
     """'mlp' classifiers (Linear -> ReLU [-> LayerNorm] -> Linear) and the 'bce' loss
     (instance_bce_with_logits) of ImageBertForMultipleChoice / OscarForMultipleChoice (modeling/modeling_bert.py:492-712),
@@ -301,8 +302,10 @@ def test_mc_head_variants_match_restated_heads(which, classifier, use_ln, loss_t
     if loss_type == "bce":
         labels = (torch.rand(B, num_labels, generator=g) if which == "image"
                   else torch.rand(B * C, num_labels, generator=g)).to(DEV)
-    else:
+    elif which == "image":
         labels = torch.randint(0, num_labels, (B,), generator=g).to(DEV)
+    else:
+        labels = bd["label"].reshape(B, C)
     loss, logits = m(shp(bd["input_ids"]), token_type_ids=shp(bd["token_type_ids"]), attention_mask=shp(bd["input_mask"]),
                      labels=labels, img_feats=shp(bd["img_feat"]))[:2]
     loss.backward()

@@ -139,6 +139,27 @@ def test_restated_mc_heads_match_live_reference(which, classifier, use_ln, loss_
     assert ours_keys == ref_keys
 
 
+def test_restated_collate_reproduces_the_synthetic_batches():
+    """oracle/collate.py (Data/VCRChunkAlign.py:690-741, utils/GetChunk_v4_vcr.py:104-140) on the ragged samples of a
+    synthetic batch gives back exactly the padded tensors the golden vectors were produced from."""
+    import collate
+    from modcr_b200.packer import unbatch
+    for kw in (dict(B=2, T=24, R=7, seed=3, min_len=6), dict(B=3, T=70, R=11, seed=5, region_pad=4)):
+        b = synth.make_batch(**kw)
+        samples = unbatch(b)
+        for n, s in enumerate(samples):
+            L = s["input_ids"].numel()
+            assert torch.equal(collate.chunk_mask_from_offsets(L, s["offsets"]), s["chunk_mask"])
+            assert torch.equal(collate.gather_index_from_offsets(s["offsets"]), b["gather_index"][n])
+        out = collate.snli_gpt_gen_collate(samples)
+        full = any(int(s["input_ids"].numel()) == kw["T"] for s in samples)
+        assert full   # make_batch always has one full-length row, so the padded width is T
+        for k in ("input_ids", "token_type_ids", "input_mask", "img_feat", "chunk_attention_mask", "total_label",
+                  "align_pos"):
+            assert torch.equal(out[k], b[k]), k
+        assert torch.equal(out["label"], b["label_onehot"])
+
+
 # ---- known-answer invariants (SURVEY.md section 4), small shapes ----------------
 def _small():
     sd = _weights(11)
