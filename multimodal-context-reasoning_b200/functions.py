@@ -23,6 +23,14 @@ def _as_bf16(t):
     return t.to(BF16)
 
 
+def _residual_add(a32, b32, M, H):
+    """fp32 ``a + b`` of two residual-stream tensors -> (bf16 copy, fp32 sum) (optional residuals, v10:212-223)."""
+    s32 = torch.empty_like(a32)
+    ops.accum_f32_2d(s32, H, a32, H, M, H)
+    ops.accum_f32_2d(s32, H, b32, H, M, H, accumulate=True)
+    return ops.to_bf16(s32).view(M, H), s32
+
+
 class EncoderRun:
     """Everything one encoder pass needs besides tensors that carry gradients."""
 
@@ -34,6 +42,9 @@ class EncoderRun:
         self.kbias, self.P, self.is_seq = kbias, P, is_seq
         self.cbits, self.cwords, self.chunk_id, self.max_chunks = cbits, cwords, chunk_id, max_chunks
         self.want_block = want_block
+        # optional residuals of the chunk-aware encoder (v10:164-165, 212-223; run_PMR_ModCR.py:747-748)
+        self.local_residual = bool(is_seq and cfg.get("add_local_residual", False))
+        self.final_residual = bool(is_seq and cfg.get("add_residual", False))
         self.drop = None                      # engine.Drop in training mode with dropout
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
@@ -86,9 +97,16 @@ class EncoderFn(torch.autograd.Function):
             if run.is_seq and i == CROSS_MODAL_START:
                 chunk_hidden = x
             pi = probs[i - (L - nprob)] if (nprob and i >= L - nprob) else None
+            x_in32 = x32
             x, x32 = E.layer_fwd(ps, "encoder.layer.%d." % i, x, x32, hist[i] if hist else None, ac, I, cfg["eps"], sv,
                                  cross, pi, drop, i)
+            if run.local_residual and cross:                 # v10:212-215: hidden = layer_out + former_hidden
+                x, x32 = _residual_add(x32, x_in32, N * S, H)
+            if run.is_seq and i == CROSS_MODAL_START:
+                chunk_hidden32 = x_in32
             saves.append(sv)
+        if run.final_residual and chunk_hidden is not None:  # v10:221-223: hidden = hidden + chunk_hidden_states
+            x, x32 = _residual_add(x32, chunk_hidden32, N * S, H)
         pooled = E.pooler_fwd(ps, x, N, S, H)
         seq_out = x.view(N, S, H)
         block = None
@@ -122,10 +140,16 @@ class EncoderFn(torch.autograd.Function):
         ws = E._empty((max(ops.attn_bwd_workspace_bytes(N, S, cfg["heads"]) // 4, 1),), F32, dev)
         dy = dy.view(N * S, H)
         dhists = [None] * ctx.n_hist
+        dy_top = dy.clone() if (run.final_residual and run.is_seq and L > CROSS_MODAL_START) else None
         for i in range(L - 1, -1, -1):
-            ac, _ = run.layer_cfg(i)
+            ac, cross = run.layer_cfg(i)
             da = dalign if (ctx.nprob and i >= L - ctx.nprob) else None
+            dy_out = dy.clone() if (run.local_residual and cross) else None
             dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws, run.drop, i)
+            if dy_out is not None:                           # the skip connection around a cross-modal layer
+                ops.add_bf16(dy, dy_out, dy)
+            if dy_top is not None and i == CROSS_MODAL_START:   # the final residual lands on the input of layer 9
+                ops.add_bf16(dy, dy_top, dy)
             ctx.saves[i] = None  # free this layer's activations
             if ctx.n_hist:
                 dhists[i] = dh

@@ -74,7 +74,9 @@ def engine_cfg(config):
     return dict(H=H, heads=heads, L=config.num_hidden_layers, I=config.intermediate_size,
                 eps=float(config.layer_norm_eps), img_eps=float(cfg_get(config, "img_layer_norm_eps", 1e-12)),
                 use_img_layernorm=int(bool(cfg_get(config, "use_img_layernorm", 0))),
-                pad_token_id=int(cfg_get(config, "pad_token_id", 0) or 0), n_cls_layers=3)
+                pad_token_id=int(cfg_get(config, "pad_token_id", 0) or 0), n_cls_layers=3,
+                add_residual=bool(cfg_get(config, "add_residual", False)),
+                add_local_residual=bool(cfg_get(config, "add_local_residual", False)))
 
 
 def check_no_dropout(module, config):

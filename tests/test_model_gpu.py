@@ -329,6 +329,47 @@ def test_mc_head_variants_match_restated_heads(which, classifier, use_ln, loss_t
     assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
 
 
+def test_seq_enc_optional_residuals_match_oracle():
+    """--add_residual / --add_local_residual (run_PMR_ModCR.py:574-575, 747-748): skip connections around the three
+    cross-modal layers and from the input of layer 9 to the output (v10:212-223); forward and gradients against the
+    restatement (pinned to the live reference in tests/test_oracle.py)."""
+    B, T, R = 1, 20, 6
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg.add_residual, cfg.add_local_residual = True, True
+    m = SeqBertImgModel(cfg)
+    sd = params.fill_params({k: v for k, v in m.state_dict().items()}, 6)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    b = synth.make_batch(B=B, T=T, R=R, seed=9)
+    bd = synth.to_device(b, DEV)
+    (out, pool, att), ch = m(bd["input_ids"], img_feats=bd["img_feat"], img_mask=bd["input_mask"][:, T:],
+                             input_mask=bd["input_mask"], attention_mask=bd["chunk_attention_mask"],
+                             token_type_ids=bd["token_type_ids"], offsets=b["offsets"], gather_index=b["gather_index"])
+    g = torch.Generator().manual_seed(1)
+    w_out, w_pool = torch.randn(out.shape, generator=g), torch.randn(pool.shape, generator=g)
+    live = b["input_mask"][:, :, None]       # padded rows carry no meaning
+    ((out.float() * (w_out * live).to(DEV)).sum() + (pool.float() * w_pool.to(DEV)).sum()).backward()
+    sdr = {"seq_enc." + k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    cfg_r = dict(CFG, add_residual=True, add_local_residual=True)
+    (o, p_, _), c_ = restate.seq_enc_forward(sdr, cfg_r, b["input_ids"], b["token_type_ids"], b["chunk_attention_mask"],
+                                             b["input_mask"], b["img_feat"], b["offsets"], b["gather_index"])
+    ((o * w_out * live).sum() + (p_ * w_pool).sum()).backward()
+    e_out = float(((out.float().cpu() - o) * live).abs().max())
+    print("residual flags: d_out %.4f (|out| max %.2f) d_pool %.4f d_chunk %.4f" % (
+        e_out, float(o.abs().max()), float((pool.float().cpu() - p_).abs().max()), nerr(ch, c_)))
+    # the four extra residual adds push |hidden| to ~30, where one bf16 ulp of the GEMM operand is 0.125: the pooled
+    # vector (tanh of a 768-term dot product of those operands) carries that rounding, hence 6e-2 instead of 2e-2
+    assert e_out < 0.02 * float(o.abs().max()) and float((pool.float().cpu() - p_).abs().max()) < 6e-2
+    named = dict(m.named_parameters())
+    errs = {}
+    for k in ("encoder.layer.11.output.dense.weight", "encoder.layer.9.attention.self.value.weight",
+              "encoder.layer.8.output.dense.weight", "encoder.layer.3.intermediate.dense.weight",
+              "encoder.layer.0.attention.self.query.weight", "img_embedding.weight", "pooler.dense.weight"):
+        errs[k] = l2err(named[k].grad, sdr["seq_enc." + k].grad)
+    print("residual flags grad rel-L2 err:", {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 0.1, errs
+
+
 def test_full_size_cfg2_invariants():
     """BASELINE.json configs[1] (32 questions x 4 choices, 128 tokens + 50 regions, prefix 10) is too large for the CPU
     oracle, so the full-size step is checked through size-independent properties of the path:

@@ -139,6 +139,34 @@ def test_restated_mc_heads_match_live_reference(which, classifier, use_ln, loss_
     assert ours_keys == ref_keys
 
 
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_restated_optional_residuals_match_live_reference():
+    """--add_residual / --add_local_residual of the run scripts (run_PMR_ModCR.py:574-575, 747-748; v10:212-223)."""
+    ns = ref_shim.load()
+    cfg = ref_shim.make_config(ns, add_residual=True, add_local_residual=True)
+    m = ns.v10.SeqBertImgModel(cfg).eval()
+    sd = params.fill_params(m.state_dict(), 6)
+    m.load_state_dict(sd)
+    b = synth.make_batch(B=1, T=20, R=6, seed=9)
+    T = 20
+    with torch.no_grad():
+        (r_out, r_pool, _), r_ch = m(b["input_ids"], img_feats=b["img_feat"], img_mask=b["input_mask"][:, T:],
+                                     input_mask=b["input_mask"], attention_mask=b["chunk_attention_mask"],
+                                     token_type_ids=b["token_type_ids"], head_mask=None, offsets=b["offsets"],
+                                     gather_index=b["gather_index"])
+        cfg_r = dict(CFG, add_residual=True, add_local_residual=True)
+        (o, pool, _), ch = restate.seq_enc_forward({"seq_enc." + k: v for k, v in sd.items()}, cfg_r, b["input_ids"],
+                                                   b["token_type_ids"], b["chunk_attention_mask"], b["input_mask"],
+                                                   b["img_feat"], b["offsets"], b["gather_index"])
+        (o0, _, _), _ = restate.seq_enc_forward({"seq_enc." + k: v for k, v in sd.items()}, CFG, b["input_ids"],
+                                                b["token_type_ids"], b["chunk_attention_mask"], b["input_mask"],
+                                                b["img_feat"], b["offsets"], b["gather_index"])
+    assert float((r_out - o).abs().max()) == 0.0 and float((r_pool - pool).abs().max()) == 0.0
+    assert float((r_ch - ch).abs().max()) == 0.0
+    assert float((o - o0).abs().max()) > 0.1     # the flags change the result
+
+
 def test_restated_collate_reproduces_the_synthetic_batches():
     """oracle/collate.py (Data/VCRChunkAlign.py:690-741, utils/GetChunk_v4_vcr.py:104-140) on the ragged samples of a
     synthetic batch gives back exactly the padded tensors the golden vectors were produced from."""
