@@ -128,13 +128,11 @@ int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t 
   g.B = W; g.ldb = Dpad;
   g.M = (int)rows; g.N = H; g.K = Dpad;
   g.bias = bias;
-  if (!use_ln) {
-    modcr::set_error("img_embed_ln_fwd: use_img_layernorm=0 is not implemented (the Oscar checkpoints of the path set it)");
-    return modcr::MODCR_ERR_UNSUPPORTED;
-  }
   g.C = pre; g.ldc = H; g.c_fp32 = 1;   // fp32 pre-LayerNorm activations
   rc = modcr::gemm_launch(g, S(stream));
   if (rc) return rc;
+  if (!use_ln)  // config without use_img_layernorm (modeling_transfomres.py:676-680): the projection is the embedding
+    return modcr::rows_place(pre, y, y32, RM(ymap), (int)rows, H, S(stream));
   modcr::RowMap id;
   return modcr::layernorm_fwd(pre, 1, id, gamma, beta, y, y32, RM(ymap), mean, rstd, (int)rows, H, eps, S(stream));
 }
@@ -148,13 +146,16 @@ int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packe
     modcr::set_error("img_embed_ln_bwd: bad shape rows=%lld Dpad=%d", (long long)rows, Dpad);
     return modcr::MODCR_ERR_SHAPE;
   }
-  if (!use_ln) {
-    modcr::set_error("img_embed_ln_bwd: use_img_layernorm=0 is not implemented");
-    return modcr::MODCR_ERR_UNSUPPORTED;
-  }
   modcr::RowMap id;
-  int rc = modcr::layernorm_bwd(dy, RM(dymap), pre, 1, id, mean, rstd, gamma, dpre, id, dgamma, dbeta, dbias, (int)rows, H,
-                                nullptr, nullptr, 0, 0.f, S(stream));
+  int rc;
+  if (!use_ln) {
+    rc = modcr::rows_gather(dy, RM(dymap), dpre, (int)rows, H, S(stream));
+    if (rc) return rc;
+    rc = modcr::colsum(dpre, H, (int)rows, H, dbias, S(stream));
+  } else {
+    rc = modcr::layernorm_bwd(dy, RM(dymap), pre, 1, id, mean, rstd, gamma, dpre, id, dgamma, dbeta, dbias, (int)rows, H,
+                              nullptr, nullptr, 0, 0.f, S(stream));
+  }
   if (rc) return rc;
   // dW[H, Dpad] = dpre^T packed      (A = dpre stored [K=rows, M=H], B = packed stored [K=rows, N=Dpad])
   modcr::GemmDesc g;

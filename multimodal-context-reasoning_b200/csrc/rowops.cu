@@ -371,6 +371,32 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t ld_src, b
   }
 }
 
+// img_embedding without LayerNorm (use_img_layernorm unset, modeling_transfomres.py:676-680): the fp32 GEMM output rows are
+// placed at their [N,S,H] positions as bf16 + fp32 (forward); the bf16 gradient rows are gathered back (backward).
+__global__ void rows_place_kernel(const float* __restrict__ src, bf16* __restrict__ y, float* __restrict__ y32, RowMap ymap,
+                                  int M, int H8) {
+  const int64_t total = (int64_t)M * H8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / H8), c = (int)(i - (int64_t)m * H8) * 8;
+    float f[8];
+    load8f(src + (int64_t)m * H8 * 8 + c, f);
+    const int64_t o = map_row(m, ymap) * H8 * 8 + c;
+    *reinterpret_cast<uint4*>(y + o) = pack8(f);
+    if (y32 != nullptr) {
+      reinterpret_cast<float4*>(y32 + o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(y32 + o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+__global__ void rows_gather_kernel(const bf16* __restrict__ dy, RowMap dymap, bf16* __restrict__ dst, int M, int H8) {
+  const int64_t total = (int64_t)M * H8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / H8), c = (int)(i - (int64_t)m * H8);
+    reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(dy + map_row(m, dymap) * H8 * 8) + c);
+  }
+}
+
 // dst(fp32) [+]= src(bf16) elementwise (used for gradients that must come back as fp32)
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n8, int accumulate) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -761,6 +787,24 @@ int cast_pad(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_
   cast_pad_kernel<<<blocks_for(rows * (ld_dst / 8), 256), 256, 0, st>>>(src, ld_src, (bf16*)dst, ld_dst, rows, cols,
                                                                          row_step);
   return check_launch("cast_pad");
+}
+
+int rows_place(const float* src, void* y, float* y32, RowMap ymap, int M, int H, cudaStream_t st) {
+  if (M <= 0 || H <= 0 || H % 8 != 0) {
+    set_error("rows_place: bad shape M=%d H=%d", M, H);
+    return MODCR_ERR_SHAPE;
+  }
+  rows_place_kernel<<<blocks_for((int64_t)M * (H / 8), 256), 256, 0, st>>>(src, (bf16*)y, y32, ymap, M, H / 8);
+  return check_launch("rows_place");
+}
+
+int rows_gather(const void* dy, RowMap dymap, void* dst, int M, int H, cudaStream_t st) {
+  if (M <= 0 || H <= 0 || H % 8 != 0) {
+    set_error("rows_gather: bad shape M=%d H=%d", M, H);
+    return MODCR_ERR_SHAPE;
+  }
+  rows_gather_kernel<<<blocks_for((int64_t)M * (H / 8), 256), 256, 0, st>>>((const bf16*)dy, dymap, (bf16*)dst, M, H / 8);
+  return check_launch("rows_gather");
 }
 
 int bf16_to_f32(const void* src, float* dst, int64_t n, int accumulate, cudaStream_t st) {

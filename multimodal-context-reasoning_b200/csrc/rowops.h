@@ -36,6 +36,8 @@ int copy_rows(const void* src, int64_t src_seq_stride, int srow0, void* dst, int
               int nrows, int H, int accumulate, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st);
 int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
+int rows_place(const float* src, void* y, float* y32, RowMap ymap, int M, int H, cudaStream_t st);
+int rows_gather(const void* dy, RowMap dymap, void* dst, int M, int H, cudaStream_t st);
 int relu_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
 int rowln_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int M, int H,
               float eps, cudaStream_t st);

@@ -329,6 +329,42 @@ def test_mc_head_variants_match_restated_heads(which, classifier, use_ln, loss_t
     assert m.bert.encoder.layer[0].attention.self.query.weight.grad is not None
 
 
+def test_global_enc_without_img_layernorm_matches_oracle():
+    """A config without ``use_img_layernorm`` (modeling_transfomres.py:600-606, 676-680): the 2054->768 projection is the
+    region embedding, no LayerNorm module in the state_dict; forward + gradients against the restatement."""
+    B, T, R, P = 1, 20, 6, 3
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     num_hidden_layers=2)
+    cfg.use_img_layernorm = None
+    m = BertImgModel(cfg)
+    assert not any(k.startswith("LayerNorm.") for k in m.state_dict())
+    sd = params.fill_params({k: v for k, v in m.state_dict().items()}, 8)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    b = synth.make_batch(B=B, T=T, R=R, seed=9)
+    bd = synth.to_device(b, DEV)
+    N = 4 * B
+    hist_cpu = [torch.randn(N, P, 768, generator=torch.Generator().manual_seed(i)) * 0.5 for i in range(2)]
+    out, pool = m(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=bd["input_mask"],
+                  img_feats=bd["img_feat"], encoder_history_states=[h.to(DEV) for h in hist_cpu])[:2]
+    g = torch.Generator().manual_seed(1)
+    w_out = torch.randn(out.shape, generator=g) * b["input_mask"][:, :, None]
+    (out.float() * w_out.to(DEV)).sum().backward()
+    sdr = {"global_enc." + k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    cfg_r = dict(CFG, use_img_layernorm=None, num_hidden_layers=2)
+    o, p_, _ = restate.global_enc_forward(sdr, cfg_r, b["input_ids"], b["token_type_ids"],
+                                          torch.cat([torch.ones(N, P), b["input_mask"]], -1), b["img_feat"], hist_cpu)
+    (o * w_out).sum().backward()
+    live = b["input_mask"][:, :, None]
+    assert float(((out.float().cpu() - o) * live).abs().max()) < 3e-2
+    assert float((pool.float().cpu() - p_).abs().max()) < 2e-2
+    named = dict(m.named_parameters())
+    errs = {k: l2err(named[k].grad, sdr["global_enc." + k].grad)
+            for k in ("img_embedding.weight", "img_embedding.bias", "encoder.layer.0.attention.self.value.weight")}
+    print("no-img-LN grad rel-L2 err:", {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 5e-2, errs
+
+
 def test_seq_enc_optional_residuals_match_oracle():
     """--add_residual / --add_local_residual (run_PMR_ModCR.py:574-575, 747-748): skip connections around the three
     cross-modal layers and from the input of layer 9 to the output (v10:212-223); forward and gradients against the
