@@ -389,6 +389,13 @@ def run_ours(args):
                 stage[slot][k].copy_(v, non_blocking=True)   # pinned host -> HBM
             ready[slot].record(copy_stream)
 
+    # The loss of step i is copied to pinned host memory asynchronously right behind the step and read by the host after
+    # step i+1 has been enqueued (one step behind, like a training loop that logs the previous step's loss), so the
+    # device never idles while the host waits; every step's loss is read inside the timed region.
+    host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_read = []
+
     def e2e_step(i):
         slot = i & 1
         cur = torch.cuda.current_stream()
@@ -398,20 +405,32 @@ def run_ours(args):
         consumed[slot].record(cur)
         prefetch(slot ^ 1)                               # next step's inputs, under this step's compute
         ls = run_step(static)
-        return ls.item()                                 # D2H read of the step's result
+        host_loss[slot:slot + 1].copy_(ls.detach().reshape(1), non_blocking=True)   # D2H of the step's result
+        loss_done[slot].record(cur)
+        if i > 0:                                        # host reads the previous step's loss
+            loss_done[slot ^ 1].synchronize()
+            losses_read.append(float(host_loss[slot ^ 1]))
+
+    def e2e_drain(last):
+        loss_done[last & 1].synchronize()
+        losses_read.append(float(host_loss[last & 1]))
     for sl in range(2):
         consumed[sl].record(torch.cuda.current_stream())
     prefetch(0)
     for i in range(2):
         e2e_step(i)
+    e2e_drain(1)
     barrier()
+    losses_read.clear()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
         e2e_step(i)
+    e2e_drain(args.steps - 1)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
+    assert len(losses_read) >= args.steps and all(l == l for l in losses_read)   # every step's loss reached the host
 
     # ---- optimiser step (reported separately): fused clip + AdamW over all 250 M parameters
     opt_ms = None
@@ -435,6 +454,33 @@ def run_ours(args):
             del opt
         except Exception as e:  # noqa: BLE001 -- the headline numbers do not depend on this section
             sys.stderr.write("bench.py: optimiser section failed: %s\n" % (str(e)[:300],))
+
+    # ---- device-side batch packer (informational): ragged samples -> one pinned buffer -> one H2D copy ->
+    # modcr_pack_batch, against the reference-shaped batch of the e2e measurement above
+    pack_info = None
+    if rank == 0:
+        try:
+            from modcr_b200 import synth
+            from modcr_b200.packer import BatchPacker, unbatch
+            samples = unbatch(synth.make_batch(B=w["B"], T=w["T"], R=w["R"], feat_dim=w["feat"],
+                                               num_choices=w["choices"], seed=88, rank=rank), w["choices"])
+            pk = BatchPacker(dev, feat_dim=w["feat"], pad_T=w["T"], pad_R=w["R"])
+            pk.pack(samples)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            p0.record()
+            for _ in range(5):
+                pk.pack(samples)
+            p1.record()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            pack_info = dict(h2d_bytes_per_step=pk.h2d_bytes, reference_shaped_h2d_bytes_per_step=h2d,
+                             device_ms=p0.elapsed_time(p1) / 5, host_ms=(t1 - t0) * 1e3 / 5,
+                             what="packer.BatchPacker: one pinned descriptor buffer + one feature block per question, "
+                                  "one H2D copy, 2 kernels (csrc/pack.cu); not part of the headline numbers")
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("bench.py: packer section failed: %s\n" % (str(e)[:300],))
 
     # ---- max over ranks
     t = torch.tensor([ms, ms_e2e], device=dev)
@@ -479,6 +525,7 @@ def run_ours(args):
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                 gpu_launches=int(launches),
+                batch_packer=pack_info,
                 optimizer_step=None if opt_ms is None else dict(
                     ms=opt_ms, what="fused clip_grad_norm + AdamW (two LR groups) over all parameters incl. the rewrite of the bf16 operand copies, 2 launches; not part "
                                     "of the fwd+bwd metric"))
