@@ -455,6 +455,44 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001 -- the headline numbers do not depend on this section
             sys.stderr.write("bench.py: optimiser section failed: %s\n" % (str(e)[:300],))
 
+    # ---- scoring path (eval / test of the run scripts, run_PMR_ModCR.py:243-353): forward-only `evaluate()` under no_grad,
+    # one CUDA graph, device-resident batch (informational; the metric of this bench is fwd+bwd)
+    scoring = None
+    if rank == 0:
+        try:
+            m.eval()
+
+            def score(bd):
+                hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(w["L"])]
+                return m.evaluate(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                                  token_type_ids=bd["token_type_ids"], encoder_history_states=hist,
+                                  chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["chunk_id"])
+            with torch.no_grad():
+                for _ in range(3):
+                    score(static)
+                torch.cuda.synchronize()
+                sg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(sg):
+                    s_out = score(static)
+                sg.replay()
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(args.steps):
+                    sg.replay()
+                s1.record()
+                torch.cuda.synchronize()
+            s_ms = s0.elapsed_time(s1) / args.steps
+            fwd_flops = flops_per_sample(w) / 3.0
+            scoring = dict(value=w["B"] / s_ms * 1e3, unit="samples/s", ms_per_batch=s_ms,
+                           tflops=w["B"] / s_ms * 1e3 * fwd_flops / 1e12,
+                           what="ChunkAlign_CLS_enc4_align.evaluate (v10:1086-1125), forward only, no_grad, graph replay")
+            del sg, s_out
+            m.train()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("bench.py: scoring section failed: %s\n" % (str(e)[:300],))
+            m.train()
+
     # ---- device-side batch packer (informational): ragged samples -> one pinned buffer -> one H2D copy ->
     # modcr_pack_batch, against the reference-shaped batch of the e2e measurement above
     pack_info = None
@@ -525,6 +563,7 @@ def run_ours(args):
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
                 gpu_launches=int(launches),
+                scoring=scoring,
                 batch_packer=pack_info,
                 optimizer_step=None if opt_ms is None else dict(
                     ms=opt_ms, what="fused clip_grad_norm + AdamW (two LR groups) over all parameters incl. the rewrite of the bf16 operand copies, 2 launches; not part "
