@@ -319,6 +319,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
           }
         }
+        fence_async_smem();   // generic-proxy reads of the stage before the TMA load that refills it (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == STAGES) {
@@ -460,7 +461,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          mbar_arrive(&inempty[bi]);
         }
         if constexpr (OUT_F32) {
 #pragma unroll
@@ -473,6 +473,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
         fence_async_smem();
+        if (HAS_IN) {
+          // Hand the input slot back only AFTER the proxy fence: this thread's generic-proxy reads of the slot must be
+          // ordered before the async-proxy write of the next TMA load into it.  (Arriving right behind the LDS let the
+          // next load overwrite the slot under a slow reader about once per 10^7 chunks: the epilogue then added the
+          // residual of the chunk 64 columns ahead -- found by scripts/gemm_race.py.)
+          const uint32_t slot_r = cnt % C::IN_DEPTH;
+          mbar_arrive(&inempty[g * C::IN_DEPTH + slot_r]);
+        }
         // double-buffered: the store issued one chunk ago (other buffer) must have been read before anyone passes
         // this barrier and starts the next chunk, which overwrites that buffer; it had a whole chunk to drain
         if (C::NBUF == 2 && issuer) tma_store_wait_read<0>();
