@@ -48,9 +48,7 @@ class BatchPacker:
     def __init__(self, device, feat_dim=2054, pad_T=None, pad_R=None, dense_chunk_mask=False):
         """``pad_T`` / ``pad_R``: pad to fixed sizes (static shapes for CUDA-graph replay) instead of the batch maxima the
         reference pads to (:699, :709-711).  ``dense_chunk_mask``: also emit the reference's fp32 ``[N,T,T]`` tensor."""
-        self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("modcr_b200: BatchPacker needs a CUDA device (no CPU path)")
+        self.device = torch.device(device)     # host_pack() works anywhere; pack() needs CUDA (no CPU path)
         self.D, self.pad_T, self.pad_R, self.dense = feat_dim, pad_T, pad_R, dense_chunk_mask
         self._pinned = None
         self.h2d_bytes = 0
@@ -60,7 +58,10 @@ class BatchPacker:
             self._pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         return self._pinned
 
-    def pack(self, samples):
+    def host_pack(self, samples, buf=None):
+        """Host half: fills the descriptor buffer (a uint8 tensor of at least the returned size; allocated when ``buf`` is
+        None) and returns ``(buf, layout)`` with ``layout = dict(N, T, R, U, hdr_bytes, tok_bytes, feat_off, total,
+        max_chunks)``.  Pure CPU work (no CUDA needed): tests decode the buffer with ``oracle/collate.py``."""
         N, D = len(samples), self.D
         lens = [int(s["input_ids"].numel()) for s in samples]
         nbox = [int(s["img_mask"].sum().item()) for s in samples]
@@ -79,7 +80,8 @@ class BatchPacker:
         hdr_b, tok_b = N * 4 * 4, N * T * 2 * 4
         feat_off = (hdr_b + tok_b + 15) & ~15
         total = feat_off + U * R * D * 4
-        buf = self._buffer(total)
+        if buf is None:
+            buf = torch.empty(total, dtype=torch.uint8)
         nb = buf.numpy()
         header = nb[:hdr_b].view(np.int32).reshape(N, 4)
         tokens = nb[hdr_b:hdr_b + tok_b].view(np.int32).reshape(N, T, 2)
@@ -109,6 +111,22 @@ class BatchPacker:
             r = min(R, f.shape[0])
             feats[u, :r] = f[:r].numpy()
             feats[u, r:] = 0.0
+        return buf, dict(N=N, T=T, R=R, U=U, hdr_bytes=hdr_b, tok_bytes=tok_b, feat_off=feat_off, total=total,
+                         max_chunks=max_chunks)
+
+    def pack(self, samples):
+        if self.device.type != "cuda":
+            raise RuntimeError("modcr_b200: BatchPacker.pack needs a CUDA device (no CPU path)")
+        D = self.D
+        # size the pinned buffer for the worst case of this batch, then fill it in place
+        N = len(samples)
+        T_ = max(int(s["input_ids"].numel()) for s in samples) if self.pad_T is None else self.pad_T
+        R_ = max(int(s["img_feat"].shape[0]) for s in samples) if self.pad_R is None else self.pad_R
+        buf = self._buffer(N * 16 + N * T_ * 8 + 16 + N * R_ * D * 4)
+        buf, lay = self.host_pack(samples, buf)
+        N, T, R = lay["N"], lay["T"], lay["R"]
+        hdr_b, tok_b, feat_off, total, max_chunks = (lay["hdr_bytes"], lay["tok_bytes"], lay["feat_off"], lay["total"],
+                                                     lay["max_chunks"])
         dev = self.device
         dbuf = torch.empty(total, dtype=torch.uint8, device=dev)
         dbuf.copy_(buf[:total], non_blocking=True)              # the ONE host-to-device copy of the batch

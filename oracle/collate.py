@@ -58,3 +58,42 @@ def snli_gpt_gen_collate(samples):
     return {"input_ids": input_ids, "token_type_ids": segment_ids, "input_mask": input_mask, "img_feat": img_feat,
             "label": target, "chunk_attention_mask": torch.stack(padded, 0), "gather_index": g("gather_index"),
             "offsets": g("offsets"), "total_label": total_label, "align_pos": align_pos}
+
+
+def decode_descriptors(buf, lay, D):
+    """Numpy restatement of what ``modcr_pack_batch`` (csrc/pack.cu) must produce from the packed descriptor buffer of
+    ``packer.BatchPacker.host_pack`` (format: include/modcr_b200.h, ``modcr_pack_desc``).  Returns the batch dict with
+    the dense chunk mask; used on the CPU to check the host half of the packer against ``snli_gpt_gen_collate``."""
+    import numpy as np
+    N, T, R, U = lay["N"], lay["T"], lay["R"], lay["U"]
+    nb = buf.numpy()
+    header = nb[:lay["hdr_bytes"]].view(np.int32).reshape(N, 4)
+    tokens = nb[lay["hdr_bytes"]:lay["hdr_bytes"] + lay["tok_bytes"]].view(np.int32).reshape(N, T, 2)
+    feats = nb[lay["feat_off"]:lay["total"]].view(np.float32).reshape(U, R, D)
+    ids = torch.zeros(N, T, dtype=torch.int64)
+    seg, lab, apos = torch.zeros_like(ids), torch.zeros_like(ids), torch.zeros_like(ids)
+    cid = torch.full((N, T), -1, dtype=torch.int32)
+    mask = torch.zeros(N, T + R)
+    cm = torch.zeros(N, T, T)
+    img = torch.zeros(N, R, D)
+    for n in range(N):
+        L, nbox, _, blk = (int(v) for v in header[n])
+        w1 = tokens[n, :L, 1].astype(np.int64) & 0xFFFFFFFF
+        ids[n, :L] = torch.from_numpy(tokens[n, :L, 0].astype(np.int64))
+        seg[n, :L] = torch.from_numpy((w1 >> 10) & 1)
+        apos[n, :L] = torch.from_numpy((w1 >> 11) & 1)
+        lab[n, :L] = torch.from_numpy(w1 >> 12)
+        c = torch.from_numpy((w1 & 1023) - 1).to(torch.int32)
+        cid[n, :L] = c
+        mask[n, :L] = 1.0
+        mask[n, T:T + nbox] = 1.0
+        m = torch.eye(L)
+        m[0, :L] = 1
+        m[L - 1, :L] = 1
+        same = (c[:, None] == c[None, :]) & (c[:, None] >= 0)
+        m[same] = 1
+        cm[n, :L, :L] = m
+        img[n, :nbox] = torch.from_numpy(feats[blk, :nbox].copy())
+    return {"input_ids": ids, "token_type_ids": seg, "total_label": lab, "align_pos": apos, "input_mask": mask,
+            "chunk_attention_mask": cm, "img_feat": img, "chunk_id": cid,
+            "label": torch.from_numpy(header[:, 2].astype(np.float32))}

@@ -186,6 +186,17 @@ def test_restated_collate_reproduces_the_synthetic_batches():
                   "align_pos"):
             assert torch.equal(out[k], b[k]), k
         assert torch.equal(out["label"], b["label_onehot"])
+        # host half of the device packer (packer.BatchPacker.host_pack, no CUDA needed): its descriptor buffer decodes
+        # to exactly the collated batch, and holds one feature block per question
+        from modcr_b200.packer import BatchPacker
+        buf, lay = BatchPacker("cpu").host_pack(samples)
+        dec = collate.decode_descriptors(buf, lay, 2054)
+        for k in ("input_ids", "token_type_ids", "input_mask", "img_feat", "chunk_attention_mask", "total_label",
+                  "align_pos", "label"):
+            assert torch.equal(dec[k], out[k]), k
+        assert lay["U"] == kw["B"] and lay["total"] <= lay["feat_off"] + kw["B"] * lay["R"] * 2054 * 4
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            BatchPacker("cpu").pack(samples)
 
 
 # ---- known-answer invariants, small shapes ----------------
