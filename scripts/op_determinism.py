@@ -66,3 +66,20 @@ aux = torch.empty(M, I, dtype=torch.bfloat16, device=dev)
 check("gemm ffn1 (+GELU, aux)", lambda: ops.gemm(a, W1, h, M, I, H, bias=b1, act=1, aux=aux), [h, aux])
 W2, b2 = rnd(H, I, sc=0.02), rnd(H, sc=0.1, dt=torch.float32)
 check("gemm ffn2 (fp32 out + fp32 res)", lambda: ops.gemm(h, W2, pre, M, H, I, bias=b2, epi_in=a32, in_op=1), [pre])
+
+# ---- backward ops whose outputs are written once (no atomics): must be bit-identical as well
+ops.prefix_attn_fwd(N, S, P, heads, 0, 0, qkv, pkv, kb, None, 0, ctx, lse)
+dctx = rnd(M, H, sc=0.1)
+dqkv = torch.empty(M, 3 * H, dtype=torch.bfloat16, device=dev)
+dpkv = torch.empty(N * P, 2 * H, dtype=torch.bfloat16, device=dev)
+ws = torch.empty(max(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, 1), dtype=torch.float32, device=dev)
+check("prefix_attn_bwd mode 0 P=10", lambda: ops.prefix_attn_bwd(N, S, P, heads, 0, 0, qkv, pkv, kb, None, 0, ctx, lse, None,
+                                                                 dctx, None, dqkv, dpkv, ws), [dqkv, dpkv])
+dh = torch.empty(M, I, dtype=torch.bfloat16, device=dev)
+dpre = rnd(M, H, sc=0.1)
+check("gemm dgrad ffn2 (x GELU')", lambda: ops.gemm(dpre, W2, dh, M, I, H, b_mn=1, epi_in=aux, in_op=2), [dh])
+dx = torch.empty(M, H, dtype=torch.bfloat16, device=dev)
+dres = rnd(M, H, sc=0.1)
+check("gemm dgrad ffn1 (+bf16 residual)", lambda: ops.gemm(dh, W1, dx, M, H, I, b_mn=1, epi_in=dres, in_op=1), [dx])
+dW = torch.empty(I, H, dtype=torch.float32, device=dev)
+check("gemm wgrad ffn1 (no split-K)", lambda: ops.gemm(dh, a, dW, I, H, M, a_mn=1, b_mn=1), [dW])
