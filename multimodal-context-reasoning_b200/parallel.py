@@ -80,11 +80,17 @@ class GradReducer:
         else:
             ctx = _Null()
         with ctx:
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
-                flat = flat.to(self.comm_dtype)
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((work, flat, grads))
+            # ONE multi-tensor kernel gathers (and, for bf16 buckets, casts) the gradients into the flat bucket -- no
+            # fp32 concatenation followed by a separate cast pass
+            dt = self.comm_dtype if self.comm_dtype is not None else grads[0].dtype
+            flat = torch.empty(sum(g.numel() for g in grads), dtype=dt, device=grads[0].device)
+            views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
+            torch._foreach_copy_(views, grads)
+            # NCCL averages inside the collective (no scale pass afterwards); other backends sum and finish() scales
+            avg = cuda and dist.get_backend(self.group) == "nccl"
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group,
+                                   async_op=True)
+        self._inflight.append((work, flat, grads, avg))
         self.launched += 1
 
     # ---------------------------------------------------------------- per step
@@ -97,11 +103,12 @@ class GradReducer:
         ctx = torch.cuda.stream(self.stream) if cuda else _Null()
         with ctx:
             scale = 1.0 / self.world
-            for work, flat, grads in self._inflight:
+            for work, flat, grads, avg in self._inflight:
                 work.wait()
-                # one scale kernel per bucket, then ONE multi-tensor copy back into the .grad tensors (a per-parameter
+                # (one scale kernel per bucket unless the collective averaged,) then ONE multi-tensor copy back into the .grad tensors (a per-parameter
                 # copy is ~500 tiny launches per step)
-                flat.mul_(scale)
+                if not avg:
+                    flat.mul_(scale)
                 views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
                 torch._foreach_copy_(grads, views)
         if cuda:
