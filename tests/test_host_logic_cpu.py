@@ -125,3 +125,29 @@ def test_bench_flop_accounting_matches_survey():
 def test_multiple_choice_head_surface():
     m = ImageBertForMultipleChoice(small_cfg(num_labels=4, num_choice=4))
     assert m.classifier.weight.shape == (4, 4 * 256)
+
+
+def test_multiple_choice_classifier_variants_surface():
+    """state_dict layout of the classifier variants (modeling/modeling_bert.py:511-530, 656-669; checked key-for-key
+    against the live reference classes in tests/test_oracle.py when the reference tree is present)."""
+    from modcr_b200.modeling_bert import OscarForMultipleChoice
+    cfg = small_cfg(num_labels=4, num_choice=4)
+    cfg.classifier, cfg.use_img_layernorm, cfg.loss_type = "mlp", 1, "bce"
+    m = ImageBertForMultipleChoice(cfg)
+    keys = {k: tuple(v.shape) for k, v in m.state_dict().items() if k.startswith("classifier.")}
+    assert keys == {"classifier.0.weight": (512, 1024), "classifier.0.bias": (512,), "classifier.2.weight": (512,),
+                    "classifier.2.bias": (512,), "classifier.3.weight": (4, 512), "classifier.3.bias": (4,)}
+    cfg2 = small_cfg(num_labels=2, num_choice=4)
+    cfg2.classifier, cfg2.loss_type = "mlp", "bce"
+    o = OscarForMultipleChoice(cfg2)
+    keys = {k: tuple(v.shape) for k, v in o.state_dict().items() if k.startswith("classifier.")}
+    assert keys == {"classifier.0.weight": (512, 256), "classifier.0.bias": (512,), "classifier.2.weight": (2, 512),
+                    "classifier.2.bias": (2,)}
+    cfg3 = small_cfg(num_labels=2)
+    cfg3.classifier = "conv"
+    with pytest.raises(ValueError, match="linear.*mlp"):
+        ImageBertForMultipleChoice(cfg3)
+    # CPU tensors never reach a kernel: the head raises instead of falling back
+    x = torch.zeros(2, 4, 6, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        m(x, img_feats=torch.zeros(2, 4, 3, 2054))
