@@ -38,6 +38,37 @@ def unbatch(batch, num_choices=4):
     return samples
 
 
+# order of the per-choice tuple the reference's ``__getitem__`` returns (Data/VCRChunkAlign.py:683-686) and the collate
+# unzips (:692-693)
+REF_FIELDS = ("img_id", "image", "text", "r_input_ids", "r_segment_ids", "r_input_mask", "input_ids", "segment_ids",
+              "input_mask", "img_feat", "img_mask", "target", "chunk_mask", "gather_index", "offsets", "ques", "ans",
+              "total_label", "align_pos")
+
+
+def samples_from_reference(inputs):
+    """``inputs`` as a DataLoader hands them to ``SNLIGPT_gen_collate``: a list (questions of the batch) of tuples (the
+    choices of a question) of 19-tuples -> flat list of sample dicts (``concat`` + ``unzip`` of :692-693)."""
+    out = []
+    for question in inputs:
+        for choice in question:
+            if len(choice) != len(REF_FIELDS):
+                raise ValueError("expected the %d-field tuple of Data/VCRChunkAlign.py:683-686, got %d fields"
+                                 % (len(REF_FIELDS), len(choice)))
+            out.append(dict(zip(REF_FIELDS, choice)))
+    return out
+
+
+def pad_language_side(samples):
+    """The RoBERTa-side fields of the batch (:695-697): ``pad_sequence(batch_first=True, padding_value=0)`` of
+    ``r_input_ids`` / ``r_input_mask`` / ``r_segment_ids``.  Host tensors; ``None`` when the samples carry none."""
+    if not samples or samples[0].get("r_input_ids") is None:
+        return None
+    from torch.nn.utils.rnn import pad_sequence
+    return {"r_input_ids": pad_sequence([s["r_input_ids"] for s in samples], batch_first=True, padding_value=0),
+            "r_attention_mask": pad_sequence([s["r_input_mask"] for s in samples], batch_first=True, padding_value=0),
+            "r_token_type_ids": pad_sequence([s["r_segment_ids"] for s in samples], batch_first=True, padding_value=0)}
+
+
 class PackedBatch(dict):
     """The batch dict of the reference contract (device tensors) plus ``chunk_bits`` / ``chunk_id`` / ``max_chunks``.
     ``chunk_attention_mask`` holds the int32 bit mask ``[N,T,ceil(T/32)]`` (``SeqBertImgModel`` accepts it in place of
@@ -114,6 +145,11 @@ class BatchPacker:
         return buf, dict(N=N, T=T, R=R, U=U, hdr_bytes=hdr_b, tok_bytes=tok_b, feat_off=feat_off, total=total,
                          max_chunks=max_chunks)
 
+    def collate(self, inputs):
+        """``collate_fn`` drop-in for ``SNLIGPT_gen_collate`` (run_PMR_ModCR.py:118-120): takes what the DataLoader
+        hands over (per-question tuples of the reference's per-choice 19-tuples, CPU tensors) and returns the batch."""
+        return self.pack(samples_from_reference(inputs))
+
     def pack(self, samples):
         if self.device.type != "cuda":
             raise RuntimeError("modcr_b200: BatchPacker.pack needs a CUDA device (no CPU path)")
@@ -151,6 +187,13 @@ class BatchPacker:
         dbuf.record_stream(torch.cuda.current_stream(dev))
         out["offsets"] = [s["offsets"] for s in samples]
         out["max_chunks"] = max_chunks
+        lang = pad_language_side(samples)                      # language-model inputs of Abstract_Specific (:695-697)
+        if lang is not None:
+            for k, v in lang.items():
+                out[k] = v.to(dev, non_blocking=True)
+        for src, dst in (("img_id", "img_id"), ("ques", "ques_str"), ("ans", "ans_str")):   # pass-through (:726-731)
+            if src in samples[0]:
+                out[dst] = [s[src] for s in samples]
         if dense is not None:
             out["dense_chunk_mask"] = dense
         return out

@@ -4,7 +4,7 @@
   next to ``offsets`` (eye + full first / last row + one block per chunk).
 * ``gather_index_from_offsets``  Data/VCRChunkAlign.py:667-670.
 * ``snli_gpt_gen_collate``  Data/VCRChunkAlign.py:690-741 (``SNLIGPT_gen_collate``), the fields the hot path consumes
-  (the RoBERTa-side ``r_*`` fields are padded the same way and are left out here).
+  (including the RoBERTa-side ``r_*`` fields when the samples carry them).
 
 The reference's data module cannot be imported (toolz / lmdb / clip ... are absent), so this is a
 line-by-line restatement; tests/test_oracle.py checks it against the synthetic batch generator, whose padded tensors
@@ -55,9 +55,14 @@ def snli_gpt_gen_collate(samples):
         item = torch.cat((item, torch.zeros((max_hypo - item.size(0), item.size(1)))), 0)
         item = torch.cat((item, torch.zeros((max_hypo, max_hypo - item.size(1)))), 1)
         padded.append(item)
-    return {"input_ids": input_ids, "token_type_ids": segment_ids, "input_mask": input_mask, "img_feat": img_feat,
-            "label": target, "chunk_attention_mask": torch.stack(padded, 0), "gather_index": g("gather_index"),
-            "offsets": g("offsets"), "total_label": total_label, "align_pos": align_pos}
+    batch = {"input_ids": input_ids, "token_type_ids": segment_ids, "input_mask": input_mask, "img_feat": img_feat,
+             "label": target, "chunk_attention_mask": torch.stack(padded, 0), "gather_index": g("gather_index"),
+             "offsets": g("offsets"), "total_label": total_label, "align_pos": align_pos}
+    if samples and samples[0].get("r_input_ids") is not None:                           # :695-697, :727-729
+        batch["r_input_ids"] = pad_sequence(g("r_input_ids"), batch_first=True, padding_value=0)
+        batch["r_attention_mask"] = pad_sequence(g("r_input_mask"), batch_first=True, padding_value=0)
+        batch["r_token_type_ids"] = pad_sequence(g("r_segment_ids"), batch_first=True, padding_value=0)
+    return batch
 
 
 def decode_descriptors(buf, lay, D):

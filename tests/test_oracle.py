@@ -197,6 +197,22 @@ def test_restated_collate_reproduces_the_synthetic_batches():
         assert lay["U"] == kw["B"] and lay["total"] <= lay["feat_off"] + kw["B"] * lay["R"] * 2054 * 4
         with pytest.raises(RuntimeError, match="no CPU path"):
             BatchPacker("cpu").pack(samples)
+        # the DataLoader-shaped input of the reference collate (per-question tuples of per-choice 19-tuples) maps back
+        # to the same samples, and the language-model side is padded like :695-697
+        from modcr_b200.packer import REF_FIELDS, pad_language_side, samples_from_reference
+        g = torch.Generator().manual_seed(1)
+        for s_ in samples:
+            n_r = int(torch.randint(5, 20, (1,), generator=g))
+            s_.update(img_id="q", image="", text="", ques="?", ans="!", r_input_ids=torch.randint(3, 99, (n_r,), generator=g),
+                      r_segment_ids=torch.zeros(n_r, dtype=torch.int64), r_input_mask=torch.ones(n_r))
+        inputs = [tuple(tuple(s_[f] for f in REF_FIELDS) for s_ in samples[q:q + 4]) for q in range(0, len(samples), 4)]
+        back = samples_from_reference(inputs)
+        assert len(back) == len(samples) and all(a[f] is b_[f] for a, b_ in zip(back, samples) for f in REF_FIELDS)
+        lang, ref_lang = pad_language_side(back), collate.snli_gpt_gen_collate(samples)
+        for k in ("r_input_ids", "r_attention_mask", "r_token_type_ids"):
+            assert torch.equal(lang[k], ref_lang[k]), k
+        with pytest.raises(ValueError, match="19-field|19"):
+            samples_from_reference([((1, 2, 3),)])
 
 
 # ---- known-answer invariants, small shapes ----------------
