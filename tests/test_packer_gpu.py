@@ -62,3 +62,24 @@ def test_packer_fixed_shapes_and_model_equivalence():
     assert torch.equal(r1[1], r2[1]) and int(r1[3]) == int(r2[3]) and int(r1[4]) == int(r2[4])
     with pytest.raises(ValueError, match="pad_T"):
         BatchPacker(DEV, pad_T=T - 8, pad_R=R).pack(samples)
+
+
+def test_collate_takes_the_reference_dataloader_tuples():
+    """``BatchPacker.collate`` as ``collate_fn``: per-question tuples of the reference's per-choice 19-tuples
+    (Data/VCRChunkAlign.py:683-686, 692-693) in, the reference's batch keys out (incl. the padded language-model side)."""
+    from modcr_b200.packer import REF_FIELDS
+    b = synth.make_batch(B=2, T=24, R=7, seed=3, min_len=6)
+    samples = unbatch(b)
+    g = torch.Generator().manual_seed(1)
+    for i, s_ in enumerate(samples):
+        n_r = int(torch.randint(5, 20, (1,), generator=g))
+        s_.update(img_id="q%d" % (i // 4), image="", text="", ques="?", ans="a%d" % i,
+                  r_input_ids=torch.randint(3, 99, (n_r,), generator=g), r_segment_ids=torch.zeros(n_r, dtype=torch.int64),
+                  r_input_mask=torch.ones(n_r))
+    inputs = [tuple(tuple(s_[f] for f in REF_FIELDS) for s_ in samples[q:q + 4]) for q in range(0, len(samples), 4)]
+    out = BatchPacker(DEV).collate(inputs)
+    ref = collate.snli_gpt_gen_collate(samples)
+    for k in ("input_ids", "token_type_ids", "total_label", "align_pos", "input_mask", "img_feat", "label",
+              "r_input_ids", "r_attention_mask", "r_token_type_ids"):
+        assert out[k].is_cuda and torch.equal(out[k].cpu(), ref[k]), k
+    assert out["img_id"] == [s_["img_id"] for s_ in samples] and out["ans_str"] == [s_["ans"] for s_ in samples]
