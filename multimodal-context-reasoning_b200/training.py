@@ -28,6 +28,13 @@ def linear_schedule_with_warmup(step, warmup_steps, total_steps):
     return max(0.0, float(total_steps - step) / float(max(1, total_steps - warmup_steps)))
 
 
+def constant_schedule_with_warmup(step, warmup_steps):
+    """LR multiplier of ``get_constant_schedule_with_warmup`` (``--scheduler constant``, run_PMR_ModCR.py:137-139)."""
+    if step < warmup_steps:
+        return float(step) / float(max(1.0, warmup_steps))
+    return 1.0
+
+
 def reference_param_groups(model, lr):
     """The two groups of run_PMR_ModCR.py:127-136: everything that requires grad at ``lr``, ``seq_enc`` at ``0.1 lr``."""
     seq = [p for n, p in model.named_parameters() if "seq_enc" in n]

@@ -151,3 +151,21 @@ def test_multiple_choice_classifier_variants_surface():
     x = torch.zeros(2, 4, 6, dtype=torch.int64)
     with pytest.raises(RuntimeError):
         m(x, img_feats=torch.zeros(2, 4, 3, 2054))
+
+
+def test_lr_schedules_match_transformers():
+    """``--scheduler linear | constant`` of the run scripts (run_PMR_ModCR.py:137-144): the multipliers handed to
+    ``FusedAdamW.set_lr`` equal what transformers' LambdaLR schedulers produce step by step."""
+    import transformers
+    from modcr_b200.training import constant_schedule_with_warmup, linear_schedule_with_warmup
+    for warm, total in ((0, 10), (3, 17), (5, 5)):
+        for kind in ("linear", "constant"):
+            opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+            sch = (transformers.get_linear_schedule_with_warmup(opt, warm, total) if kind == "linear"
+                   else transformers.get_constant_schedule_with_warmup(opt, warm))
+            for step in range(total + 3):
+                ours = (linear_schedule_with_warmup(step, warm, total) if kind == "linear"
+                        else constant_schedule_with_warmup(step, warm))
+                assert abs(ours - sch.get_last_lr()[0]) < 1e-12, (kind, warm, total, step)
+                opt.step()
+                sch.step()
