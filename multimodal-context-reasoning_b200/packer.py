@@ -191,6 +191,7 @@ class BatchPacker:
         if lang is not None:
             for k, v in lang.items():
                 out[k] = v.to(dev, non_blocking=True)
+        out["image"], out["text"] = None, None                 # the CLIP inputs are disabled in the reference too (:725)
         for src, dst in (("img_id", "img_id"), ("ques", "ques_str"), ("ans", "ans_str")):   # pass-through (:726-731)
             if src in samples[0]:
                 out[dst] = [s[src] for s in samples]
