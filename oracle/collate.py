@@ -102,3 +102,25 @@ def decode_descriptors(buf, lay, D):
     return {"input_ids": ids, "token_type_ids": seg, "total_label": lab, "align_pos": apos, "input_mask": mask,
             "chunk_attention_mask": cm, "img_feat": img, "chunk_id": cid,
             "label": torch.from_numpy(header[:, 2].astype(np.float32))}
+
+
+def edge_case_samples(feat_dim=2054):
+    """Degenerate but legal samples for the collate / packer tests: a sequence of only [CLS][SEP] (no chunk at all), a
+    single one-token chunk, mixed chunk lengths, one chunk covering every inner token; the four share one feature block
+    with fewer boxes than rows."""
+    g = torch.Generator().manual_seed(12)
+    feat = torch.randn(3, feat_dim, generator=g)
+    feat[2:] = 0
+    fmask = torch.tensor([1.0, 1.0, 0.0])
+
+    def sample(L, offs):
+        ids = torch.arange(100, 100 + L)
+        ids[0], ids[-1] = 101, 102
+        tl = torch.zeros(L, dtype=torch.int64)
+        if L > 2:
+            tl[1] = 2
+        return dict(input_ids=ids, segment_ids=torch.zeros(L, dtype=torch.int64), input_mask=torch.ones(L), img_feat=feat,
+                    img_mask=fmask, target=torch.tensor(int(L == 7)), chunk_mask=chunk_mask_from_offsets(L, offs),
+                    gather_index=gather_index_from_offsets(offs), offsets=offs, total_label=tl,
+                    align_pos=(tl != 0).long())
+    return [sample(2, []), sample(3, [[1]]), sample(7, [[1, 2], [3], [4, 5]]), sample(5, [[1, 2, 3]])]

@@ -215,6 +215,21 @@ def test_restated_collate_reproduces_the_synthetic_batches():
             samples_from_reference([((1, 2, 3),)])
 
 
+def test_packer_host_half_on_degenerate_samples():
+    """[CLS][SEP]-only sequences (no chunk), one-token chunks, a chunk spanning all inner tokens, fewer boxes than rows."""
+    import collate
+    from modcr_b200.packer import BatchPacker
+    ss = collate.edge_case_samples()
+    ref = collate.snli_gpt_gen_collate(ss)
+    buf, lay = BatchPacker("cpu").host_pack(ss)
+    dec = collate.decode_descriptors(buf, lay, 2054)
+    assert (lay["T"], lay["R"], lay["U"]) == (7, 2, 1)
+    for k in ("input_ids", "token_type_ids", "input_mask", "img_feat", "chunk_attention_mask", "total_label", "align_pos",
+              "label"):
+        assert torch.equal(dec[k], ref[k]), k
+    assert bool((dec["chunk_id"][0] == -1).all()) and dec["chunk_id"][2].tolist() == [-1, 0, 0, 1, 2, 2, -1]
+
+
 # ---- known-answer invariants (SURVEY.md section 4), small shapes ----------------
 def _small():
     sd = _weights(11)

@@ -37,6 +37,19 @@ def test_packer_matches_restated_collate_bit_exact(B, T, R, region_pad, seed):
     assert pk.h2d_bytes <= N * 16 + N * Tm * 8 + 16 + (N // 4) * Rm * 2054 * 4
 
 
+def test_packer_degenerate_samples():
+    """[CLS][SEP]-only sequences (no chunk), one-token chunks, a chunk spanning all inner tokens, fewer boxes than rows."""
+    ss = collate.edge_case_samples()
+    ref = collate.snli_gpt_gen_collate(ss)
+    out = BatchPacker(DEV, dense_chunk_mask=True).pack(ss)
+    for k in ("input_ids", "token_type_ids", "total_label", "align_pos", "input_mask", "img_feat", "label"):
+        assert torch.equal(out[k].cpu(), ref[k]), k
+    assert torch.equal(out["dense_chunk_mask"].cpu(), ref["chunk_attention_mask"])
+    bits, _ = E.make_chunk_bits(ref["chunk_attention_mask"].to(DEV))
+    assert torch.equal(out["chunk_attention_mask"], bits)
+    assert out["gather_index"][2].tolist() == [-1, 0, 0, 1, 2, 2, -1] and bool((out["gather_index"][0] == -1).all())
+
+
 def test_packer_fixed_shapes_and_model_equivalence():
     """pad_T / pad_R (static shapes for graph replay) and: the model fed by the packer == the model fed by the
     reference-shaped batch, bit for bit (same kernels, same inputs)."""
