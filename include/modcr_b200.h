@@ -215,6 +215,16 @@ int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, 
                      const int32_t* blk_chunk, int32_t nblocks, const float* hyper, const float* grad_sq, float beta1,
                      float beta2, float eps, void* stream);
 
+/* Gradient buckets of the data-parallel all-reduce (the reference's bucketing helper is
+ * utils/distributed.py:46-97, flat 10 MiB buffers filled by torch copies): ONE launch copies up to MODCR_MULTI_MAX
+ * tensors, dst[i][0..n[i]) = scale * src[i][0..n[i]), casting fp32 <-> bf16 on the way (src_bf16 / dst_bf16 give the two
+ * element types).  src / dst / n are HOST arrays of `count` entries (the device pointers they hold travel by value in
+ * the kernel parameters, so the call can be captured into a CUDA graph).  Used to gather a layer's fp32 gradients into
+ * the bf16 bucket as soon as its wgrads have landed and to scatter the reduced bucket back. */
+#define MODCR_MULTI_MAX 64
+int modcr_multi_copy(const void* const* src, void* const* dst, const int64_t* n, int32_t count, int32_t src_bf16,
+                     int32_t dst_bf16, float scale, void* stream);
+
 /* Training-mode dropout of the hidden-state sites (a_transformers/modeling_bert.py:209, 371, 449;
  * modeling_transfomres.py:681; v10:343, 832, 866): out16 = in16 * m (bf16, may alias), io32 = io32 * m (+ res32),
  * m = keep / (1 - p) with keep(seed, site, element index) a counter-based hash -- the backward pass regenerates the mask

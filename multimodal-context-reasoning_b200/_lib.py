@@ -84,6 +84,7 @@ SIGNATURES = {
     "modcr_grad_clip": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_float, c_void_p],
     "modcr_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_float, c_float, c_float,
                          c_void_p],
+    "modcr_multi_copy": [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_float, c_void_p],
     "modcr_dropout": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, C.c_uint32, c_float, c_void_p],
     "modcr_cross_attn_q1_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p,
                                 C.c_uint32, c_float, c_void_p],

@@ -230,6 +230,12 @@ int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, 
   return modcr::adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta1, beta2, eps, S(stream));
 }
 
+int modcr_multi_copy(const void* const* src, void* const* dst, const int64_t* n, int32_t count, int32_t src_bf16,
+                     int32_t dst_bf16, float scale, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::multi_copy(src, dst, n, count, src_bf16, dst_bf16, scale, S(stream));
+}
+
 int modcr_dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed,
                   uint32_t site, float p, void* stream) {
   ARCH_OR_RETURN();

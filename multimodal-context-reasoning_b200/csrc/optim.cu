@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "rowops.h"
 #include "tma_host.h"
 
@@ -26,6 +28,7 @@ namespace modcr {
 
 constexpr int OPT_CHUNK = 8192;   // elements per block
 constexpr int OPT_THREADS = 256;
+constexpr int MULTI_MAX = 64;     // tensors per multi_copy launch (MODCR_MULTI_MAX)
 
 struct OptTensor {   // mirrors modcr_optim_tensor (include/modcr_b200.h)
   float* p;
@@ -145,6 +148,111 @@ __global__ void __launch_bounds__(OPT_THREADS) grad_clip_kernel(const OptTensor*
   } else {
     for (int64_t i = base + threadIdx.x; i < end; i += OPT_THREADS) g[i] *= clip;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-tensor copy / cast of the data-parallel gradient buckets (parallel.GradReducer; the reference's only bucketing
+// logic is the dead Horovod helper utils/distributed.py:46-97): up to MULTI_MAX (src, dst, n) triples travel BY VALUE in the
+// kernel parameters -- no device-side table, so the launch can sit in a captured CUDA graph -- and one launch gathers
+// the fp32 gradients of a layer into the (bf16 or fp32) bucket, or scatters the reduced bucket back, optionally scaled.
+struct MultiCopyArgs {
+  const void* src[MULTI_MAX];
+  void* dst[MULTI_MAX];
+  int64_t n[MULTI_MAX];
+  int32_t blk0[MULTI_MAX + 1];   // first block of tensor i (prefix sum of ceil(n / OPT_CHUNK))
+  int32_t count;
+  int32_t src_bf16, dst_bf16;
+  float scale;
+};
+
+template <bool SRC16, bool DST16>
+__global__ void __launch_bounds__(OPT_THREADS) multi_copy_kernel(const __grid_constant__ MultiCopyArgs a) {
+  int lo = 0, hi = a.count - 1;            // tensor of this block: last i with blk0[i] <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.blk0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  using SrcT = typename std::conditional<SRC16, __nv_bfloat16, float>::type;
+  using DstT = typename std::conditional<DST16, __nv_bfloat16, float>::type;
+  const SrcT* __restrict__ src = reinterpret_cast<const SrcT*>(a.src[lo]);
+  DstT* __restrict__ dst = reinterpret_cast<DstT*>(a.dst[lo]);
+  const int64_t n = a.n[lo];
+  const int64_t base = (int64_t)((int)blockIdx.x - a.blk0[lo]) * OPT_CHUNK;
+  const int64_t end = min(base + (int64_t)OPT_CHUNK, n);
+  const float sc = a.scale;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) & (SRC16 ? 7 : 15)) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst) & (DST16 ? 7 : 15)) == 0);
+  int64_t i = base + threadIdx.x * 4;
+  if (vec) {
+    for (; i + 4 <= end; i += OPT_THREADS * 4) {
+      float4 x;
+      if (SRC16) {
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(src + i));
+        const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+        const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        x = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+      } else {
+        x = __ldg(reinterpret_cast<const float4*>(src + i));
+      }
+      x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc;
+      if (DST16) {
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(x.x, x.y), h2 = __floats2bfloat162_rn(x.z, x.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&l2);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h2);
+        *reinterpret_cast<uint2*>(dst + i) = pk;
+      } else {
+        *reinterpret_cast<float4*>(dst + i) = x;
+      }
+    }
+    // ragged tail of the chunk (n % 4 != 0): the thread whose vector straddles `end`
+    if (i < end) {
+      for (int64_t j = i; j < end; ++j) {
+        const float x = SRC16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[j]) : reinterpret_cast<const float*>(src)[j];
+        if (DST16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16(x * sc);
+        else reinterpret_cast<float*>(dst)[j] = x * sc;
+      }
+    }
+  } else {
+    for (int64_t j = base + threadIdx.x; j < end; j += OPT_THREADS) {
+      const float x = SRC16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[j]) : reinterpret_cast<const float*>(src)[j];
+      if (DST16) reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16(x * sc);
+      else reinterpret_cast<float*>(dst)[j] = x * sc;
+    }
+  }
+}
+
+int multi_copy(const void* const* src, void* const* dst, const int64_t* n, int count, int src_bf16, int dst_bf16, float scale,
+               cudaStream_t st) {
+  if (count <= 0) return MODCR_OK;
+  if (count > MULTI_MAX || src == nullptr || dst == nullptr || n == nullptr) {
+    set_error("multi_copy: 1..64 (src, dst, n) triples per call");
+    return MODCR_ERR_SHAPE;
+  }
+  MultiCopyArgs a;
+  int64_t blocks = 0;
+  for (int i = 0; i < count; ++i) {
+    if (src[i] == nullptr || dst[i] == nullptr || n[i] < 0) {
+      set_error("multi_copy: null tensor or negative length");
+      return MODCR_ERR_SHAPE;
+    }
+    a.src[i] = src[i]; a.dst[i] = dst[i]; a.n[i] = n[i];
+    a.blk0[i] = (int32_t)blocks;
+    blocks += (n[i] + OPT_CHUNK - 1) / OPT_CHUNK;
+    if (blocks > 0x7fffffff) {
+      set_error("multi_copy: too many elements for one launch");
+      return MODCR_ERR_SHAPE;
+    }
+  }
+  for (int i = count; i <= MULTI_MAX; ++i) a.blk0[i] = (int32_t)blocks;
+  for (int i = count; i < MULTI_MAX; ++i) { a.src[i] = nullptr; a.dst[i] = nullptr; a.n[i] = 0; }
+  a.count = count; a.src_bf16 = src_bf16; a.dst_bf16 = dst_bf16; a.scale = scale;
+  if (blocks == 0) return MODCR_OK;
+  if (src_bf16 && dst_bf16) multi_copy_kernel<true, true><<<(unsigned)blocks, OPT_THREADS, 0, st>>>(a);
+  else if (src_bf16) multi_copy_kernel<true, false><<<(unsigned)blocks, OPT_THREADS, 0, st>>>(a);
+  else if (dst_bf16) multi_copy_kernel<false, true><<<(unsigned)blocks, OPT_THREADS, 0, st>>>(a);
+  else multi_copy_kernel<false, false><<<(unsigned)blocks, OPT_THREADS, 0, st>>>(a);
+  return check_launch("multi_copy");
 }
 
 int grad_sqnorm(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,

@@ -67,6 +67,10 @@ int grad_clip(const void* meta, const void* grads, const int32_t* blk_tensor, co
               const float* grad_sq, float max_norm, cudaStream_t st);
 int adamw_step(const void* meta, const void* grads, const int32_t* blk_tensor, const int32_t* blk_chunk, int nblocks,
                const float* hyper, const float* grad_sq, float b1, float b2, float eps, cudaStream_t st);
+// dst[i][0..n[i]) = scale * src[i][0..n[i]) for up to 64 tensors per launch, fp32 <-> bf16 (gradient buckets, csrc/optim.cu);
+// src / dst / n are host arrays
+int multi_copy(const void* const* src, void* const* dst, const int64_t* n, int count, int src_bf16, int dst_bf16, float scale,
+               cudaStream_t st);
 // training-mode dropout with a counter-based mask (seed read from device memory): out16 = in16 * m, io32 = io32 * m (+ res32)
 int dropout(const void* in16, void* out16, float* io32, const float* res32, int64_t n, const uint32_t* seed, uint32_t site,
             float p, cudaStream_t st);

@@ -49,9 +49,13 @@ _RNG_STATE = {}
 
 
 def manual_seed(seed):
-    """Seed the dropout masks of every device (the state advances by an LCG step per encoder / head forward)."""
-    _RNG_STATE.clear()
-    _RNG_STATE["seed"] = int(seed) & 0x7FFFFFFF
+    """Seed the dropout masks of every device (the state advances by an LCG step per encoder / head forward).
+    Existing per-device state tensors are reseeded IN PLACE: a captured CUDA graph has their addresses baked in."""
+    seed = int(seed) & 0x7FFFFFFF
+    _RNG_STATE["seed"] = seed
+    for key, st in _RNG_STATE.items():
+        if key != "seed":
+            st.fill_(seed)
 
 
 def next_seed(dev):

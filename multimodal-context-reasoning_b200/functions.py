@@ -7,11 +7,13 @@ import torch
 
 from . import engine as E
 from . import ops
+from . import parallel
 
 BF16, F32 = torch.bfloat16, torch.float32
 
 # seq_enc mask schedule (v10:168-206): layers 0-2 chunk-local, 3-8 key padding, >= 9 cross-modal
 CHUNK_LAYERS, CROSS_MODAL_START = 3, 9
+CROSS_MODAL_LAYERS = (9, 10, 11)       # v10:168; a deeper encoder keeps the cross-modal mask from layer 9 on (v10:193-206)
 
 
 def _as_bf16(t):
@@ -46,6 +48,9 @@ class EncoderRun:
         self.local_residual = bool(is_seq and cfg.get("add_local_residual", False))
         self.final_residual = bool(is_seq and cfg.get("add_residual", False))
         self.drop = None                      # engine.Drop in training mode with dropout
+        # grad mode of the CALLER: inside Function.forward it is always off, and ctx.needs_input_grad only mirrors
+        # requires_grad of the inputs, so under torch.no_grad() (evaluate(), frozen encoders) nothing is saved
+        self.want_grad = torch.is_grad_enabled()
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
         self.S = self.T + self.R
@@ -77,7 +82,7 @@ class EncoderFn(torch.autograd.Function):
         ps, cfg = run.ps, run.cfg
         N, S, H, L, I = run.N, run.S, cfg["H"], cfg["L"], cfg["I"]
         dev = run.input_ids.device
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = run.want_grad and any(ctx.needs_input_grad)
         hist = [_as_bf16(h).view(N * run.P, H) for h in hist_in] if n_hist else None
         emb_save = {} if need_grad else None
         x, x32 = E.embeddings_fwd(ps, cfg, run.input_ids, run.token_type_ids, run.position_ids, run.img_feats,
@@ -100,7 +105,7 @@ class EncoderFn(torch.autograd.Function):
             x_in32 = x32
             x, x32 = E.layer_fwd(ps, "encoder.layer.%d." % i, x, x32, hist[i] if hist else None, ac, I, cfg["eps"], sv,
                                  cross, pi, drop, i)
-            if run.local_residual and cross:                 # v10:212-215: hidden = layer_out + former_hidden
+            if run.local_residual and i in CROSS_MODAL_LAYERS:   # v10:212-215: hidden = layer_out + former_hidden
                 x, x32 = _residual_add(x32, x_in32, N * S, H)
             if run.is_seq and i == CROSS_MODAL_START:
                 chunk_hidden32 = x_in32
@@ -130,6 +135,17 @@ class EncoderFn(torch.autograd.Function):
         N, S, H, L, I = run.N, run.S, cfg["H"], cfg["L"], cfg["I"]
         dev = run.input_ids.device
         grads = {}
+        # data parallel: the weight gradients of each layer go to the bucketed all-reduce as soon as they are enqueued
+        # (reverse layer order), so the collective of layer i runs under the backward kernels of layers i-1..0
+        red, handed = parallel.active_reducer(), set()
+
+        def hand_off():
+            if red is None:
+                return
+            new = [k for k in grads if k not in handed and grads[k] is not None and red.owns(ps.named[k])]
+            if new:
+                red.handoff([(ps.named[k], grads[k]) for k in new])
+                handed.update(new)
         if d_seq is None:
             dy = torch.zeros((N, S, H), dtype=BF16, device=dev)
         else:
@@ -144,13 +160,14 @@ class EncoderFn(torch.autograd.Function):
         for i in range(L - 1, -1, -1):
             ac, cross = run.layer_cfg(i)
             da = dalign if (ctx.nprob and i >= L - ctx.nprob) else None
-            dy_out = dy.clone() if (run.local_residual and cross) else None
+            dy_out = dy.clone() if (run.local_residual and i in CROSS_MODAL_LAYERS) else None
             dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws, run.drop, i)
             if dy_out is not None:                           # the skip connection around a cross-modal layer
                 ops.add_bf16(dy, dy_out, dy)
             if dy_top is not None and i == CROSS_MODAL_START:   # the final residual lands on the input of layer 9
                 ops.add_bf16(dy, dy_top, dy)
             ctx.saves[i] = None  # free this layer's activations
+            hand_off()
             if ctx.n_hist:
                 dhists[i] = dh
             if run.is_seq and i == CROSS_MODAL_START and d_chunk is not None and d_chunk.numel():
@@ -158,6 +175,7 @@ class EncoderFn(torch.autograd.Function):
         if run.drop is not None and run.drop.p_hidden > 0.0:
             ops.dropout(dy, dy, None, None, N * S * H, run.drop.seed, run.drop.site(0, 0), run.drop.p_hidden)
         E.embeddings_bwd(ps, cfg, ctx.emb_save, dy.view(N, S, H), grads)
+        hand_off()
         out_h = []
         for i in range(ctx.n_hist):
             g = dhists[i].view(N, run.P, H)
@@ -166,7 +184,7 @@ class EncoderFn(torch.autograd.Function):
                 ops.bf16_to_f32(g, g32)
                 g = g32.to(ctx.hist_dtypes[i])
             out_h.append(g)
-        out_p = [grads.get(n) for n in run.names]
+        out_p = [None if n in handed else grads.get(n) for n in run.names]   # handed-off tensors are already p.grad
         return (None, None, *out_h, *out_p)
 
 
@@ -174,6 +192,7 @@ class ClsHeadRun:
     def __init__(self, ps, names, cfg, N, T, S):
         self.ps, self.names, self.cfg, self.N, self.T, self.S = ps, names, cfg, N, T, S
         self.drop = None                      # engine.Drop in training mode with dropout
+        self.want_grad = torch.is_grad_enabled()   # see EncoderRun
 
 
 class ClsLayer2HeadFn(torch.autograd.Function):
@@ -189,7 +208,7 @@ class ClsLayer2HeadFn(torch.autograd.Function):
         N, T, S, H, I = run.N, run.T, run.S, cfg["H"], cfg["I"]
         dev = g_out.device
         L3 = 3 * (T - 1)
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = run.want_grad and any(ctx.needs_input_grad)
         cat = E._empty((N, 2 * H), BF16, dev)
         ops.copy_rows(g_pool.contiguous(), 1, 0, cat, 2, 0, N, 1, H)      # [global_CLS | chunk_CLS]
         ops.copy_rows(s_pool.contiguous(), 1, 0, cat, 2, 1, N, 1, H)

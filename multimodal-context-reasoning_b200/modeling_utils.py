@@ -116,11 +116,17 @@ class CaptionPreTrainedModel(nn.Module):
         self.apply(self._init_weights)
 
     # ---- token-embedding resize (run_PMR_ModCR.py:730 adds 45 "<|detN|>" tokens)
+    def _base_model(self):
+        """The encoder that owns the embeddings: ``self`` for BertImgModel / SeqBertImgModel, ``self.bert`` for the
+        *ForMultipleChoice wrappers (HF ``base_model_prefix`` convention)."""
+        return getattr(self, self.base_model_prefix, self)
+
     def get_input_embeddings(self):
-        return self.embeddings.word_embeddings
+        return self._base_model().embeddings.word_embeddings
 
     def resize_token_embeddings(self, new_num_tokens=None):
-        old = self.get_input_embeddings()
+        base = self._base_model()
+        old = base.embeddings.word_embeddings
         if new_num_tokens is None or new_num_tokens == old.num_embeddings:
             return old
         new = nn.Embedding(new_num_tokens, old.embedding_dim, padding_idx=old.padding_idx)
@@ -128,9 +134,10 @@ class CaptionPreTrainedModel(nn.Module):
         self._init_weights(new)
         n = min(old.num_embeddings, new_num_tokens)
         new.weight.data[:n] = old.weight.data[:n]
-        self.embeddings.word_embeddings = new
+        base.embeddings.word_embeddings = new
         self.config.vocab_size = new_num_tokens
-        self._param_store = None
+        base.config.vocab_size = new_num_tokens
+        base._param_store = None
         return new
 
     # ---- checkpoints
@@ -145,7 +152,10 @@ class CaptionPreTrainedModel(nn.Module):
         """``path`` is a directory with ``config.json`` + ``pytorch_model.bin`` or a weights file.
         Keys are matched with and without the ``bert.`` prefix; old ``gamma``/``beta`` LayerNorm
         names are renamed (modeling/modeling_utils.py:1256-1269); missing / unexpected keys are
-        tolerated and reported on ``model.load_info`` exactly like the reference's loader."""
+        tolerated and reported on ``model.load_info`` exactly like the reference's loader.  A key whose SHAPE differs
+        (e.g. a vocabulary-resized ``word_embeddings``) raises, like HF's loader (``size mismatch``) -- it is never
+        silently left at its random initialisation.  A prefix-less encoder checkpoint loads into a wrapper model
+        (``OscarForMultipleChoice.bert.*``) and a ``bert.``-prefixed one into a bare encoder."""
         path = pretrained_model_name_or_path
         if config is None:
             config = BertConfig.from_pretrained(path)
@@ -162,14 +172,24 @@ class CaptionPreTrainedModel(nn.Module):
                 nk = nk.replace("beta", "bias") if "beta" in nk else nk
                 renamed[nk] = v
             own = model.state_dict()
-            load = {}
+            load, mismatched = {}, []
             pfx = cls.base_model_prefix + "."
             for k, v in renamed.items():
-                kk = k[len(pfx):] if (k.startswith(pfx) and k[len(pfx):] in own) else k
-                if kk in own and tuple(own[kk].shape) == tuple(v.shape):
-                    load[kk] = v
+                if k in own:
+                    kk = k
+                elif k.startswith(pfx) and k[len(pfx):] in own:      # "bert.x" checkpoint -> bare encoder
+                    kk = k[len(pfx):]
+                elif pfx + k in own:                                    # bare-encoder checkpoint -> wrapper model
+                    kk = pfx + k
                 else:
                     unexpected.append(k)
+                    continue
+                if tuple(own[kk].shape) != tuple(v.shape):
+                    mismatched.append("%s: checkpoint %s vs model %s" % (k, tuple(v.shape), tuple(own[kk].shape)))
+                    continue
+                load[kk] = v
+            if mismatched:
+                raise RuntimeError("from_pretrained: size mismatch for " + "; ".join(mismatched))
             missing = [k for k in own if k not in load]
             model.load_state_dict(load, strict=False)
         model.load_info = dict(missing_keys=missing, unexpected_keys=unexpected)

@@ -182,6 +182,31 @@ def adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta
                                             _p(grad_sq), beta1, beta2, eps, _stream()), "adamw_step")
 
 
+def multi_copy(srcs, dsts, scale=1.0):
+    """dst[i] = scale * src[i] for lists of contiguous CUDA tensors (fp32 or bf16, any mix of the two between the lists
+    but uniform inside each); 64 tensors per launch."""
+    if len(srcs) != len(dsts):
+        raise ValueError("multi_copy: %d sources for %d destinations" % (len(srcs), len(dsts)))
+    if not srcs:
+        return
+    sdt, ddt = srcs[0].dtype, dsts[0].dtype
+    for s_, d_ in zip(srcs, dsts):
+        if s_.dtype != sdt or d_.dtype != ddt or s_.dtype not in (F32, BF16) or d_.dtype not in (F32, BF16):
+            raise RuntimeError("modcr_b200: multi_copy takes fp32 / bf16 tensors, one dtype per list")
+        if not (s_.is_cuda and d_.is_cuda):
+            raise RuntimeError("modcr_b200: multi_copy needs CUDA tensors (no CPU path)")
+        if s_.numel() != d_.numel() or not s_.is_contiguous() or not d_.is_contiguous():
+            raise RuntimeError("modcr_b200: multi_copy needs contiguous tensors of equal length")
+    lib, st = _lib.load(), _stream()
+    for i in range(0, len(srcs), 64):
+        ss, dd = srcs[i:i + 64], dsts[i:i + 64]
+        k = len(ss)
+        sp = (C.c_void_p * k)(*[t.data_ptr() for t in ss])
+        dp = (C.c_void_p * k)(*[t.data_ptr() for t in dd])
+        nn = (C.c_int64 * k)(*[t.numel() for t in ss])
+        _lib.check(lib.modcr_multi_copy(sp, dp, nn, k, int(sdt == BF16), int(ddt == BF16), float(scale), st), "multi_copy")
+
+
 def dropout(in16, out16, io32, res32, n, seed, site, p):
     """out16 = in16 * m (bf16), io32 = io32 * m (+ res32) (fp32, in place); m = keep / (1 - p), mask = f(seed, site, i)."""
     _lib.check(_lib.load().modcr_dropout(_p(in16), _p(out16), _p(io32), _p(res32), n, _p(seed), site, float(p), _stream()),

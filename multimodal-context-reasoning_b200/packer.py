@@ -76,18 +76,28 @@ class PackedBatch(dict):
 
 
 class BatchPacker:
-    def __init__(self, device, feat_dim=2054, pad_T=None, pad_R=None, dense_chunk_mask=False):
+    def __init__(self, device, feat_dim=2054, pad_T=None, pad_R=None, dense_chunk_mask=False, n_buffers=2):
         """``pad_T`` / ``pad_R``: pad to fixed sizes (static shapes for CUDA-graph replay) instead of the batch maxima the
-        reference pads to (:699, :709-711).  ``dense_chunk_mask``: also emit the reference's fp32 ``[N,T,T]`` tensor."""
+        reference pads to (:699, :709-711).  ``dense_chunk_mask``: also emit the reference's fp32 ``[N,T,T]`` tensor.
+        ``n_buffers``: pinned staging buffers in rotation -- the host may fill buffer i+1 while the asynchronous copy of
+        buffer i is still queued; a buffer is rewritten only after the event recorded behind its copy has completed."""
         self.device = torch.device(device)     # host_pack() works anywhere; pack() needs CUDA (no CPU path)
         self.D, self.pad_T, self.pad_R, self.dense = feat_dim, pad_T, pad_R, dense_chunk_mask
-        self._pinned = None
+        self._slots = [[None, None, None] for _ in range(max(1, int(n_buffers)))]   # [pinned, device buffer, copy event]
+        self._next = 0
         self.h2d_bytes = 0
 
     def _buffer(self, nbytes):
-        if self._pinned is None or self._pinned.numel() < nbytes:
-            self._pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        return self._pinned
+        """Next staging slot ``[pinned, device, event]`` of the rotation, safe to overwrite: waits (host side) for the copy
+        that last read the pinned half and for the kernels that last read the device half."""
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % len(self._slots)
+        if slot[2] is not None:
+            slot[2].synchronize()
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            slot[1] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return slot
 
     def host_pack(self, samples, buf=None):
         """Host half: fills the descriptor buffer (a uint8 tensor of at least the returned size; allocated when ``buf`` is
@@ -150,27 +160,13 @@ class BatchPacker:
         hands over (per-question tuples of the reference's per-choice 19-tuples, CPU tensors) and returns the batch."""
         return self.pack(samples_from_reference(inputs))
 
-    def pack(self, samples):
-        if self.device.type != "cuda":
-            raise RuntimeError("modcr_b200: BatchPacker.pack needs a CUDA device (no CPU path)")
-        D = self.D
-        # size the pinned buffer for the worst case of this batch, then fill it in place
-        N = len(samples)
-        T_ = max(int(s["input_ids"].numel()) for s in samples) if self.pad_T is None else self.pad_T
-        R_ = max(int(s["img_feat"].shape[0]) for s in samples) if self.pad_R is None else self.pad_R
-        buf = self._buffer(N * 16 + N * T_ * 8 + 16 + N * R_ * D * 4)
-        buf, lay = self.host_pack(samples, buf)
-        N, T, R = lay["N"], lay["T"], lay["R"]
-        hdr_b, tok_b, feat_off, total, max_chunks = (lay["hdr_bytes"], lay["tok_bytes"], lay["feat_off"], lay["total"],
-                                                     lay["max_chunks"])
-        dev = self.device
-        dbuf = torch.empty(total, dtype=torch.uint8, device=dev)
-        dbuf.copy_(buf[:total], non_blocking=True)              # the ONE host-to-device copy of the batch
-        self.h2d_bytes = total
-        d_header = dbuf[:hdr_b].view(I32)
-        d_tokens = dbuf[hdr_b:hdr_b + tok_b].view(I32)
-        d_feats = dbuf[feat_off:total].view(F32)
-        cw = (T + 31) // 32
+    DEVICE_FIELDS = ("input_ids", "token_type_ids", "total_label", "align_pos", "label", "label_long", "input_mask",
+                     "gather_index", "chunk_attention_mask", "img_feat")
+
+    def alloc_outputs(self, N, T, R):
+        """The device tensors ``pack`` fills.  Allocate once and pass as ``out=`` to keep their addresses fixed -- the
+        inputs of a captured CUDA graph (``bench.py``'s end-to-end loop packs a new batch into them every step)."""
+        dev, D, cw = self.device, self.D, (T + 31) // 32
         out = PackedBatch(
             input_ids=torch.empty((N, T), dtype=I64, device=dev), token_type_ids=torch.empty((N, T), dtype=I64, device=dev),
             total_label=torch.empty((N, T), dtype=I64, device=dev), align_pos=torch.empty((N, T), dtype=I64, device=dev),
@@ -179,12 +175,65 @@ class BatchPacker:
             gather_index=torch.empty((N, T), dtype=I32, device=dev),
             chunk_attention_mask=torch.empty((N, T, cw), dtype=I32, device=dev),
             img_feat=torch.empty((N, R, D), dtype=F32, device=dev))
-        dense = torch.empty((N, T, T), dtype=F32, device=dev) if self.dense else None
+        if self.dense:
+            out["dense_chunk_mask"] = torch.empty((N, T, T), dtype=F32, device=dev)
+        return out
+
+    def stage(self, samples, copy_stream=None):
+        """Host half + the ONE host-to-device copy of the batch (on ``copy_stream`` when given, so it runs under the
+        step that is executing).  Returns a handle for ``expand``."""
+        if self.device.type != "cuda":
+            raise RuntimeError("modcr_b200: BatchPacker.pack needs a CUDA device (no CPU path)")
+        D = self.D
+        # size the staging buffers for the worst case of this batch, then fill the pinned one in place
+        N = len(samples)
+        T_ = max(int(s["input_ids"].numel()) for s in samples) if self.pad_T is None else self.pad_T
+        R_ = max(int(s["img_feat"].shape[0]) for s in samples) if self.pad_R is None else self.pad_R
+        slot = self._buffer(N * 16 + N * T_ * 8 + 16 + N * R_ * D * 4)
+        _, lay = self.host_pack(samples, slot[0])
+        total = lay["total"]
+        stream = copy_stream if copy_stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            slot[1][:total].copy_(slot[0][:total], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(stream)
+        slot[2] = copied              # until ``expand`` replaces it with the event behind the kernels
+        self.h2d_bytes = total
+        return dict(slot=slot, lay=lay, samples=samples, copied=copied)
+
+    def expand(self, handle, out=None):
+        """Device half on the current stream: waits for the copy, then ``modcr_pack_batch`` writes the padded batch."""
+        slot, lay, samples = handle["slot"], handle["lay"], handle["samples"]
+        N, T, R, D = lay["N"], lay["T"], lay["R"], self.D
+        hdr_b, tok_b, feat_off, total, max_chunks = (lay["hdr_bytes"], lay["tok_bytes"], lay["feat_off"], lay["total"],
+                                                     lay["max_chunks"])
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(handle["copied"])
+        dbuf = slot[1]
+        d_header = dbuf[:hdr_b].view(I32)
+        d_tokens = dbuf[hdr_b:hdr_b + tok_b].view(I32)
+        d_feats = dbuf[feat_off:total].view(F32)
+        if out is None:
+            out = self.alloc_outputs(N, T, R)
+        elif tuple(out["input_ids"].shape) != (N, T) or tuple(out["img_feat"].shape) != (N, R, D):
+            raise ValueError("out= tensors were allocated for another batch shape")
+        dense = out.get("dense_chunk_mask") if self.dense else None
         ops.pack_batch(d_header, d_tokens, d_feats, N, T, R, D, out["input_ids"], out["input_mask"],
                        token_type_ids=out["token_type_ids"], total_label=out["total_label"], align_pos=out["align_pos"],
                        label=out["label_long"], label_f=out["label"], chunk_id=out["gather_index"],
                        chunk_bits=out["chunk_attention_mask"], chunk_mask=dense, img_feat=out["img_feat"])
-        dbuf.record_stream(torch.cuda.current_stream(dev))
+        done = torch.cuda.Event()
+        done.record(cur)
+        slot[2] = done                # the slot may be refilled once these kernels have read the device buffer
+        return self._finish(out, samples, max_chunks)
+
+    def pack(self, samples, out=None, copy_stream=None):
+        """``stage`` + ``expand``.  ``out``: tensors from ``alloc_outputs`` to fill in place."""
+        return self.expand(self.stage(samples, copy_stream), out)
+
+    def _finish(self, out, samples, max_chunks):
+        dev = self.device
         out["offsets"] = [s["offsets"] for s in samples]
         out["max_chunks"] = max_chunks
         lang = pad_language_side(samples)                      # language-model inputs of Abstract_Specific (:695-697)
@@ -195,6 +244,4 @@ class BatchPacker:
         for src, dst in (("img_id", "img_id"), ("ques", "ques_str"), ("ans", "ans_str")):   # pass-through (:726-731)
             if src in samples[0]:
                 out[dst] = [s[src] for s in samples]
-        if dense is not None:
-            out["dense_chunk_mask"] = dense
         return out

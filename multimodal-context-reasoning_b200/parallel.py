@@ -7,10 +7,10 @@ the only bucketing logic in its tree is the dead Horovod helper utils/distribute
 buckets).  The path shards by *questions*: every rank draws its own batch, runs the full replica and
 the only exchange step is the gradient mean -- so there is exactly one collective.
 
-Buckets are filled in gradient-arrival order from ``register_post_accumulate_grad_hook``; a full bucket
-is flattened and all-reduced on a side stream while autograd keeps running the remaining backward
-kernels.  Parameters that never receive a gradient never enter a bucket, so nothing
-waits for them.
+Buckets are filled in gradient-arrival order -- layer by layer from inside the encoder's backward program
+(``GradReducer.handoff``), from ``register_post_accumulate_grad_hook`` for the heads -- and all-reduced on a side
+stream while the remaining backward kernels run.  Parameters that never receive a gradient
+never enter a bucket, so nothing waits for them.
 """
 import os
 
@@ -36,89 +36,201 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
-class GradReducer:
-    """Bucketed, backward-overlapped gradient mean over the data-parallel group."""
+_ACTIVE = None
 
-    def __init__(self, params, bucket_mb=64, group=None, comm_dtype=None):
+
+def active_reducer():
+    """The reducer the backward programs hand their gradients to (``None`` on a single GPU)."""
+    return _ACTIVE
+
+
+class GradReducer:
+    """Bucketed gradient mean over the data-parallel group, overlapped with backward LAYER BY LAYER.
+
+    Two producers feed the buckets:
+
+    * ``handoff`` -- called from inside the coarse backward nodes (``functions.EncoderFn.backward``) as soon as the
+      weight gradients of one encoder layer have been enqueued, in reverse layer order.  The reducer installs the tensors
+      as ``p.grad`` itself (the node returns ``None`` for them), so what it averages in place is exactly what the
+      optimiser reads.  Only the gradients of the last layer processed plus the embeddings are still in flight when
+      backward returns.
+    * ``register_post_accumulate_grad_hook`` for every other parameter (heads, prefix, scorer).
+
+    Per bucket, on a side stream: ONE ``modcr_multi_copy`` launch per hand-off gathers (and casts to ``comm_dtype``) the
+    gradients into the flat bucket, NCCL averages inside the collective, ONE launch per 64 tensors scatters the means
+    back.  Parameters that never receive a gradient never enter a bucket.
+
+    Gradient accumulation (run_PMR_ModCR.py:211-227): wrap every micro-step but the last in ``no_sync()``; the last one
+    reduces the accumulated ``.grad``.  ``finish()`` must follow exactly one synchronising backward: a parameter that is
+    enqueued twice before ``finish()`` raises."""
+
+    def __init__(self, params, bucket_mb=25, group=None, comm_dtype=None, handoff=True):
         """``comm_dtype=torch.bfloat16`` halves the bytes on NVLink (the sum is then formed in bf16, like DDP's bf16
         compression hook); ``None`` reduces in the gradients' own dtype (fp32)."""
+        global _ACTIVE
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
+        self._mine = {id(p) for p in self.params}
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_dtype = comm_dtype
-        self._cur, self._cur_bytes, self._inflight = [], 0, []
+        self.sync = True
+        self._seen = set()
+        self._bucket = None            # dict(flat=, used=, grads=[...]) being filled
+        self._flats, self._free = [], []   # flat buffers, recycled step after step (stable addresses for graph replay)
+        self._pending = []             # gloo: (work, flat, used, grads)
         self._handles = []
         self.stream = None
         self.launched = 0
         if self.world > 1:
             for p in self.params:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            if handoff:
+                _ACTIVE = self
 
-    # ---------------------------------------------------------------- hooks
+    # ---------------------------------------------------------------- producers
+    def no_sync(self):
+        """Context manager of the accumulation micro-steps that do not end in a reduction."""
+        return _NoSync(self)
+
+    def owns(self, p):
+        return id(p) in self._mine
+
+    def handoff(self, pairs):
+        """``pairs``: (parameter, gradient tensor) of one layer, complete on the current stream.  Installs / accumulates
+        ``p.grad`` and, unless inside ``no_sync()``, enqueues the gradients for reduction."""
+        ps = []
+        for p, g in pairs:
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+            ps.append(p)
+        if self.sync and self.world > 1:
+            self._enqueue(ps)
+
     def _on_grad(self, p):
-        if p.grad is None:
+        if p.grad is None or not self.sync:
             return
-        self._cur.append(p)
-        self._cur_bytes += p.grad.numel() * p.grad.element_size()
-        if self._cur_bytes >= self.bucket_bytes:
-            self._launch()
+        self._enqueue([p])
+
+    # ---------------------------------------------------------------- buckets
+    def _side(self, cuda):
+        if not cuda:
+            return _Null()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()                      # these gradients are complete on the compute stream here
+        self.stream.wait_event(ev)
+        return torch.cuda.stream(self.stream)
+
+    def _new_flat(self, numel, like):
+        dt = self.comm_dtype if self.comm_dtype is not None else like.dtype
+        for i, f in enumerate(self._free):
+            if f.numel() >= numel and f.dtype == dt and f.device == like.device:
+                return self._free.pop(i)
+        f = torch.empty(numel, dtype=dt, device=like.device)
+        self._flats.append(f)
+        return f
+
+    def _enqueue(self, ps):
+        for p in ps:
+            if id(p) in self._seen:
+                raise RuntimeError("GradReducer: a parameter was enqueued twice before finish() -- finish() must follow "
+                                   "exactly one synchronising backward (use no_sync() for accumulation micro-steps)")
+            self._seen.add(id(p))
+        grads = [p.grad for p in ps]
+        need = sum((g.numel() + 7) & ~7 for g in grads)          # 16-byte aligned slots
+        cuda = grads[0].is_cuda
+        with self._side(cuda):
+            b = self._bucket
+            esz = 2 if self.comm_dtype in (torch.bfloat16, torch.float16) else grads[0].element_size()
+            cap = max(self.bucket_bytes // esz, 8)
+            if b is not None and b["used"] + need > b["flat"].numel():
+                self._launch()
+                b = None
+            if b is None:
+                b = self._bucket = dict(flat=self._new_flat(max(cap, need), grads[0]), used=0, grads=[], views=[])
+            views = []
+            for g in grads:
+                views.append(b["flat"][b["used"]:b["used"] + g.numel()].view_as(g))
+                b["used"] += (g.numel() + 7) & ~7
+            _copy_many(grads, views)
+            b["grads"] += grads
+            b["views"] += views
+            if b["used"] * esz >= self.bucket_bytes:
+                self._launch()
 
     def _launch(self):
-        if not self._cur:
+        """All-reduce the bucket being filled (caller holds the side-stream context)."""
+        b, self._bucket = self._bucket, None
+        if b is None or not b["grads"]:
             return
-        bucket, self._cur, self._cur_bytes = self._cur, [], 0
-        grads = [p.grad for p in bucket]
-        cuda = grads[0].is_cuda
-        if cuda:
-            if self.stream is None:
-                self.stream = torch.cuda.Stream()
-            ev = torch.cuda.Event()
-            ev.record()                      # gradients of this bucket are complete on the compute stream here
-            self.stream.wait_event(ev)
-            ctx = torch.cuda.stream(self.stream)
-        else:
-            ctx = _Null()
-        with ctx:
-            # ONE multi-tensor kernel gathers (and, for bf16 buckets, casts) the gradients into the flat bucket -- no
-            # fp32 concatenation followed by a separate cast pass
-            dt = self.comm_dtype if self.comm_dtype is not None else grads[0].dtype
-            flat = torch.empty(sum(g.numel() for g in grads), dtype=dt, device=grads[0].device)
-            views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
-            torch._foreach_copy_(views, grads)
-            # NCCL averages inside the collective (no scale pass afterwards); other backends sum and finish() scales
-            avg = cuda and dist.get_backend(self.group) == "nccl"
-            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group,
-                                   async_op=True)
-        self._inflight.append((work, flat, grads, avg))
+        flat = b["flat"][:b["used"]]
+        cuda = flat.is_cuda
+        avg = cuda and dist.get_backend(self.group) == "nccl"    # NCCL averages inside the collective
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.launched += 1
+        if cuda:
+            work.wait()                   # stream-level: the side stream waits for NCCL, the host does not
+            _copy_many(b["views"], b["grads"], 1.0 if avg else 1.0 / self.world)
+            self._free.append(b["flat"])  # stream-ordered reuse on the side stream
+        else:
+            self._pending.append((work, b))
 
     # ---------------------------------------------------------------- per step
     def finish(self):
-        """Flush the partial bucket, wait for every all-reduce and write the means back into ``.grad``."""
+        """Flush the partial bucket and make the compute stream wait for every reduction; afterwards ``.grad`` holds the
+        mean over ranks."""
         if self.world <= 1:
+            self._seen.clear()
             return
-        self._launch()
-        cuda = bool(self._inflight) and self._inflight[0][1].is_cuda
-        ctx = torch.cuda.stream(self.stream) if cuda else _Null()
-        with ctx:
-            scale = 1.0 / self.world
-            for work, flat, grads, avg in self._inflight:
-                work.wait()
-                # (one scale kernel per bucket unless the collective averaged,) then ONE multi-tensor copy back into the .grad tensors (a per-parameter
-                # copy is ~500 tiny launches per step)
-                if not avg:
-                    flat.mul_(scale)
-                views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
-                torch._foreach_copy_(grads, views)
+        cuda = self.stream is not None
+        if self._bucket is not None:
+            with (torch.cuda.stream(self.stream) if self._bucket["flat"].is_cuda else _Null()):
+                self._launch()
+        for work, b in self._pending:
+            work.wait()
+            _copy_many(b["views"], b["grads"], 1.0 / self.world)
+            self._free.append(b["flat"])
+        self._pending = []
         if cuda:
             torch.cuda.current_stream().wait_stream(self.stream)
-        self._inflight = []
+        self._seen.clear()
 
     def remove(self):
+        global _ACTIVE
         for h in self._handles:
             h.remove()
         self._handles = []
+        if _ACTIVE is self:
+            _ACTIVE = None
+
+
+def _copy_many(srcs, dsts, scale=1.0):
+    """dst[i] = scale * src[i].  CUDA: ``modcr_multi_copy`` (csrc/optim.cu, one launch per 64 tensors).  Host tensors
+    (the world-size-2 gloo tests of this plumbing) use torch's multi-tensor copy."""
+    if srcs[0].is_cuda:
+        from . import ops
+        ops.multi_copy([s.contiguous() for s in srcs], dsts, scale)
+        return
+    torch._foreach_copy_(dsts, srcs)
+    if scale != 1.0:
+        torch._foreach_mul_(dsts, scale)
+
+
+class _NoSync:
+    def __init__(self, red):
+        self.red = red
+
+    def __enter__(self):
+        self.prev, self.red.sync = self.red.sync, False
+        return self.red
+
+    def __exit__(self, *a):
+        self.red.sync = self.prev
+        return False
 
 
 class _Null:

@@ -65,6 +65,27 @@ def test_resize_token_embeddings_keeps_old_rows():
     assert g.config.vocab_size == 109
 
 
+def test_from_pretrained_raises_on_size_mismatch_and_maps_the_bert_prefix_both_ways():
+    from modcr_b200.modeling_bert import OscarForMultipleChoice
+    torch.manual_seed(2)
+    g = BertImgModel(small_cfg())
+    sd = g.state_dict()
+    # a vocabulary-resized checkpoint must not leave word_embeddings silently at its random init (HF raises too)
+    bad = dict(sd)
+    bad["embeddings.word_embeddings.weight"] = torch.zeros(64 + 45, 256)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        BertImgModel.from_pretrained(None, config=small_cfg(), state_dict=bad)
+    # a prefix-less encoder checkpoint loads into the wrapper's ``bert.`` submodule
+    w = OscarForMultipleChoice.from_pretrained(None, config=small_cfg(), state_dict=sd)
+    assert torch.equal(w.bert.encoder.layer[1].output.dense.weight, g.encoder.layer[1].output.dense.weight)
+    assert sorted(w.load_info["missing_keys"]) == ["classifier.bias", "classifier.weight"]
+    assert not w.load_info["unexpected_keys"]
+    # the wrappers resize / expose the embeddings of their encoder
+    assert w.get_input_embeddings() is w.bert.embeddings.word_embeddings
+    w.resize_token_embeddings(70)
+    assert w.bert.embeddings.word_embeddings.weight.shape == (70, 256) and w.bert.config.vocab_size == 70
+
+
 def test_cpu_tensors_are_rejected_loudly():
     g = BertImgModel(small_cfg())
     ids = torch.randint(1, 60, (2, 6))

@@ -34,34 +34,20 @@ def l2err(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def bf16_operand_floor(g, b, prefix, sd):
-    """max |dlogits| of the fp32 ORACLE itself when nothing but the tensor-core operands (GEMM inputs, weights,
-    Q/K/V) are rounded to bf16 -- the error any bf16-compute implementation of this case carries.  ClsLayer2 scores
-    are unscaled 768-dim dot products (v10:822-827), which amplifies operand rounding on some inputs; the logit
-    tolerance is the north-star 2e-2 unless this intrinsic floor is larger."""
-    import torch.nn.functional as F
-    orig = restate.linear
-    r = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
-
-    def linear(sd_, name, x):
-        y = F.linear(r(x), r(sd_[name + ".weight"]), sd_.get(name + ".bias"))
-        return r(y) if any(s in name for s in ("query", "key", "value")) else y
-    restate.linear = linear
-    try:
-        with torch.no_grad():
-            _, ex = restate.chunkalign_forward(sd, CFG, b, prefix)
-    finally:
-        restate.linear = orig
-    return float((ex["logits"] - g["logits"]).abs().max())
+def case_cfg(meta):
+    """Oracle-side config dict of a golden case (``cfg_over`` holds the Oscar-large overrides of cfg-5)."""
+    return restate.default_cfg(**meta.get("cfg_over", {}))
 
 
-def build(wseed):
-    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+def build(wseed, cfg_o=CFG):
+    cfg = BertConfig(vocab_size=cfg_o["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     hidden_size=cfg_o["hidden_size"], num_hidden_layers=cfg_o["num_hidden_layers"],
+                     num_attention_heads=cfg_o["num_attention_heads"], intermediate_size=cfg_o["intermediate_size"])
     m = ChunkAlign_CLS_enc4_align(BertImgModel(cfg), SeqBertImgModel(cfg), 4)
-    ref_keys = dict(statedict.chunkalign_keys(CFG))
+    ref_keys = dict(statedict.chunkalign_keys(cfg_o))
     own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     assert own == ref_keys, "state_dict surface differs from the reference"
-    sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), wseed)
+    sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(cfg_o)), wseed)
     m.load_state_dict(sd, strict=True)
     return m.to(DEV)
 
@@ -69,14 +55,16 @@ def build(wseed):
 def run_case(name):
     g = torch.load(os.path.join(GOLD, name + ".pt"))
     meta = g["meta"]
-    m = build(meta["wseed"])
+    cfg_o = case_cfg(meta)
+    L, H = cfg_o["num_hidden_layers"], cfg_o["hidden_size"]
+    m = build(meta["wseed"], cfg_o)
     b = synth.make_batch(B=meta["B"], T=meta["T"], R=meta["R"], seed=meta["seed"], region_pad=meta["region_pad"])
     bd = synth.to_device(b, DEV)
     N = b["input_ids"].shape[0]
     prefix, hist = None, None
     if meta["P"] > 0:
-        prefix = synth.make_prefix(12, meta["P"], 768, seed=meta["seed"] + 1).to(DEV).requires_grad_(True)
-        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(12)]
+        prefix = synth.make_prefix(L, meta["P"], H, seed=meta["seed"] + 1).to(DEV).requires_grad_(True)
+        hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(L)]
     m.train()
     out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
             token_type_ids=bd["token_type_ids"], encoder_history_states=hist, offsets=b["offsets"],
@@ -85,8 +73,23 @@ def run_case(name):
     return g, m, out, prefix
 
 
-@pytest.mark.parametrize("name", ["ragged_small", "cfg1_noprefix", "cfg1_prefix10"])
+LOGIT_TOL = 2e-2        # BASELINE.json north_star: logits within 2e-2 absolute of the fp32 reference
+GRAD_TOL = 5e-2         # relative L2 error per gradient tensor (bf16 gradient stream through 12-24 layers)
+
+
+def ambiguous_align_rows(g, b_cpu, err):
+    """Aligned rows whose reference argmax over regions is decided by less than ``2 * err`` in the head-summed block
+    (at random init the rows are near-uniform): the only rows whose argmax -- and hence ``correct`` -- may legitimately
+    differ from the fp32 reference under a block error of ``err``."""
+    blk = g["align_block"][b_cpu["align_pos"] == 1]
+    top2 = blk.masked_fill(blk == 0, -1e5).topk(2, dim=-1).values
+    return int(((top2[:, 0] - top2[:, 1]) < 2.0 * err).sum())
+
+
+@pytest.mark.parametrize("name", ["ragged_small", "cfg1_noprefix", "cfg1_prefix10", "cfg3_vcr", "cfg5_large"])
 def test_chunkalign_forward_backward_matches_reference_golden(name):
+    """cfg-1 (BASELINE configs[0]), a ragged small case, cfg-3 (VCR shape T=200 / R=100: tiled attention kernels, dQ
+    workspace path) and cfg-5 (Oscar-large 24L/1024/16H), each forward + backward against the REAL reference."""
     g, m, out, prefix = run_case(name)
     loss_cls, matched, align_loss, correct, total = out
     rep = dict(dloss=abs(float(loss_cls) - float(g["loss_cls"])), dalign=abs(float(align_loss) - float(g["align_loss"])),
@@ -102,18 +105,16 @@ def test_chunkalign_forward_backward_matches_reference_golden(name):
     print(name, rep, inter)
     meta = g["meta"]
     b_cpu = synth.make_batch(B=meta["B"], T=meta["T"], R=meta["R"], seed=meta["seed"], region_pad=meta["region_pad"])
-    sd_cpu = params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), meta["wseed"])
-    pf_cpu = synth.make_prefix(12, meta["P"], 768, seed=meta["seed"] + 1) if meta["P"] > 0 else None
-    floor = bf16_operand_floor(g, b_cpu, pf_cpu, sd_cpu)
-    tol = max(2e-2, 2.0 * floor)
-    print(name, "bf16-operand floor of the oracle: %.4f -> logit tolerance %.4f" % (floor, tol))
+    print(name, "margins: dlogits %.4f of %.4f, dblock %.4f of 0.02, dloss %.4f of 0.01" % (
+        rep["dlogits"], LOGIT_TOL, rep["dblock"], rep["dloss"]))
     assert rep["dblock"] < 2e-2, rep
-    assert rep["dlogits"] < tol, rep                     # north_star tolerance (2e-2) unless the case's bf16 floor is larger
-    assert rep["dloss"] < max(1e-2, floor) and rep["dalign"] < 1e-2, rep
+    assert rep["dlogits"] < LOGIT_TOL, rep               # north_star tolerance, no per-case relaxation
+    assert rep["dloss"] < 1e-2 and rep["dalign"] < 1e-2, rep
     assert bool((m.last_pred.cpu() == g["pre"]).all()), "argmax choice differs"
     assert bool((matched.cpu() == g["matched"]).all())
     assert int(total) == g["total_sum"]                  # bit-exact row selection (align_pos indexing)
-    assert abs(int(correct) - g["correct"]) <= 1         # argmax over near-uniform rows at random init
+    # `correct` = argmax hits over the aligned rows: may differ only on rows the reference itself decides by < 2 dblock
+    assert abs(int(correct) - g["correct"]) <= ambiguous_align_rows(g, b_cpu, rep["dblock"]), (int(correct), g["correct"])
     (loss_cls + align_loss).backward()
     named = dict(m.named_parameters())
     worst = {}
@@ -142,12 +143,61 @@ def test_chunkalign_forward_backward_matches_reference_golden(name):
         worst[k] = l2err(got, ref)
     print(name, "grad rel-L2 err:", {k: round(v, 4) for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:8]})
     # relative L2 error per gradient tensor.  The loss gradient itself carries the forward's bf16 logit error (the
-    # head's unscaled softmax amplifies it, see bf16_operand_floor) on top of the bf16 gradient stream.
-    bad = {k: v for k, v in worst.items() if v > 1e-1}
+    # head's unscaled 768-dim softmax scores, v10:822-827, amplify it) on top of the bf16 gradient stream.
+    bad = {k: v for k, v in worst.items() if v > GRAD_TOL}
     assert not bad, bad
     # parameters the reference never gives a gradient
     none_grad = [k for k, p in named.items() if p.grad is None]
     assert all((".attention." in k and k.startswith("cls_layer.")) or k == "seq_enc.edge_dense.weight" for k in none_grad), none_grad
+
+
+def test_cfg2_256_questions_argmax_agreement_with_reference():
+    """north_star: "identical argmax choice on at least 99.9 % of examples" and logits within 2e-2, measured over 256
+    questions (1024 sequences) at the cfg-2 shapes against forward-only outputs of the REAL reference
+    (tests/golden/cfg2_fwd256.pt, oracle/make_golden.py::run_forward_many).  With 256 examples 99.9 % means all of
+    them; a disagreement is printed with the reference's own top-2 margin."""
+    g = torch.load(os.path.join(GOLD, "cfg2_fwd256.pt"))
+    meta = g["meta"]
+    m = build(meta["wseed"]).eval()
+    prefix = synth.make_prefix(12, meta["P"], 768, seed=meta["seed0"] - 1).to(DEV)
+    nb, B = meta["n_batches"], meta["B"]
+    per_call = 4                                   # golden batches per model call: 32 questions = the cfg-2 batch
+    agree = total = 0
+    worst_logit = worst_expl = 0.0
+    disagreements = []
+    with torch.no_grad():
+        for i0 in range(0, nb, per_call):
+            bs = [synth.make_batch(B=B, T=meta["T"], R=meta["R"], seed=meta["seed0"] + i) for i in range(i0, i0 + per_call)]
+            cat = {k: torch.cat([b[k] for b in bs]) for k in ("input_ids", "token_type_ids", "input_mask", "img_feat",
+                                                              "label", "chunk_attention_mask", "total_label", "align_pos")}
+            gi = [t for b in bs for t in b["gather_index"]]
+            offs = [o for b in bs for o in b["offsets"]]
+            bd = {k: v.to(DEV) for k, v in cat.items()}
+            N = cat["input_ids"].shape[0]
+            hist = [prefix[l].unsqueeze(0).expand(N, -1, -1) for l in range(12)]
+            out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                    token_type_ids=bd["token_type_ids"], encoder_history_states=hist, offsets=offs,
+                    chunk_attention_mask=bd["chunk_attention_mask"], gather_index=gi, align_pos=bd["align_pos"],
+                    total_label=bd["total_label"])
+            ref_logits = g["logits"][i0:i0 + per_call].reshape(-1, 2)
+            ref_expl = g["logit_expl"][i0:i0 + per_call].reshape(-1, 4)
+            ref_pre = g["pre"][i0:i0 + per_call].reshape(-1)
+            ref_matched = g["matched"][i0:i0 + per_call].reshape(-1)
+            worst_logit = max(worst_logit, float((m.last_logits.cpu() - ref_logits).abs().max()))
+            worst_expl = max(worst_expl, float((m.last_logit_expl.cpu() - ref_expl).abs().max()))
+            same = m.last_pred.cpu() == ref_pre
+            agree += int(same.sum())
+            total += same.numel()
+            for q in (~same).nonzero().flatten().tolist():
+                top2 = ref_expl[q].topk(2).values
+                disagreements.append((i0 * B + q, float(top2[0] - top2[1])))
+            assert bool((out[1].cpu() == ref_matched)[same].all())
+            assert int(out[4]) == sum(g["total_sum"][i0:i0 + per_call])      # bit-exact aligned-row selection
+    print("cfg2 x %d questions: argmax agreement %d/%d, max|dlogit| %.4f, max|d logit_expl| %.4f, disagreements %s"
+          % (total, agree, total, worst_logit, worst_expl, disagreements))
+    assert total == nb * B == 256
+    assert worst_logit < LOGIT_TOL
+    assert agree / total >= 0.999, disagreements
 
 
 def test_eval_no_grad_and_prefix_invariants():

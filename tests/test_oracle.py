@@ -19,27 +19,30 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 CFG = restate.default_cfg()
 
 
-def _weights(seed):
-    return params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), seed)
+def _weights(seed, cfg=CFG):
+    return params.fill_params(statedict.materialise(statedict.chunkalign_keys(cfg)), seed)
 
 
 def _case(name):
     g = torch.load(os.path.join(GOLD, name + ".pt"))
     m = g["meta"]
+    cfg = restate.default_cfg(**m.get("cfg_over", {}))          # cfg-5: the Oscar-large overrides
     b = synth.make_batch(B=m["B"], T=m["T"], R=m["R"], seed=m["seed"], region_pad=m["region_pad"])
-    prefix = synth.make_prefix(12, m["P"], 768, seed=m["seed"] + 1) if m["P"] > 0 else None
-    return g, b, prefix, _weights(m["wseed"])
+    prefix = (synth.make_prefix(cfg["num_hidden_layers"], m["P"], cfg["hidden_size"], seed=m["seed"] + 1)
+              if m["P"] > 0 else None)
+    return g, b, prefix, _weights(m["wseed"], cfg), cfg
 
 
-@pytest.mark.parametrize("name", ["ragged_small", "cfg1_prefix10", "cfg1_noprefix"])
+@pytest.mark.parametrize("name", ["ragged_small", "cfg1_prefix10", "cfg1_noprefix", "cfg3_vcr", "cfg5_large"])
 def test_restatement_matches_reference_golden(name):
-    g, b, prefix, sd = _case(name)
+    g, b, prefix, sd, cfg = _case(name)
     grad_names = [k for k in g["grads"] if "[" not in k]
     for k in grad_names:
         sd[k].requires_grad_(True)
     if prefix is not None:
         prefix.requires_grad_(True)
-    (loss_cls, matched, align_loss, correct, total), ex = restate.chunkalign_forward(sd, CFG, b, prefix)
+    with torch.set_grad_enabled(name == "ragged_small"):
+        (loss_cls, matched, align_loss, correct, total), ex = restate.chunkalign_forward(sd, cfg, b, prefix)
     # same torch ops on the same machine class: tight tolerances
     assert abs(float(loss_cls) - float(g["loss_cls"])) < 1e-5
     assert abs(float(align_loss) - float(g["align_loss"])) < 1e-5
@@ -55,6 +58,23 @@ def test_restatement_matches_reference_golden(name):
         for k in grad_names:
             torch.testing.assert_close(sd[k].grad, g["grads"][k], atol=2e-6, rtol=2e-3)
         torch.testing.assert_close(prefix.grad[:, :, ::4], g["grads"]["prefix[:,:,::4]"], atol=2e-6, rtol=2e-3)
+
+
+def test_restatement_matches_reference_golden_forward_many():
+    """Two of the 32 batches of the 256-question forward-only golden (tests/golden/cfg2_fwd256.pt, REAL reference):
+    the restatement reproduces logits / argmax / alignment statistics of each."""
+    g = torch.load(os.path.join(GOLD, "cfg2_fwd256.pt"))
+    m = g["meta"]
+    sd = _weights(m["wseed"])
+    prefix = synth.make_prefix(12, m["P"], 768, seed=m["seed0"] - 1)
+    for i in (0, m["n_batches"] - 1):
+        b = synth.make_batch(B=m["B"], T=m["T"], R=m["R"], seed=m["seed0"] + i)
+        with torch.no_grad():
+            (_, matched, align_loss, correct, total), ex = restate.chunkalign_forward(sd, CFG, b, prefix)
+        torch.testing.assert_close(ex["logits"], g["logits"][i], atol=1e-5, rtol=1e-4)
+        assert bool((ex["pre"] == g["pre"][i]).all()) and bool((matched == g["matched"][i]).all())
+        assert correct == g["correct"][i] and total == g["total_sum"][i]
+        assert abs(float(align_loss) - g["align_loss"][i]) < 1e-5
 
 
 @pytest.mark.reference

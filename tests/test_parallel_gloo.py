@@ -45,6 +45,42 @@ def _worker(rank, world, port, q):
     net(x * 2).pow(2).mean().backward()
     red.finish()
     ok = ok and all(p.grad is not None for p in net.parameters())
+    # ---- hand-off path (what functions.EncoderFn.backward does per layer) mixed with hook-driven parameters
+    red.remove()
+    w = [torch.nn.Parameter(torch.zeros(5, 7)), torch.nn.Parameter(torch.zeros(11)), torch.nn.Parameter(torch.zeros(3, 3))]
+    red2 = parallel.GradReducer(w, bucket_mb=0.0001, comm_dtype=None)
+    ok = ok and parallel.active_reducer() is red2
+    gs = [torch.full_like(p, float(rank + 1) * (i + 1)) for i, p in enumerate(w)]
+    red2.handoff([(w[0], gs[0].clone()), (w[1], gs[1].clone())])      # installed as .grad by the reducer
+    (w[2] * gs[2]).sum().backward()                                    # arrives through the post-accumulate hook
+    red2.finish()
+    for i, p in enumerate(w):
+        ok = ok and torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)), atol=1e-6)
+    # ---- gradient accumulation: the micro-step inside no_sync() only accumulates, the last one reduces the sum
+    for p in w:
+        p.grad = None
+    before = red2.launched
+    with red2.no_sync():
+        red2.handoff([(w[0], gs[0].clone())])
+        (w[2] * gs[2]).sum().backward()
+    launched = red2.launched - before
+    red2.handoff([(w[0], gs[0].clone())])
+    (w[2] * gs[2]).sum().backward()
+    red2.finish()
+    ok = ok and launched == 0 and torch.allclose(w[0].grad, torch.full_like(w[0], 3.0), atol=1e-6)
+    ok = ok and torch.allclose(w[2].grad, torch.full_like(w[2], 9.0), atol=1e-6) and w[1].grad is None
+    # ---- a second synchronising backward before finish() is an error, not a silent double average
+    for p in w:
+        p.grad = None
+    red2.handoff([(w[0], gs[0].clone())])
+    try:
+        red2.handoff([(w[0], gs[0].clone())])
+        ok = False
+    except RuntimeError:
+        pass
+    red2.finish()
+    red2.remove()
+    ok = ok and parallel.active_reducer() is None
     loss = parallel.allreduce_mean_scalar(torch.tensor(float(rank)))
     ok = ok and abs(float(loss) - 0.5) < 1e-6
     q.put((rank, bool(ok)))
