@@ -18,12 +18,23 @@ build/%.o: $(CSRC)/%.cu $(HDRS)
 $(LIB): $(CU_OBJS)
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
 
+# developer build with the clock64() timeline of attn_bwd_kernel compiled in (scripts/attn_bwd_trace.py); never loaded by
+# the package unless MODCR_B200_LIB points at it
+TRACE_LIB  := $(PKG)/libmodcr_b200_trace.so
+TRACE_OBJS := $(patsubst $(CSRC)/%.cu,build_trace/%.o,$(CU_SRCS))
+build_trace/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build_trace
+	$(NVCC) $(NVFLAGS) -DMODCR_ATTN_TRACE -Iinclude -c $< -o $@
+$(TRACE_LIB): $(TRACE_OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^
+trace: $(TRACE_LIB)
+
 cuda_tests: build/test_gemm
 
 build/test_gemm: tests/cuda/test_gemm.cu build/gemm.o build/tma_host.o
 	$(NVCC) $(NVFLAGS) -o $@ $^
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build build_trace $(LIB) $(TRACE_LIB)
 
-.PHONY: all clean cuda_tests
+.PHONY: all clean cuda_tests trace

@@ -35,7 +35,18 @@ WORKLOADS = {
                  L=12, H=768, heads=12, I=3072),
     "cfg5": dict(name="cfg-5 Oscar-large PMR shape", B=32, choices=4, T=128, R=50, feat=2054, P=10,
                  L=24, H=1024, heads=16, I=4096),
+    # kernel-only sweep (run_attention_sweep), not a model workload
+    "cfg4": dict(name="cfg-4 prefix-length sweep 0/10/32/64 of the fused prefix-attention kernel at sequence 256"),
 }
+
+
+def config_dict(w, n_gpus, dropout=False):
+    """The workload description both arms print (the reference arm runs a bounded sample of exactly this workload)."""
+    return dict(workload=w["name"], questions_per_gpu=w["B"], choices=w["choices"], text_tokens=w["T"], regions=w["R"],
+                region_feat_dim=w["feat"], prefix_len=w["P"], encoder="%dL/%d/%dH x2" % (w["L"], w["H"], w["heads"]),
+                parallelism="dp%d" % n_gpus, loss="loss_cls + align_loss",
+                dropout=("hidden 0.3 / attention 0.1 (reference training configuration)" if dropout else 0.0),
+                l2="per-step working set (>10 GB) far exceeds the 126 MB L2; every e2e step packs a different batch")
 
 
 def flops_per_sample(w):
@@ -62,6 +73,22 @@ def peaks():
         except Exception:
             pass
     return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained cuBLAS bf16 on this pool)", {}
+
+
+def ncu_traffic(w):
+    """DRAM bytes (read + write) per launch of the dominant kernel family -- the GEMM launches of one encoder layer,
+    averaged -- from the committed `ncu --set full` capture (profiles/r02_ncu_traffic.json, written by
+    scripts/summarize_ncu_full.py from the .ncu-rep of the same workload).  None when no capture for this workload is
+    committed."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        e = d.get(w["name"])
+        if e and e.get("gemm_launches"):
+            return float(e["gemm_dram_bytes_per_launch"]), "profiles/r02_ncu_traffic.json (%d gemm_kernel launches, ncu --set full)" % e["gemm_launches"]
+    except Exception:
+        pass
+    return None, None
 
 
 class ClockSampler:
@@ -111,7 +138,8 @@ def oracle_step_fn(B, w, seed=88):
     import restate
     import statedict
     from modcr_b200 import synth
-    cfg = restate.default_cfg()
+    cfg = restate.default_cfg(num_hidden_layers=w["L"], hidden_size=w["H"], num_attention_heads=w["heads"],
+                              intermediate_size=w["I"])
     sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(cfg)), 0)
     names = [k for k, v in sd.items() if torch.is_floating_point(v)]
     for k in names:
@@ -125,32 +153,47 @@ def oracle_step_fn(B, w, seed=88):
         for k in names:
             sd[k].grad = None
         prefix.grad = None
-        return float(loss_cls + align_loss)
+        return float((loss_cls + align_loss).detach())
     return step
 
 
+REF_MAX_QUESTIONS = 8          # host-memory bound of the fp32 CPU path (dense [N,h,S,S] probabilities of 24 layers kept for backward)
+REF_BUDGET_S = 150.0           # the whole --steps K --warmup W run of the reference arm stays within a few minutes
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (the restatement pinned bit-exact to the reference classes;
+    /root/reference does not exist on the GPU box), all host threads, on a bounded sample of OUR arm's workload: as many
+    questions per step (<= 8, <= the workload's batch) as keep the whole run inside REF_BUDGET_S, sized from a probe step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = 2                                      # bounded sample: cfg-2 shapes at 2 questions per step
-    step = oracle_step_fn(Bs, WORKLOAD)
-    for _ in range(max(args.warmup, 1)):
+    w = dict(WORKLOADS[args.workload if args.workload in WORKLOADS else "cfg2"])
+    warm = max(args.warmup, 1)
+    probe = oracle_step_fn(2, w)
+    probe()
+    t0 = time.perf_counter()
+    probe()
+    per_q = (time.perf_counter() - t0) / 2.0
+    del probe
+    Bs = int(max(2, min(REF_MAX_QUESTIONS, w["B"], REF_BUDGET_S / (per_q * (args.steps + warm)))))
+    step = oracle_step_fn(Bs, w)
+    for _ in range(warm):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = Bs / dt
-    sample = "oracle/restate.py fp32 on CPU, %d questions x 4 choices per step (T=128,R=50,P=10), %d threads" % (Bs, cores)
+    sample = ("oracle/restate.py (fp32 CPU restatement pinned to the reference classes), %d of the workload's %d questions "
+              "x 4 choices per step at the same T/R/P/encoder, %d threads" % (Bs, w["B"], cores))
     line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
-                warmup=max(args.warmup, 1), ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", config=dict(workload=WORKLOAD["name"], **{k: WORKLOAD[k] for k in
-                                                                                        ("T", "R", "P", "L", "H")},
-                                                           sample_questions_per_step=Bs),
+                warmup=warm, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=config_dict(w, args.gpus, args.dropout),
+                sample_questions_per_step=Bs,
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -244,6 +287,75 @@ def kernel_roofline(w, dev, peak_tf, hbm_gbs):
     return dom, per
 
 
+def run_attention_sweep(args):
+    """BASELINE.json configs[3]: prefix-length sweep (0/10/32/64) of the fused prefix-attention kernel at sequence 256
+    (N=128 sequences x 12 heads x 64), forward and backward timed alone with CUDA events on the launching stream, an
+    L2-sized buffer written between launches.  Algorithmic FLOPs per (sequence, layer): forward 4 S (S+P) H, backward
+    twice that."""
+    import torch
+    from modcr_b200 import ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    BF16 = torch.bfloat16
+    N, S, heads = 128, 256, 12
+    H = heads * 64
+    peak, _, raw = peaks()
+    burst = float(raw.get("bf16_tflops", 1590.0))
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    reps = max(args.steps, 3)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            fn()
+            b.record(st)
+            b.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps * 1e-3
+    sampler = ClockSampler(0)
+    sampler.start()
+    rows, fl_tot, t_tot, launches = [], 0.0, 0.0, 0
+    for P in (0, 10, 32, 64):
+        g = torch.Generator(device="cpu").manual_seed(P)
+        qkv = (torch.randn(N, S, 3 * H, generator=g) * 0.5).to(dev, BF16)
+        pkv = (torch.randn(N, P, 2 * H, generator=g) * 0.5).to(dev, BF16) if P > 0 else None
+        kbias = torch.zeros(N, P + S, device=dev)
+        ctx, lse = torch.empty(N, S, H, dtype=BF16, device=dev), torch.empty(N, heads, S, device=dev)
+        dctx = (torch.randn(N, S, H, generator=g) * 0.5).to(dev, BF16)
+        dqkv = torch.empty(N, S, 3 * H, dtype=BF16, device=dev)
+        dpkv = torch.empty(N, P, 2 * H, dtype=BF16, device=dev) if P > 0 else None
+        ws = torch.empty(max(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, 1), device=dev)
+        tf = timed(lambda: ops.prefix_attn_fwd(N, S, P, heads, 0, 0, qkv, pkv, kbias, None, 0, ctx, lse, None))
+        tb = timed(lambda: ops.prefix_attn_bwd(N, S, P, heads, 0, 0, qkv, pkv, kbias, None, 0, ctx, lse, None, dctx, None,
+                                               dqkv, dpkv, ws))
+        fa = 4.0 * S * (S + P) * H * N
+        rows.append(dict(P=P, fwd_us=tf * 1e6, bwd_us=tb * 1e6, fwd_tflops=fa / tf / 1e12, bwd_tflops=2 * fa / tb / 1e12,
+                         fwd_frac=fa / tf / 1e12 / burst, bwd_frac=2 * fa / tb / 1e12 / burst))
+        fl_tot += 3 * fa
+        t_tot += tf + tb
+        launches += 2 * (reps + max(args.warmup, 3))
+    clocks = sampler.stop()
+    val = fl_tot / t_tot / 1e12
+    line = dict(metric="prefix-attention fwd+bwd TFLOP/s (cfg-4 prefix-length sweep)", value=val, unit="TFLOP/s", n_gpus=1,
+                steps=reps, warmup=max(args.warmup, 3), ms_per_step=t_tot * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=WORKLOADS["cfg4"]["name"], sequences=N, seq_len=S, heads=heads, head_dim=64,
+                            prefix_lens=[0, 10, 32, 64], l2="192 MB buffer written between timed launches"),
+                roofline=dict(bound="tensor", achieved=val, peak=burst, unit="TFLOP/s", frac=val / burst, traffic=None,
+                              scope="attention core only (QK^T, softmax, PV and their backward), each launch timed alone; "
+                                    "BURST cuBLAS bf16 peak of MEASURED_PEAKS.json"),
+                sweep=rows, clocks=clocks, gpu_launches=launches)
+    print(json.dumps(line), flush=True)
+
+
 def build_model(w, dev):
     import torch
     from modcr_b200.modeling_bert import BertImgModel
@@ -259,20 +371,20 @@ def build_model(w, dev):
     return m, prefix
 
 
-TENSOR_KEYS = ("input_ids", "token_type_ids", "input_mask", "img_feat", "label", "chunk_attention_mask", "total_label",
-               "align_pos", "chunk_id")
+N_DISTINCT_BATCHES = 4      # the e2e loop cycles through this many different ragged batches
 
 
-def host_batch(w, seed, rank):
-    """Synthetic PMR batch in pinned host memory; the ragged gather_index lists are packed once on the
-    host into the int32 [N,T] chunk-id tensor (SURVEY.md section 7 'hard parts')."""
-    import torch
-    from modcr_b200 import engine, synth
-    b = synth.make_batch(B=w["B"], T=w["T"], R=w["R"], feat_dim=w["feat"], num_choices=w["choices"], seed=seed, rank=rank)
-    chunk_id, _ = engine.pack_chunk_ids(b["gather_index"], w["T"], "cpu")
-    b["chunk_id"] = chunk_id
-    hb = {k: b[k].contiguous().pin_memory() for k in TENSOR_KEYS}
-    return hb
+def ragged_batches(w, rank):
+    """What a DataLoader hands to the collate function: per-(question, choice) ragged samples (host memory) of
+    N_DISTINCT_BATCHES different synthetic batches."""
+    from modcr_b200 import synth
+    from modcr_b200.packer import unbatch
+    out = []
+    for i in range(N_DISTINCT_BATCHES):
+        b = synth.make_batch(B=w["B"], T=w["T"], R=w["R"], feat_dim=w["feat"], num_choices=w["choices"],
+                             seed=88 + 1000 * i, rank=rank)
+        out.append(unbatch(b, w["choices"]))
+    return out
 
 
 def run_ours(args):
@@ -290,16 +402,23 @@ def run_ours(args):
         w["p_hidden"], w["p_attn"] = 0.3, 0.1
     m, prefix = build_model(w, dev)
     N = w["B"] * w["choices"]
-    hb = host_batch(w, 88, rank)
-    db = {k: v.to(dev) for k, v in hb.items()}
+    # Input path = the device-side batch packer: ragged samples -> ONE pinned buffer -> ONE H2D copy ->
+    # modcr_pack_batch writes the padded batch (bit-packed chunk mask, int32 chunk ids) into fixed device tensors, which
+    # are the inputs of the captured graph.
+    from modcr_b200.packer import BatchPacker
+    batches = ragged_batches(w, rank)
+    pk = BatchPacker(dev, feat_dim=w["feat"], pad_T=w["T"], pad_R=w["R"], n_buffers=2)
+    static = pk.alloc_outputs(N, w["T"], w["R"])
+    pk.pack(batches[0], out=static)
+    db = static
     comm_dtype = None if args.fp32_allreduce else torch.bfloat16
     reducer = parallel.GradReducer(list(m.parameters()) + [prefix], comm_dtype=comm_dtype) if world > 1 else None
 
     def fwd_bwd(bd):
         hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(w["L"])]
-        out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+        out = m(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label_long"],
                 token_type_ids=bd["token_type_ids"], encoder_history_states=hist,
-                chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["chunk_id"],
+                chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["gather_index"],
                 align_pos=bd["align_pos"], total_label=bd["total_label"])
         loss = out[0] + out[2]
         loss.backward()
@@ -324,7 +443,6 @@ def run_ours(args):
     barrier()
     # Steady-state steps are replayed from ONE CUDA graph of the whole fwd+bwd (static shapes, caller-owned
     # buffers): ~700 kernel launches per step would otherwise be bounded by Python/ctypes launch overhead.
-    static = {k: v.clone() for k, v in db.items()}
     graph, g_loss, launches_per_step = None, None, None
     if not args.no_graph:
         try:
@@ -373,40 +491,32 @@ def run_ours(args):
     loss_val = float(loss)
 
     # ---- end to end through the public call with host buffers (`e2e`)
-    # Every step's inputs travel pinned host -> HBM inside the timed region; the copy of step i+1 is issued on a copy
-    # stream while step i computes (double-buffered staging tensors), then moved into the graph's static input buffers
-    # by a device-to-device copy at the start of its step.  The step's result (loss) is read back to the host each step.
-    h2d = sum(v.numel() * v.element_size() for v in hb.values())
+    # Every step consumes a DIFFERENT ragged batch that starts in host memory: host pack into a pinned buffer + one H2D
+    # copy on a copy stream (issued while the previous step computes), then -- inside the step, on the compute stream --
+    # the two pack kernels that expand it into the graph's input tensors, the step itself, and the D2H read of the loss.
     copy_stream = torch.cuda.Stream()
-    stage = [{k: torch.empty_like(v) for k, v in static.items()} for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def prefetch(slot):
-        copy_stream.wait_event(consumed[slot])          # the step that used this staging slot has taken its inputs
-        with torch.cuda.stream(copy_stream):
-            for k, v in hb.items():
-                stage[slot][k].copy_(v, non_blocking=True)   # pinned host -> HBM
-            ready[slot].record(copy_stream)
-
     # The loss of step i is copied to pinned host memory asynchronously right behind the step and read by the host after
     # step i+1 has been enqueued (one step behind, like a training loop that logs the previous step's loss), so the
     # device never idles while the host waits; every step's loss is read inside the timed region.
     host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_done = [torch.cuda.Event(), torch.cuda.Event()]
     losses_read = []
+    staged = {}
+    pack_launches = [0]
+
+    def stage(i):
+        staged[i] = pk.stage(batches[i % len(batches)], copy_stream)     # host pack + the one H2D copy of batch i
 
     def e2e_step(i):
         slot = i & 1
         cur = torch.cuda.current_stream()
-        cur.wait_event(ready[slot])
-        for k in hb:
-            static[k].copy_(stage[slot][k], non_blocking=True)
-        consumed[slot].record(cur)
-        prefetch(slot ^ 1)                               # next step's inputs, under this step's compute
+        l0_ = _lib.launch_count()
+        pk.expand(staged.pop(i), out=static)             # waits for the copy; pack kernels write the graph inputs
+        pack_launches[0] = _lib.launch_count() - l0_
         ls = run_step(static)
         host_loss[slot:slot + 1].copy_(ls.detach().reshape(1), non_blocking=True)   # D2H of the step's result
         loss_done[slot].record(cur)
+        stage(i + 1)                                     # next batch: host work + H2D under this step's compute
         if i > 0:                                        # host reads the previous step's loss
             loss_done[slot ^ 1].synchronize()
             losses_read.append(float(host_loss[slot ^ 1]))
@@ -414,23 +524,26 @@ def run_ours(args):
     def e2e_drain(last):
         loss_done[last & 1].synchronize()
         losses_read.append(float(host_loss[last & 1]))
-    for sl in range(2):
-        consumed[sl].record(torch.cuda.current_stream())
-    prefetch(0)
+    stage(0)
     for i in range(2):
         e2e_step(i)
     e2e_drain(1)
+    staged.clear()
     barrier()
     losses_read.clear()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage(0)        # pipeline fill; the K timed steps below each stage one batch (host pack + H2D) inside the clock
     f0.record()
     for i in range(args.steps):
         e2e_step(i)
     e2e_drain(args.steps - 1)
     f1.record()
     barrier()
+    staged.clear()
     ms_e2e = f0.elapsed_time(f1) / args.steps
+    h2d = pk.h2d_bytes
     assert len(losses_read) >= args.steps and all(l == l for l in losses_read)   # every step's loss reached the host
+    distinct_losses = len({round(l, 6) for l in losses_read})
 
     # ---- optimiser step (reported separately): fused clip + AdamW over all 250 M parameters
     opt_ms = None
@@ -464,9 +577,9 @@ def run_ours(args):
 
             def score(bd):
                 hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(w["L"])]
-                return m.evaluate(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label"],
+                return m.evaluate(bd["input_ids"], bd["img_feat"], input_mask=bd["input_mask"], label=bd["label_long"],
                                   token_type_ids=bd["token_type_ids"], encoder_history_states=hist,
-                                  chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["chunk_id"])
+                                  chunk_attention_mask=bd["chunk_attention_mask"], gather_index=bd["gather_index"])
             with torch.no_grad():
                 for _ in range(3):
                     score(static)
@@ -493,30 +606,24 @@ def run_ours(args):
             sys.stderr.write("bench.py: scoring section failed: %s\n" % (str(e)[:300],))
             m.train()
 
-    # ---- device-side batch packer (informational): ragged samples -> one pinned buffer -> one H2D copy ->
-    # modcr_pack_batch, against the reference-shaped batch of the e2e measurement above
+    # ---- host cost of the input path (informational; it runs under the previous step in the e2e loop above)
     pack_info = None
     if rank == 0:
         try:
-            from modcr_b200 import synth
-            from modcr_b200.packer import BatchPacker, unbatch
-            samples = unbatch(synth.make_batch(B=w["B"], T=w["T"], R=w["R"], feat_dim=w["feat"],
-                                               num_choices=w["choices"], seed=88, rank=rank), w["choices"])
-            pk = BatchPacker(dev, feat_dim=w["feat"], pad_T=w["T"], pad_R=w["R"])
-            pk.pack(samples)
             torch.cuda.synchronize()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
-            p0.record()
-            for _ in range(5):
-                pk.pack(samples)
-            p1.record()
-            t1 = time.perf_counter()
-            torch.cuda.synchronize()
-            pack_info = dict(h2d_bytes_per_step=pk.h2d_bytes, reference_shaped_h2d_bytes_per_step=h2d,
-                             device_ms=p0.elapsed_time(p1) / 5, host_ms=(t1 - t0) * 1e3 / 5,
-                             what="packer.BatchPacker: one pinned descriptor buffer + one feature block per question, "
-                                  "one H2D copy, 2 kernels (csrc/pack.cu); not part of the headline numbers")
+            for i in range(4):
+                pk.host_pack(batches[i % len(batches)], pk._slots[0][0])
+            host_ms = (time.perf_counter() - t0) * 1e3 / 4
+            ref_bytes = (N * w["T"] * 8 * 4 + N * (w["T"] + w["R"]) * 4 + N * w["R"] * w["feat"] * 4 + N * 8 +
+                         N * w["T"] * w["T"] * 4 + N * w["T"] * 4)
+            pack_info = dict(h2d_bytes_per_step=pk.h2d_bytes, reference_shaped_h2d_bytes_per_step=ref_bytes,
+                             host_pack_ms=host_ms, pack_kernels_per_step=pack_launches[0],
+                             distinct_batches=len(batches), distinct_losses_read=distinct_losses,
+                             what="packer.BatchPacker inside the e2e loop: ragged samples -> one pinned descriptor buffer "
+                                  "(+ one feature block per question) -> one H2D copy -> modcr_pack_batch (csrc/pack.cu) "
+                                  "writes the graph's input tensors; the reference-shaped padded batch would be "
+                                  "reference_shaped_h2d_bytes_per_step")
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("bench.py: packer section failed: %s\n" % (str(e)[:300],))
 
@@ -535,6 +642,7 @@ def run_ours(args):
     hbm_gbs = float(peak_raw.get("hbm_gbs", 6650.0))
     burst_tf = float(peak_raw.get("bf16_tflops", 1590.0))
     dom, per_kernel = (None, None)
+    traffic, traffic_src = ncu_traffic(w)
     if not args.no_kernel_roofline:
         try:
             dom, per_kernel = kernel_roofline(w, dev, burst_tf, hbm_gbs)
@@ -542,16 +650,13 @@ def run_ours(args):
             sys.stderr.write("bench.py: kernel roofline section failed: %s\n" % (str(e)[:300],))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                config=dict(workload=w["name"], questions_per_gpu=w["B"], choices=w["choices"], text_tokens=w["T"],
-                            regions=w["R"], region_feat_dim=w["feat"], prefix_len=w["P"], encoder="%dL/%d/%dH x2" % (w["L"], w["H"], w["heads"]),
-                            parallelism="dp%d" % world,
-                            grad_allreduce=(None if world == 1 else ("fp32" if args.fp32_allreduce else "bf16") +
-                                            " buckets of 64 MB, NCCL, overlapped with backward"), l2="per-step working set (>10 GB) far exceeds the 126 MB L2",
-                            dropout=("hidden 0.3 / attention 0.1 (reference training configuration)" if args.dropout
-                                     else 0.0), loss="loss_cls + align_loss", final_loss=loss_val,
-                            launch="cuda-graph replay" if graph is not None else "eager"),
+                config=config_dict(w, world, args.dropout),
+                run=dict(final_loss=loss_val, launch="cuda-graph replay" if graph is not None else "eager",
+                         grad_allreduce=(None if world == 1 else ("fp32" if args.fp32_allreduce else "bf16") +
+                                         " buckets of 25 MB handed off per encoder layer from inside backward, NCCL, "
+                                         "overlapped with the remaining backward kernels")),
                 roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                              traffic=None, scope="whole fwd+bwd step: algorithmic FLOPs/sample (%.1f GF, SURVEY 8d) x "
+                              traffic=traffic, traffic_source=traffic_src, scope="whole fwd+bwd step: algorithmic FLOPs/sample (%.1f GF, SURVEY 8d) x "
                               "samples/s per GPU, against the SUSTAINED cuBLAS peak (the step runs for seconds under the "
                               "power cap)" % (fps / 1e9), peak_source=peak_src,
                               dominant_kernel=None if dom is None else dict(
@@ -561,7 +666,9 @@ def run_ours(args):
                                         "BURST cuBLAS peak"),
                               kernels=per_kernel),
                 clocks=clocks,
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e,
+                         what="ragged host samples -> BatchPacker (host pack + ONE H2D copy + pack kernels) -> captured "
+                              "fwd+bwd -> D2H of the loss; a different batch every step, all inside the timed region"),
                 gpu_launches=int(launches),
                 scoring=scoring,
                 batch_packer=pack_info,
@@ -571,16 +678,18 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = oracle_step_fn(2, w)
+        Bs = 4
+        step = oracle_step_fn(Bs, w)
         step()
         ts = []
-        for _ in range(2):
+        for _ in range(3):
             t0 = time.perf_counter()
             step()
             ts.append(time.perf_counter() - t0)
-        line["cpu_baseline"] = dict(value=2 / statistics.median(ts), unit=UNIT, cores=cores, kind="port",
-                                    sample="oracle/restate.py (fp32 CPU restatement of the reference), 2 questions x 4 "
-                                           "choices per step at the same T/R/P, 1 warm-up + 2 timed fwd+bwd")
+        line["cpu_baseline"] = dict(value=Bs / statistics.median(ts), unit=UNIT, cores=cores, kind="port",
+                                    sample="oracle/restate.py (fp32 CPU restatement pinned to the reference classes), %d "
+                                           "of the workload's %d questions x 4 choices per step at the same T/R/P/encoder, "
+                                           "1 warm-up + 3 timed fwd+bwd, all %d host threads" % (Bs, w["B"], cores))
     print(json.dumps(line), flush=True)
 
 
@@ -594,7 +703,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 (default) is the configuration the metric is quoted on; cfg3 / cfg5 are the other "
-                         "BASELINE.json shapes")
+                         "BASELINE.json model shapes; cfg4 is the prefix-length sweep of the attention kernel alone")
     ap.add_argument("--no-kernel-roofline", action="store_true", help="skip the per-kernel CUDA-event timings")
     ap.add_argument("--no-optimizer", action="store_true", help="skip the separately reported optimiser-step timing")
     ap.add_argument("--dropout", action="store_true",
@@ -603,7 +712,11 @@ def main():
     ap.add_argument("--fp32-allreduce", action="store_true",
                     help="N>1: all-reduce the fp32 gradients as they are (default: bf16 buckets, half the NVLink bytes)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "cfg4":
+        if args.impl == "reference" or int(os.environ.get("RANK", "0")) != 0:
+            return
+        run_attention_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

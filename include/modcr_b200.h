@@ -165,6 +165,10 @@ typedef struct modcr_attn_desc {
   const uint32_t* drop_seed;
   uint32_t drop_site;
   float drop_p;
+  /* int64 [N,T] or NULL (align_pos of the batch contract, Data/VCRChunkAlign.py:733): when given, only text rows with a
+   * non-zero entry are written to probs_img (forward) / read from it and given dalign (backward) -- the alignment loss
+   * (v10:1071-1077) selects exactly those rows, so the other 97 % of the [N,heads,T,R] block never travel.  NULL: all rows. */
+  const int64_t* row_sel;
 } modcr_attn_desc;
 int modcr_prefix_attn_fwd(const modcr_attn_desc* d, void* stream);
 int modcr_prefix_attn_bwd(const modcr_attn_desc* d, void* stream);
@@ -174,10 +178,14 @@ int modcr_prefix_attn_bwd(const modcr_attn_desc* d, void* stream);
 int modcr_chunk_mean_q(void* q, int64_t ld, int32_t N, int32_t S, int32_t H, const int32_t* chunk_id, int32_t T,
                        int32_t max_chunks, void* stream);
 
-/* Alignment loss (v10:982-987, 1071-1077).  probs: fp32 [nl,N,heads,T,R]; out[4] = {loss, M, correct, sum}. */
+/* Alignment loss (v10:982-987, 1071-1077).  probs: fp32 [nl,N,heads,T,R]; out[4] = {loss, M, correct, sum}.
+ * block [N,T,R] = sum over the nl * heads slices (the reference's stack(...).sum(1).sum(1)); with align_pos / total_label /
+ * row_loss / out given: masked_fill(block == 0, -1e5) -> softmax over R -> CrossEntropy(probabilities, total_label) over
+ * the rows with align_pos == 1 (double softmax as written, v10:1073-1077).  row_sel (optional, = align_pos): rows without
+ * a non-zero entry were never written by modcr_prefix_attn_fwd(row_sel) and get a zero block row. */
 int modcr_align_softmax_ce_fwd(const float* probs, int32_t nl, int32_t heads, const int64_t* align_pos,
-                               const int64_t* total_label, float* block, float* row_loss, float* out, int32_t N,
-                               int32_t T, int32_t R, void* stream);
+                               const int64_t* total_label, const int64_t* row_sel, float* block, float* row_loss,
+                               float* out, int32_t N, int32_t T, int32_t R, void* stream);
 int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label,
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
                                void* stream);
@@ -334,6 +342,12 @@ int modcr_rowln_fwd(const void* x, const float* gamma, const float* beta, void* 
                     int32_t H, float eps, void* stream);
 int modcr_rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream);
+/* Rows that enter the encoder already embedded (the prompt embeddings of the language-model side,
+ * modeling/modeling_ensemble.py:498-503 `prompt_embeddings=`): rows_place writes fp32 rows src [M,H] into the bf16
+ * hidden-state buffer y (and its fp32 twin y32) at the physical rows given by ymap; rows_gather is its adjoint on the
+ * bf16 gradient (dst [M,H] bf16). */
+int modcr_rows_place(const float* src, void* y, float* y32, modcr_rowmap ymap, int32_t M, int32_t H, void* stream);
+int modcr_rows_gather(const void* dy, modcr_rowmap dymap, void* dst, int32_t M, int32_t H, void* stream);
 int modcr_key_bias(const float* mask, float* kbias, int64_t total, void* stream);
 int modcr_chunk_bits(const float* chunk_mask, uint32_t* bits, int32_t N, int32_t T, int32_t cwords, void* stream);
 int modcr_accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int32_t cols,

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmodcr_b200.so")
+# MODCR_B200_LIB: developer override (e.g. the `make trace` build with kernel timelines compiled in)
+LIB_PATH = os.environ.get("MODCR_B200_LIB") or os.path.join(_HERE, "libmodcr_b200.so")
 
 c_void_p, c_int, c_i32, c_i64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -32,7 +33,7 @@ class AttnDesc(C.Structure):
                 ("qkv", c_void_p), ("pkv", c_void_p), ("kbias", c_void_p), ("cbits", c_void_p), ("cwords", c_i32),
                 ("ctx", c_void_p), ("lse", c_void_p), ("probs_img", c_void_p),
                 ("dctx", c_void_p), ("dalign", c_void_p), ("dqkv", c_void_p), ("dpkv", c_void_p), ("dq_ws", c_void_p),
-                ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float)]
+                ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float), ("row_sel", c_void_p)]
 
 
 class ScorerDesc(C.Structure):
@@ -76,8 +77,8 @@ SIGNATURES = {
     "modcr_prefix_attn_fwd": [C.POINTER(AttnDesc), c_void_p],
     "modcr_prefix_attn_bwd": [C.POINTER(AttnDesc), c_void_p],
     "modcr_chunk_mean_q": [c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p, c_i32, c_i32, c_void_p],
-    "modcr_align_softmax_ce_fwd": [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32,
-                                   c_i32, c_i32, c_void_p],
+    "modcr_align_softmax_ce_fwd": [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_i32, c_i32, c_i32, c_void_p],
     "modcr_align_softmax_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i32, c_i32, c_i32,
                                    c_void_p],
     "modcr_grad_sqnorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p],
@@ -107,6 +108,8 @@ SIGNATURES = {
     "modcr_rowln_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                         c_void_p],
     "modcr_tanh_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "modcr_rows_place": [c_void_p, c_void_p, c_void_p, RowMap, c_i32, c_i32, c_void_p],
+    "modcr_rows_gather": [c_void_p, RowMap, c_void_p, c_i32, c_i32, c_void_p],
     "modcr_key_bias": [c_void_p, c_void_p, c_i64, c_void_p],
     "modcr_chunk_bits": [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p],
     "modcr_accum_f32_2d": [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i32, c_i32, c_void_p],

@@ -38,6 +38,22 @@ namespace modcr {
 typedef __nv_bfloat16 bf16;
 constexpr float NEG_BIAS = -10000.0f;
 
+// Developer timeline of attn_bwd_kernel (build with -DMODCR_ATTN_TRACE, `make trace`): the first TRACE_CTAS CTAs record
+// clock64() at fixed points of the row-thread / MMA-thread programs; read back with modcr_debug_read_attn_trace().
+#ifdef MODCR_ATTN_TRACE
+constexpr int TRACE_CTAS = 32, TRACE_SLOTS = 128;
+__device__ long long g_attn_trace[TRACE_CTAS * TRACE_SLOTS];
+// CTAs [0,16) (first wave) and [600,616) (a later wave) are recorded
+#define TR(slot)                                                                                   \
+  do {                                                                                             \
+    int cta_ = blockIdx.y * gridDim.x + blockIdx.x;                                                \
+    if (cta_ >= 600) cta_ -= 584;                                                                  \
+    if (cta_ < TRACE_CTAS && (slot) < TRACE_SLOTS) g_attn_trace[cta_ * TRACE_SLOTS + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
+
 struct AttnParams {
   int N, S, P, Ppad, T, R, heads, H;
   int Kp;      // key rows seen by the MMAs (multiple of 16): Ppad + round16(S); Ppad = round16(P)
@@ -62,6 +78,7 @@ struct AttnParams {
   uint32_t drop_site, drop_thr;
   float drop_inv;              // 1 / (1 - p)
   int kid_split, kid_sub;      // logical key id of shared-memory key row kk: kk < kid_split ? S + kk : kk - kid_sub
+  const int64_t* row_sel;      // [N,T] or nullptr: text rows whose text->region probabilities are wanted (align_pos)
 };
 
 // logical key id of shared-memory key row kk (same in every kernel, whatever its row order): sequence key j -> j,
@@ -236,7 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: MMA operands live in uniform registers
 
   if (warp == 4) {
     if (lane == 0) {
@@ -289,7 +306,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
     float* pimg_row = nullptr;
-    if (p.probs_img != nullptr && alive && q_txt)
+    if (p.probs_img != nullptr && alive && q_txt && (p.row_sel == nullptr || __ldg(p.row_sel + (size_t)n * p.T + q) != 0))
       pimg_row = p.probs_img + (((size_t)n * p.heads + h) * p.T + q) * p.R;
 
     mbar_wait(bar_s, 0);   // S complete: the Q and K tiles are dead, P blocks 0/1 may overlay them
@@ -447,7 +464,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: MMA operands live in uniform registers
 
   if (warp == 7) {
     // ---------------------------------------------------------------------- TMA producer
@@ -607,6 +624,9 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         float* pimg_row = nullptr;
         if (p.probs_img != nullptr && alive && q_txt)
           pimg_row = p.probs_img + (((size_t)n * p.heads + h) * p.T + q) * p.R;
+        // rows of this warp whose probabilities are wanted (row_sel = align_pos: the alignment loss reads no other row)
+        const bool row_wanted = pimg_row != nullptr && (p.row_sel == nullptr || __ldg(p.row_sel + (size_t)n * p.T + q) != 0);
+        const uint32_t want_mask = p.probs_img != nullptr ? __ballot_sync(0xffffffffu, row_wanted) : 0u;
 
         // ---- pass 1: row maximum
         mbar_wait(&s_full[g], i & 1);
@@ -651,7 +671,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           // writes 128-byte row segments.
           if (issuer) tma_store_wait_read<0>();   // the previous item's ctx store has finished reading the tile
           named_bar_sync(bar_id, gthreads);
-          if (warp_alive) {
+          if (warp_alive && want_mask != 0u) {
             const uint32_t tile = smem_u32(sO) + (uint32_t)(warp & 3) * 4096u;
             const int q0 = g * 128 + (warp & 3) * 32;          // first q row of this warp
             float* pbase = p.probs_img + (((size_t)n * p.heads + h) * p.T) * p.R;
@@ -666,7 +686,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float pr = 0.f;
-                if (j < wcols) {
+                if (j < wcols && row_wanted) {
                   pr = fast_ex2(masked_s2<MODE>(v[j], c1, sBias[c0 + j], c0 + j, q, q_txt, p.T, wd) - m) * inv;
                   if (p.drop_thr != 0)   // the alignment head consumes the post-dropout probabilities (v10:982)
                     pr = drop_keep_row(drow, drop_key_id(p, c0 + j), p.drop_thr) ? pr * p.drop_inv : 0.f;
@@ -680,7 +700,7 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                 float pr;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pr) : "r"(tile + r * 128 + ((lane ^ r) << 2)));
                 const int qr = q0 + r;
-                if (col_ok && qr < p.T && qr < p.S) pbase[(size_t)qr * p.R + (col - p.T)] = pr;
+                if (col_ok && ((want_mask >> r) & 1u)) pbase[(size_t)qr * p.R + (col - p.T)] = pr;
               }
               __syncwarp();
             }
@@ -716,12 +736,16 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 // values: the exp / dS math of step i runs while the tensor core computes S/dP(i+1) and dV/dK/dQ(i-1).  With at most two q tiles (S <= 256) the dQ accumulators
 // of both tiles stay resident in TMEM across key blocks (columns 256.. and 448..), so dQ is written once, as bf16,
 // and the fp32 workspace round trip disappears; longer sequences flush dQ per step through the workspace.
-// P and dS of one 32-column chunk from the S / dP accumulator values already in registers.
-// DALIGN: the chunk overlaps the region columns and the alignment-loss gradient has to be added to dP.
-template <int MODE, bool SAFE, bool DALIGN>
-DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, const float* sBias, int c0, int kk0,
-                           int nb, int q, bool q_txt, uint32_t w, float lse2, float delta_s, const float* darow,
-                           uint32_t* pp, uint32_t* dd, uint32_t drow = 0, uint32_t dseed = 0) {
+// P and dS of one 32-column chunk from the S / dP accumulator values already in registers.  ONE instance per mask mode:
+// the partial last key block (stale TMEM columns beyond the MMA width) and the alignment-loss gradient on the region
+// columns are handled by the caller with two small warp-uniform loops over sv / dp before this runs, instead of four
+// template variants of the whole body (the row-thread program has to stay inside the instruction cache: the variant
+// code made every first visit of a branch cost thousands of cycles of instruction fetch, ncu `no_instructions` and the
+// clock64() timeline in profiles/r02_attn_bwd_trace_before.log).
+template <int MODE>
+DEVINL void bwd_chunk_math(const AttnParams& p, float c1, const float* sv, const float* dp, const float* sBias, int kk0,
+                           int q, bool q_txt, uint32_t w, float lse2, float delta_s, uint32_t* pp, uint32_t* dd,
+                           uint32_t drow = 0) {
 #pragma unroll
   for (int g4 = 0; g4 < 8; ++g4) {   // 4 columns at a time keeps the live register set small
     const float4 b4 = *reinterpret_cast<const float4*>(sBias + kk0 + 4 * g4);
@@ -731,15 +755,8 @@ DEVINL void bwd_chunk_math(const AttnParams& p, float c1, float* sv, float* dp, 
     for (int e = 0; e < 4; ++e) {
       const int j = 4 * g4 + e;
       const int kk = kk0 + j;
-      float acc = sv[j], g = dp[j];
-      if (SAFE && c0 + j >= nb) {  // TMEM columns beyond this block's MMA width hold stale data
-        acc = 0.f;
-        g = 0.f;
-      }
-      pr[e] = fast_ex2(masked_s2<MODE>(acc, c1, bb[e], kk, q, q_txt, p.T, w) - lse2);
-      if (DALIGN) {
-        if (kk >= p.T && kk < p.S) g += __ldg(darow + (kk - p.T));
-      }
+      float g = dp[j];
+      pr[e] = fast_ex2(masked_s2<MODE>(sv[j], c1, bb[e], kk, q, q_txt, p.T, w) - lse2);
       float pd = pr[e];
       if (p.drop_thr != 0) {   // uniform: dV uses D o P, dS uses D o dP (D = keep / (1 - p)); delta is unchanged
         const float dm = drop_keep_row(drow, drop_key_id(p, kk), p.drop_thr) ? p.drop_inv : 0.f;
@@ -776,8 +793,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_v = bars + 1;
   uint64_t* qfull = bars + 2;    // [2]
   uint64_t* qempty = bars + 4;   // [2]
-  uint64_t* bar_sdp = bars + 6;       // [2] S/dP of a 64-key sub-block complete
-  uint64_t* bar_cons = bars + 8;      // [2] ... and loaded into registers by every row thread
+  uint64_t* bar_sdp = bars + 6;       // S/dP of a step complete
+  uint64_t* bar_cons = bars + 8;      // ... and loaded into registers by every row thread
   uint64_t* bar_pds = bars + 10;
   uint64_t* bar_free = bars + 11;     // dV/dK/dQ MMAs of a step retired: P/dS smem free, dQ (and dK/dV) readable
   uint64_t* bar_dkv_free = bars + 12; // dK/dV accumulators of a key block have been read out
@@ -790,7 +807,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const float c1 = p.scale * LOG2E;
   constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ0 = 256, COL_DK = 320, COL_DV = 384, COL_DQ1 = 448;
   const bool dq_resident = p.nqt <= 2;   // uniform over the grid
+  // at most two q tiles: the Q / dO ring IS the set of q tiles (stage = q tile), loaded once and reused by every key
+  // block instead of being streamed again per key block
+  const bool q_resident = p.nqt <= 2;
   const int total_steps = p.nkb * p.nqt;
+  if (tid == 0) TR(0);
+  if (tid == 8 * 32) TR(64);
 
   if (warp == 9) {
     // ---------------------------------------------------------------------- TMA producer
@@ -806,10 +828,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         mbar_init(&qfull[i], 1);
         mbar_init(&qempty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&bar_sdp[i], 1);
-        mbar_init(&bar_cons[i], 256);
-      }
+      mbar_init(bar_sdp, 1);
+      mbar_init(bar_cons, 256);
       mbar_init(bar_pds, 256);
       mbar_init(bar_free, 1);
       mbar_init(bar_dkv_free, 256);
@@ -828,7 +848,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tmem_alloc<512>(tmem_slot);
   } else {
     stage_bias(sBias, p.nkb * 128, p, n, tid, 256);
-    // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q] (log2 domain, +inf for dead rows)
+    // delta[q] = sum_d dO[q,d] O[q,d] (+ sum_r P_img[q,r] dAlign[q,r]) ; lse[q] (log2 domain, +inf for dead rows).
+    // (Computing the dO . O part from TMA-staged O tiles inside the step pipeline was measured SLOWER, 233 vs 229 us:
+    // these strided reads already overlap the K/V loads, profiles/r02_attn_time_6*.log.)
     for (int r = tid; r < p.nqt * 128; r += 256) {
       float d = 0.f, l = INFINITY;
       if (r < p.S) {
@@ -851,23 +873,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             d = fmaf(fa.y, fb.y, d);
           }
         }
-        if (p.dalign != nullptr && p.probs_img != nullptr && r < p.T) {
+        // alignment term: only rows that feed the alignment loss carry a gradient (row_sel = align_pos; without it every
+        // text row is assumed to).  Two independent accumulators + 128-bit loads keep the loads in flight instead of a
+        // 50-deep dependent chain per row (that chain was 15k cycles of prologue per CTA in the mode-2 layers).
+        if (p.dalign != nullptr && p.probs_img != nullptr && r < p.T &&
+            (p.row_sel == nullptr || __ldg(p.row_sel + (size_t)n * p.T + r) != 0)) {
           const float* pi = p.probs_img + (((size_t)n * p.heads + h) * p.T + r) * p.R;
           const float* da = p.dalign + ((size_t)n * p.T + r) * p.R;
-          for (int j = 0; j < p.R; ++j) d = fmaf(__ldg(pi + j), __ldg(da + j), d);
+          float d0 = 0.f, d1 = 0.f;
+          int j = 0;
+          if ((p.R & 3) == 0) {
+            for (; j + 8 <= p.R; j += 8) {
+              const float4 x0 = __ldg(reinterpret_cast<const float4*>(pi + j)), y0 = __ldg(reinterpret_cast<const float4*>(da + j));
+              const float4 x1 = __ldg(reinterpret_cast<const float4*>(pi + j + 4)), y1 = __ldg(reinterpret_cast<const float4*>(da + j + 4));
+              d0 = fmaf(x0.x, y0.x, fmaf(x0.y, y0.y, fmaf(x0.z, y0.z, fmaf(x0.w, y0.w, d0))));
+              d1 = fmaf(x1.x, y1.x, fmaf(x1.y, y1.y, fmaf(x1.z, y1.z, fmaf(x1.w, y1.w, d1))));
+            }
+          }
+          for (; j + 2 <= p.R; j += 2) {
+            d0 = fmaf(__ldg(pi + j), __ldg(da + j), d0);
+            d1 = fmaf(__ldg(pi + j + 1), __ldg(da + j + 1), d1);
+          }
+          if (j < p.R) d0 = fmaf(__ldg(pi + j), __ldg(da + j), d0);
+          d += d0 + d1;
         }
       }
       sDelta[r] = d;
       sLse[r] = l;
     }
+    if (tid == 0) TR(1);
   }
+  if (lane == 0) TR(100 + warp);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: MMA operands live in uniform registers
+  if (tid == 0) TR(2);
+  if (tid == 8 * 32) TR(65);
 
+#ifdef MODCR_ATTN_TRACE
+  if (warp == 9 && lane == 1) {   // observer: true completion times of the MMA groups
+    for (int step = 0; step < total_steps && step < 4; ++step) {
+      mbar_wait(bar_sdp, step & 1);
+      TR(112 + step * 3 + 4);
+      mbar_wait(bar_free, step & 1);
+      TR(114 + step * 3 + 4);
+    }
+  }
+#endif
   if (warp == 9) {
-    if (lane == 0) {
+    if (lane == 0 && !q_resident) {
       for (int step = 2; step < total_steps; ++step) {
         const int qt = step % p.nqt;
         const int s = step & 1;
@@ -886,65 +941,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);
       const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);
-      // S = Q K^T and dP = dO V^T of step `step`, 64-key sub-block `c`
-      auto issue_sdp = [&](int step, int c) {
+      // Descriptors are built ONCE per operand and advanced by adding the byte offset >> 4 to the 64-bit value (the
+      // address field is the low 14 bits and shared-memory addresses never carry out of it): the issuing thread is the
+      // bottleneck of this kernel -- the MMAs are N = 64 and retire faster than a thread that rebuilds two descriptors
+      // per instruction can issue them (clock64() timeline, profiles/r02_attn_bwd_trace_*.log).
+      const uint64_t k_km = make_smem_desc(k_addr, 0, 1024), v_km = make_smem_desc(v_addr, 0, 1024);         // K-major rows
+      const uint64_t k_mn = make_smem_desc(k_addr, 8192, 1024);                                               // as B of dQ
+      const uint64_t p_mn = make_smem_desc(p_addr, 16384, 1024), ds_mn = make_smem_desc(ds_addr, 16384, 1024);
+      const uint64_t ds_km = make_smem_desc(ds_addr, 0, 1024);
+      uint64_t q_km[2], do_km[2], q_mn[2], do_mn[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uint32_t qa = smem_u32(sQ + s * 16384), da = smem_u32(sDO + s * 16384);
+        q_km[s] = make_smem_desc(qa, 0, 1024);
+        do_km[s] = make_smem_desc(da, 0, 1024);
+        q_mn[s] = make_smem_desc(qa, 8192, 1024);
+        do_mn[s] = make_smem_desc(da, 8192, 1024);
+      }
+      // S = Q K^T and dP = dO V^T of step `step` over the whole key block: N = nb (<= 128) per instruction.  The small
+      // MMAs of this kernel read both operands from shared memory and are bound by that read, not by the tensor pipe
+      // (~90 cycles per M=128 x N=64 x K=16 instruction against a 32-cycle floor, profiles/r02_attn_bwd_trace_6.log):
+      // one N=128 instruction re-reads the 4 KB A slice once instead of twice.
+      auto issue_sdp = [&](int step) {
         const int kb = step / p.nqt;
-        const int nb = min(128, p.Kp - kb * 128) - c * 64;   // keys left in this sub-block
-        if (nb > 0) {
-          const uint32_t idesc_s = make_idesc_bf16(128, min(nb, 64), 0, 0);
-          const int s = step & 1;
-          const uint32_t q_addr = smem_u32(sQ + s * 16384), do_addr = smem_u32(sDO + s * 16384);
-          if (c == 0) {
-            mbar_wait(&qfull[s], (step >> 1) & 1);
-            tc_fence_after();
-          }
-          const uint32_t kv_off = kb * 16384 + c * 8192;
+        const int nb = min(128, p.Kp - kb * 128);
+        const uint32_t idesc_s = make_idesc_bf16(128, nb, 0, 0);
+        const int s = q_resident ? step % p.nqt : (step & 1);
+        mbar_wait(&qfull[s], q_resident ? 0u : (uint32_t)((step >> 1) & 1));
+        tc_fence_after();
+        const uint32_t kv_off = (uint32_t)(kb * 16384) >> 4;
+        const uint64_t qd = s ? q_km[1] : q_km[0], dod = s ? do_km[1] : do_km[0];
+        const uint64_t kd = k_km + kv_off, vd = v_km + kv_off;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + COL_S + c * 64, make_smem_desc(q_addr + k * 32, 0, 1024),
-                      make_smem_desc(k_addr + kv_off + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_S, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + COL_DP + c * 64, make_smem_desc(do_addr + k * 32, 0, 1024),
-                      make_smem_desc(v_addr + kv_off + k * 32, 0, 1024), idesc_s, k > 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_sdp[c]);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + COL_DP, dod + 2 * k, vd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_sdp);
       };
       mbar_wait(bar_k, 0);
       mbar_wait(bar_v, 0);
-      issue_sdp(0, 0);
-      issue_sdp(0, 1);
+      TR(66);
+      issue_sdp(0);
+      TR(67);
       int step = 0;
       for (int kb = 0; kb < p.nkb; ++kb) {
         const int nb = min(128, p.Kp - kb * 128);
         for (int qt = 0; qt < p.nqt; ++qt, ++step) {
-          const int s = step & 1;
-          const uint32_t q_addr = smem_u32(sQ + s * 16384), do_addr = smem_u32(sDO + s * 16384);
-          for (int c = 0; c < 2; ++c) {
-            mbar_wait(&bar_cons[c], step & 1);   // S/dP(step, c) are in registers: the columns can be overwritten
-            tc_fence_after();
-            if (step + 1 < total_steps) issue_sdp(step + 1, c);
-          }
+          const int s = q_resident ? qt : (step & 1);
+          mbar_wait(bar_cons, step & 1);   // S/dP(step) are in registers: the columns can be overwritten
+          tc_fence_after();
+          if (step + 1 < total_steps) issue_sdp(step + 1);
+          TR(68 + step * 6 + 1);
           mbar_wait(bar_pds, step & 1);   // P/dS(step) in smem
+          TR(68 + step * 6 + 2);
           if (qt == 0 && kb > 0) mbar_wait(bar_dkv_free, (kb - 1) & 1);
           tc_fence_after();
           const uint32_t acc0 = qt > 0 ? 1u : 0u;
+          const uint64_t dod = s ? do_mn[1] : do_mn[0], qd = s ? q_mn[1] : q_mn[0];
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO
-            umma_bf16(tmem_base + COL_DV, make_smem_desc(p_addr + ks * 2048, 16384, 1024),
-                      make_smem_desc(do_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : acc0);
+          for (int ks = 0; ks < 8; ++ks)  // dV += P^T dO      (k-step = 16 q rows = 2048 B of either operand)
+            umma_bf16(tmem_base + COL_DV, p_mn + 128 * ks, dod + 128 * ks, idesc_t, ks > 0 ? 1u : acc0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // dK += dS^T Q
-            umma_bf16(tmem_base + COL_DK, make_smem_desc(ds_addr + ks * 2048, 16384, 1024),
-                      make_smem_desc(q_addr + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : acc0);
+            umma_bf16(tmem_base + COL_DK, ds_mn + 128 * ks, qd + 128 * ks, idesc_t, ks > 0 ? 1u : acc0);
           const uint32_t col_dq = (dq_resident && qt == 1) ? COL_DQ1 : COL_DQ0;
           const uint32_t accq = (dq_resident && kb > 0) ? 1u : 0u;
           const int ksteps = nb >> 4;
-          for (int ks = 0; ks < ksteps; ++ks)  // dQ (+)= dS K_kb
-            umma_bf16(tmem_base + col_dq, make_smem_desc(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
-                      make_smem_desc(k_addr + kb * 16384 + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : accq);
+          const uint64_t kd = k_mn + (uint32_t)(kb * 16384 >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // dQ (+)= dS K_kb    (k-step = 16 keys: +32 B inside a 64-key block of dS, +2048 B of K)
+            if (ks < ksteps)
+              umma_bf16(tmem_base + col_dq, ds_km + (ks >> 2) * 1024 + (ks & 3) * 2, kd + 128 * ks, idesc_q,
+                        ks > 0 ? 1u : accq);
           umma_commit(&qempty[s]);
           umma_commit(bar_free);
+          TR(68 + step * 6 + 3);
         }
       }
     }
@@ -1010,11 +1081,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           dst = p.dqkv + ((size_t)n * p.S + (kk - p.Ppad)) * H3 + p.H + h * 64 + half * p.H;
         float acc[64];
         const uint32_t col = half == 0 ? COL_DK : COL_DV;
+        if (tid == 0) TR(110 + kb * 3);
         tmem_ld_32x32(taddr + col, reinterpret_cast<uint32_t*>(acc));
         tmem_ld_32x32(taddr + col + 32, reinterpret_cast<uint32_t*>(acc) + 32);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_dkv_free);
+        if (tid == 0) TR(111 + kb * 3);
         if (dst != nullptr) {
           uint4* out = reinterpret_cast<uint4*>(dst);
 #pragma unroll
@@ -1039,30 +1112,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const bool alive = q < p.S;
         const bool q_txt = q < p.T;
         const uint32_t drow = p.drop_thr != 0 ? drop_hash(dseed, p.drop_site, (uint32_t)((n * p.heads + h) * p.S + q)) : 0u;
-        const float lse2 = sLse[q], delta = sDelta[q];
+        const float lse2 = sLse[q];
+        const float delta = sDelta[q];
         const uint32_t* crow = (MODE != 0 && alive && q_txt) ? p.cbits + ((size_t)n * p.T + q) * p.cwords : nullptr;
         const float* darow =
-            (p.dalign != nullptr && alive && q_txt) ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
+            (p.dalign != nullptr && alive && q_txt && (p.row_sel == nullptr || __ldg(p.row_sel + (size_t)n * p.T + q) != 0))
+                ? p.dalign + ((size_t)n * p.T + q) * p.R : nullptr;
         // this thread's two 32-column chunks of the 128-key block are interleaved with the other half's
         // (c0 = 32*half and 32*half + 64) so that a partial last block stays balanced between the two warps
         const bool warp_alive = (qt * 128 + (warp & 3) * 32) < p.S;
         const float delta_s = delta * p.scale;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
           const int c0 = half * 32 + i * 64;
           const int kk0 = kb * 128 + c0;
           const bool live = warp_alive && c0 < nb;
           float sv[32], dp[32];
           uint32_t pp[16], dd[16];
-          mbar_wait(&bar_sdp[i], step & 1);
-          tc_fence_after();
+          if (i == 0) {
+            mbar_wait(bar_sdp, step & 1);
+            tc_fence_after();
+          }
+          if (tid == 0) TR(3 + step * 12 + i * 6);
           if (live) {
             tmem_ld_32x32(taddr + COL_S + c0, reinterpret_cast<uint32_t*>(sv));
             tmem_ld_32x32(taddr + COL_DP + c0, reinterpret_cast<uint32_t*>(dp));
             tmem_ld_wait();
           }
-          tc_fence_before();
-          mbar_arrive(&bar_cons[i]);
+          if (i == 1) {   // both chunks of this thread are in registers
+            tc_fence_before();
+            mbar_arrive(bar_cons);
+          }
+          if (tid == 0) TR(4 + step * 12 + i * 6);
           if (!live) {
             // dead q rows (rows >= S) or key columns beyond this block: P = dS = 0, no TMEM traffic, no math
 #pragma unroll
@@ -1072,28 +1153,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             }
           } else {
             const uint32_t w = (crow != nullptr && (kk0 >> 5) < p.cwords) ? __ldg(crow + (kk0 >> 5)) : 0u;
-            const bool img = darow != nullptr && kk0 + 32 > p.T && kk0 < p.S;
-            const bool safe = c0 + 32 > nb;
-            if (img) {
-              if (safe)
-                bwd_chunk_math<MODE, true, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                 pp, dd, drow, dseed);
-              else
-                bwd_chunk_math<MODE, false, true>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                  pp, dd, drow, dseed);
-            } else {
-              if (safe)
-                bwd_chunk_math<MODE, true, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s, darow,
-                                                  pp, dd, drow, dseed);
-              else
-                bwd_chunk_math<MODE, false, false>(p, c1, sv, dp, sBias, c0, kk0, nb, q, q_txt, w, lse2, delta_s,
-                                                   darow, pp, dd, drow, dseed);
+            if (c0 + 32 > nb) {   // partial last key block: TMEM columns beyond the MMA width hold stale data
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (c0 + j >= nb) {
+                  sv[j] = 0.f;
+                  dp[j] = 0.f;
+                }
+              }
             }
+            if (darow != nullptr && kk0 + 32 > p.T && kk0 < p.S) {   // region columns: + gradient of the alignment loss
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int kk = kk0 + j;
+                if (kk >= p.T && kk < p.S) dp[j] += __ldg(darow + (kk - p.T));
+              }
+            }
+            bwd_chunk_math<MODE>(p, c1, sv, dp, sBias, kk0, q, q_txt, w, lse2, delta_s, pp, dd, drow);
           }
+          if (tid == 0) TR(5 + step * 12 + i * 6);
           if (i == 0 && step > 0) {
             // the MMAs of the previous step have retired (they ran under the math above): its P/dS tiles are free
             // and its accumulators readable
             mbar_wait(bar_free, (step - 1) & 1);
+            if (tid == 0) TR(6 + step * 12);
             tc_fence_after();
             // flush mode re-uses the single dQ accumulator every step: drain it before this step's MMAs may start
             if (!dq_resident) read_out(prev_kb, prev_qt);
@@ -1109,21 +1192,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar_pds);
+        if (tid == 0) TR(7 + step * 12);
         // resident mode: nothing this step's MMAs write is still unread (dK/dV of a new key block wait for
         // bar_dkv_free), so the read-out runs after the hand-off, when the P/dS registers are dead
         if (step > 0 && dq_resident) read_out(prev_kb, prev_qt);
+        if (tid == 0) TR(8 + step * 12);
         prev_kb = kb;
         prev_qt = qt;
       }
     }
     mbar_wait(bar_free, (step - 1) & 1);
     tc_fence_after();
+    if (tid == 0) TR(60);
     read_out(prev_kb, prev_qt);
+    if (tid == 0) TR(61);
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) TR(62);
   if (warp == 8) tmem_dealloc<512>(tmem_base);
 }
+
+#ifdef MODCR_ATTN_TRACE
+int attn_trace_read(long long* host, int max_entries) {
+  const int n = TRACE_CTAS * TRACE_SLOTS < max_entries ? TRACE_CTAS * TRACE_SLOTS : max_entries;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(host, g_attn_trace, (size_t)n * sizeof(long long)) == cudaSuccess ? n : -1;
+}
+#else
+int attn_trace_read(long long*, int) { return 0; }
+#endif
 
 // ============================================================================ host
 static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
@@ -1160,6 +1258,7 @@ static int fill_params(const AttnDesc& a, AttnParams& p, bool bwd) {
   p.ctx = (const bf16*)a.ctx; p.dctx = (const bf16*)a.dctx; p.dalign = a.dalign;
   p.dqkv = (bf16*)a.dqkv; p.dpkv = (bf16*)a.dpkv; p.dq_ws = a.dq_ws;
   p.kid_split = p.Ppad; p.kid_sub = p.Ppad;
+  p.row_sel = a.row_sel;
   p.drop_seed = a.drop_seed; p.drop_site = a.drop_site; p.drop_thr = 0; p.drop_inv = 1.f;
   if (a.drop_p > 0.f) {
     if (!(a.drop_p < 1.f) || a.drop_seed == nullptr) {

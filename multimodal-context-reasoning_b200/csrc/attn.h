@@ -23,6 +23,8 @@ struct AttnDesc {
   void* ctx = nullptr;                  // bf16 [N,S,H]    forward output
   float* lse = nullptr;                 // fp32 [N,heads,S]
   float* probs_img = nullptr;           // fp32 [N,heads,T,S-T] normalised text->region probabilities (optional)
+  const int64_t* row_sel = nullptr;     // int64 [N,T] (align_pos) or null: only rows with a non-zero entry are written to /
+                                        // read from probs_img and receive dalign (the alignment loss uses no other row)
   // backward only
   const void* dctx = nullptr;           // bf16 [N,S,H]
   const float* dalign = nullptr;        // fp32 [N,T,S-T] upstream gradient of the head-summed block (optional)
@@ -38,5 +40,7 @@ struct AttnDesc {
 int attn_fwd_launch(const AttnDesc& a, cudaStream_t stream);
 int attn_bwd_launch(const AttnDesc& a, cudaStream_t stream);
 size_t attn_bwd_workspace_bytes(int N, int S, int heads);
+// developer builds (-DMODCR_ATTN_TRACE) only: copies the recorded clock64() timeline of attn_bwd_kernel to the host
+int attn_trace_read(long long* host, int max_entries);
 
 }  // namespace modcr

@@ -169,7 +169,7 @@ int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packe
 static void to_attn(const modcr_attn_desc* d, modcr::AttnDesc& a) {
   a.N = d->N; a.S = d->S; a.P = d->P; a.heads = d->heads; a.T = d->T; a.mode = d->mode; a.scale = d->scale;
   a.qkv = d->qkv; a.pkv = d->pkv; a.kbias = d->kbias; a.cbits = d->cbits; a.cwords = d->cwords;
-  a.ctx = d->ctx; a.lse = d->lse; a.probs_img = d->probs_img;
+  a.ctx = d->ctx; a.lse = d->lse; a.probs_img = d->probs_img; a.row_sel = d->row_sel;
   a.dctx = d->dctx; a.dalign = d->dalign; a.dqkv = d->dqkv; a.dpkv = d->dpkv; a.dq_ws = d->dq_ws;
   a.drop_seed = d->drop_seed; a.drop_site = d->drop_site; a.drop_p = d->drop_p;
 }
@@ -201,10 +201,11 @@ int modcr_chunk_mean_q(void* q, int64_t ld, int32_t N, int32_t S_, int32_t H, co
 }
 
 int modcr_align_softmax_ce_fwd(const float* probs, int32_t nl, int32_t heads, const int64_t* align_pos,
-                               const int64_t* total_label, float* block, float* row_loss, float* out, int32_t N,
-                               int32_t T, int32_t R, void* stream) {
+                               const int64_t* total_label, const int64_t* row_sel, float* block, float* row_loss,
+                               float* out, int32_t N, int32_t T, int32_t R, void* stream) {
   ARCH_OR_RETURN();
-  return modcr::align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, block, row_loss, out, N, T, R, S(stream));
+  return modcr::align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, row_sel, block, row_loss, out, N, T, R,
+                                     S(stream));
 }
 int modcr_align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label,
                                const float* out, float gout, float* dblock, int32_t N, int32_t T, int32_t R,
@@ -351,6 +352,14 @@ int modcr_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* str
   ARCH_OR_RETURN();
   return modcr::tanh_bwd(dy, y, dx, n, S(stream));
 }
+int modcr_rows_place(const float* src, void* y, float* y32, modcr_rowmap ymap, int32_t M, int32_t H, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::rows_place(src, y, y32, RM(ymap), M, H, S(stream));
+}
+int modcr_rows_gather(const void* dy, modcr_rowmap dymap, void* dst, int32_t M, int32_t H, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::rows_gather(dy, RM(dymap), dst, M, H, S(stream));
+}
 int modcr_key_bias(const float* mask, float* kbias, int64_t total, void* stream) {
   ARCH_OR_RETURN();
   return modcr::key_bias(mask, kbias, total, S(stream));
@@ -364,5 +373,10 @@ int modcr_accum_f32_2d(float* dst, int64_t ld_dst, const float* src, int64_t ld_
   ARCH_OR_RETURN();
   return modcr::accum_f32_2d(dst, ld_dst, src, ld_src, rows, cols, accumulate, S(stream));
 }
+
+#ifdef MODCR_ATTN_TRACE
+/* developer build only (make trace): not part of include/modcr_b200.h */
+int modcr_debug_read_attn_trace(long long* host, int32_t max_entries) { return modcr::attn_trace_read(host, max_entries); }
+#endif
 
 }  // extern "C"

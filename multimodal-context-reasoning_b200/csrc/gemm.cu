@@ -171,7 +171,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (NCTA == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive
   else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler: MMA operands live in uniform registers
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

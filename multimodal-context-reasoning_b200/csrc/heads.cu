@@ -56,37 +56,68 @@ DEVINL float block_max(float v, float* sh) {
 // ============================================================================ alignment loss
 constexpr int AL_MAXR = 8;  // R <= 256
 
-// probs: [nl, N, heads, T, R] fp32.  One warp per (n, t) row.
+// probs: [nl, N, heads, T, R] fp32.  One warp per (n, t) row; the nl * heads slices of a row are summed in a fixed order
+// (per head: layers, then heads -- the reference's stack(...).sum(1).sum(1), v10:982) into lane-striped registers.
+// row_sel (optional, = align_pos): rows without a non-zero entry were never written by the attention kernel and get a
+// zero row.  VW = elements per load: 4 (128-bit) when R % 4 == 0, 2 when R is even, else 1.
+template <int VW>
 __global__ void __launch_bounds__(256) align_fwd_kernel(const float* __restrict__ probs, int nl, int heads,
                                                         const int64_t* __restrict__ align_pos,
-                                                        const int64_t* __restrict__ total_label, float* __restrict__ block,
+                                                        const int64_t* __restrict__ total_label,
+                                                        const int64_t* __restrict__ row_sel, float* __restrict__ block,
                                                         float* __restrict__ row_loss, int N, int T, int R) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= N * T) return;
   const int n = row / T, t = row - n * T;
+  // a[i * VW + e] = column (lane + 32 i) * VW + e
   float a[AL_MAXR];
 #pragma unroll
   for (int i = 0; i < AL_MAXR; ++i) a[i] = 0.f;
-  for (int h = 0; h < heads; ++h) {
-    float tmp[AL_MAXR];
+  const bool wanted = row_sel == nullptr || row_sel[row] != 0;
+  if (wanted) {
+    for (int h = 0; h < heads; ++h) {
+      float tmp[AL_MAXR];
 #pragma unroll
-    for (int i = 0; i < AL_MAXR; ++i) tmp[i] = 0.f;
-    for (int l = 0; l < nl; ++l) {
-      const float* src = probs + ((((size_t)l * N + n) * heads + h) * T + t) * R;
+      for (int i = 0; i < AL_MAXR; ++i) tmp[i] = 0.f;
+      for (int l = 0; l < nl; ++l) {
+        const float* src = probs + ((((size_t)l * N + n) * heads + h) * T + t) * R;
 #pragma unroll
-      for (int i = 0; i < AL_MAXR; ++i) {
-        const int r = lane + 32 * i;
-        if (r < R) tmp[i] += __ldg(src + r);
+        for (int i = 0; i < AL_MAXR / VW; ++i) {
+          const int r = (lane + 32 * i) * VW;
+          if (r < R) {
+            if (VW == 4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src + r));
+              tmp[4 * i] += v.x; tmp[4 * i + 1] += v.y; tmp[4 * i + 2] += v.z; tmp[4 * i + 3] += v.w;
+            } else if (VW == 2) {
+              const float2 v = __ldg(reinterpret_cast<const float2*>(src + r));
+              tmp[2 * i] += v.x; tmp[2 * i + 1] += v.y;
+            } else {
+              tmp[i] += __ldg(src + r);
+            }
+          }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < AL_MAXR; ++i) a[i] += tmp[i];
     }
-#pragma unroll
-    for (int i = 0; i < AL_MAXR; ++i) a[i] += tmp[i];
   }
+  // hand the columns to the lane-strided layout of the softmax below (column lane + 32 i) through the block row itself
 #pragma unroll
-  for (int i = 0; i < AL_MAXR; ++i) {
-    const int r = lane + 32 * i;
-    if (r < R) block[(size_t)row * R + r] = a[i];
+  for (int i = 0; i < AL_MAXR / VW; ++i) {
+    const int r = (lane + 32 * i) * VW;
+    if (r < R) {
+#pragma unroll
+      for (int e = 0; e < VW; ++e) block[(size_t)row * R + r + e] = a[i * VW + e];
+    }
+  }
+  if (VW != 1) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < AL_MAXR; ++i) {
+      const int r = lane + 32 * i;
+      a[i] = r < R ? block[(size_t)row * R + r] : 0.f;
+    }
   }
   float loss = 0.f, correct = 0.f;
   if (align_pos != nullptr && align_pos[row] == 1) {
@@ -154,10 +185,10 @@ __global__ void __launch_bounds__(256) align_fwd_kernel(const float* __restrict_
 }
 
 // out[0] = mean loss over aligned rows, out[1] = #aligned rows, out[2] = #correct, out[3] = loss sum
-__global__ void __launch_bounds__(256) align_reduce_kernel(const float* __restrict__ row_loss,
-                                                           const int64_t* __restrict__ align_pos, float* __restrict__ out,
-                                                           int rows) {
-  __shared__ float sh[8];
+__global__ void __launch_bounds__(1024) align_reduce_kernel(const float* __restrict__ row_loss,
+                                                            const int64_t* __restrict__ align_pos, float* __restrict__ out,
+                                                            int rows) {
+  __shared__ float sh[32];
   float s = 0.f, c = 0.f, m = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) {
     if (align_pos[i] == 1) {
@@ -248,15 +279,22 @@ __global__ void __launch_bounds__(256) align_bwd_kernel(const float* __restrict_
 }
 
 int align_softmax_ce_fwd(const float* probs, int nl, int heads, const int64_t* align_pos, const int64_t* total_label,
-                         float* block, float* row_loss, float* out, int N, int T, int R, cudaStream_t st) {
+                         const int64_t* row_sel, float* block, float* row_loss, float* out, int N, int T, int R,
+                         cudaStream_t st) {
   if (R <= 0 || R > 32 * AL_MAXR || N <= 0 || T <= 0 || nl <= 0) {
     set_error("align_softmax_ce: bad shape N=%d T=%d R=%d (R <= %d)", N, T, R, 32 * AL_MAXR);
     return MODCR_ERR_SHAPE;
   }
   const int rows = N * T;
-  align_fwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, block, row_loss, N, T, R);
+  const bool al16 = (reinterpret_cast<uintptr_t>(probs) & 15) == 0, al8 = (reinterpret_cast<uintptr_t>(probs) & 7) == 0;
+  if ((R & 3) == 0 && al16)
+    align_fwd_kernel<4><<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, row_sel, block, row_loss, N, T, R);
+  else if ((R & 1) == 0 && al8)
+    align_fwd_kernel<2><<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, row_sel, block, row_loss, N, T, R);
+  else
+    align_fwd_kernel<1><<<(rows + 7) / 8, 256, 0, st>>>(probs, nl, heads, align_pos, total_label, row_sel, block, row_loss, N, T, R);
   if (align_pos != nullptr && row_loss != nullptr && out != nullptr) {
-    align_reduce_kernel<<<1, 256, 0, st>>>(row_loss, align_pos, out, rows);
+    align_reduce_kernel<<<1, 1024, 0, st>>>(row_loss, align_pos, out, rows);
     count_launches(1);
   }
   return check_launch("align_softmax_ce_fwd");

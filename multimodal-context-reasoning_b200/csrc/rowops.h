@@ -53,7 +53,8 @@ int chunk_mean_q(void* q, int64_t ld, int N, int S, int H, const int32_t* chunk_
 // softmax over R, rows with align_pos==1, CE(probabilities, total_label) -- double softmax as written.
 //   probs: fp32 [nl, N, heads, T, R]; block: [N,T,R]; row_loss: [N*T, 2]; out: [4] = {loss, M, correct, loss sum}
 int align_softmax_ce_fwd(const float* probs, int nl, int heads, const int64_t* align_pos, const int64_t* total_label,
-                         float* block, float* row_loss, float* out, int N, int T, int R, cudaStream_t st);
+                         const int64_t* row_sel, float* block, float* row_loss, float* out, int N, int T, int R,
+                         cudaStream_t st);
 int align_softmax_ce_bwd(const float* block, const int64_t* align_pos, const int64_t* total_label, const float* out,
                          float gout, float* dblock, int N, int T, int R, cudaStream_t st);
 

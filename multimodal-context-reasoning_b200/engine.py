@@ -234,12 +234,14 @@ def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None, drop=None, site=0):
 # -------------------------------------------------------------------------------------------- attention block
 class AttnCfg:
     """Static description of one self-attention call."""
-    __slots__ = ("N", "S", "H", "heads", "P", "T", "mode", "kbias", "cbits", "cwords", "chunk_id", "max_chunks")
+    __slots__ = ("N", "S", "H", "heads", "P", "T", "mode", "kbias", "cbits", "cwords", "chunk_id", "max_chunks",
+                 "row_sel")
 
     def __init__(self, N, S, H, heads, P=0, T=0, mode=0, kbias=None, cbits=None, cwords=0, chunk_id=None,
-                 max_chunks=0):
+                 max_chunks=0, row_sel=None):
         self.N, self.S, self.H, self.heads, self.P, self.T, self.mode = N, S, H, heads, P, T, mode
         self.kbias, self.cbits, self.cwords, self.chunk_id, self.max_chunks = kbias, cbits, cwords, chunk_id, max_chunks
+        self.row_sel = row_sel      # int64 [N,T] (align_pos): the only text rows whose text->region probabilities travel
 
 
 def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, probs_img=None, drop=None, site=0):
@@ -261,7 +263,7 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     lse = _empty((N, heads, S), F32, dev)
     adrop = (drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None
     ops.prefix_attn_fwd(N, S, P, heads, ac.T, ac.mode, qkv, pkv, ac.kbias, ac.cbits, ac.cwords, ctx, lse, probs_img,
-                        drop=adrop)
+                        drop=adrop, row_sel=ac.row_sel if probs_img is not None else None)
     pre1 = _empty((M, H), F32, dev)                                         # fp32 residual stream
     if drop is not None and drop.p_hidden > 0.0:
         # BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)  (a_transformers/modeling_bert.py:369-373)
@@ -307,7 +309,8 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop
     use_align = dalign if sv["probs_img"] is not None else None
     ops.prefix_attn_bwd(N, S, P, heads, ac.T, ac.mode, sv["qkv"], sv["pkv"], ac.kbias, ac.cbits, ac.cwords, sv["ctx"],
                         sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws,
-                        drop=(drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None)
+                        drop=(drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None,
+                        row_sel=ac.row_sel if use_align is not None else None)
     if sv["chunk"]:
         ops.chunk_mean_q(dqkv, 3 * H, N, S, H, ac.chunk_id, ac.T, ac.max_chunks)   # self-adjoint operator
     wgrad(dqkv, sv["x"], 3 * H, H, M, zeroed=dWqkv, bias_out=dbqkv)
@@ -341,17 +344,22 @@ def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None, drop=None, la
 
 
 # -------------------------------------------------------------------------------------------- embeddings
-def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, save):
+def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, save, pre_rows=None):
     """BertEmbeddings + img_embedding (+LayerNorm) written into one [N,S,H] buffer
-    (a_transformers/modeling_bert.py:184-211; modeling_transfomres.py:676-684; v10:339-345)."""
+    (a_transformers/modeling_bert.py:184-211; modeling_transfomres.py:676-684; v10:339-345).
+    ``pre_rows`` (fp32 [N,Pn,H]): rows that arrive already embedded and are placed IN FRONT of the text rows -- the
+    prompt embeddings of the language-model side (modeling/modeling_ensemble.py:498-503)."""
     dev = input_ids.device
     N, T = input_ids.shape
     H = cfg["H"]
     R = 0 if img_feats is None else img_feats.shape[1]
-    S = T + R
+    Pn = 0 if pre_rows is None else pre_rows.shape[1]
+    S = Pn + T + R
     x0, x0_32 = _empty((N, S, H), BF16, dev), _empty((N, S, H), F32, dev)
     tmean, trstd = _empty((N * T,), F32, dev), _empty((N * T,), F32, dev)
-    tmap = ops.rowmap(T, S, 0)
+    tmap = ops.rowmap(T, S, Pn)
+    if Pn:
+        ops.rows_place(pre_rows.to(F32).contiguous().view(N * Pn, H), x0, x0_32, ops.rowmap(Pn, S, 0), N * Pn, H)
     ids = input_ids.contiguous()
     tts = None if token_type_ids is None else token_type_ids.contiguous()
     pos = None if position_ids is None else position_ids.expand(N, T).contiguous()
@@ -359,7 +367,7 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
                          ps.f32("embeddings.token_type_embeddings.weight"),
                          ps.f32("embeddings.position_embeddings.weight"), ps.f32("embeddings.LayerNorm.weight"),
                          ps.f32("embeddings.LayerNorm.bias"), x0, tmap, tmean, trstd, N, T, H, cfg["eps"], y32=x0_32)
-    sv = dict(ids=ids, tts=tts, pos=pos, tmean=tmean, trstd=trstd, N=N, T=T, R=R, S=S)
+    sv = dict(ids=ids, tts=tts, pos=pos, tmean=tmean, trstd=trstd, N=N, T=T, R=R, S=S, Pn=Pn)
     if R > 0:
         D = img_feats.shape[2]
         Dpad = (D + 63) // 64 * 64
@@ -373,7 +381,7 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
                              ps.f32("img_embedding.bias"),
                              ps.f32("LayerNorm.weight") if use_ln else None,
                              ps.f32("LayerNorm.bias") if use_ln else None, use_ln, cfg["img_eps"], packed, pre, x0,
-                             ops.rowmap(R, S, T), imean, irstd, H, y32=x0_32)
+                             ops.rowmap(R, S, Pn + T), imean, irstd, H, y32=x0_32)
         sv.update(packed=packed, pre=pre, imean=imean, irstd=irstd, D=D, Dpad=Dpad)
     if save is not None:
         save.update(sv)
@@ -381,14 +389,16 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
 
 
 def embeddings_bwd(ps, cfg, sv, dx0, grads):
+    """Returns the bf16 gradient [N,Pn,H] of the pre-embedded rows (None without them)."""
     dev = dx0.device
     N, T, R, S, H = sv["N"], sv["T"], sv["R"], sv["S"], cfg["H"]
+    Pn = sv.get("Pn", 0)
     word = ps.f32("embeddings.word_embeddings.weight")
     type_ = ps.f32("embeddings.token_type_embeddings.weight")
     pos = ps.f32("embeddings.position_embeddings.weight")
     dw, dt, dp = torch.zeros_like(word), torch.zeros_like(type_), torch.zeros_like(pos)
     dg, db = _zeros((H,), F32, dev), _zeros((H,), F32, dev)
-    ops.txt_embed_ln_bwd(dx0, ops.rowmap(T, S, 0), sv["ids"], sv["tts"], sv["pos"], word, type_, pos,
+    ops.txt_embed_ln_bwd(dx0, ops.rowmap(T, S, Pn), sv["ids"], sv["tts"], sv["pos"], word, type_, pos,
                          ps.f32("embeddings.LayerNorm.weight"), sv["tmean"], sv["trstd"], dw, dt, dp, dg, db, N, T, H,
                          cfg["pad_token_id"])
     grads["embeddings.word_embeddings.weight"] = dw
@@ -402,7 +412,7 @@ def embeddings_bwd(ps, cfg, sv, dx0, grads):
         dWp = _empty((H, Dpad), F32, dev)
         dbias = _zeros((H,), F32, dev)
         dgi, dbi = (_zeros((H,), F32, dev), _zeros((H,), F32, dev)) if use_ln else (None, None)
-        ops.img_embed_ln_bwd(dx0, ops.rowmap(R, S, T), sv["packed"], sv["pre"], sv["imean"], sv["irstd"],
+        ops.img_embed_ln_bwd(dx0, ops.rowmap(R, S, Pn + T), sv["packed"], sv["pre"], sv["imean"], sv["irstd"],
                              ps.f32("LayerNorm.weight") if use_ln else None, use_ln, dpre, dWp, dbias, dgi, dbi, rows,
                              Dpad, H)
         dW = _empty((H, D), F32, dev)
@@ -410,6 +420,11 @@ def embeddings_bwd(ps, cfg, sv, dx0, grads):
         grads["img_embedding.weight"], grads["img_embedding.bias"] = dW, dbias
         if use_ln:
             grads["LayerNorm.weight"], grads["LayerNorm.bias"] = dgi, dbi
+    if Pn:
+        dpre_rows = _empty((N, Pn, H), BF16, dev)
+        ops.rows_gather(dx0, ops.rowmap(Pn, S, 0), dpre_rows, N * Pn, H)
+        return dpre_rows
+    return None
 
 
 # -------------------------------------------------------------------------------------------- pooler

@@ -37,13 +37,17 @@ class EncoderRun:
     """Everything one encoder pass needs besides tensors that carry gradients."""
 
     def __init__(self, ps, names, cfg, input_ids, token_type_ids, position_ids, img_feats, kbias, P, is_seq=False,
-                 cbits=None, cwords=0, chunk_id=None, max_chunks=0, want_block=False):
+                 cbits=None, cwords=0, chunk_id=None, max_chunks=0, want_block=False, n_pre=0, align_rows=None):
         self.ps, self.names, self.cfg = ps, names, cfg
         self.input_ids, self.token_type_ids, self.position_ids, self.img_feats = (input_ids, token_type_ids,
                                                                                    position_ids, img_feats)
         self.kbias, self.P, self.is_seq = kbias, P, is_seq
         self.cbits, self.cwords, self.chunk_id, self.max_chunks = cbits, cwords, chunk_id, max_chunks
         self.want_block = want_block
+        # int64 [N,T] align_pos: the alignment loss reads only these rows of the text->region block (v10:1075-1076), so only
+        # they are emitted by the attention kernels; None = the whole [N,T,R] block (debug / .align_block of a bare seq_enc)
+        self.align_rows = align_rows
+        self.n_pre = n_pre                    # rows that arrive already embedded (prompt embeddings), in front of the text
         # optional residuals of the chunk-aware encoder (v10:164-165, 212-223; run_PMR_ModCR.py:747-748)
         self.local_residual = bool(is_seq and cfg.get("add_local_residual", False))
         self.final_residual = bool(is_seq and cfg.get("add_residual", False))
@@ -53,7 +57,7 @@ class EncoderRun:
         self.want_grad = torch.is_grad_enabled()
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
-        self.S = self.T + self.R
+        self.S = self.n_pre + self.T + self.R
 
     def layer_cfg(self, i):
         c = self.cfg
@@ -65,14 +69,15 @@ class EncoderRun:
                 mode, cross = 2, True
         T = self.T if (self.is_seq) else 0
         ac = E.AttnCfg(self.N, self.S, c["H"], c["heads"], self.P, T, mode, self.kbias, self.cbits, self.cwords,
-                       self.chunk_id, self.max_chunks)
+                       self.chunk_id, self.max_chunks, self.align_rows)
         return ac, cross
 
 
 class EncoderFn(torch.autograd.Function):
     """BertImgModel / SeqBertImgModel forward+backward as one node.
 
-    inputs : run, n_hist, hist_0..hist_{n-1} ([N,P,H]), then the parameters in ``run.names`` order
+    inputs : run, n_hist, hist_0..hist_{n-1} ([N,P,H]), [pre-embedded rows [N,Pn,H] when ``run.n_pre``], then the
+             parameters in ``run.names`` order
     outputs: sequence_output [N,S,H] bf16, pooled [N,H] bf16, chunk_hidden_states [N,S,H] bf16 (seq),
              align_block [N,T,R] fp32 (seq, head- and layer-summed text->region probabilities)"""
 
@@ -84,9 +89,10 @@ class EncoderFn(torch.autograd.Function):
         dev = run.input_ids.device
         need_grad = run.want_grad and any(ctx.needs_input_grad)
         hist = [_as_bf16(h).view(N * run.P, H) for h in hist_in] if n_hist else None
+        pre_rows = tensors[n_hist] if run.n_pre else None
         emb_save = {} if need_grad else None
         x, x32 = E.embeddings_fwd(ps, cfg, run.input_ids, run.token_type_ids, run.position_ids, run.img_feats,
-                                  emb_save)
+                                  emb_save, pre_rows)
         drop = run.drop
         if drop is not None and drop.p_hidden > 0.0:
             # BertEmbeddings.dropout and the img_embedding dropout (a_transformers 209; transfomres 681, v10:343)
@@ -117,9 +123,11 @@ class EncoderFn(torch.autograd.Function):
         block = None
         if nprob:
             block = E._empty((N, run.T, run.R), F32, dev)
-            ops.align_softmax_ce_fwd(probs, nprob, cfg["heads"], None, None, block, None, None, N, run.T, run.R)
+            ops.align_softmax_ce_fwd(probs, nprob, cfg["heads"], None, None, block, None, None, N, run.T, run.R,
+                                     row_sel=run.align_rows)
         ctx.run, ctx.n_hist, ctx.saves, ctx.emb_save = run, n_hist, saves, emb_save
         ctx.hist, ctx.hist_dtypes = hist, [h.dtype for h in hist_in]
+        ctx.pre_dtype = pre_rows.dtype if pre_rows is not None else None
         ctx.x_last, ctx.pooled, ctx.nprob = x, pooled, nprob
         ch = chunk_hidden.view(N, S, H) if chunk_hidden is not None else torch.empty(0, device=dev, dtype=BF16)
         bl = block if block is not None else torch.empty(0, device=dev, dtype=F32)
@@ -174,7 +182,7 @@ class EncoderFn(torch.autograd.Function):
                 ops.add_bf16(dy, d_chunk.to(BF16).contiguous(), dy)
         if run.drop is not None and run.drop.p_hidden > 0.0:
             ops.dropout(dy, dy, None, None, N * S * H, run.drop.seed, run.drop.site(0, 0), run.drop.p_hidden)
-        E.embeddings_bwd(ps, cfg, ctx.emb_save, dy.view(N, S, H), grads)
+        dpre = E.embeddings_bwd(ps, cfg, ctx.emb_save, dy.view(N, S, H), grads)
         hand_off()
         out_h = []
         for i in range(ctx.n_hist):
@@ -184,8 +192,13 @@ class EncoderFn(torch.autograd.Function):
                 ops.bf16_to_f32(g, g32)
                 g = g32.to(ctx.hist_dtypes[i])
             out_h.append(g)
+        out_pre = []
+        if run.n_pre:
+            g32 = E._empty((N, run.n_pre, H), F32, dev)
+            ops.bf16_to_f32(dpre, g32)
+            out_pre = [g32.to(ctx.pre_dtype)]
         out_p = [None if n in handed else grads.get(n) for n in run.names]   # handed-off tensors are already p.grad
-        return (None, None, *out_h, *out_p)
+        return (None, None, *out_h, *out_pre, *out_p)
 
 
 class ClsHeadRun:

@@ -37,13 +37,15 @@ class SeqBertImgModel(_EncoderModelBase):
 
     def forward(self, input_ids, token_type_ids=None, attention_mask=None, input_mask=None, position_ids=None,
                 head_mask=None, img_feats=None, img_mask=None, encoder_history_states=None, offsets=None,
-                gather_index=None, _want_align_block=True):
+                gather_index=None, _want_align_block=True, _align_rows=None):
         """``attention_mask`` is the 0/1 chunk mask ``[N,T,T]`` (or its int32 bit-packed form ``[N,T,ceil(T/32)]``
         from ``packer.BatchPacker``); ``input_mask`` ``[N,T+R]`` the key padding
         mask; ``gather_index`` the ragged per-sequence chunk ids (or an already packed int32 ``[N,T]``
         tensor with -1 outside the chunked span).  Returns ``((sequence_output, pooled_output, attentions),
         chunk_hidden_states)`` like v10:360; ``attentions.align_block`` is the fp32 ``[N,T,R]`` sum over the
-        last three layers and all heads of ``probs[:, :T, T:]``."""
+        last three layers and all heads of ``probs[:, :T, T:]``.  ``_align_rows`` (int64 ``[N,T]``, the batch's
+        ``align_pos``): only those rows of the block are computed (the alignment loss reads no other, v10:1075-1076);
+        the rest of the block is zero."""
         if head_mask is not None:
             raise NotImplementedError("head_mask is always None on the ModCR path")
         if encoder_history_states:
@@ -68,7 +70,8 @@ class SeqBertImgModel(_EncoderModelBase):
         ps, names, params = self._store()
         run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, 0,
                          is_seq=True, cbits=cbits, cwords=cwords, chunk_id=chunk_id, max_chunks=max_chunks,
-                         want_block=_want_align_block)
+                         want_block=_want_align_block,
+                         align_rows=None if _align_rows is None else _align_rows.to(torch.int64).contiguous())
         run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
                                cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 2 << 20)
         seq_out, pooled, chunk_hidden, block = EncoderFn.apply(run, 0, *params)
@@ -114,6 +117,9 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         self.classifier = nn.Linear(H, 2)
         self.cls_loss_fct = nn.CrossEntropyLoss()
         self._head_store = None
+        # True: the text->region block is computed on the aligned rows only (all the loss reads); False materialises the
+        # whole [N,T,R] block (``last_align_block`` then equals the reference's `attention_weights` everywhere)
+        self.sparse_align_block = True
 
     # ------------------------------------------------------------------ plumbing
     def _head_params(self):
@@ -126,7 +132,7 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         return ps, list(named.keys()), list(named.values())
 
     def _encode(self, input_ids, img_feat, input_mask, token_type_ids, position_ids, encoder_history_states, offsets,
-                chunk_attention_mask, gather_index, want_block):
+                chunk_attention_mask, gather_index, want_block, align_rows=None):
         N, T = input_ids.shape
         g = self.global_enc(input_ids, img_feats=img_feat, attention_mask=input_mask, position_ids=position_ids,
                             token_type_ids=token_type_ids, head_mask=None,
@@ -134,7 +140,8 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         (s_out, s_pool, att), chunk_hidden = self.seq_enc(
             input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
             attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
-            head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
+            head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block,
+            _align_rows=align_rows)
         ps, names, params = self._head_params()
         cfg = engine_cfg(self.global_enc.config)
         cfg["n_cls_layers"] = self.cls_layer_num
@@ -160,7 +167,8 @@ class ChunkAlign_CLS_enc4_align(nn.Module):
         here the host sync is left to the caller)."""
         want_block = total_label is not None
         cls, att = self._encode(input_ids, img_feat, input_mask, token_type_ids, position_ids, encoder_history_states,
-                                offsets, chunk_attention_mask, gather_index, want_block)
+                                offsets, chunk_attention_mask, gather_index, want_block,
+                                align_pos if (want_block and self.sparse_align_block) else None)
         loss_cls_0, logits, mp, pred, matched_0 = ScorerFn.apply(
             cls, self.classifier.weight, self.classifier.bias, label.long().contiguous(), None, 2, self.num_labels, True)
         self.last_logits, self.last_logit_expl, self.last_pred = logits, mp, pred
@@ -267,7 +275,8 @@ class ChunkAlign_CLS_enc4_align_ensemble(nn.Module):
             (s_out, s_pool, att), chunk_hidden = self.seq_enc(
                 input_ids, img_feats=img_feat, img_mask=input_mask[:, T:], input_mask=input_mask,
                 attention_mask=chunk_attention_mask, position_ids=position_ids, token_type_ids=token_type_ids,
-                head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block)
+                head_mask=None, offsets=offsets, gather_index=gather_index, _want_align_block=want_block,
+                _align_rows=align_pos if want_block else None)
             align_loss = None
             if want_block:
                 align_loss, _ = AlignLossFn.apply(att.align_block, align_pos, total_label)

@@ -118,7 +118,7 @@ def img_embed_ln_bwd(dy, dymap, packed, pre, mean, rstd, gamma, use_ln, dpre, dW
 
 # --------------------------------------------------------------------------- attention
 def _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, dctx=None,
-               dalign=None, dqkv=None, dpkv=None, dq_ws=None, drop=None):
+               dalign=None, dqkv=None, dpkv=None, dq_ws=None, drop=None, row_sel=None):
     d = AttnDesc()
     d.N, d.S, d.P, d.heads, d.T, d.mode = N, S, P, heads, T, mode
     d.scale = 0.125
@@ -127,18 +127,23 @@ def _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse
     d.dctx, d.dalign, d.dqkv, d.dpkv, d.dq_ws = _p(dctx), _p(dalign), _p(dqkv), _p(dpkv), _p(dq_ws)
     if drop is not None:                      # (seed tensor, site, p): attention-probability dropout
         d.drop_seed, d.drop_site, d.drop_p = _p(drop[0]), int(drop[1]), float(drop[2])
+    _chk(row_sel, I64, "row_sel (align_pos)")
+    d.row_sel = _p(row_sel)
     return d
 
 
-def prefix_attn_fwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, drop=None):
-    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, drop=drop)
+def prefix_attn_fwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img=None, drop=None,
+                    row_sel=None):
+    """``row_sel`` (int64 [N,T], the batch's ``align_pos``): only rows with a non-zero entry are written to ``probs_img``."""
+    d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, drop=drop,
+                   row_sel=row_sel)
     _lib.check(_lib.load().modcr_prefix_attn_fwd(C.byref(d), _stream()), "prefix_attn_fwd")
 
 
 def prefix_attn_bwd(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
-                    dpkv, dq_ws, drop=None):
+                    dpkv, dq_ws, drop=None, row_sel=None):
     d = _attn_desc(N, S, P, heads, T, mode, qkv, pkv, kbias, cbits, cwords, ctx, lse, probs_img, dctx, dalign, dqkv,
-                   dpkv, dq_ws, drop)
+                   dpkv, dq_ws, drop, row_sel)
     _lib.check(_lib.load().modcr_prefix_attn_bwd(C.byref(d), _stream()), "prefix_attn_bwd")
 
 
@@ -154,11 +159,12 @@ def chunk_mean_q(q, ld, N, S, H, chunk_id, T, max_chunks):
 
 
 # --------------------------------------------------------------------------- heads
-def align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, block, row_loss, out, N, T, R):
+def align_softmax_ce_fwd(probs, nl, heads, align_pos, total_label, block, row_loss, out, N, T, R, row_sel=None):
     _chk(align_pos, I64, "align_pos")
     _chk(total_label, I64, "total_label")
-    _lib.check(_lib.load().modcr_align_softmax_ce_fwd(_p(probs), nl, heads, _p(align_pos), _p(total_label), _p(block),
-                                                      _p(row_loss), _p(out), N, T, R, _stream()),
+    _chk(row_sel, I64, "row_sel (align_pos)")
+    _lib.check(_lib.load().modcr_align_softmax_ce_fwd(_p(probs), nl, heads, _p(align_pos), _p(total_label), _p(row_sel),
+                                                      _p(block), _p(row_loss), _p(out), N, T, R, _stream()),
                "align_softmax_ce_fwd")
 
 
@@ -348,6 +354,17 @@ def rowln_fwd(x, gamma, beta, y, mean, rstd, M, H, eps):
 def rowln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, H):
     _lib.check(_lib.load().modcr_rowln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma), _p(dbeta),
                                            M, H, _stream()), "rowln_bwd")
+
+
+def rows_place(src32, y, y32, ymap, M, H):
+    """fp32 rows [M,H] -> bf16 y (+ fp32 y32) at the physical rows of ``ymap``."""
+    _chk(src32, F32, "rows_place src")
+    _lib.check(_lib.load().modcr_rows_place(_p(src32), _p(y), _p(y32), ymap, M, H, _stream()), "rows_place")
+
+
+def rows_gather(dy, dymap, dst, M, H):
+    """bf16 gradient rows at ``dymap`` -> contiguous bf16 [M,H]."""
+    _lib.check(_lib.load().modcr_rows_gather(_p(dy), dymap, _p(dst), M, H, _stream()), "rows_gather")
 
 
 def key_bias(mask, kbias):

@@ -303,7 +303,9 @@ def _attn_ref(qkv, pkv, am, heads, T, dctx, dalign):
 
 @pytest.mark.parametrize("mode,P,S,T", [(0, 0, 178, 128), (0, 10, 178, 128), (1, 0, 178, 128), (2, 0, 178, 128),
                                         (0, 64, 256, 0), (2, 0, 300, 200), (0, 10, 300, 200), (0, 0, 40, 0),
-                                        (0, 3, 130, 0)])
+                                        (0, 3, 130, 0),
+                                        # BASELINE.json configs[3]: prefix-length sweep 0/10/32/64 at sequence 256
+                                        (0, 0, 256, 0), (0, 10, 256, 0), (0, 32, 256, 0)])
 def test_prefix_attention_fwd_bwd(mode, P, S, T):
     N, heads = 3, 4
     H = heads * 64
@@ -364,6 +366,59 @@ def test_prefix_attention_fwd_bwd(mode, P, S, T):
     assert nerr(dq, gq) < 2e-2, "dQ"
     if P > 0:
         assert nerr(dpkv, pkv_r.grad) < 2e-2, "dprefix"
+
+
+def test_prefix_attention_row_selection_of_the_alignment_block():
+    """``row_sel`` (= align_pos): the mode-2 kernels emit / consume the per-head text->region probabilities of the selected
+    rows only.  Selected rows are bit-identical to the dense run, unselected rows of the buffer are never written, and the
+    backward pass equals the dense one fed a gradient that is zero on the unselected rows."""
+    N, heads, S, T = 3, 4, 178, 128
+    H, R = heads * 64, S - T
+    qkv = rnd(N, S, 3 * H, seed=21)
+    key_mask = torch.ones(N, S, device=DEV)
+    lens = [T, T // 2, T - 7]
+    for n in range(N):
+        key_mask[n, lens[n]:T] = 0.0
+    cm = _chunk_mask(N, T, lens, 5).to(DEV)
+    cwords = (T + 31) // 32
+    kbias = torch.empty(N, S, device=DEV)
+    ops.key_bias(key_mask, kbias)
+    cbits = torch.zeros(N, T, cwords, dtype=torch.int32, device=DEV)
+    ops.chunk_bits(cm, cbits, N, T, cwords)
+    g = torch.Generator().manual_seed(5)
+    sel = (torch.rand(N, T, generator=g) < 0.04).to(torch.int64)
+    sel[0, 3] = 1
+    sel = sel.to(DEV)
+    outs = {}
+    for name, rs in (("dense", None), ("sparse", sel)):
+        ctx = torch.empty(N, S, H, dtype=torch.bfloat16, device=DEV)
+        lse = torch.empty(N, heads, S, device=DEV)
+        probs = torch.full((N, heads, T, R), -7.0, device=DEV)
+        ops.prefix_attn_fwd(N, S, 0, heads, T, 2, qkv, None, kbias, cbits, cwords, ctx, lse, probs, row_sel=rs)
+        dctx = rnd(N, S, H, seed=13)
+        dalign = (torch.randn(N, T, R, generator=g) * 0.5).to(DEV) * sel.unsqueeze(-1).float()
+        dqkv = torch.zeros(N, S, 3 * H, dtype=torch.bfloat16, device=DEV)
+        ws = torch.empty(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, device=DEV)
+        if name == "sparse":
+            dalign_in = outs["dense"][4]
+        else:
+            dalign_in = dalign
+        ops.prefix_attn_bwd(N, S, 0, heads, T, 2, qkv, None, kbias, cbits, cwords, ctx, lse, probs, dctx, dalign_in, dqkv,
+                            None, ws, row_sel=rs)
+        outs[name] = (ctx, lse, probs, dqkv, dalign_in)
+    d, s_ = outs["dense"], outs["sparse"]
+    assert torch.equal(d[0], s_[0]) and torch.equal(d[1], s_[1])
+    m4 = sel.bool().unsqueeze(1).expand(N, heads, T)
+    assert torch.equal(d[2][m4], s_[2][m4])                       # selected rows: identical
+    assert bool((s_[2][~m4] == -7.0).all())                       # the others were never written
+    assert nerr(s_[3], d[3]) < 1e-6 or torch.equal(s_[3], d[3])   # same gradient
+    # and the head-summed block of the selected rows only
+    blk_d = torch.empty(N, T, R, device=DEV)
+    blk_s = torch.empty(N, T, R, device=DEV)
+    ops.align_softmax_ce_fwd(d[2], 1, heads, None, None, blk_d, None, None, N, T, R)
+    ops.align_softmax_ce_fwd(s_[2], 1, heads, None, None, blk_s, None, None, N, T, R, row_sel=sel)
+    assert torch.equal(blk_d[sel.bool()], blk_s[sel.bool()]) and float(blk_s[~sel.bool()].abs().max()) == 0.0
+    torch.testing.assert_close(blk_d, d[2].sum(1), atol=1e-6, rtol=1e-6)
 
 
 def test_chunk_mean_q_matches_index_add_gather():
@@ -868,3 +923,26 @@ def test_gemm_epilogue_dropout_and_layernorm_masked_gradient():
     assert nerr(dx, x.grad) < 1e-2
     assert nerr(dxm, x.grad * keep) < 1e-2
     assert nerr(dbias, (x.grad * keep).sum(0)) < 1e-2
+
+
+def test_multi_copy_gathers_and_scatters_gradient_buckets():
+    """modcr_multi_copy (csrc/optim.cu): fp32 <-> bf16, scale, odd lengths and unaligned slots, > 64 tensors."""
+    g = torch.Generator().manual_seed(9)
+    sizes = [768 * 768, 3072, 7, 1, 30567 * 8 + 3, 2, 8191, 8193] + [5 + i for i in range(70)]
+    srcs = [torch.randn(n, generator=g).to(DEV) for n in sizes]
+    flat = torch.full((sum(sizes) + 16,), float("nan"), dtype=torch.bfloat16, device=DEV)
+    views, off = [], 1                                   # deliberately unaligned first slot
+    for n in sizes:
+        views.append(flat[off:off + n])
+        off += n
+    ops.multi_copy(srcs, views, 0.5)
+    for s_, v in zip(srcs, views):
+        assert torch.equal(v, (s_ * 0.5).to(torch.bfloat16))
+    back = [torch.empty_like(s_) for s_ in srcs]
+    ops.multi_copy(views, back, 2.0)
+    for s_, b_ in zip(srcs, back):
+        assert torch.equal(b_, (s_ * 0.5).to(torch.bfloat16).float() * 2.0)
+    f32 = [torch.empty_like(s_) for s_ in srcs[:5]]
+    ops.multi_copy(srcs[:5], f32)
+    assert all(torch.equal(a, b) for a, b in zip(srcs[:5], f32))
+    assert bool(torch.isnan(flat[0].float())) and bool(torch.isnan(flat[off:].float()).all())   # nothing outside the slots

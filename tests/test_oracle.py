@@ -384,3 +384,44 @@ def test_abstract_specific_restatement_matches_live_reference():
     named = dict(m.named_parameters())
     for k in watch:
         torch.testing.assert_close(named[k].grad, sdr[k].grad, atol=1e-7, rtol=1e-4)
+
+
+def test_standin_roberta_oracle_matches_huggingface_roberta():
+    """SURVEY 8 f4 (parity UNPINNED vs the reference's missing local_transformers blob): the stand-in oracle of the
+    language-model side (oracle/standin_roberta.py) against HuggingFace RobertaModel of the installed transformers --
+    embeddings incl. the padding-aware position ids, prompt embeddings concatenated after the embedding layer, the
+    post-LN encoder, the pooler."""
+    import standin_roberta
+    from transformers import RobertaConfig, RobertaModel
+    hc = RobertaConfig(vocab_size=120, hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256,
+                       max_position_embeddings=40, type_vocab_size=1, pad_token_id=1, hidden_dropout_prob=0.0,
+                       attention_probs_dropout_prob=0.0, layer_norm_eps=1e-5)
+    hc._attn_implementation = "eager"
+    torch.manual_seed(3)
+    hf = RobertaModel(hc, add_pooling_layer=True).eval()
+    sd = {k: v.clone() for k, v in hf.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    ids = torch.randint(3, 120, (3, 12), generator=g)
+    ids[1, 8:] = 1
+    ids[2, 5:] = 1
+    am = (ids != 1).float()
+    prompt = torch.randn(3, 4, 128, generator=g)
+    pmask = torch.ones(3, 4)
+    cfg = dict(num_hidden_layers=3, num_attention_heads=2, layer_norm_eps=1e-5, pad_token_id=1)
+    with torch.no_grad():
+        # no prompts: the whole HF model, untouched
+        ref = hf(input_ids=ids, attention_mask=am)
+        seq, pooled = standin_roberta.roberta_prompt_forward(sd, cfg, ids, None, am)
+        torch.testing.assert_close(seq * am.unsqueeze(-1), ref.last_hidden_state * am.unsqueeze(-1), atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(pooled, ref.pooler_output, atol=2e-5, rtol=1e-4)
+        # prompts: HF's own embedding layer / encoder / pooler objects around the concatenation
+        e = hf.embeddings(input_ids=ids, token_type_ids=torch.zeros_like(ids))
+        x = torch.cat([prompt, e], 1)
+        ext = (1.0 - torch.cat([pmask, am], 1))[:, None, None, :] * -10000.0
+        out = hf.encoder(x, attention_mask=ext)
+        hseq = out[0] if isinstance(out, tuple) else out.last_hidden_state
+        hpool = hf.pooler(hseq)
+        seq, pooled = standin_roberta.roberta_prompt_forward(sd, cfg, ids, None, am, prompt, pmask)
+        keep = torch.cat([pmask, am], 1).unsqueeze(-1)
+        torch.testing.assert_close(seq * keep, hseq * keep, atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(pooled, hpool, atol=2e-5, rtol=1e-4)
