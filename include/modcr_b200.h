@@ -57,7 +57,8 @@ size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
  *   img_embedding   modeling/modeling_transfomres.py:676-681
  * and their dgrad / wgrad in the backward pass (autograd of the reference).
  *   a_mn = 0: A stored [M,K];  a_mn = 1: A stored [K,M]      (same for B with N)
- *   act: 0 none, 1 GELU(erf), 2 tanh, 3 ReLU;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in)
+ *   act: 0 none, 1 GELU(erf), 2 tanh, 3 ReLU;  in_op: 0 none, 1 C = f(acc) + in, 2 C = f(acc) * GELU'(in),
+ *   3 C = f(acc) + LayerNorm(in) (see in_mean .. in_beta below)
  *   aux: optional bf16 copy of the pre-activation;  c_fp32 + accumulate / split_k: wgrad
  *   a_colsum (a_mn = 1 only): a_colsum[m] += sum_k A[k,m], fp32 -- the bias gradient dY^T 1 of the Linear whose weight
  *   gradient dW = dY^T X this call computes, summed from the dY tiles the kernel stages anyway (replaces the reference's
@@ -85,6 +86,15 @@ typedef struct modcr_gemm_desc {
   const uint32_t* drop_seed;
   uint32_t drop_site;
   float drop_p;
+  /* in_op = 3 (fp32 C and fp32 epi_in only): the residual is LayerNorm(epi_in), rebuilt in the epilogue from the
+   * PRE-LayerNorm tensor the previous block keeps for its backward pass, its row statistics and the LayerNorm's affine
+   * parameters:  C = f(acc + bias) + (in[m,n] - in_mean[m]) * in_rstd[m] * in_gamma[n] + in_beta[n].
+   * BertSelfOutput / BertOutput (a_transformers/modeling_bert.py:369-373, 447-451) add `input_tensor`, which IS the previous
+   * LayerNorm's output: this keeps the residual stream in fp32 without ever writing an fp32 copy of a LayerNorm output. */
+  const float* in_mean;
+  const float* in_rstd;
+  const float* in_gamma;
+  const float* in_beta;
 } modcr_gemm_desc;
 int modcr_gemm(const modcr_gemm_desc* d, void* stream);
 
@@ -131,7 +141,9 @@ int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* in
 int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t Dpad, const void* W,
                            const float* bias, const float* gamma, const float* beta, int32_t use_ln, float eps,
                            void* packed, float* pre, void* y, float* y32, modcr_rowmap ymap, float* mean,
-                           float* rstd, int32_t H, void* stream);
+                           float* rstd, int32_t H, const float* extra32, void* stream);
+/* extra32 (fp32 [rows,H] or NULL): added to the projection inside the GEMM epilogue before the LayerNorm -- the
+ * type + box-position term of BertImgModel_gtToken (modcr_pos_type_embed_fwd; modeling/modeling_bert.py:393). */
 /* dW_pad: fp32 [H, Dpad] (overwritten); dbias/dgamma/dbeta accumulate; dpre: bf16 [rows, H] workspace. */
 int modcr_img_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const void* packed, const float* pre,
                            const float* mean, const float* rstd, const float* gamma, int32_t use_ln, void* dpre,
@@ -342,6 +354,19 @@ int modcr_rowln_fwd(const void* x, const float* gamma, const float* beta, void* 
                     int32_t H, float eps, void* stream);
 int modcr_rowln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                     float* dgamma, float* dbeta, int32_t M, int32_t H, void* stream);
+/* Box-position + token-type part of the region embedding of BertImgModel_gtToken (modeling/modeling_bert.py:312-316,
+ * 390-394):  out[r,:] = img_token_type_embeddings[tt[r]] + LayerNorm_pos(img_pos_linear(pos[r,0:7])), fp32 [rows,H].
+ * K = 7 is no tensor-core shape (one warp per row, fp32); `out` is then the fp32 epilogue input (in_op 1) of the 2054 -> H
+ * feature-projection GEMM, so the three-way sum of :393 happens in that GEMM's epilogue.  mean / rstd [rows] are the
+ * statistics of LayerNorm_pos for the backward pass, which takes d = gradient of the sum (bf16 [rows,H]) and accumulates
+ * dW_pos [H,7], db_pos, dgamma_pos, dbeta_pos [H], dtype_emb [2,H] (all fp32, pre-zeroed by the caller). */
+int modcr_pos_type_embed_fwd(const float* pos, const int64_t* tt, const float* W_pos, const float* b_pos,
+                             const float* gamma_pos, const float* beta_pos, const float* type_emb, float* out,
+                             float* mean, float* rstd, int32_t rows, int32_t H, float eps, void* stream);
+int modcr_pos_type_embed_bwd(const void* d, const float* pos, const int64_t* tt, const float* W_pos, const float* b_pos,
+                             const float* gamma_pos, const float* mean, const float* rstd, float* dW_pos, float* db_pos,
+                             float* dgamma_pos, float* dbeta_pos, float* dtype_emb, int32_t rows, int32_t H, void* stream);
+
 /* Rows that enter the encoder already embedded (the prompt embeddings of the language-model side,
  * modeling/modeling_ensemble.py:498-503 `prompt_embeddings=`): rows_place writes fp32 rows src [M,H] into the bf16
  * hidden-state buffer y (and its fp32 twin y32) at the physical rows given by ymap; rows_gather is its adjoint on the

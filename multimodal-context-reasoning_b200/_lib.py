@@ -20,7 +20,8 @@ class GemmDesc(C.Structure):
                 ("M", c_i32), ("N", c_i32), ("K", c_i32),
                 ("alpha", c_float), ("bias", c_void_p), ("act", c_i32),
                 ("aux", c_void_p), ("ldaux", c_i64), ("epi_in", c_void_p), ("ld_in", c_i64), ("in_op", c_i32),
-                ("a_colsum", c_void_p), ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float)]
+                ("a_colsum", c_void_p), ("drop_seed", c_void_p), ("drop_site", C.c_uint32), ("drop_p", c_float),
+                ("in_mean", c_void_p), ("in_rstd", c_void_p), ("in_gamma", c_void_p), ("in_beta", c_void_p)]
 
 
 class RowMap(C.Structure):
@@ -71,7 +72,8 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
                                c_i64, c_void_p],
     "modcr_img_embed_ln_fwd": [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_float,
-                               c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_void_p],
+                               c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p, c_i32, c_void_p,
+                               c_void_p],
     "modcr_img_embed_ln_bwd": [c_void_p, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_void_p],
     "modcr_prefix_attn_fwd": [C.POINTER(AttnDesc), c_void_p],
@@ -108,6 +110,10 @@ SIGNATURES = {
     "modcr_rowln_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                         c_void_p],
     "modcr_tanh_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "modcr_pos_type_embed_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_i32, c_i32, c_float, c_void_p],
+    "modcr_pos_type_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p],
     "modcr_rows_place": [c_void_p, c_void_p, c_void_p, RowMap, c_i32, c_i32, c_void_p],
     "modcr_rows_gather": [c_void_p, RowMap, c_void_p, c_i32, c_i32, c_void_p],
     "modcr_key_bias": [c_void_p, c_void_p, c_i64, c_void_p],

@@ -76,6 +76,7 @@ int modcr_gemm(const modcr_gemm_desc* d, void* stream) {
   g.aux = d->aux; g.ldaux = d->ldaux; g.epi_in = d->epi_in; g.ld_in = d->ld_in; g.in_op = d->in_op;
   g.a_colsum = d->a_colsum;
   g.drop_seed = d->drop_seed; g.drop_site = d->drop_site; g.drop_p = d->drop_p;
+  g.in_mean = d->in_mean; g.in_rstd = d->in_rstd; g.in_gamma = d->in_gamma; g.in_beta = d->in_beta;
   return modcr::gemm_launch(g, S(stream));
 }
 
@@ -115,7 +116,7 @@ int modcr_txt_embed_ln_bwd(const void* dy, modcr_rowmap dymap, const int64_t* in
 int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t Dpad, const void* W,
                            const float* bias, const float* gamma, const float* beta, int32_t use_ln, float eps,
                            void* packed, float* pre, void* y, float* y32, modcr_rowmap ymap, float* mean, float* rstd,
-                           int32_t H, void* stream) {
+                           int32_t H, const float* extra32, void* stream) {
   ARCH_OR_RETURN();
   if (rows <= 0 || D <= 0 || Dpad < D || Dpad % 8 != 0 || rows > 0x7fffffff) {
     modcr::set_error("img_embed_ln_fwd: bad shape rows=%lld D=%d Dpad=%d", (long long)rows, D, Dpad);
@@ -129,6 +130,9 @@ int modcr_img_embed_ln_fwd(const float* feats, int64_t rows, int32_t D, int32_t 
   g.M = (int)rows; g.N = H; g.K = Dpad;
   g.bias = bias;
   g.C = pre; g.ldc = H; g.c_fp32 = 1;   // fp32 pre-LayerNorm activations
+  if (extra32 != nullptr) {             // + type / box-position term, summed in the epilogue
+    g.epi_in = extra32; g.ld_in = H; g.in_op = 1;
+  }
   rc = modcr::gemm_launch(g, S(stream));
   if (rc) return rc;
   if (!use_ln)  // config without use_img_layernorm (modeling_transfomres.py:676-680): the projection is the embedding
@@ -351,6 +355,19 @@ int modcr_rowln_bwd(const void* dy, const void* x, const float* mean, const floa
 int modcr_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
   ARCH_OR_RETURN();
   return modcr::tanh_bwd(dy, y, dx, n, S(stream));
+}
+int modcr_pos_type_embed_fwd(const float* pos, const int64_t* tt, const float* W_pos, const float* b_pos,
+                             const float* gamma_pos, const float* beta_pos, const float* type_emb, float* out,
+                             float* mean, float* rstd, int32_t rows, int32_t H, float eps, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::pos_type_fwd(pos, tt, W_pos, b_pos, gamma_pos, beta_pos, type_emb, out, mean, rstd, rows, H, eps, S(stream));
+}
+int modcr_pos_type_embed_bwd(const void* d, const float* pos, const int64_t* tt, const float* W_pos, const float* b_pos,
+                             const float* gamma_pos, const float* mean, const float* rstd, float* dW_pos, float* db_pos,
+                             float* dgamma_pos, float* dbeta_pos, float* dtype_emb, int32_t rows, int32_t H, void* stream) {
+  ARCH_OR_RETURN();
+  return modcr::pos_type_bwd(d, pos, tt, W_pos, b_pos, gamma_pos, mean, rstd, dW_pos, db_pos, dgamma_pos, dbeta_pos, dtype_emb,
+                             rows, H, S(stream));
 }
 int modcr_rows_place(const float* src, void* y, float* y32, modcr_rowmap ymap, int32_t M, int32_t H, void* stream) {
   ARCH_OR_RETURN();

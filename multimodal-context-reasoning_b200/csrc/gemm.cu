@@ -52,6 +52,11 @@ struct GemmParams {
   const uint32_t* drop_seed;
   uint32_t drop_site, drop_thr;
   float drop_inv;
+  // in_op 3: residual = LayerNorm(in) rebuilt from the pre-LayerNorm tensor, its row statistics and the affine parameters
+  const float* in_mean;
+  const float* in_rstd;
+  const float* in_gamma;
+  const float* in_beta;
 };
 
 template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
@@ -72,6 +77,10 @@ struct Cfg {
   static constexpr int NCHUNK = BN / CHUNK_COLS;
   static constexpr int NBUF = 2;                      // out (and aux) buffers per group
   static constexpr int IN_DEPTH = 2;                  // epilogue-input buffers per group
+  // (A variant of the fp32-residual epilogue without shared-memory staging -- every thread reading / writing the 64
+  // contiguous bytes of its own row straight from / to global memory -- was measured SLOWER, 79 vs 50 us for the K = 768
+  // dense-output GEMM: a row-per-thread 128-bit access touches 32 different lines per warp instruction and the L1 /
+  // LSU wavefronts, not the barriers, become the limit.  profiles/r02_bench_direct_epilogue.log)
   static constexpr int OUT_BUFS = 2 * NBUF * (HAS_AUX ? 2 : 1);
   static constexpr int IN_BUFS = HAS_IN ? 2 * IN_DEPTH : 0;
   static constexpr int BIAS_BYTES = 2 * 128 * 4;      // per group: the 128 bias values of its chunks of one tile
@@ -358,11 +367,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const bool add_bias = (p.bias != nullptr) && (tc.split == 0);
+      const bool in_ln = OUT_F32 && HAS_IN && p.in_mean != nullptr;   // uniform
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (in_ln && m0 + row < p.M) {
+        ln_mean = __ldg(p.in_mean + m0 + row);
+        ln_rstd = __ldg(p.in_rstd + m0 + row);
+      }
       if (add_bias) {
         // stage this tile's bias values of the group's chunks (thread i: chunk g + 2 (i / CC), column i % CC); every
         // thread of the group is past its last bias read of the previous tile (it passed that chunk's barrier)
         const int col = tc.n * BN + (g + 2 * (gt / CC)) * CC + (gt % CC);
-        sBias[gt] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        sBias[gt] = (add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
         named_bar_sync(bar_id, 128);
       }
       mbar_wait(&tfull[as], aphase);
@@ -435,13 +450,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t in_s = smem_u32(sIn + bi * C::CHUNK_BYTES);
           mbar_wait(&infull[bi], (cnt / C::IN_DEPTH) & 1);
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
+            if (in_ln && n0 < p.N) {   // ... + LayerNorm(in): same arithmetic as ln_fwd_kernel, (x - mean) * rstd * gamma + beta
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 f = lds128f(in_s + sw64_offset(row, j));
-              v[4 * j + 0] += f.x;
-              v[4 * j + 1] += f.y;
-              v[4 * j + 2] += f.z;
-              v[4 * j + 3] += f.w;
+              for (int j = 0; j < 4; ++j) {
+                const float4 f = lds128f(in_s + sw64_offset(row, j));
+                // gamma / beta: warp-uniform 128-bit loads (one L1 line per chunk; staging them in shared memory next to
+                // the bias would cost this kernel a pipeline stage)
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.in_gamma + n0 + 4 * j));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.in_beta + n0 + 4 * j));
+                v[4 * j + 0] += (f.x - ln_mean) * ln_rstd * g4.x + b4.x;
+                v[4 * j + 1] += (f.y - ln_mean) * ln_rstd * g4.y + b4.y;
+                v[4 * j + 2] += (f.z - ln_mean) * ln_rstd * g4.z + b4.z;
+                v[4 * j + 3] += (f.w - ln_mean) * ln_rstd * g4.w + b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 f = lds128f(in_s + sw64_offset(row, j));
+                v[4 * j + 0] += f.x;
+                v[4 * j + 1] += f.y;
+                v[4 * j + 2] += f.z;
+                v[4 * j + 3] += f.w;
+              }
             }
           } else if constexpr (!OUT_F32) {
 #pragma unroll
@@ -582,6 +612,14 @@ static int launch_n(const GemmDesc& g, cudaStream_t stream) {
   p.in_op = g.in_op;
   p.reduce_add = (g.accumulate || split > 1) ? 1 : 0;
   p.a_colsum = g.a_colsum;
+  p.in_mean = nullptr; p.in_rstd = nullptr; p.in_gamma = nullptr; p.in_beta = nullptr;
+  if (g.in_op == 3) {
+    if (!(OUT_F32 && HAS_IN) || g.N % 16 != 0 || g.in_mean == nullptr || g.in_rstd == nullptr || g.in_gamma == nullptr || g.in_beta == nullptr) {
+      set_error("gemm: in_op 3 (LayerNorm of the epilogue input) needs fp32 C / input and the four LayerNorm pointers");
+      return MODCR_ERR_UNSUPPORTED;
+    }
+    p.in_mean = g.in_mean; p.in_rstd = g.in_rstd; p.in_gamma = g.in_gamma; p.in_beta = g.in_beta;
+  }
   p.drop_seed = g.drop_seed; p.drop_site = g.drop_site; p.drop_thr = 0; p.drop_inv = 1.f;
   if (g.drop_p > 0.f) {
     if (g.drop_seed == nullptr || !(g.drop_p < 1.f) || (double)g.M * g.N >= 4294967296.0 || g.split_k > 1 || g.accumulate) {
@@ -658,8 +696,8 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
       set_error("gemm: fp32 output does not support an aux output");
       return MODCR_ERR_UNSUPPORTED;
     }
-    if (has_in) {  // fp32 residual stream: C(fp32) = acc + bias + in(fp32)
-      if (g.in_op != 1 || g.a_mn || g.b_mn || g.accumulate || g.split_k > 1) {
+    if (has_in) {  // fp32 residual stream: C(fp32) = acc + bias + in(fp32)   [in_op 3: + LayerNorm(in)]
+      if ((g.in_op != 1 && g.in_op != 3) || g.a_mn || g.b_mn || g.accumulate || g.split_k > 1) {
         set_error("gemm: fp32 epilogue input supports only in_op=1 on the NT layout without split-K");
         return MODCR_ERR_UNSUPPORTED;
       }

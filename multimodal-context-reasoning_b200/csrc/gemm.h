@@ -23,7 +23,12 @@ struct GemmDesc {
   int64_t ldaux = 0;
   const void* epi_in = nullptr;  // optional bf16 [M,N] epilogue input tile
   int64_t ld_in = 0;
-  int in_op = 0;             // 1: C = f(acc) + in ; 2: C = f(acc) * gelu'(in)
+  int in_op = 0;             // 1: C = f(acc) + in ; 2: C = f(acc) * gelu'(in) ;
+                             // 3 (fp32 in / out): C = f(acc) + LayerNorm(in) = f(acc) + (in - mean[m]) rstd[m] gamma[n] + beta[n]
+  const float* in_mean = nullptr;   // in_op 3: fp32 [M] row statistics of `in` ...
+  const float* in_rstd = nullptr;
+  const float* in_gamma = nullptr;  // ... and fp32 [N] affine parameters of the LayerNorm that produced the residual
+  const float* in_beta = nullptr;
   float* a_colsum = nullptr; // optional fp32 [M]: += sum_k A[k,m] (A MN-major only; the bias gradient of a wgrad)
   // training-mode dropout of f(acc + bias) before the epilogue input: mask = hash(*drop_seed, drop_site, m * N + n)
   const uint32_t* drop_seed = nullptr;

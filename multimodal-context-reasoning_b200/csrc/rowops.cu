@@ -117,6 +117,189 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x,
   }
 }
 
+// ---------------------------------------------------------------------------- box-position + type embedding (g1)
+// BertImgModel_gtToken (modeling/modeling_bert.py:312-316, 390-394): every region row gets, next to its 2054 -> H feature
+// projection,   e[j] = img_token_type_embeddings[tt][j] + LayerNorm_pos(img_pos_linear(pos))[j]
+// with pos the 7 box numbers of the region.  K = 7 is no tensor-core shape: one warp per row computes the 7-term
+// products in fp32 (W_pos [H,7] staged transposed in shared memory), normalises and adds the type row; the result is the
+// fp32 epilogue input of the feature-projection GEMM, which adds it to acc + bias (modcr_gemm in_op 1).
+constexpr int POSD = 7;
+
+__global__ void __launch_bounds__(256) pos_type_fwd_kernel(const float* __restrict__ pos, const int64_t* __restrict__ tt,
+                                                           const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                           const float* __restrict__ gam, const float* __restrict__ bet,
+                                                           const float* __restrict__ type_emb, float* __restrict__ out,
+                                                           float* __restrict__ mean, float* __restrict__ rstd, int rows, int H,
+                                                           float eps) {
+  extern __shared__ float sW[];   // [POSD][H] transposed, then bias [H]
+  for (int i = threadIdx.x; i < H * POSD; i += blockDim.x) sW[(i % POSD) * H + i / POSD] = __ldg(Wp + i);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sW[POSD * H + i] = __ldg(bp + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += gridDim.x * (blockDim.x >> 5)) {
+    float pv[POSD];
+#pragma unroll
+    for (int k = 0; k < POSD; ++k) pv[k] = __ldg(pos + (size_t)row * POSD + k);
+    float t[LN_MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = sW[POSD * H + c + j];
+#pragma unroll
+          for (int k = 0; k < POSD; ++k) a = fmaf(pv[k], sW[k * H + c + j], a);
+          t[i][j] = a;
+          s += a;
+        }
+      }
+    const float mu = warp_sum(s) / (float)H;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = t[i][j] - mu;
+          v = fmaf(d, d, v);
+        }
+      }
+    const float rs = rsqrtf(warp_sum(v) / (float)H + eps);
+    const float* te = type_emb + (size_t)(tt != nullptr ? tt[row] : 0) * H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+        float g[8], b[8], e[8], o[8];
+        load8f(gam + c, g);
+        load8f(bet + c, b);
+        load8f(te + c, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (t[i][j] - mu) * rs * g[j] + b[j] + e[j];
+        store8f(out + (size_t)row * H + c, o);
+      }
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+  }
+}
+
+// backward of the above from d(sum) [rows,H] (bf16, = the gradient of the feature-projection GEMM's output):
+//   dtype_emb[tt] += d ; through LayerNorm_pos: dgamma += d * that, dbeta += d, dt = rstd (g - mean(g) - that mean(g that)),
+//   g = d * gamma ; dW_pos[j,k] += dt[j] pos[k] ; db_pos[j] += dt[j]
+// Column sums are kept per CTA in shared memory over its rows and leave with one atomicAdd per element and CTA.
+__global__ void __launch_bounds__(256) pos_type_bwd_kernel(const bf16* __restrict__ d, const float* __restrict__ pos,
+                                                           const int64_t* __restrict__ tt, const float* __restrict__ Wp,
+                                                           const float* __restrict__ bp, const float* __restrict__ gam,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float* __restrict__ dWp, float* __restrict__ dbp,
+                                                           float* __restrict__ dgam, float* __restrict__ dbet,
+                                                           float* __restrict__ dtype, int rows, int H) {
+  extern __shared__ float sm[];
+  float* sW = sm;                      // [POSD][H] + bias [H]
+  float* acc = sW + (POSD + 1) * H;    // dW^T [POSD][H] | db [H] | dgam [H] | dbet [H] | dtype [2][H]
+  const int nacc = (POSD + 5) * H;
+  for (int i = threadIdx.x; i < H * POSD; i += blockDim.x) sW[(i % POSD) * H + i / POSD] = __ldg(Wp + i);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) sW[POSD * H + i] = __ldg(bp + i);
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nv = H >> 8;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += gridDim.x * (blockDim.x >> 5)) {
+    float pv[POSD];
+#pragma unroll
+    for (int k = 0; k < POSD; ++k) pv[k] = __ldg(pos + (size_t)row * POSD + k);
+    const float mu = mean[row], rs = rstd[row];
+    const int ty = tt != nullptr ? (int)tt[row] : 0;
+    float xh[LN_MAXV][8], g[LN_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+        float dv[8], gm[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(d + (size_t)row * H) + lane + 32 * i), dv);
+        load8f(gam + c, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = sW[POSD * H + c + j];
+#pragma unroll
+          for (int k = 0; k < POSD; ++k) a = fmaf(pv[k], sW[k * H + c + j], a);
+          xh[i][j] = (a - mu) * rs;
+          g[i][j] = dv[j] * gm[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+          atomicAdd(acc + (POSD + 1) * H + c + j, dv[j] * xh[i][j]);   // dgamma
+          atomicAdd(acc + (POSD + 2) * H + c + j, dv[j]);              // dbeta
+          atomicAdd(acc + (POSD + 3 + ty) * H + c + j, dv[j]);         // dtype_emb[tt]
+        }
+      }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const int c = (lane + 32 * i) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dt = rs * (g[i][j] - s1 - xh[i][j] * s2);
+          atomicAdd(acc + POSD * H + c + j, dt);                       // db_pos
+#pragma unroll
+          for (int k = 0; k < POSD; ++k) atomicAdd(acc + k * H + c + j, dt * pv[k]);
+        }
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * POSD; i += blockDim.x) atomicAdd(dWp + i, acc[(i % POSD) * H + i / POSD]);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(dbp + i, acc[POSD * H + i]);
+    atomicAdd(dgam + i, acc[(POSD + 1) * H + i]);
+    atomicAdd(dbet + i, acc[(POSD + 2) * H + i]);
+    atomicAdd(dtype + i, acc[(POSD + 3) * H + i]);
+    atomicAdd(dtype + H + i, acc[(POSD + 4) * H + i]);
+  }
+}
+
+int pos_type_fwd(const float* pos, const int64_t* tt, const float* Wp, const float* bp, const float* gam, const float* bet,
+                 const float* type_emb, float* out, float* mean, float* rstd, int rows, int H, float eps, cudaStream_t st) {
+  if (rows <= 0 || H <= 0 || H % 256 != 0 || H > 1024) {
+    set_error("pos_type_fwd: bad shape rows=%d H=%d (H a multiple of 256, <= 1024)", rows, H);
+    return MODCR_ERR_SHAPE;
+  }
+  const size_t smem = (size_t)(POSD + 1) * H * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pos_type_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  const int blocks = rows < 8 * 148 ? (rows + 7) / 8 : 148 * 2;
+  pos_type_fwd_kernel<<<blocks, 256, smem, st>>>(pos, tt, Wp, bp, gam, bet, type_emb, out, mean, rstd, rows, H, eps);
+  return check_launch("pos_type_fwd");
+}
+
+int pos_type_bwd(const void* d, const float* pos, const int64_t* tt, const float* Wp, const float* bp, const float* gam,
+                 const float* mean, const float* rstd, float* dWp, float* dbp, float* dgam, float* dbet, float* dtype,
+                 int rows, int H, cudaStream_t st) {
+  if (rows <= 0 || H <= 0 || H % 256 != 0 || H > 1024) {
+    set_error("pos_type_bwd: bad shape rows=%d H=%d", rows, H);
+    return MODCR_ERR_SHAPE;
+  }
+  const size_t smem = (size_t)((POSD + 1) + (POSD + 5)) * H * sizeof(float);   // 80 KB at H = 1024
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(pos_type_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr = true;
+  }
+  const int blocks = rows < 8 * 148 ? (rows + 7) / 8 : 148;
+  pos_type_bwd_kernel<<<blocks, 256, smem, st>>>((const bf16*)d, pos, tt, Wp, bp, gam, mean, rstd, dWp, dbp, dgam, dbet, dtype,
+                                                 rows, H);
+  return check_launch("pos_type_bwd");
+}
+
 // ---------------------------------------------------------------------------- LayerNorm bwd
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias += sum_rows dx (bias of the Linear

@@ -36,6 +36,12 @@ int copy_rows(const void* src, int64_t src_seq_stride, int srow0, void* dst, int
               int nrows, int H, int accumulate, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* y, int64_t n, cudaStream_t st);
 int tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);
+// box-position projection (7 -> H) + LayerNorm + type embedding of BertImgModel_gtToken (modeling_bert.py:312-316, 390-394)
+int pos_type_fwd(const float* pos, const int64_t* tt, const float* Wp, const float* bp, const float* gam, const float* bet,
+                 const float* type_emb, float* out, float* mean, float* rstd, int rows, int H, float eps, cudaStream_t st);
+int pos_type_bwd(const void* d, const float* pos, const int64_t* tt, const float* Wp, const float* bp, const float* gam,
+                 const float* mean, const float* rstd, float* dWp, float* dbp, float* dgam, float* dbet, float* dtype,
+                 int rows, int H, cudaStream_t st);
 int rows_place(const float* src, void* y, float* y32, RowMap ymap, int M, int H, cudaStream_t st);
 int rows_gather(const void* dy, RowMap dymap, void* dst, int M, int H, cudaStream_t st);
 int relu_bwd(const void* dy, const void* y, void* dx, int64_t n, cudaStream_t st);

@@ -181,10 +181,42 @@ def wgrad(dY, X, out_f, in_f, rows, ldy=None, ldx=None, out=None, zeroed=None, b
     return dW
 
 
+# -------------------------------------------------------------------------------------------- fp32 residual stream
+class LnRes:
+    """An fp32 residual that is the OUTPUT OF A LAYERNORM, kept as what its backward pass stores anyway -- the pre-LayerNorm
+    tensor, its row statistics and the affine parameters -- instead of a second, fp32 copy of the output.  The dense-output
+    GEMM that adds it (BertSelfOutput / BertOutput: ``LayerNorm(dense(x) + input_tensor)``,
+    a_transformers/modeling_bert.py:369-373, 447-451) rebuilds ``(pre - mean) * rstd * gamma + beta`` in its epilogue
+    (``modcr_gemm`` in_op 3): 70 MB less written per LayerNorm at cfg-2, 48 LayerNorms per step."""
+    __slots__ = ("pre", "mean", "rstd", "gamma", "beta", "eps")
+
+    def __init__(self, pre, mean, rstd, gamma, beta, eps):
+        self.pre, self.mean, self.rstd, self.gamma, self.beta, self.eps = pre, mean, rstd, gamma, beta, eps
+
+
+def res_kw(res):
+    """Keyword arguments of ``ops.gemm`` that add the fp32 residual ``res`` (a dense fp32 tensor or an ``LnRes``)."""
+    if isinstance(res, LnRes):
+        return dict(epi_in=res.pre, in_ln=(res.mean, res.rstd, res.gamma.detach(), res.beta.detach()))
+    return dict(epi_in=res, in_op=1)
+
+
+def res_dense(res):
+    """The residual as a dense fp32 tensor (only the optional-residual paths of the chunk-aware encoder need it)."""
+    if not isinstance(res, LnRes):
+        return res
+    M, H = res.pre.shape
+    dev = res.pre.device
+    y, y32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
+    ops.layernorm_fwd(res.pre, res.gamma.detach(), res.beta.detach(), y, _empty((M,), F32, dev), _empty((M,), F32, dev), M, H,
+                      res.eps, y32=y32)
+    return y32
+
+
 # -------------------------------------------------------------------------------------------- FFN block
 def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save, drop=None, site=0):
     """BertIntermediate + BertOutput (a_transformers/modeling_bert.py:434-437, 447-451).
-    ``a`` is the bf16 tensor-core operand, ``a32`` the fp32 residual; returns ``(y, y32)``."""
+    ``a`` is the bf16 tensor-core operand, ``a32`` the fp32 residual (dense tensor or ``LnRes``); returns ``(y, LnRes)``."""
     dev = a.device
     W1, W2 = ps.bf16(pfx + "intermediate.dense.weight"), ps.bf16(pfx + "output.dense.weight")
     gact = _empty((M, I), BF16, dev)
@@ -193,17 +225,17 @@ def ffn_fwd(ps, pfx, a, a32, M, H, I, eps, save, drop=None, site=0):
     pre2 = _empty((M, H), F32, dev)                                         # fp32 residual stream
     if drop is not None and drop.p_hidden > 0.0:
         # BertOutput: LayerNorm(dropout(dense(y)) + x)  (a_transformers/modeling_bert.py:447-451)
-        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1,
-                 drop=(drop.seed, site, drop.p_hidden))
+        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"),
+                 drop=(drop.seed, site, drop.p_hidden), **res_kw(a32))
     else:
-        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), epi_in=a32, in_op=1)
-    y, y32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
+        ops.gemm(gact, W2, pre2, M, H, I, bias=ps.f32(pfx + "output.dense.bias"), **res_kw(a32))
+    y = _empty((M, H), BF16, dev)
     mean2, rstd2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
-    ops.layernorm_fwd(pre2, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), y, mean2,
-                      rstd2, M, H, eps, y32=y32)
+    g2_, b2_ = ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias")
+    ops.layernorm_fwd(pre2, g2_, b2_, y, mean2, rstd2, M, H, eps)
     if save is not None:
         save.update(a=a, u=u, gact=gact, pre2=pre2, mean2=mean2, rstd2=rstd2)
-    return y, y32
+    return y, LnRes(pre2, mean2, rstd2, g2_, b2_, eps)
 
 
 def ffn_bwd(ps, pfx, sv, dy, M, H, I, grads, z=None, drop=None, site=0):
@@ -268,18 +300,18 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     if drop is not None and drop.p_hidden > 0.0:
         # BertSelfOutput: LayerNorm(dropout(dense(ctx)) + x)  (a_transformers/modeling_bert.py:369-373)
         ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
-                 epi_in=x32, in_op=1, drop=(drop.seed, site + 1, drop.p_hidden))
+                 drop=(drop.seed, site + 1, drop.p_hidden), **res_kw(x32))
     else:
         ops.gemm(ctx, ps.bf16(pfx + "output.dense.weight"), pre1, M, H, H, bias=ps.f32(pfx + "output.dense.bias"),
-                 epi_in=x32, in_op=1)
-    a, a32 = _empty((M, H), BF16, dev), _empty((M, H), F32, dev)
+                 **res_kw(x32))
+    a = _empty((M, H), BF16, dev)
     mean1, rstd1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
-    ops.layernorm_fwd(pre1, ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias"), a, mean1,
-                      rstd1, M, H, eps, y32=a32)
+    g1_, b1_ = ps.f32(pfx + "output.LayerNorm.weight"), ps.f32(pfx + "output.LayerNorm.bias")
+    ops.layernorm_fwd(pre1, g1_, b1_, a, mean1, rstd1, M, H, eps)
     if save is not None:
         save.update(x=x, hist=hist, qkv=qkv, pkv=pkv, ctx=ctx, lse=lse, pre1=pre1, mean1=mean1, rstd1=rstd1,
                     chunk=do_chunk_cross, probs_img=probs_img)
-    return a, a32
+    return a, LnRes(pre1, mean1, rstd1, g1_, b1_, eps)
 
 
 def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop=None, site=0):
@@ -344,11 +376,14 @@ def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None, drop=None, la
 
 
 # -------------------------------------------------------------------------------------------- embeddings
-def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, save, pre_rows=None):
+def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, save, pre_rows=None, img_extra=None):
     """BertEmbeddings + img_embedding (+LayerNorm) written into one [N,S,H] buffer
     (a_transformers/modeling_bert.py:184-211; modeling_transfomres.py:676-684; v10:339-345).
     ``pre_rows`` (fp32 [N,Pn,H]): rows that arrive already embedded and are placed IN FRONT of the text rows -- the
-    prompt embeddings of the language-model side (modeling/modeling_ensemble.py:498-503)."""
+    prompt embeddings of the language-model side (modeling/modeling_ensemble.py:498-503).
+    ``img_extra`` = (img_pos_feat fp32 [N,R,7], img_token_type_ids int64 [N,R]): the region embedding of
+    ``BertImgModel_gtToken`` (modeling/modeling_bert.py:390-397): type embedding + LayerNorm(Linear(7 -> H)(box)) + feature
+    projection, summed in the projection GEMM's epilogue, then the image LayerNorm."""
     dev = input_ids.device
     N, T = input_ids.shape
     H = cfg["H"]
@@ -377,11 +412,21 @@ def embeddings_fwd(ps, cfg, input_ids, token_type_ids, position_ids, img_feats, 
         pre = _empty((rows, H), F32, dev)
         imean, irstd = _empty((rows,), F32, dev), _empty((rows,), F32, dev)
         use_ln = cfg["use_img_layernorm"]
+        extra32 = None
+        if img_extra is not None:
+            posf = img_extra[0].to(F32).contiguous().view(rows, 7)
+            tti = None if img_extra[1] is None else img_extra[1].to(torch.int64).contiguous().view(rows)
+            extra32 = _empty((rows, H), F32, dev)
+            pmean, prstd = _empty((rows,), F32, dev), _empty((rows,), F32, dev)
+            ops.pos_type_embed_fwd(posf, tti, ps.f32("img_pos_linear.weight"), ps.f32("img_pos_linear.bias"),
+                                   ps.f32("img_pos_layer_norm.weight"), ps.f32("img_pos_layer_norm.bias"),
+                                   ps.f32("img_token_type_embeddings.weight"), extra32, pmean, prstd, rows, H, 1e-12)
+            sv.update(posf=posf, tti=tti, pmean=pmean, prstd=prstd)
         ops.img_embed_ln_fwd(feats, rows, D, Dpad, ps.padded("img_embedding.weight", Dpad),
                              ps.f32("img_embedding.bias"),
                              ps.f32("LayerNorm.weight") if use_ln else None,
                              ps.f32("LayerNorm.bias") if use_ln else None, use_ln, cfg["img_eps"], packed, pre, x0,
-                             ops.rowmap(R, S, Pn + T), imean, irstd, H, y32=x0_32)
+                             ops.rowmap(R, S, Pn + T), imean, irstd, H, y32=x0_32, extra32=extra32)
         sv.update(packed=packed, pre=pre, imean=imean, irstd=irstd, D=D, Dpad=Dpad)
     if save is not None:
         save.update(sv)
@@ -420,6 +465,14 @@ def embeddings_bwd(ps, cfg, sv, dx0, grads):
         grads["img_embedding.weight"], grads["img_embedding.bias"] = dW, dbias
         if use_ln:
             grads["LayerNorm.weight"], grads["LayerNorm.bias"] = dgi, dbi
+        if "posf" in sv:    # type + box-position term of BertImgModel_gtToken: d(sum) = dpre
+            z = _zeros_many([(H, 7), (H,), (H,), (H,), (2, H)], dev)
+            ops.pos_type_embed_bwd(dpre, sv["posf"], sv["tti"], ps.f32("img_pos_linear.weight"), ps.f32("img_pos_linear.bias"),
+                                   ps.f32("img_pos_layer_norm.weight"), sv["pmean"], sv["prstd"], z[0], z[1], z[2], z[3], z[4],
+                                   rows, H)
+            grads["img_pos_linear.weight"], grads["img_pos_linear.bias"] = z[0], z[1]
+            grads["img_pos_layer_norm.weight"], grads["img_pos_layer_norm.bias"] = z[2], z[3]
+            grads["img_token_type_embeddings.weight"] = z[4]
     if Pn:
         dpre_rows = _empty((N, Pn, H), BF16, dev)
         ops.rows_gather(dx0, ops.rowmap(Pn, S, 0), dpre_rows, N * Pn, H)

@@ -27,6 +27,7 @@ def _as_bf16(t):
 
 def _residual_add(a32, b32, M, H):
     """fp32 ``a + b`` of two residual-stream tensors -> (bf16 copy, fp32 sum) (optional residuals, v10:212-223)."""
+    a32, b32 = E.res_dense(a32), E.res_dense(b32)
     s32 = torch.empty_like(a32)
     ops.accum_f32_2d(s32, H, a32, H, M, H)
     ops.accum_f32_2d(s32, H, b32, H, M, H, accumulate=True)
@@ -37,7 +38,8 @@ class EncoderRun:
     """Everything one encoder pass needs besides tensors that carry gradients."""
 
     def __init__(self, ps, names, cfg, input_ids, token_type_ids, position_ids, img_feats, kbias, P, is_seq=False,
-                 cbits=None, cwords=0, chunk_id=None, max_chunks=0, want_block=False, n_pre=0, align_rows=None):
+                 cbits=None, cwords=0, chunk_id=None, max_chunks=0, want_block=False, n_pre=0, align_rows=None,
+                 img_extra=None):
         self.ps, self.names, self.cfg = ps, names, cfg
         self.input_ids, self.token_type_ids, self.position_ids, self.img_feats = (input_ids, token_type_ids,
                                                                                    position_ids, img_feats)
@@ -48,6 +50,7 @@ class EncoderRun:
         # they are emitted by the attention kernels; None = the whole [N,T,R] block (debug / .align_block of a bare seq_enc)
         self.align_rows = align_rows
         self.n_pre = n_pre                    # rows that arrive already embedded (prompt embeddings), in front of the text
+        self.img_extra = img_extra            # (img_pos_feat, img_token_type_ids) of BertImgModel_gtToken
         # optional residuals of the chunk-aware encoder (v10:164-165, 212-223; run_PMR_ModCR.py:747-748)
         self.local_residual = bool(is_seq and cfg.get("add_local_residual", False))
         self.final_residual = bool(is_seq and cfg.get("add_residual", False))
@@ -55,6 +58,7 @@ class EncoderRun:
         # grad mode of the CALLER: inside Function.forward it is always off, and ctx.needs_input_grad only mirrors
         # requires_grad of the inputs, so under torch.no_grad() (evaluate(), frozen encoders) nothing is saved
         self.want_grad = torch.is_grad_enabled()
+        self.keep_attn, self.attn_debug = False, None    # lazy dense-attention debug path (AttentionsNotMaterialised)
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
         self.S = self.n_pre + self.T + self.R
@@ -92,7 +96,7 @@ class EncoderFn(torch.autograd.Function):
         pre_rows = tensors[n_hist] if run.n_pre else None
         emb_save = {} if need_grad else None
         x, x32 = E.embeddings_fwd(ps, cfg, run.input_ids, run.token_type_ids, run.position_ids, run.img_feats,
-                                  emb_save, pre_rows)
+                                  emb_save, pre_rows, run.img_extra)
         drop = run.drop
         if drop is not None and drop.p_hidden > 0.0:
             # BertEmbeddings.dropout and the img_embedding dropout (a_transformers 209; transfomres 681, v10:343)
@@ -109,8 +113,17 @@ class EncoderFn(torch.autograd.Function):
                 chunk_hidden = x
             pi = probs[i - (L - nprob)] if (nprob and i >= L - nprob) else None
             x_in32 = x32
+            if run.keep_attn and sv is None:
+                sv = {}
             x, x32 = E.layer_fwd(ps, "encoder.layer.%d." % i, x, x32, hist[i] if hist else None, ac, I, cfg["eps"], sv,
                                  cross, pi, drop, i)
+            if run.keep_attn:
+                if run.attn_debug is None:
+                    run.attn_debug = []
+                run.attn_debug.append(dict(qkv=sv["qkv"], pkv=sv["pkv"], lse=sv["lse"], kbias=ac.kbias, cbits=ac.cbits,
+                                           mode=ac.mode, N=N, S=S, P=ac.P, heads=ac.heads, T=ac.T))
+                if not need_grad:
+                    sv = None
             if run.local_residual and i in CROSS_MODAL_LAYERS:   # v10:212-215: hidden = layer_out + former_hidden
                 x, x32 = _residual_add(x32, x_in32, N * S, H)
             if run.is_seq and i == CROSS_MODAL_START:
@@ -250,14 +263,15 @@ class ClsLayer2HeadFn(torch.autograd.Function):
             pre = E._empty((N, H), F32, dev)
             if hdrop:                                                      # LayerNorm(dropout(dense(.)) + cls), v10:831-833
                 ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"),
-                         epi_in=cls32, in_op=1, drop=(drop.seed, drop.site(i, 1), drop.p_hidden))
+                         drop=(drop.seed, drop.site(i, 1), drop.p_hidden), **E.res_kw(cls32))
             else:
                 ops.gemm(pooled, ps.bf16(pfx + "dense.weight"), pre, N, H, H, bias=ps.f32(pfx + "dense.bias"),
-                         epi_in=cls32, in_op=1)
-            c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
+                         **E.res_kw(cls32))
+            c = E._empty((N, H), BF16, dev)
             mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
-            ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
-                              cfg["eps"], y32=c32)
+            gam, bet = ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias")
+            ops.layernorm_fwd(pre, gam, bet, c, mean, rstd, N, H, cfg["eps"])
+            c32 = E.LnRes(pre, mean, rstd, gam, bet, cfg["eps"])
             if sv is not None:
                 sv.update(cls_in=cls, q=q, k=k, w=w, pooled=pooled, pre=pre, mean=mean, rstd=rstd)
             cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv, drop, drop.site(i, 2) if drop else 0)
@@ -361,15 +375,16 @@ def _cls_lyx_forward(ps, cfg, word_len, g_out, s_out, c_hid, g_pool, s_pool, n_l
         ops.cross_attn_q1_fwd(q, k, v, att, N, L3, H, heads, lse, drop=adrop)   # word_mask is never forwarded (v10:856-857)
         pre = E._empty((N, H), F32, dev)
         if drop is not None and drop.p_hidden > 0.0:                     # LayerNorm(dropout(CLS_ensem_1) + cls), v10:866-867
-            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
-                     in_op=1, drop=(drop.seed, drop.site(i, 1), drop.p_hidden))
+            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"),
+                     drop=(drop.seed, drop.site(i, 1), drop.p_hidden), **E.res_kw(cls32))
         else:
-            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"), epi_in=cls32,
-                     in_op=1)                                            # + cls (residual of the LayerNorm)
-        c, c32 = E._empty((N, H), BF16, dev), E._empty((N, H), F32, dev)
+            ops.gemm(att, ps.bf16(xa + "out_proj.weight"), pre, N, H, H, bias=ps.f32(xa + "out_proj.bias"),
+                     **E.res_kw(cls32))                                  # + cls (residual of the LayerNorm)
+        c = E._empty((N, H), BF16, dev)
         mean, rstd = E._empty((N,), F32, dev), E._empty((N,), F32, dev)
-        ops.layernorm_fwd(pre, ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias"), c, mean, rstd, N, H,
-                          cfg["eps"], y32=c32)
+        gam, bet = ps.f32(pfx + "LayerNorm.weight"), ps.f32(pfx + "LayerNorm.bias")
+        ops.layernorm_fwd(pre, gam, bet, c, mean, rstd, N, H, cfg["eps"])
+        c32 = E.LnRes(pre, mean, rstd, gam, bet, cfg["eps"])
         if sv is not None:
             sv.update(cls_in=cls, q=q, k=k, v=v, att=att, lse=lse, pre=pre, mean=mean, rstd=rstd)
         cls, cls32 = E.ffn_fwd(ps, pfx, c, c32, N, H, I, cfg["eps"], sv, drop, drop.site(i, 2) if drop else 0)

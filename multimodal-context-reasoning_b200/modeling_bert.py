@@ -20,25 +20,105 @@ BertLayerNorm = nn.LayerNorm
 
 class AttentionsNotMaterialised:
     """Stands where the reference returns the tuple of dense ``[N,h,S,K]`` probability tensors
-    (``output_attentions=True``, run_PMR_ModCR.py:726).  The fused kernel never writes them to HBM;
-    what the path consumes -- the head- and layer-summed text->region block of the last three
-    layers (v10:982) -- is available as ``.align_block``."""
+    (``output_attentions=True``, run_PMR_ModCR.py:726; produced at modeling/modeling_bert.py:74).  The fused kernel never
+    writes them to HBM; what the path consumes -- the head- and layer-summed text->region block of the last three layers
+    (v10:982) -- is available as ``.align_block``.
 
-    def __init__(self, align_block=None):
+    DEBUG path: with ``model.materialise_attentions = True`` the encoder keeps, per layer, the Q|K|V buffer, the prefix K/V,
+    the log-sum-exp rows and the mask description, and ``attentions[i]`` rebuilds the reference's dense fp32
+    ``[N, heads, S, P+S]`` tensor of layer ``i`` lazily from them: ``exp(Q K^T / 8 + mask - lse)`` with the additive mask
+    of SURVEY A.2 (torch ops on the device -- an inspection facility, never on the training / scoring path; dropout
+    masks are not applied, so in training mode it is the pre-dropout tensor)."""
+
+    def __init__(self, align_block=None, layers=None):
         self.align_block = align_block
-
-    def __getitem__(self, i):
-        raise NotImplementedError("dense attention probabilities are not materialised by the fused prefix-attention "
-                                  "kernel; use .align_block (sum over the last 3 layers and heads of probs[:, :T, T:])")
+        self._layers = layers           # list of dicts (qkv, pkv, lse, kbias, cmask bits, mode, dims) or None
 
     def __len__(self):
-        return 0
+        return 0 if self._layers is None else len(self._layers)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __getitem__(self, i):
+        if self._layers is None:
+            raise NotImplementedError("dense attention probabilities are not materialised by the fused prefix-attention "
+                                      "kernel; set model.materialise_attentions = True for the lazy debug path, or use "
+                                      ".align_block (sum over the last 3 layers and heads of probs[:, :T, T:])")
+        if isinstance(i, slice):
+            return tuple(self[j] for j in range(*i.indices(len(self))))
+        d = self._layers[i]
+        N, S, P, heads, T, mode = d["N"], d["S"], d["P"], d["heads"], d["T"], d["mode"]
+        H = heads * 64
+        qkv = d["qkv"].view(N, S, 3 * H).float()
+        q, k = qkv[..., :H], qkv[..., H:2 * H]
+        if P > 0:
+            k = torch.cat([d["pkv"].view(N, P, 2 * H)[..., :H].float(), k], 1)
+        hd = lambda t: t.reshape(N, -1, heads, 64).permute(0, 2, 1, 3)  # noqa: E731
+        scores = hd(q) @ hd(k).transpose(-1, -2) * 0.125
+        am = d["kbias"].view(N, 1, 1, P + S).expand(N, 1, S, P + S).clone()     # (1 - mask) * -10000, SURVEY A.2
+        if mode != 0:
+            cw = d["cbits"].shape[-1]
+            bits = ((d["cbits"].unsqueeze(-1) >> torch.arange(32, device=am.device)) & 1).reshape(N, T, cw * 32)[:, :, :T]
+            am[:, 0, :T, :T] = (1.0 - bits.float()) * -10000.0
+            am[:, 0, T:, :T] = -10000.0
+            if mode == 2:
+                R = S - T
+                eye = torch.eye(R, device=am.device)
+                am[:, 0, T:, T:] = (1.0 - eye) * -10000.0
+        return torch.exp(scores + am - d["lse"].view(N, heads, S, 1))
 
 
 # ------------------------------------------------------------------------------------------------
-# parameter containers (names = reference state_dict keys)
-class BertEmbeddings(nn.Module):
+# building blocks (names = reference state_dict keys).  Training and scoring run the WHOLE encoder as one autograd node
+# (``functions.EncoderFn``); the ``forward`` methods below are the reference's per-module entry points
+# (a_transformers/modeling_bert.py:184-211, 237-265, 369-373, 434-451, 640-646; modeling/modeling_bert.py:34-155) on the same
+# kernels for callers that drive a block by hand: INFERENCE ONLY -- they return bf16 tensors without an autograd graph.
+def _as_rows(t):
+    """[N,S,H] activation -> (bf16 [N*S,H] operand, fp32 [N*S,H] residual copy)."""
+    N, S, H = t.shape
+    t32 = t.detach().to(torch.float32).contiguous().view(N * S, H)
+    tb = t.detach().contiguous().view(N * S, H) if t.dtype == torch.bfloat16 else E.ops.to_bf16(t32)
+    return tb, t32
+
+
+def _key_bias_from_mask(attention_mask, N, K):
+    """The reference hands its blocks the ADDITIVE extended mask ``(1 - mask) * -10000`` of shape [N,1,1,K]
+    (modeling_transfomres.py:628-641); the kernels take exactly that vector per sequence."""
+    if attention_mask is None:
+        return torch.zeros((N, K), dtype=torch.float32, device="cuda")
+    if attention_mask.dim() == 4 and attention_mask.shape[1] == 1 and attention_mask.shape[2] == 1:
+        return attention_mask.reshape(N, K).to(torch.float32).contiguous()
+    raise NotImplementedError("per-query masks ([N,1,S,K]) are built inside SeqBertImgModel (3-phase schedule, v10:171-232); "
+                              "the stand-alone blocks take the [N,1,1,K] key mask")
+
+
+class _Block(nn.Module):
+    """bf16 operand copies of this block's own parameters, keyed by the names the engine programs use."""
+    _engine_prefix = ""
+
+    def _ps(self):
+        named = {self._engine_prefix + k: p for k, p in self.named_parameters()}
+        ps = getattr(self, "_block_store", None)
+        if ps is None or ps.named.keys() != named.keys() or any(ps.named[k] is not named[k] for k in named):
+            for k, p in named.items():
+                if p.dtype != torch.float32 or not p.is_cuda:
+                    raise RuntimeError("modcr_b200: parameter %s must be a float32 CUDA tensor (no CPU / PyTorch fallback)" % k)
+            ps = E.ParamStore(named)
+            object.__setattr__(self, "_block_store", ps)
+        return ps
+
+
+class BertEmbeddings(_Block):
     """a_transformers/modeling_bert.py:166-234."""
+    _engine_prefix = "embeddings."
+
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None):
+        """:184-211 (eval): LayerNorm(word + token_type + position) -> bf16 [N,T,H]."""
+        cfg = dict(H=self.word_embeddings.embedding_dim, eps=float(self.LayerNorm.eps))
+        with torch.no_grad():
+            x, _ = E.embeddings_fwd(self._ps(), cfg, input_ids, token_type_ids, position_ids, None, None)
+        return x
 
     def __init__(self, config):
         super().__init__()
@@ -51,9 +131,40 @@ class BertEmbeddings(nn.Module):
         self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
 
 
-class CaptionBertSelfAttention(nn.Module):
-    """modeling/modeling_bert.py:25-75 -- ``forward(hidden_states, attention_mask, head_mask=None,
-    history_state=None)``; executed inside the encoder node (fused QKV GEMM + prefix attention)."""
+class CaptionBertSelfAttention(_Block):
+    """modeling/modeling_bert.py:25-75 (and v10:45-107 with the chunk-mean queries): fused QKV GEMM + prefix attention."""
+
+    def forward(self, hidden_states, attention_mask, head_mask=None, history_state=None, do_chunk_cross=False, offsets=None,
+                gather_index=None):
+        """Returns ``(context_layer [N,S,H],)`` like :75 without ``output_attentions``.  ``history_state`` [N,P,H]: prefix
+        hidden states whose K/V rows are prepended (:36-44); ``attention_mask`` the additive [N,1,1,P+S] key mask."""
+        if head_mask is not None:
+            raise NotImplementedError("head_mask is always None on the ModCR path")
+        N, S, H = hidden_states.shape
+        heads = self.num_attention_heads
+        P = 0 if history_state is None else history_state.shape[1]
+        with torch.no_grad():
+            ps = self._ps()
+            x, _ = _as_rows(hidden_states)
+            Wqkv, bqkv = ps.qkv("")
+            qkv = torch.empty((N * S, 3 * H), dtype=torch.bfloat16, device=x.device)
+            E.ops.gemm(x, Wqkv, qkv, N * S, 3 * H, H, bias=bqkv)
+            pkv = None
+            if P > 0:
+                hb, _ = _as_rows(history_state)
+                pkv = torch.empty((N * P, 2 * H), dtype=torch.bfloat16, device=x.device)
+                E.ops.gemm(hb, Wqkv[H:], pkv, N * P, 2 * H, H, bias=bqkv[H:])
+            if do_chunk_cross:
+                if gather_index is None:
+                    raise ValueError("do_chunk_cross needs gather_index (v10:66-78)")
+                T = max(int(g.numel()) for g in gather_index) + 2
+                chunk_id, max_chunks = E.pack_chunk_ids(gather_index, T, x.device)
+                E.ops.chunk_mean_q(qkv, 3 * H, N, S, H, chunk_id, T, max_chunks)
+            kbias = _key_bias_from_mask(attention_mask, N, P + S)
+            ctx = torch.empty((N * S, H), dtype=torch.bfloat16, device=x.device)
+            lse = torch.empty((N, heads, S), dtype=torch.float32, device=x.device)
+            E.ops.prefix_attn_fwd(N, S, P, heads, 0, 0, qkv, pkv, kbias, None, 0, ctx, lse, None)
+        return (ctx.view(N, S, H),)
 
     def __init__(self, config):
         super().__init__()
@@ -66,7 +177,27 @@ class CaptionBertSelfAttention(nn.Module):
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
 
 
-class BertSelfOutput(nn.Module):
+def _dense_residual_ln(block, hidden_states, input_tensor):
+    """LayerNorm(dense(hidden_states) + input_tensor) (a_transformers/modeling_bert.py:369-373, 447-451), eval."""
+    N, S, H = input_tensor.shape
+    K = hidden_states.shape[-1]
+    with torch.no_grad():
+        ps = block._ps()
+        hb, _ = _as_rows(hidden_states)
+        _, r32 = _as_rows(input_tensor)
+        pre = torch.empty((N * S, H), dtype=torch.float32, device=hb.device)
+        E.ops.gemm(hb, ps.bf16("dense.weight"), pre, N * S, H, K, bias=ps.f32("dense.bias"), epi_in=r32, in_op=1)
+        y = torch.empty((N * S, H), dtype=torch.bfloat16, device=hb.device)
+        mean, rstd = (torch.empty((N * S,), dtype=torch.float32, device=hb.device) for _ in range(2))
+        E.ops.layernorm_fwd(pre, ps.f32("LayerNorm.weight"), ps.f32("LayerNorm.bias"), y, mean, rstd, N * S, H,
+                            float(block.LayerNorm.eps))
+    return y.view(N, S, H)
+
+
+class BertSelfOutput(_Block):
+    def forward(self, hidden_states, input_tensor):
+        return _dense_residual_ln(self, hidden_states, input_tensor)
+
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
@@ -75,19 +206,38 @@ class BertSelfOutput(nn.Module):
 
 
 class CaptionBertAttention(nn.Module):
+    def forward(self, input_tensor, attention_mask, head_mask=None, history_state=None, **chunk_kw):
+        """modeling/modeling_bert.py:86-93: ``(attention_output,)``."""
+        self_outputs = self.self(input_tensor, attention_mask, head_mask, history_state, **chunk_kw)
+        return (self.output(self_outputs[0], input_tensor),) + self_outputs[1:]
+
     def __init__(self, config):
         super().__init__()
         self.self = CaptionBertSelfAttention(config)
         self.output = BertSelfOutput(config)
 
 
-class BertIntermediate(nn.Module):
+class BertIntermediate(_Block):
+    def forward(self, hidden_states):
+        """a_transformers/modeling_bert.py:434-437: gelu(dense(x)) with the GELU in the GEMM epilogue."""
+        N, S, H = hidden_states.shape
+        I = self.dense.out_features
+        with torch.no_grad():
+            ps = self._ps()
+            hb, _ = _as_rows(hidden_states)
+            out = torch.empty((N * S, I), dtype=torch.bfloat16, device=hb.device)
+            E.ops.gemm(hb, ps.bf16("dense.weight"), out, N * S, I, H, bias=ps.f32("dense.bias"), act=1)
+        return out.view(N, S, I)
+
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
 
 
-class BertOutput(nn.Module):
+class BertOutput(_Block):
+    def forward(self, hidden_states, input_tensor):
+        return _dense_residual_ln(self, hidden_states, input_tensor)
+
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
@@ -96,6 +246,11 @@ class BertOutput(nn.Module):
 
 
 class CaptionBertLayer(nn.Module):
+    def forward(self, hidden_states, attention_mask, head_mask=None, history_state=None, **chunk_kw):
+        """modeling/modeling_bert.py:107-116 / modeling_transfomres.py:481-489: ``(layer_output,)``."""
+        attention_output = self.attention(hidden_states, attention_mask, head_mask, history_state, **chunk_kw)[0]
+        return (self.output(self.intermediate(attention_output), attention_output),)
+
     def __init__(self, config):
         super().__init__()
         self.attention = CaptionBertAttention(config)
@@ -104,6 +259,14 @@ class CaptionBertLayer(nn.Module):
 
 
 class CaptionBertEncoder(nn.Module):
+    def forward(self, hidden_states, attention_mask, head_mask=None, encoder_history_states=None):
+        """modeling/modeling_bert.py:128-155: the layer loop with ``history_state = encoder_history_states[i]``;
+        returns ``(hidden_states,)`` (inference; the model-level forward is the trained path)."""
+        for i, layer in enumerate(self.layer):
+            hist = None if encoder_history_states is None else encoder_history_states[i]
+            hidden_states = layer(hidden_states, attention_mask, None if head_mask is None else head_mask[i], hist)[0]
+        return (hidden_states,)
+
     def __init__(self, config):
         super().__init__()
         self.output_attentions = cfg_get(config, "output_attentions", False)
@@ -111,7 +274,17 @@ class CaptionBertEncoder(nn.Module):
         self.layer = nn.ModuleList([CaptionBertLayer(config) for _ in range(config.num_hidden_layers)])
 
 
-class BertPooler(nn.Module):
+class BertPooler(_Block):
+    _engine_prefix = "pooler."
+
+    def forward(self, hidden_states):
+        """a_transformers/modeling_bert.py:640-646: tanh(dense(hidden_states[:, 0])) with the tanh in the GEMM epilogue."""
+        N, S, H = hidden_states.shape
+        with torch.no_grad():
+            hb, _ = _as_rows(hidden_states)
+            out = E.pooler_fwd(self._ps(), hb, N, S, H)
+        return out
+
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
@@ -196,10 +369,72 @@ class BertImgModel(_EncoderModelBase):
         run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P)
         run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
                                cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 1 << 20)
+        run.keep_attn = bool(getattr(self, "materialise_attentions", False))
         seq_out, pooled, _, _ = EncoderFn.apply(run, len(hist), *hist, *params)
         outputs = (seq_out, pooled)
         if cfg_get(self.config, "output_attentions", False):
-            outputs = outputs + (AttentionsNotMaterialised(),)
+            outputs = outputs + (AttentionsNotMaterialised(layers=run.attn_debug),)
+        return outputs
+
+
+class BertImgModel_gtToken(_EncoderModelBase):
+    """modeling/modeling_bert.py:293-412: ``BertImgModel`` whose region embedding also carries the box geometry and a
+    region type --
+
+        img_embedding(img_feats) + img_token_type_embeddings(img_token_type_ids)
+                                 + img_pos_layer_norm(img_pos_linear(img_pos_feat [N,R,7]))     (:390-394)
+
+    followed by the image LayerNorm (``use_img_layernorm``, :396-397) and dropout (:400).  The three-way sum runs in the
+    epilogue of the tcgen05 feature-projection GEMM (the type + box term, a K = 7 product that is no tensor-core shape,
+    is produced by ``modcr_pos_type_embed_fwd`` and enters as the GEMM's fp32 epilogue input); state-dict keys are the
+    reference's (``img_token_type_embeddings``, ``img_pos_layer_norm``, ``img_pos_linear``).  NB the reference class
+    cannot be constructed as shipped: ``FusedLayerNorm`` (:313) is used while its import (:19) is commented out; the
+    oracle shim binds it to ``torch.nn.LayerNorm`` (same arithmetic)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self._build(config)
+        self.img_token_type_embeddings = nn.Embedding(2, config.hidden_size)
+        self.img_pos_layer_norm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.img_pos_linear = nn.Linear(7, config.hidden_size)
+        self.init_weights()
+
+    def forward(self, input_ids, token_type_ids=None, attention_mask=None, position_ids=None, head_mask=None,
+                img_feats=None, img_token_type_ids=None, img_pos_feat=None, encoder_history_states=None):
+        if head_mask is not None:
+            raise NotImplementedError("head_mask is always None on the ModCR path (modeling_transfomres.py:656-657)")
+        N, T = input_ids.shape
+        R = 0 if img_feats is None else img_feats.shape[1]
+        S = T + R
+        hist = list(encoder_history_states) if encoder_history_states else []
+        P = hist[0].shape[1] if hist else 0
+        dev = input_ids.device
+        if attention_mask is None:
+            attention_mask = torch.ones((N, P + S), dtype=torch.float32, device=dev)
+        if attention_mask.dim() != 2:
+            raise NotImplementedError("only 2-D key-padding masks are implemented for BertImgModel_gtToken")
+        if attention_mask.shape[1] == S and P > 0:
+            attention_mask = torch.cat([torch.ones((N, P), dtype=attention_mask.dtype, device=dev), attention_mask], -1)
+        if attention_mask.shape[1] != P + S:
+            raise ValueError("attention_mask has %d keys, expected P+S = %d" % (attention_mask.shape[1], P + S))
+        extra = None
+        if img_feats is not None:
+            if img_pos_feat is None or tuple(img_pos_feat.shape) != (N, R, 7):
+                raise ValueError("img_pos_feat must be [N,R,7] (modeling_bert.py:314)")
+            if img_token_type_ids is None:
+                img_token_type_ids = torch.zeros((N, R), dtype=torch.int64, device=dev)
+            extra = (img_pos_feat, img_token_type_ids)
+        kbias = E.make_key_bias(attention_mask)
+        ps, names, params = self._store()
+        run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P,
+                         img_extra=extra)
+        run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
+                               cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 8 << 20)
+        run.keep_attn = bool(getattr(self, "materialise_attentions", False))
+        seq_out, pooled, _, _ = EncoderFn.apply(run, len(hist), *hist, *params)
+        outputs = (seq_out, pooled)
+        if cfg_get(self.config, "output_attentions", False):
+            outputs = outputs + (AttentionsNotMaterialised(layers=run.attn_debug),)
         return outputs
 
 

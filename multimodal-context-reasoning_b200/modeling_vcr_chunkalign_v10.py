@@ -74,8 +74,9 @@ class SeqBertImgModel(_EncoderModelBase):
                          align_rows=None if _align_rows is None else _align_rows.to(torch.int64).contiguous())
         run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
                                cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 2 << 20)
+        run.keep_attn = bool(getattr(self, "materialise_attentions", False))
         seq_out, pooled, chunk_hidden, block = EncoderFn.apply(run, 0, *params)
-        att = AttentionsNotMaterialised(block if block.numel() else None)
+        att = AttentionsNotMaterialised(block if block.numel() else None, layers=run.attn_debug)
         return (seq_out, pooled, att), (chunk_hidden if chunk_hidden.numel() else None)
 
 

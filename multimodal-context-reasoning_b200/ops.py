@@ -39,9 +39,12 @@ def rowmap(rows_per_seq=0, seq_stride=0, row0=0):
 
 # --------------------------------------------------------------------------- GEMM
 def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=None, act=0, aux=None,
-         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None, a_colsum=None, drop=None):
+         epi_in=None, in_op=0, accumulate=0, split_k=1, alpha=1.0, ld_in=None, ldaux=None, a_colsum=None, drop=None,
+         in_ln=None):
     """C[M,N] = epi(alpha * A B^T); operands are raw 2-D views described by (ptr, ld).
-    ``a_colsum`` (a_mn=1): fp32 [M] that receives += sum_k A[k,m] (the bias gradient of a wgrad)."""
+    ``a_colsum`` (a_mn=1): fp32 [M] that receives += sum_k A[k,m] (the bias gradient of a wgrad).
+    ``in_ln`` = (mean [M], rstd [M], gamma [N], beta [N]) with fp32 ``epi_in`` / ``C``: the residual is
+    LayerNorm(epi_in), rebuilt in the epilogue (in_op 3)."""
     d = GemmDesc()
     d.A, d.B, d.C = A.data_ptr(), B.data_ptr(), C_.data_ptr()
     d.lda = lda if lda is not None else (M if a_mn else K)
@@ -59,6 +62,13 @@ def gemm(A, B, C_, M, N, K, lda=None, ldb=None, ldc=None, a_mn=0, b_mn=0, bias=N
     d.epi_in = _p(epi_in)
     d.ld_in = ld_in if ld_in is not None else N
     d.in_op = in_op if epi_in is not None else 0
+    if in_ln is not None:
+        if epi_in is None or epi_in.dtype != F32 or C_.dtype != F32:
+            raise RuntimeError("modcr_b200: gemm in_ln needs an fp32 epilogue input and an fp32 output")
+        for t_, nm in zip(in_ln, ("in_mean", "in_rstd", "in_gamma", "in_beta")):
+            _chk(t_, F32, nm)
+        d.in_op = 3
+        d.in_mean, d.in_rstd, d.in_gamma, d.in_beta = (_p(t_) for t_ in in_ln)
     d.a_colsum = _p(a_colsum)
     if drop is not None:                      # (seed tensor, site, p): dropout of f(acc + bias) before `epi_in`
         d.drop_seed, d.drop_site, d.drop_p = _p(drop[0]), int(drop[1]), float(drop[2])
@@ -101,12 +111,13 @@ def txt_embed_ln_bwd(dy, dymap, ids, tts, pos_ids, word, type_, pos, gamma, mean
 
 
 def img_embed_ln_fwd(feats, rows, D, Dpad, W, bias, gamma, beta, use_ln, eps, packed, pre, y, ymap, mean, rstd, H,
-                     y32=None):
+                     y32=None, extra32=None):
     _chk(feats, F32, "img_feats")
     _chk(pre, F32, "img_embed pre-LN workspace")
+    _chk(extra32, F32, "img_embed extra term")
     _lib.check(_lib.load().modcr_img_embed_ln_fwd(_p(feats), rows, D, Dpad, _p(W), _p(bias), _p(gamma), _p(beta),
                                                   int(use_ln), eps, _p(packed), _p(pre), _p(y), _p(y32), ymap,
-                                                  _p(mean), _p(rstd), H, _stream()), "img_embed_ln_fwd")
+                                                  _p(mean), _p(rstd), H, _p(extra32), _stream()), "img_embed_ln_fwd")
 
 
 def img_embed_ln_bwd(dy, dymap, packed, pre, mean, rstd, gamma, use_ln, dpre, dW_pad, dbias, dgamma, dbeta, rows,
@@ -354,6 +365,19 @@ def rowln_fwd(x, gamma, beta, y, mean, rstd, M, H, eps):
 def rowln_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, M, H):
     _lib.check(_lib.load().modcr_rowln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma), _p(dbeta),
                                            M, H, _stream()), "rowln_bwd")
+
+
+def pos_type_embed_fwd(pos, tt, Wp, bp, gam, bet, type_emb, out, mean, rstd, rows, H, eps):
+    _chk(pos, F32, "img_pos_feat")
+    _chk(tt, I64, "img_token_type_ids")
+    _lib.check(_lib.load().modcr_pos_type_embed_fwd(_p(pos), _p(tt), _p(Wp), _p(bp), _p(gam), _p(bet), _p(type_emb), _p(out),
+                                                    _p(mean), _p(rstd), rows, H, eps, _stream()), "pos_type_embed_fwd")
+
+
+def pos_type_embed_bwd(d, pos, tt, Wp, bp, gam, mean, rstd, dWp, dbp, dgam, dbet, dtype, rows, H):
+    _lib.check(_lib.load().modcr_pos_type_embed_bwd(_p(d), _p(pos), _p(tt), _p(Wp), _p(bp), _p(gam), _p(mean), _p(rstd),
+                                                    _p(dWp), _p(dbp), _p(dgam), _p(dbet), _p(dtype), rows, H, _stream()),
+               "pos_type_embed_bwd")
 
 
 def rows_place(src32, y, y32, ymap, M, H):

@@ -75,7 +75,7 @@ class GradReducer:
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_dtype = comm_dtype
         self.sync = True
-        self._seen = set()
+        self._seen = {}
         self._bucket = None            # dict(flat=, used=, grads=[...]) being filled
         self._flats, self._free = [], []   # flat buffers, recycled step after step (stable addresses for graph replay)
         self._pending = []             # gloo: (work, flat, used, grads)
@@ -107,10 +107,14 @@ class GradReducer:
                 p.grad.add_(g)
             ps.append(p)
         if self.sync and self.world > 1:
-            self._enqueue(ps)
+            self._enqueue(ps, "hand-off")
 
     def _on_grad(self, p):
         if p.grad is None or not self.sync:
+            return
+        # autograd still runs AccumulateGrad (and this hook) for an input whose backward returned None: a parameter the
+        # node handed off itself is already on its way
+        if self._seen.get(id(p)) == "hand-off":
             return
         self._enqueue([p])
 
@@ -134,12 +138,13 @@ class GradReducer:
         self._flats.append(f)
         return f
 
-    def _enqueue(self, ps):
+    def _enqueue(self, ps, via="hook"):
         for p in ps:
             if id(p) in self._seen:
-                raise RuntimeError("GradReducer: a parameter was enqueued twice before finish() -- finish() must follow "
-                                   "exactly one synchronising backward (use no_sync() for accumulation micro-steps)")
-            self._seen.add(id(p))
+                raise RuntimeError("GradReducer: a parameter (shape %s, first enqueued by %s, now by %s) was enqueued twice "
+                                   "before finish() -- finish() must follow exactly one synchronising backward (use "
+                                   "no_sync() for accumulation micro-steps)" % (tuple(p.shape), self._seen[id(p)], via))
+            self._seen[id(p)] = via
         grads = [p.grad for p in ps]
         need = sum((g.numel() + 7) & ~7 for g in grads)          # 16-byte aligned slots
         cuda = grads[0].is_cuda

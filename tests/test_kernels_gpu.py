@@ -118,6 +118,30 @@ def test_gemm_fp32_residual_stream():
     assert nerr(C, ref) < 1e-4
 
 
+def test_gemm_fp32_residual_rebuilt_from_the_previous_layernorm():
+    """modcr_gemm in_op 3: C = A B^T + bias + LayerNorm(in) with the LayerNorm output rebuilt in the epilogue from the
+    pre-LayerNorm tensor, its row statistics and gamma / beta (BertSelfOutput / BertOutput add the previous LayerNorm's
+    output, a_transformers/modeling_bert.py:369-373, 447-451) -- against the two-kernel form (LayerNorm with an fp32 copy,
+    then the fp32 residual add) and against torch; a ragged M exercises the row guard."""
+    for (M, N, K) in ((712, 768, 3072), (128 * 178, 768, 768), (130, 1024, 1024)):
+        A, B = rnd(M, K, seed=1), rnd(N, K, scale=0.03, seed=2)
+        bias = rnd(N, seed=3, dtype=torch.float32)
+        pre = rnd(M, N, seed=4, dtype=torch.float32, scale=1.5)
+        gam = 1.0 + 0.1 * rnd(N, seed=5, dtype=torch.float32)
+        bet = 0.05 * rnd(N, seed=6, dtype=torch.float32)
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        y32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+        mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+        ops.layernorm_fwd(pre, gam, bet, y, mean, rstd, M, N, 1e-12, y32=y32)
+        C2 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+        ops.gemm(A, B, C2, M, N, K, bias=bias, epi_in=y32, in_op=1)
+        C3 = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+        ops.gemm(A, B, C3, M, N, K, bias=bias, epi_in=pre, in_ln=(mean, rstd, gam, bet))
+        ref = A.float() @ B.float().t() + bias + torch.nn.functional.layer_norm(pre, (N,), gam, bet, 1e-12)
+        assert float((C3 - C2).abs().max()) < 2e-5, (M, N, K)          # same arithmetic, two routes
+        assert nerr(C3, ref) < 2e-3, (M, N, K)
+
+
 def test_layernorm_fp32_input_dual_output():
     M, H = 333, 768
     x = rnd(M, H, scale=2.0, seed=1, dtype=torch.float32)

@@ -169,7 +169,9 @@ def test_chunkalign_forward_backward_matches_reference_golden(name):
     # relative L2 error per gradient tensor.  The loss gradient itself carries the forward's bf16 logit error (the
     # head's unscaled 768-dim softmax scores, v10:822-827, amplify it) on top of the bf16 gradient stream.
     gfl = GRAD_FLOOR[name]["per_key"]
-    bad = {k: (v, gfl.get(k)) for k, v in worst.items() if v > max(GRAD_TOL, FLOOR_SLACK * gfl.get(k, 0.0))}
+    # per tensor: 5 %, or that tensor's own forward-rounding floor with 25 % slack plus 2 % for the bf16 gradient stream
+    # of the backward pass (the floor fixture rounds the forward operands only)
+    bad = {k: (v, gfl.get(k)) for k, v in worst.items() if v > max(GRAD_TOL, FLOOR_SLACK * gfl.get(k, 0.0) + 0.02)}
     print(name, "grad rel-L2: worst ours %.4f, worst bf16-operand floor of the oracle %.4f" % (
         max(worst.values()), GRAD_FLOOR[name]["max"]))
     assert not bad, bad
@@ -840,3 +842,146 @@ def test_roberta_prompt_model_matches_standin_oracle__parity_unpinned_vs_missing
     assert e_seq < 2e-2 and e_pool < 2e-2
     assert max(errs.values()) < GRAD_TOL, errs
     assert set(m.state_dict().keys()) == set(sd.keys())
+
+
+def test_dense_attention_probabilities_on_request_match_the_oracle():
+    """``output_attentions`` of the reference (run_PMR_ModCR.py:726, modeling/modeling_bert.py:74): with
+    ``materialise_attentions`` the drop-in modules rebuild the dense [N,h,S,K] probabilities of any layer lazily from the
+    kept Q|K|V / log-sum-exp buffers -- all three mask phases of seq_enc and the prefix keys of global_enc against the
+    fp32 oracle (which tests/test_oracle.py pins to the live reference)."""
+    g = torch.load(os.path.join(GOLD, "ragged_small.pt"))
+    meta = g["meta"]
+    m = build(meta["wseed"]).eval()
+    b = synth.make_batch(B=meta["B"], T=meta["T"], R=meta["R"], seed=meta["seed"], region_pad=meta["region_pad"])
+    bd = synth.to_device(b, DEV)
+    N, T = b["input_ids"].shape
+    sd = params.fill_params(statedict.materialise(statedict.chunkalign_keys(CFG)), meta["wseed"])
+    prefix = synth.make_prefix(12, meta["P"], 768, seed=meta["seed"] + 1)
+    m.seq_enc.materialise_attentions = True
+    m.global_enc.materialise_attentions = True
+    with torch.no_grad():
+        (s_out, s_pool, att), _ = m.seq_enc(bd["input_ids"], img_feats=bd["img_feat"], img_mask=bd["input_mask"][:, T:],
+                                            input_mask=bd["input_mask"], attention_mask=bd["chunk_attention_mask"],
+                                            token_type_ids=bd["token_type_ids"], offsets=b["offsets"],
+                                            gather_index=b["gather_index"])
+        g_out = m.global_enc(bd["input_ids"], img_feats=bd["img_feat"], attention_mask=bd["input_mask"],
+                             token_type_ids=bd["token_type_ids"],
+                             encoder_history_states=[prefix[i].to(DEV).unsqueeze(0).expand(N, -1, -1) for i in range(12)])
+        (_, _, s_att), _ = restate.seq_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"],
+                                                   b["chunk_attention_mask"], b["input_mask"], b["img_feat"], b["offsets"],
+                                                   b["gather_index"])
+        gmask = torch.cat([torch.ones(N, meta["P"]), b["input_mask"]], -1)
+        _, _, g_att = restate.global_enc_forward(sd, CFG, b["input_ids"], b["token_type_ids"], gmask,
+                                                 b["img_feat"], [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(12)])
+    assert len(att) == 12 and len(g_out[2]) == 12
+    for i in (0, 2, 5, 9, 11):                      # chunk-local, key padding, cross-modal (chunk-mean queries) layers
+        got = att[i].cpu()
+        assert tuple(got.shape) == tuple(s_att[i].shape)
+        assert float((got - s_att[i]).abs().max()) < 1.5e-2, i
+        assert torch.equal(got == 0, s_att[i] == 0), i            # the exact zeros of the additive -10000 masks
+    for i in (0, 11):
+        got = g_out[2][i].cpu()
+        assert tuple(got.shape) == (N, 12, T + meta["R"], meta["P"] + T + meta["R"])
+        assert float((got - g_att[i]).abs().max()) < 1.5e-2, i
+    # default: nothing is kept, indexing says how to get it
+    m.seq_enc.materialise_attentions = False
+    with torch.no_grad():
+        (_, _, att2), _ = m.seq_enc(bd["input_ids"], img_feats=bd["img_feat"], img_mask=bd["input_mask"][:, T:],
+                                    input_mask=bd["input_mask"], attention_mask=bd["chunk_attention_mask"],
+                                    token_type_ids=bd["token_type_ids"], offsets=b["offsets"], gather_index=b["gather_index"])
+    with pytest.raises(NotImplementedError):
+        att2[0]
+
+
+
+def test_gttoken_region_embedding_with_box_projection_matches_oracle():
+    """north_star kernel (1) / BertImgModel_gtToken (modeling/modeling_bert.py:312-316, 390-400): 2054 -> H feature projection
+    + Linear(7 -> H)(box) through its own LayerNorm + region type embedding, summed in the projection GEMM's epilogue, image
+    LayerNorm -- forward and the gradients of every embedding parameter against the fp32 restatement that
+    tests/test_oracle.py pins bit-exactly to the live reference class."""
+    from modcr_b200.modeling_bert import BertImgModel_gtToken
+    ocfg = restate.default_cfg(num_hidden_layers=2)
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     num_hidden_layers=2)
+    m = BertImgModel_gtToken(cfg)
+    sd = params.fill_params({k: v.clone() for k, v in m.state_dict().items()}, 5)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    b = synth.make_batch(B=2, T=24, R=9, seed=9)
+    g = torch.Generator().manual_seed(3)
+    N, R = b["img_feat"].shape[:2]
+    pos = torch.rand(N, R, 7, generator=g)
+    tt = torch.randint(0, 2, (N, R), generator=g)
+    proj = torch.randn(N, 768, generator=g)
+    out = m(b["input_ids"].to(DEV), token_type_ids=b["token_type_ids"].to(DEV), attention_mask=b["input_mask"].to(DEV),
+            img_feats=b["img_feat"].to(DEV), img_token_type_ids=tt.to(DEV), img_pos_feat=pos.to(DEV))
+    (out[1].float() * proj.to(DEV)).sum().backward()
+    watch = ["img_pos_linear.weight", "img_pos_linear.bias", "img_pos_layer_norm.weight", "img_pos_layer_norm.bias",
+             "img_token_type_embeddings.weight", "img_embedding.weight", "img_embedding.bias", "LayerNorm.weight",
+             "LayerNorm.bias", "encoder.layer.0.attention.self.value.weight"]
+    sdr = {k: v.clone() for k, v in sd.items()}
+    for k in watch:
+        sdr[k].requires_grad_(True)
+    seq_r, pooled_r, _ = restate.global_enc_forward(sdr, ocfg, b["input_ids"], b["token_type_ids"], b["input_mask"],
+                                                    b["img_feat"], None, pfx="", img_pos_feat=pos, img_token_type_ids=tt)
+    (pooled_r * proj).sum().backward()
+    named = dict(m.named_parameters())
+    errs = {k: l2err(named[k].grad, sdr[k].grad) for k in watch}
+    e_seq = nerr(out[0], seq_r)
+    print("BertImgModel_gtToken: seq nerr %.4f, max|d pooled| %.4f, grad rel-L2 %s" % (
+        e_seq, float((out[1].float().cpu() - pooled_r.detach()).abs().max()), {k: round(v, 4) for k, v in errs.items()}))
+    assert e_seq < 2e-2 and float((out[1].float().cpu() - pooled_r.detach()).abs().max()) < 2e-2
+    assert max(errs.values()) < GRAD_TOL, errs
+    assert set(m.state_dict().keys()) >= {"img_token_type_embeddings.weight", "img_pos_layer_norm.weight", "img_pos_linear.weight"}
+
+
+def test_per_module_forwards_match_the_oracle_blocks():
+    """SURVEY 8(b) "signatures to keep verbatim": the building blocks can be driven by hand like the reference's modules --
+    ``BertEmbeddings``, ``CaptionBertSelfAttention(hidden_states, attention_mask, head_mask, history_state)``,
+    ``BertSelfOutput``, ``BertIntermediate``, ``BertOutput``, ``CaptionBertLayer``, ``CaptionBertEncoder``, ``BertPooler``
+    (a_transformers/modeling_bert.py:184-211, 369-373, 434-451, 640-646; modeling/modeling_bert.py:34-155) -- each against
+    the fp32 oracle function of the same block (inference entry points on the same kernels)."""
+    ocfg = restate.default_cfg(num_hidden_layers=2)
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     num_hidden_layers=2)
+    m = BertImgModel(cfg)
+    sd = params.fill_params({k: v.clone() for k, v in m.state_dict().items()}, 7)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    b = synth.make_batch(B=1, T=20, R=6, seed=4)
+    N, T = b["input_ids"].shape
+    P = 3
+    g = torch.Generator().manual_seed(1)
+    hist = torch.randn(N, P, 768, generator=g) * 0.5
+    # embeddings
+    e = m.embeddings(b["input_ids"].to(DEV), b["token_type_ids"].to(DEV))
+    e_ref = restate.bert_embeddings(sd, "embeddings.", b["input_ids"], b["token_type_ids"], 1e-12)
+    assert nerr(e, e_ref) < 1e-2
+    h = torch.cat([e_ref, restate.img_embedding(sd, "", b["img_feat"], 1, 1e-12)], 1)
+    S = h.shape[1]
+    kmask = torch.cat([torch.ones(N, P), b["input_mask"]], -1)
+    ext = (1.0 - kmask)[:, None, None, :] * -10000.0
+    hd, extd, histd = h.to(DEV), ext.to(DEV), hist.to(DEV)
+    pfx = "encoder.layer.0."
+    # self-attention with prefix history
+    ctx = m.encoder.layer[0].attention.self(hd, extd, None, histd)[0]
+    ctx_ref, _ = restate.self_attention(sd, pfx + "attention.self.", h, ext, 12, hist)
+    assert tuple(ctx.shape) == (N, S, 768) and nerr(ctx, ctx_ref) < 2e-2
+    a = m.encoder.layer[0].attention.output(ctx_ref.to(DEV), hd)
+    a_ref = restate.self_output(sd, pfx + "attention.output.", ctx_ref, h, 1e-12)
+    assert nerr(a, a_ref) < 2e-2
+    inter = m.encoder.layer[0].intermediate(a_ref.to(DEV))
+    inter_ref = restate.gelu(restate.linear(sd, pfx + "intermediate.dense", a_ref))
+    assert nerr(inter, inter_ref) < 2e-2
+    lo = m.encoder.layer[0](hd, extd, None, histd)[0]
+    lo_ref, _ = restate.bert_layer(sd, pfx, h, ext, 12, 1e-12, hist)
+    assert nerr(lo, lo_ref) < 2e-2
+    enc = m.encoder(hd, extd, [None, None], [histd, histd])[0]
+    x = h
+    for i in range(2):
+        x, _ = restate.bert_layer(sd, "encoder.layer.%d." % i, x, ext, 12, 1e-12, hist)
+    assert nerr(enc, x) < 2e-2
+    pooled = m.pooler(enc)
+    assert float((pooled.float().cpu() - restate.pooler(sd, "", x)).abs().max()) < 2e-2
+    with pytest.raises(NotImplementedError):
+        m.encoder.layer[0].attention.self(hd, torch.zeros(N, 1, S, P + S, device=DEV), None, histd)

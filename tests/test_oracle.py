@@ -425,3 +425,34 @@ def test_standin_roberta_oracle_matches_huggingface_roberta():
         keep = torch.cat([pmask, am], 1).unsqueeze(-1)
         torch.testing.assert_close(seq * keep, hseq * keep, atol=2e-5, rtol=1e-4)
         torch.testing.assert_close(pooled, hpool, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_restated_gttoken_region_embedding_matches_live_reference():
+    """BertImgModel_gtToken (modeling/modeling_bert.py:293-412): box projection Linear(7->H) + LayerNorm, region type
+    embedding and feature projection summed, image LayerNorm, encoder, pooler -- restatement vs the live class
+    (``FusedLayerNorm``, whose import the reference has commented out, bound to torch.nn.LayerNorm)."""
+    ns = ref_shim.load()
+    if not hasattr(ns.mbert, "FusedLayerNorm"):
+        ns.mbert.FusedLayerNorm = torch.nn.LayerNorm
+    cfg = ref_shim.make_config(ns, num_hidden_layers=2, output_attentions=False)
+    m = ns.mbert.BertImgModel_gtToken(cfg)
+    sd = params.fill_params(m.state_dict(), 5)
+    m.load_state_dict(sd)
+    m.eval()
+    b = synth.make_batch(B=1, T=16, R=6, seed=9)
+    g = torch.Generator().manual_seed(3)
+    N, R = b["img_feat"].shape[:2]
+    pos = torch.rand(N, R, 7, generator=g)
+    tt = torch.randint(0, 2, (N, R), generator=g)
+    with torch.no_grad():
+        ref = m(b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=b["input_mask"], img_feats=b["img_feat"],
+                img_token_type_ids=tt, img_pos_feat=pos)
+        ocfg = restate.default_cfg(num_hidden_layers=2)
+        seq, pooled, _ = restate.global_enc_forward({k: v for k, v in sd.items()}, ocfg, b["input_ids"], b["token_type_ids"],
+                                                    b["input_mask"], b["img_feat"], None, pfx="", img_pos_feat=pos,
+                                                    img_token_type_ids=tt)
+    assert float((ref[0] - seq).abs().max()) == 0.0 and float((ref[1] - pooled).abs().max()) == 0.0
+    assert {"img_token_type_embeddings.weight", "img_pos_layer_norm.weight", "img_pos_layer_norm.bias", "img_pos_linear.weight",
+            "img_pos_linear.bias"} <= set(sd.keys())

@@ -51,8 +51,19 @@ def _worker(rank, world, port, q):
     red2 = parallel.GradReducer(w, bucket_mb=0.0001, comm_dtype=None)
     ok = ok and parallel.active_reducer() is red2
     gs = [torch.full_like(p, float(rank + 1) * (i + 1)) for i, p in enumerate(w)]
-    red2.handoff([(w[0], gs[0].clone()), (w[1], gs[1].clone())])      # installed as .grad by the reducer
-    (w[2] * gs[2]).sum().backward()                                    # arrives through the post-accumulate hook
+    class _Node(torch.autograd.Function):      # a backward node that hands its parameter gradients off itself
+        @staticmethod
+        def forward(ctx, x, a, b):
+            ctx.ab = (a, b)
+            return x * 1.0
+
+        @staticmethod
+        def backward(ctx, dy):
+            a, b = ctx.ab
+            red2.handoff([(a, gs[0].clone()), (b, gs[1].clone())])   # installed as .grad by the reducer
+            return dy, None, None                                    # autograd still fires their hooks (ignored)
+    x = torch.ones(2, requires_grad=True)
+    (_Node.apply(x, w[0], w[1]).sum() + (w[2] * gs[2]).sum()).backward()   # w[2] arrives through the post-accumulate hook
     red2.finish()
     for i, p in enumerate(w):
         ok = ok and torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)), atol=1e-6)
