@@ -664,7 +664,32 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           inv = sum > 0.f ? 1.0f / sum : 0.f;
           if (alive) p.lse[((size_t)n * p.heads + h) * p.S + q] = (m + log2f(sum)) * LN2;
         }
-        if (p.probs_img != nullptr) {  // uniform over the CTA
+        if (p.probs_img != nullptr && p.row_sel != nullptr) {  // uniform over the CTA
+          // Row-selected form (row_sel = align_pos, ~4 rows of a sequence): the few wanted rows write their own R
+          // probabilities; the TMEM loads are warp-collective, the exp / store work is done by the wanted lanes only.
+          if (warp_alive && want_mask != 0u) {
+            const int first = (p.T >> 5) << 5;
+            for (int c0 = first; c0 < p.Kp; c0 += 32) {
+              const int wcols = min(32, p.Kp - c0);
+              float v[32];
+              if (wcols == 32) tmem_ld_32x32(taddr + c0, reinterpret_cast<uint32_t*>(v));
+              else tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t*>(v));
+              tmem_ld_wait();
+              if (row_wanted) {
+                const uint32_t wd = (crow != nullptr && (c0 >> 5) < p.cwords) ? __ldg(crow + (c0 >> 5)) : 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int kk = c0 + j;
+                  if (j < wcols && kk >= p.T && kk < p.S) {
+                    float pr = fast_ex2(masked_s2<MODE>(v[j], c1, sBias[kk], kk, q, q_txt, p.T, wd) - m) * inv;
+                    if (p.drop_thr != 0) pr = drop_keep_row(drow, drop_key_id(p, kk), p.drop_thr) ? pr * p.drop_inv : 0.f;
+                    pimg_row[kk - p.T] = pr;
+                  }
+                }
+              }
+            }
+          }
+        } else if (p.probs_img != nullptr) {  // uniform over the CTA
           // Normalised text->region probabilities of this head (v10:982 consumes their sum over heads and layers).
           // A thread owns a ROW, global memory wants a row's columns side by side: each warp transposes its
           // 32 x 32 block through its 4 KB slice of the group's O staging tile (XOR-swizzled, conflict-free) and
@@ -880,21 +905,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             (p.row_sel == nullptr || __ldg(p.row_sel + (size_t)n * p.T + r) != 0)) {
           const float* pi = p.probs_img + (((size_t)n * p.heads + h) * p.T + r) * p.R;
           const float* da = p.dalign + ((size_t)n * p.T + r) * p.R;
-          float d0 = 0.f, d1 = 0.f;
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
           int j = 0;
-          if ((p.R & 3) == 0) {
-            for (; j + 8 <= p.R; j += 8) {
-              const float4 x0 = __ldg(reinterpret_cast<const float4*>(pi + j)), y0 = __ldg(reinterpret_cast<const float4*>(da + j));
-              const float4 x1 = __ldg(reinterpret_cast<const float4*>(pi + j + 4)), y1 = __ldg(reinterpret_cast<const float4*>(da + j + 4));
-              d0 = fmaf(x0.x, y0.x, fmaf(x0.y, y0.y, fmaf(x0.z, y0.z, fmaf(x0.w, y0.w, d0))));
-              d1 = fmaf(x1.x, y1.x, fmaf(x1.y, y1.y, fmaf(x1.z, y1.z, fmaf(x1.w, y1.w, d1))));
+          if ((p.R & 1) == 0) {   // even R: every row starts 8-byte aligned; 64-bit loads, 8 in flight per array
+#pragma unroll 4
+            for (; j + 4 <= p.R; j += 4) {
+              const float2 x0 = __ldg(reinterpret_cast<const float2*>(pi + j)), y0 = __ldg(reinterpret_cast<const float2*>(da + j));
+              const float2 x1 = __ldg(reinterpret_cast<const float2*>(pi + j + 2)), y1 = __ldg(reinterpret_cast<const float2*>(da + j + 2));
+              d0 = fmaf(x0.x, y0.x, d0);
+              d1 = fmaf(x0.y, y0.y, d1);
+              d2 = fmaf(x1.x, y1.x, d2);
+              d3 = fmaf(x1.y, y1.y, d3);
             }
           }
-          for (; j + 2 <= p.R; j += 2) {
-            d0 = fmaf(__ldg(pi + j), __ldg(da + j), d0);
-            d1 = fmaf(__ldg(pi + j + 1), __ldg(da + j + 1), d1);
-          }
-          if (j < p.R) d0 = fmaf(__ldg(pi + j), __ldg(da + j), d0);
+          for (; j < p.R; ++j) d0 = fmaf(__ldg(pi + j), __ldg(da + j), d0);
+          d0 += d2;
+          d1 += d3;
           d += d0 + d1;
         }
       }

@@ -388,6 +388,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float v[CC];
         if constexpr (CC == 32) tmem_ld_32x32(taddr, reinterpret_cast<uint32_t*>(v));
         else tmem_ld_32x16(taddr, reinterpret_cast<uint32_t*>(v));
+        // in_op 3: this chunk's gamma / beta (warp-uniform 128-bit loads, one L1 line each) are requested here, under the
+        // TMEM load and the wait for the residual tile, instead of on the critical path behind that wait.  (Staging them
+        // in shared memory next to the bias would cost this kernel a pipeline stage.)
+        float4 lg[OUT_F32 ? 4 : 1], lb[OUT_F32 ? 4 : 1];
+        if constexpr (OUT_F32 && HAS_IN) {
+          const int nc = tc.n * BN + c * C::CHUNK_COLS;
+          if (in_ln && nc < p.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              lg[j] = __ldg(reinterpret_cast<const float4*>(p.in_gamma + nc + 4 * j));
+              lb[j] = __ldg(reinterpret_cast<const float4*>(p.in_beta + nc + 4 * j));
+            }
+          }
+        }
         tmem_ld_wait();
         if (c + 2 >= C::NCHUNK) {  // this group's last read of the accumulator: hand the TMEM stage back
           tc_fence_before();
@@ -454,10 +468,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 f = lds128f(in_s + sw64_offset(row, j));
-                // gamma / beta: warp-uniform 128-bit loads (one L1 line per chunk; staging them in shared memory next to
-                // the bias would cost this kernel a pipeline stage)
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.in_gamma + n0 + 4 * j));
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.in_beta + n0 + 4 * j));
+                const float4 g4 = lg[j], b4 = lb[j];
                 v[4 * j + 0] += (f.x - ln_mean) * ln_rstd * g4.x + b4.x;
                 v[4 * j + 1] += (f.y - ln_mean) * ln_rstd * g4.y + b4.y;
                 v[4 * j + 2] += (f.z - ln_mean) * ln_rstd * g4.z + b4.z;

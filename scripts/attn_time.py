@@ -27,7 +27,7 @@ def timed(fn, reps=8):
 
 
 g = torch.Generator().manual_seed(0)
-for mode, P in ((0, 10), (0, 0), (1, 0), (2, 0)):
+for mode, P, variant in ((0, 10, ""), (0, 0, ""), (1, 0, ""), (2, 0, "dense"), (2, 0, "sparse"), (2, 0, "noprobs")):
     qkv = (torch.randn(N, S, 3 * H, generator=g) * 0.5).to(dev, BF16)
     pkv = (torch.randn(N, P, 2 * H, generator=g) * 0.5).to(dev, BF16) if P else None
     kbias = torch.zeros(N, P + S, device=dev)
@@ -38,10 +38,16 @@ for mode, P in ((0, 10), (0, 0), (1, 0), (2, 0)):
     dqkv = torch.empty(N, S, 3 * H, dtype=BF16, device=dev)
     dpkv = torch.empty(N, P, 2 * H, dtype=BF16, device=dev) if P else None
     ws = torch.empty(max(ops.attn_bwd_workspace_bytes(N, S, heads) // 4, 1), device=dev)
-    probs = torch.empty(N, heads, T, R, device=dev) if mode == 2 else None
-    dalign = torch.randn(N, T, R, device=dev) * 0.1 if mode == 2 else None
+    probs = torch.empty(N, heads, T, R, device=dev) if (mode == 2 and variant != "noprobs") else None
+    sel = None
+    if variant == "sparse":      # ~4 aligned rows per sequence, like the synthetic batches
+        sel = (torch.rand(N, T, generator=g) < 4.0 / T).to(torch.int64).to(dev)
+    dalign = torch.randn(N, T, R, device=dev) * 0.1 if probs is not None else None
+    if sel is not None:
+        dalign = dalign * sel.unsqueeze(-1).float()
     Tm = T if mode else 0
-    tf = timed(lambda: ops.prefix_attn_fwd(N, S, P, heads, Tm, mode, qkv, pkv, kbias, cbits, cw if mode else 0, ctx, lse, probs))
+    tf = timed(lambda: ops.prefix_attn_fwd(N, S, P, heads, Tm, mode, qkv, pkv, kbias, cbits, cw if mode else 0, ctx, lse, probs,
+                                           row_sel=sel))
     tb = timed(lambda: ops.prefix_attn_bwd(N, S, P, heads, Tm, mode, qkv, pkv, kbias, cbits, cw if mode else 0, ctx, lse, probs,
-                                           dctx, dalign, dqkv, dpkv, ws))
-    print("mode %d P=%2d S=%d: fwd %.1f us  bwd %.1f us" % (mode, P, S, tf, tb), flush=True)
+                                           dctx, dalign, dqkv, dpkv, ws, row_sel=sel))
+    print("mode %d P=%2d S=%d %-7s: fwd %.1f us  bwd %.1f us" % (mode, P, S, variant, tf, tb), flush=True)
