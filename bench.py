@@ -294,8 +294,13 @@ def kernel_roofline(w, dev, peak_tf, hbm_gbs):
     per, fl, tm, by = [], 0.0, 0.0, 0.0
     for name, flops, nbytes, fn in cases:
         sec = timed(fn)
+        # with the L2 flushed every operand comes from HBM: the launch's floor is the larger of its tensor time at the
+        # burst peak and its algorithmic bytes at the copy bandwidth (the fp32-residual GEMMs with K = H are HBM-bound)
+        t_floor, h_floor = flops / (peak_tf * 1e12), nbytes / (hbm_gbs * 1e9)
         per.append(dict(kernel="gemm_kernel", case=name, us=sec * 1e6, achieved=flops / sec / 1e12, unit="TFLOP/s",
-                        frac=flops / sec / 1e12 / peak_tf, algorithmic_bytes=nbytes))
+                        frac=flops / sec / 1e12 / peak_tf, algorithmic_bytes=nbytes,
+                        hbm_frac=nbytes / sec / 1e9 / hbm_gbs, bound="hbm" if h_floor > t_floor else "tensor",
+                        frac_of_floor=max(t_floor, h_floor) / sec))
         fl += flops
         tm += sec
         by += nbytes
@@ -454,7 +459,11 @@ def run_ours(args):
     pk.pack(batches[0], out=static)
     db = static
     comm_dtype = None if args.fp32_allreduce else torch.bfloat16
-    reducer = parallel.GradReducer(list(m.parameters()) + [prefix], comm_dtype=comm_dtype) if world > 1 else None
+    reducer = None
+    if world > 1 and not args.no_allreduce:
+        reducer = parallel.GradReducer(list(m.parameters()) + [prefix], comm_dtype=comm_dtype,
+                                       handoff=not args.no_handoff, windows=args.comm_windows,
+                                       bucket_mb=args.bucket_mb)
 
     def fwd_bwd(bd):
         hist = [prefix[i].unsqueeze(0).expand(N, -1, -1) for i in range(w["L"])]
@@ -531,6 +540,18 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if sampler else None
     loss_val = float(loss)
+
+    if args.trace_out:
+        # diagnostic (never a bench value): CUPTI timeline (chrome trace) of two more steps, every kernel of every stream
+        # incl. NCCL's, one file per rank -- scripts/comm_overlap.py reads them
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                run_step(static)
+            barrier()
+        prof.export_chrome_trace("%s.rank%d.json" % (args.trace_out, rank))
+        barrier()
 
     # ---- end to end through the public call with host buffers (`e2e`)
     # Every step consumes a DIFFERENT ragged batch that starts in host memory: host pack into a pinned buffer + one H2D
@@ -753,6 +774,15 @@ def main():
     ap.add_argument("--dropout", action="store_true",
                     help="second row of SURVEY 8(d): train with the reference's dropout (hidden 0.3 / attention 0.1) "
                          "instead of the deterministic parity configuration")
+    ap.add_argument("--no-allreduce", action="store_true",
+                    help="N>1 diagnostic: no gradient exchange at all (N independent replicas: the max-over-ranks floor)")
+    ap.add_argument("--comm-windows", action="store_true",
+                    help="N>1: issue each layer's gradient all-reduce beside the next layer's attention backward kernel")
+    ap.add_argument("--bucket-mb", type=float, default=25.0, help="N>1: gradient bucket size")
+    ap.add_argument("--trace-out", default=None,
+                    help="diagnostic: write a CUPTI kernel timeline of two extra steps to <path>.rank<r>.json")
+    ap.add_argument("--no-handoff", action="store_true",
+                    help="N>1 diagnostic: buckets filled from autograd hooks only (one hand-off per encoder, round-1 behaviour)")
     ap.add_argument("--fp32-allreduce", action="store_true",
                     help="N>1: all-reduce the fp32 gradients as they are (default: bf16 buckets, half the NVLink bytes)")
     args = ap.parse_args()

@@ -44,6 +44,12 @@ const char* modcr_last_error_string(void);
 /* number of CUDA kernels this library has launched in the calling process (monotonic) */
 uint64_t modcr_launch_count(void);
 
+/* SM budget of the persistent kernels (GEMM, persistent attention forward): they launch one CTA (pair) per SM with a static
+ * tile partition, so CTAs of a concurrent NCCL collective must find free SMs instead of queueing one of these kernels
+ * behind them.  sms <= 0 restores "all SMs"; returns the previous value.  Takes effect for the launches enqueued after
+ * the call (including launches captured into a CUDA graph). */
+int modcr_set_sm_limit(int32_t sms);
+
 /* Workspace query.  op: 1 = prefix_attn_bwd {N,S,heads}; 2 = img_embed_ln {rows, feat_dim, H} */
 size_t modcr_workspace_bytes(int op, const int64_t* dims, int ndims);
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "modcr_last_error_string": [],
     "modcr_launch_count": [],
     "modcr_workspace_bytes": [c_int, C.POINTER(c_i64), c_int],
+    "modcr_set_sm_limit": [c_i32],
     "modcr_gemm": [C.POINTER(GemmDesc), c_void_p],
     "modcr_layernorm_fwd": [c_void_p, c_i32, RowMap, c_void_p, c_void_p, c_void_p, c_void_p, RowMap, c_void_p, c_void_p,
                             c_i32, c_i32, c_float, c_void_p],
@@ -151,6 +152,11 @@ def load():
         fn.restype = _RESTYPES.get(name, c_int)
     _lib = lib
     return lib
+
+
+def set_sm_limit(sms):
+    """SM budget of the persistent kernels (0 = all); returns the previous value."""
+    return int(load().modcr_set_sm_limit(int(sms)))
 
 
 def launch_count():

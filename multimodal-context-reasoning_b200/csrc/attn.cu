@@ -986,7 +986,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       // S = Q K^T and dP = dO V^T of step `step` over the whole key block: N = nb (<= 128) per instruction.  The small
       // MMAs of this kernel read both operands from shared memory and are bound by that read, not by the tensor pipe
-      // (~90 cycles per M=128 x N=64 x K=16 instruction against a 32-cycle floor, profiles/r02_attn_bwd_trace_6.log):
+      // (~90 cycles per M=128 x N=64 x K=16 instruction against a 32-cycle floor, profiles/r02_attn_bwd_trace_after_hoist.log):
       // one N=128 instruction re-reads the 4 KB A slice once instead of twice.
       auto issue_sdp = [&](int step) {
         const int kb = step / p.nqt;
@@ -1358,7 +1358,9 @@ static int launch_fwd_persist(const AttnParams& p, const CUtensorMap& tmQKV, con
     if (sms <= 0) sms = 148;
   }
   const int total = p.N * p.heads;
-  const int grid = total < sms ? total : sms;
+  const int lim = sm_limit();
+  const int avail = (lim > 0 && lim < sms) ? lim : sms;
+  const int grid = total < avail ? total : avail;
   kern<<<grid, 256, smem, stream>>>(tmQKV, tmTail, tmPKV, tmA, tmB, p, lay);
   return check_launch("prefix_attn_fwd");
 }

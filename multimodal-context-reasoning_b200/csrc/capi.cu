@@ -235,6 +235,8 @@ int modcr_adamw_step(const modcr_optim_tensor* meta, const float* const* grads, 
   return modcr::adamw_step(meta, grads, blk_tensor, blk_chunk, nblocks, hyper, grad_sq, beta1, beta2, eps, S(stream));
 }
 
+int modcr_set_sm_limit(int32_t sms) { return modcr::set_sm_limit(sms); }
+
 int modcr_multi_copy(const void* const* src, void* const* dst, const int64_t* n, int32_t count, int32_t src_bf16,
                      int32_t dst_bf16, float scale, void* stream) {
   ARCH_OR_RETURN();

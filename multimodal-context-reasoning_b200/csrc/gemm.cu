@@ -59,7 +59,7 @@ struct GemmParams {
   const float* in_beta;
 };
 
-template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32, bool WIDE = false>
 struct Cfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -71,7 +71,10 @@ struct Cfg {
   // of the previous one still reads its buffer, the input of chunk k+1 is in flight while chunk k is processed, and
   // one block barrier per chunk suffices.
   static constexpr int ES = OUT_F32 ? 4 : 2;
-  static constexpr int CHUNK_COLS = OUT_F32 ? 16 : 32;
+  // WIDE (fp32 output with an fp32 epilogue input, K <= 1024): 32-column fp32 chunks = 128-byte rows (SWIZZLE_128B), half
+  // as many chunk hand-offs (block barrier + TMA store + two mbarrier round trips each) per tile, paid for with a
+  // 3-stage instead of a 4-stage operand ring -- the short-K dense-output GEMM is bound by its epilogue, not its ring
+  static constexpr int CHUNK_COLS = OUT_F32 ? (WIDE ? 32 : 16) : 32;
   static constexpr int ROW_BYTES = CHUNK_COLS * ES;
   static constexpr int CHUNK_BYTES = 128 * ROW_BYTES;
   static constexpr int NCHUNK = BN / CHUNK_COLS;
@@ -114,12 +117,12 @@ DEVINL TileCoord decode_tile(const GemmParams& p, int t) {
   return c;
 }
 
-template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32, bool WIDE = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
             const __grid_constant__ CUtensorMap tmIn, const GemmParams p) {
-  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32, WIDE>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -354,6 +357,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool issuer = (q == 0 && lane == 0);
     const uint32_t bar_id = 1 + g;
     constexpr int CC = C::CHUNK_COLS;
+    // byte offset of 16-byte piece `piece` of this thread's row inside a chunk buffer (64- or 128-byte rows)
+    auto swz = [](uint32_t r, uint32_t piece) -> uint32_t {
+      return C::ROW_BYTES == 128 ? sw128_offset(r, piece) : sw64_offset(r, piece);
+    };
     uint8_t* out_base = sOut + g * C::NBUF * C::CHUNK_BYTES;
     uint8_t* aux_base = sOut + (2 * C::NBUF + g * C::NBUF) * C::CHUNK_BYTES;
     float* sBias = sBiasG + g * 128;
@@ -391,12 +398,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // in_op 3: this chunk's gamma / beta (warp-uniform 128-bit loads, one L1 line each) are requested here, under the
         // TMEM load and the wait for the residual tile, instead of on the critical path behind that wait.  (Staging them
         // in shared memory next to the bias would cost this kernel a pipeline stage.)
-        float4 lg[OUT_F32 ? 4 : 1], lb[OUT_F32 ? 4 : 1];
+        float4 lg[OUT_F32 ? CC / 4 : 1], lb[OUT_F32 ? CC / 4 : 1];
         if constexpr (OUT_F32 && HAS_IN) {
           const int nc = tc.n * BN + c * C::CHUNK_COLS;
           if (in_ln && nc < p.N) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CC / 4; ++j) {
               lg[j] = __ldg(reinterpret_cast<const float4*>(p.in_gamma + nc + 4 * j));
               lb[j] = __ldg(reinterpret_cast<const float4*>(p.in_beta + nc + 4 * j));
             }
@@ -466,8 +473,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if constexpr (OUT_F32) {  // fp32 residual stream: C = f(acc) + in (fp32 tile)
             if (in_ln && n0 < p.N) {   // ... + LayerNorm(in): same arithmetic as ln_fwd_kernel, (x - mean) * rstd * gamma + beta
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 f = lds128f(in_s + sw64_offset(row, j));
+              for (int j = 0; j < CC / 4; ++j) {
+                const float4 f = lds128f(in_s + swz(row, j));
                 const float4 g4 = lg[j], b4 = lb[j];
                 v[4 * j + 0] += (f.x - ln_mean) * ln_rstd * g4.x + b4.x;
                 v[4 * j + 1] += (f.y - ln_mean) * ln_rstd * g4.y + b4.y;
@@ -476,8 +483,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 f = lds128f(in_s + sw64_offset(row, j));
+              for (int j = 0; j < CC / 4; ++j) {
+                const float4 f = lds128f(in_s + swz(row, j));
                 v[4 * j + 0] += f.x;
                 v[4 * j + 1] += f.y;
                 v[4 * j + 2] += f.z;
@@ -505,8 +512,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if constexpr (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts128f(out_s + sw64_offset(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < CC / 4; ++j)
+            sts128f(out_s + swz(row, j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -560,7 +567,8 @@ static int num_sms() {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  return g_num_sms;
+  const int lim = sm_limit();
+  return (lim > 0 && lim < g_num_sms) ? lim : g_num_sms;
 }
 
 // MODCR_GEMM_NCTA=1 forces the single-CTA kernel (A/B comparison of the two data paths; default: CTA pairs)
@@ -573,10 +581,10 @@ static int gemm_ncta() {
   return g_ncta;
 }
 
-template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int NCTA, int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32, bool WIDE = false>
 static int launch_n(const GemmDesc& g, cudaStream_t stream) {
-  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
-  auto kern = gemm_kernel<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>;
+  using C = Cfg<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32, WIDE>;
+  auto kern = gemm_kernel<NCTA, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -668,10 +676,20 @@ static int launch_n(const GemmDesc& g, cudaStream_t stream) {
   return check_launch("gemm");
 }
 
-template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, bool HAS_AUX, bool HAS_IN, bool OUT_F32, bool WIDE = false>
 static int launch(const GemmDesc& g, cudaStream_t stream) {
-  if (gemm_ncta() == 2) return launch_n<2, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>(g, stream);
-  return launch_n<1, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32>(g, stream);
+  if (gemm_ncta() == 2) return launch_n<2, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32, WIDE>(g, stream);
+  return launch_n<1, BN, A_MN, B_MN, HAS_AUX, HAS_IN, OUT_F32, WIDE>(g, stream);
+}
+
+// MODCR_GEMM_WIDE=0 disables the 32-column fp32 epilogue chunks of the short-K fp32-residual GEMM (A/B comparison)
+static bool gemm_wide_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MODCR_GEMM_WIDE");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // Same cost model as engine.py::_split_k: waves of (tile, split) units over the CTA pairs x (k-blocks per unit + a fixed
@@ -712,6 +730,7 @@ int gemm_launch(const GemmDesc& g, cudaStream_t stream) {
         set_error("gemm: fp32 epilogue input supports only in_op=1 on the NT layout without split-K");
         return MODCR_ERR_UNSUPPORTED;
       }
+      if (g.K <= 1024 && gemm_wide_enabled()) return launch<256, false, false, false, true, true, true>(g, stream);
       return launch<256, false, false, false, true, true>(g, stream);
     }
     if (g.split_k > 1 && !g.accumulate) {

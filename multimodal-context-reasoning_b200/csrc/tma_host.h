@@ -33,5 +33,7 @@ enum : int {
 int check_launch(const char* what);   // also counts one kernel launch
 unsigned long long launch_count();
 void count_launches(int n);           // extra launches behind a single check_launch
+int sm_limit();                       // SM budget of the persistent kernels (0 = all)
+int set_sm_limit(int sms);            // returns the previous budget
 
 }  // namespace modcr

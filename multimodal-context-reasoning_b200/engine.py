@@ -314,8 +314,10 @@ def attention_fwd(ps, pfx, x, x32, hist, ac, eps, save, do_chunk_cross=False, pr
     return a, LnRes(pre1, mean1, rstd1, g1_, b1_, eps)
 
 
-def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop=None, site=0):
-    """Returns (dx, dhist).  ``z``: pre-zeroed (dgam, dbet, dbo, dbqkv, dWo, dWqkv) from ``_zeros_many``."""
+def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop=None, site=0, before_core=None):
+    """Returns (dx, dhist).  ``z``: pre-zeroed (dgam, dbet, dbo, dbqkv, dWo, dWqkv) from ``_zeros_many``.
+    ``before_core()`` is called right before the attention-core kernel is launched (the data-parallel reducer issues its
+    collectives there, ``parallel.GradReducer.open_window``)."""
     dev = da.device
     N, S, H, heads, P = ac.N, ac.S, ac.H, ac.heads, ac.P
     M = N * S
@@ -339,6 +341,8 @@ def attention_bwd(ps, pfx, sv, da, ac, grads, dalign=None, ws=None, z=None, drop
     if ws is None:
         ws = _empty((ops.attn_bwd_workspace_bytes(N, S, heads) // 4,), F32, dev)
     use_align = dalign if sv["probs_img"] is not None else None
+    if before_core is not None:
+        before_core()
     ops.prefix_attn_bwd(N, S, P, heads, ac.T, ac.mode, sv["qkv"], sv["pkv"], ac.kbias, ac.cbits, ac.cwords, sv["ctx"],
                         sv["lse"], sv["probs_img"] if use_align is not None else None, dctx, use_align, dqkv, dpkv, ws,
                         drop=(drop.seed, site, drop.p_attn) if (drop is not None and drop.p_attn > 0.0) else None,
@@ -367,12 +371,12 @@ def layer_fwd(ps, pfx, x, x32, hist, ac, I, eps, save, do_chunk_cross=False, pro
     return ffn_fwd(ps, pfx, a, a32, ac.N * ac.S, ac.H, I, eps, save, drop, site + 2)
 
 
-def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None, drop=None, layer=0):
+def layer_bwd(ps, pfx, sv, dy, ac, I, grads, dalign=None, ws=None, drop=None, layer=0, before_core=None):
     H = ac.H
     z = _zeros_many([(H,), (H,), (H,), (I,), (H, I), (I, H), (H,), (H,), (H,), (3 * H,), (H, H), (3 * H, H)], dy.device)
     site = drop.site(layer + 1, 0) if drop is not None else 0
     da = ffn_bwd(ps, pfx, sv, dy, ac.N * ac.S, H, I, grads, z[:6], drop, site + 2)
-    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws, z[6:], drop, site)
+    return attention_bwd(ps, pfx + "attention.", sv, da, ac, grads, dalign, ws, z[6:], drop, site, before_core)
 
 
 # -------------------------------------------------------------------------------------------- embeddings

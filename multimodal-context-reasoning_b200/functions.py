@@ -182,7 +182,8 @@ class EncoderFn(torch.autograd.Function):
             ac, cross = run.layer_cfg(i)
             da = dalign if (ctx.nprob and i >= L - ctx.nprob) else None
             dy_out = dy.clone() if (run.local_residual and i in CROSS_MODAL_LAYERS) else None
-            dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws, run.drop, i)
+            dy, dh = E.layer_bwd(ps, "encoder.layer.%d." % i, ctx.saves[i], dy, ac, I, grads, da, ws, run.drop, i,
+                                 red.open_window if red is not None else None)
             if dy_out is not None:                           # the skip connection around a cross-modal layer
                 ops.add_bf16(dy, dy_out, dy)
             if dy_top is not None and i == CROSS_MODAL_START:   # the final residual lands on the input of layer 9

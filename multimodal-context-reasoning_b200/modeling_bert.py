@@ -12,8 +12,7 @@ from torch import nn
 
 from . import engine as E
 from .functions import DropoutFn, EncoderFn, EncoderRun, MlpHiddenFn, ScorerFn
-from .modeling_utils import (BertConfig, CaptionPreTrainedModel, ImgPreTrainedModel, cfg_get, check_no_dropout,  # noqa: F401
-                             engine_cfg)
+from .modeling_utils import BertConfig, CaptionPreTrainedModel, ImgPreTrainedModel, cfg_get, engine_cfg  # noqa: F401
 
 BertLayerNorm = nn.LayerNorm
 

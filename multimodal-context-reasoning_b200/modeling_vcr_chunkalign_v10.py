@@ -13,7 +13,7 @@ from .functions import (AlignLossFn, ClsHeadRun, ClsLayer2HeadFn, ClsLyxHeadFn, 
                         cls_lyx_head_forward)
 from .modeling_bert import (AttentionsNotMaterialised, BertIntermediate, BertOutput, CaptionBertAttention,
                             _EncoderModelBase)
-from .modeling_utils import cfg_get, check_no_dropout, engine_cfg
+from .modeling_utils import cfg_get, engine_cfg
 
 NEG = -10000.0
 
@@ -94,11 +94,6 @@ class ClsLayer2(nn.Module):
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
         self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
-
-
-def _init_like_reference(module, std=0.02):
-    # heads are plain nn.Modules in the reference: torch default init; kept as is
-    return module
 
 
 class ChunkAlign_CLS_enc4_align(nn.Module):

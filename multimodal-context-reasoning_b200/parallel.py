@@ -29,12 +29,25 @@ def init_from_env(backend=None):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # the collectives share the SMs with the backward kernels: cap their CTAs (GradReducer reserves as many SMs)
+            if COMM_SMS > 0:
+                os.environ.setdefault("NCCL_MAX_CTAS", str(COMM_SMS))
             torch.cuda.set_device(local)
-            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+            # the collective's CTAs are placed ahead of the queued CTAs of the backward kernel they run beside
+            # (GradReducer.open_window)
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=COMM_HIGH_PRIORITY)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local), pg_options=opts)
         else:
             dist.init_process_group(backend)
     return rank, local, world
 
+
+# SMs the persistent kernels leave to the NCCL CTAs while gradient buckets are in flight (0 = off, the default: measured at
+# 8 GPUs, cfg-2 -- 38.3 ms / step with NCCL's own CTA count and full-width kernels, 39.2 / 40.6 / 41.6 ms with 4 / 8 / 16
+# SMs reserved and NCCL capped to as many CTAs, profiles/r02_bench_cfg2_n8_comm*.log)
+COMM_SMS = int(os.environ.get("MODCR_COMM_SMS", "0"))
+COMM_HIGH_PRIORITY = os.environ.get("MODCR_COMM_PRIORITY", "1") != "0"
+_SKIP_COLLECTIVE = os.environ.get("MODCR_DEBUG_SKIP_COLLECTIVE", "0") == "1"
 
 _ACTIVE = None
 
@@ -60,11 +73,17 @@ class GradReducer:
     gradients into the flat bucket, NCCL averages inside the collective, ONE launch per 64 tensors scatters the means
     back.  Parameters that never receive a gradient never enter a bucket.
 
+    ``windows=True``: the collectives are not issued when a bucket fills but when the backward program calls
+    ``open_window()`` -- right before a long kernel with many more CTAs than SMs (the attention backward of the next
+    layer), on high-priority streams.  A collective kernel holds its SMs until every rank has arrived; the persistent GEMMs
+    partition their tiles statically over all SMs, so one that starts beside a collective cannot finish before it (the
+    CTAs that found no SM run last).  Beside a many-CTA kernel the collective only costs its share of the SMs.
+
     Gradient accumulation (run_PMR_ModCR.py:211-227): wrap every micro-step but the last in ``no_sync()``; the last one
     reduces the accumulated ``.grad``.  ``finish()`` must follow exactly one synchronising backward: a parameter that is
     enqueued twice before ``finish()`` raises."""
 
-    def __init__(self, params, bucket_mb=25, group=None, comm_dtype=None, handoff=True):
+    def __init__(self, params, bucket_mb=25, group=None, comm_dtype=None, handoff=True, windows=False):
         """``comm_dtype=torch.bfloat16`` halves the bytes on NVLink (the sum is then formed in bf16, like DDP's bf16
         compression hook); ``None`` reduces in the gradients' own dtype (fp32)."""
         global _ACTIVE
@@ -75,6 +94,7 @@ class GradReducer:
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.comm_dtype = comm_dtype
         self.sync = True
+        self.windows = bool(windows) and handoff
         self._seen = {}
         self._bucket = None            # dict(flat=, used=, grads=[...]) being filled
         self._flats, self._free = [], []   # flat buffers, recycled step after step (stable addresses for graph replay)
@@ -82,6 +102,7 @@ class GradReducer:
         self._handles = []
         self.stream = None
         self.launched = 0
+        self._sm_reserved = False
         if self.world > 1:
             for p in self.params:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -123,7 +144,7 @@ class GradReducer:
         if not cuda:
             return _Null()
         if self.stream is None:
-            self.stream = torch.cuda.Stream()
+            self.stream = torch.cuda.Stream(priority=-1 if COMM_HIGH_PRIORITY else 0)
         ev = torch.cuda.Event()
         ev.record()                      # these gradients are complete on the compute stream here
         self.stream.wait_event(ev)
@@ -148,6 +169,12 @@ class GradReducer:
         grads = [p.grad for p in ps]
         need = sum((g.numel() + 7) & ~7 for g in grads)          # 16-byte aligned slots
         cuda = grads[0].is_cuda
+        if cuda and not self._sm_reserved and COMM_SMS > 0:
+            # from the first bucket of the step until finish(): the persistent GEMM / attention kernels leave COMM_SMS
+            # SMs to the collectives instead of queueing a whole kernel behind them
+            from . import _lib
+            _lib.set_sm_limit(torch.cuda.get_device_properties(grads[0].device).multi_processor_count - COMM_SMS)
+            self._sm_reserved = True
         with self._side(cuda):
             b = self._bucket
             esz = 2 if self.comm_dtype in (torch.bfloat16, torch.float16) else grads[0].element_size()
@@ -164,8 +191,17 @@ class GradReducer:
             _copy_many(grads, views)
             b["grads"] += grads
             b["views"] += views
-            if b["used"] * esz >= self.bucket_bytes:
+            if b["used"] * esz >= self.bucket_bytes and not self.windows:
                 self._launch()
+
+    def open_window(self):
+        """Called by a backward program right before it launches a long many-CTA kernel: issue the collective of what has
+        been handed off so far (``windows=True`` only), ordered behind the compute stream *here*."""
+        b = self._bucket
+        if not self.windows or b is None or not b["grads"]:
+            return
+        with self._side(b["flat"].is_cuda):
+            self._launch()
 
     def _launch(self):
         """All-reduce the bucket being filled (caller holds the side-stream context)."""
@@ -175,10 +211,15 @@ class GradReducer:
         flat = b["flat"][:b["used"]]
         cuda = flat.is_cuda
         avg = cuda and dist.get_backend(self.group) == "nccl"    # NCCL averages inside the collective
-        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if _SKIP_COLLECTIVE:              # timing diagnostic only (gather + scatter without the exchange): wrong gradients
+            work = None
+        else:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group,
+                                   async_op=True)
         self.launched += 1
         if cuda:
-            work.wait()                   # stream-level: the side stream waits for NCCL, the host does not
+            if work is not None:
+                work.wait()               # stream-level: the side stream waits for NCCL, the host does not
             _copy_many(b["views"], b["grads"], 1.0 if avg else 1.0 / self.world)
             self._free.append(b["flat"])  # stream-ordered reuse on the side stream
         else:
@@ -202,6 +243,10 @@ class GradReducer:
         self._pending = []
         if cuda:
             torch.cuda.current_stream().wait_stream(self.stream)
+        if self._sm_reserved:
+            from . import _lib
+            _lib.set_sm_limit(0)
+            self._sm_reserved = False
         self._seen.clear()
 
     def remove(self):

@@ -92,6 +92,23 @@ def _worker(rank, world, port, q):
     red2.finish()
     red2.remove()
     ok = ok and parallel.active_reducer() is None
+    # ---- windows: nothing is reduced when a bucket fills, only when the backward program opens a window (or at finish)
+    for p in w:
+        p.grad = None
+    red3 = parallel.GradReducer(w, bucket_mb=0.0001, comm_dtype=None, windows=True)
+    red3.handoff([(w[0], gs[0].clone())])
+    ok = ok and red3.launched == 0
+    red3.open_window()
+    ok = ok and red3.launched == 1
+    red3.open_window()                               # nothing new: no collective
+    ok = ok and red3.launched == 1
+    red3.handoff([(w[1], gs[1].clone())])
+    red3.handoff([(w[2], gs[2].clone())])            # does not fit behind w[1]: the full bucket goes first
+    red3.finish()
+    ok = ok and red3.launched == 3
+    for i, p in enumerate(w):
+        ok = ok and torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)), atol=1e-6)
+    red3.remove()
     loss = parallel.allreduce_mean_scalar(torch.tensor(float(rank)))
     ok = ok and abs(float(loss) - 0.5) < 1e-6
     q.put((rank, bool(ok)))

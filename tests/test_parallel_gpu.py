@@ -107,8 +107,9 @@ def _model_worker(rank, world, port, q):
             singles.append(grab())
         want = [None if a is None else sum(s[i] for s in singles) / world for i, a in enumerate(singles[0])]
         res = {}
-        for comm, tol in ((None, 1e-4), (torch.bfloat16, 1e-2)):    # fp32: atomics order only
-            red = parallel.GradReducer(plist, bucket_mb=25, comm_dtype=comm)
+        # fp32: atomics order only; the last case issues the collectives at the attention-backward windows
+        for comm, tol, windows in ((None, 1e-4, False), (torch.bfloat16, 1e-2, False), (torch.bfloat16, 1e-2, True)):
+            red = parallel.GradReducer(plist, bucket_mb=25, comm_dtype=comm, windows=windows)
             assert parallel.active_reducer() is red
             step(rank)
             red.finish()
@@ -121,7 +122,7 @@ def _model_worker(rank, world, port, q):
                     continue
                 n += 1
                 worst = max(worst, float((gv - wv).norm() / wv.norm().clamp_min(1e-20)))
-            res[str(comm)] = (worst, tol, red.launched, n)
+            res[str(comm) + ("+windows" if windows else "")] = (worst, tol, red.launched, n)
             assert worst < tol, (comm, worst)
             assert red.launched >= 20          # per-layer buckets, not one per encoder
             # a second step re-uses the reducer and its flat buffers
