@@ -451,7 +451,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int j = 0; j < CC; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < CC; j += 2) {
+            const float2 r = gelu_fast2(make_float2(v[j], v[j + 1]));
+            v[j] = r.x;
+            v[j + 1] = r.y;
+          }
         } else if (p.act == 2) {
 #pragma unroll
           for (int j = 0; j < CC; ++j) v[j] = tanhf(v[j]);
@@ -503,8 +507,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   v[8 * j + 2 * e] += f.x;
                   v[8 * j + 2 * e + 1] += f.y;
                 } else {
-                  v[8 * j + 2 * e] *= gelu_grad_fast(f.x);
-                  v[8 * j + 2 * e + 1] *= gelu_grad_fast(f.y);
+                  const float2 r = __fmul2_rn(make_float2(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]), gelu_grad_fast2(f));
+                  v[8 * j + 2 * e] = r.x;
+                  v[8 * j + 2 * e + 1] = r.y;
                 }
               }
             }

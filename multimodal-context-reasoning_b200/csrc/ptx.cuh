@@ -311,6 +311,33 @@ DEVINL float gelu_grad_fast(float x) {
   return fmaf(x * e, 0.3989422804014327f, cdf);
 }
 
+// Two elements per instruction: FMUL2 / FFMA2 of sm_100 (`mul/fma.rn.f32x2`) halve the FP32 issue slots of the GELU
+// epilogues, which are issue-bound with two epilogue warps per scheduler (ncu, profiles/r02_ncu_gemm_layer_summary.txt:
+// dgrad ffn2 x GELU' issue-active 45 %, tensor pipe 47 %).  Each lane rounds exactly like the scalar form above.
+DEVINL float2 gelu_tanh_arg2(float2 x, float2& x2) {
+  x2 = __fmul2_rn(x, x);
+  const float2 x2c = make_float2(fminf(x2.x, 50.0f), fminf(x2.y, 50.0f));
+  float2 q = __ffma2_rn(x2c, make_float2(-3.51517510e-04f, -3.51517510e-04f), make_float2(3.70056508e-02f, 3.70056508e-02f));
+  q = __ffma2_rn(x2c, q, make_float2(7.97507879e-01f, 7.97507879e-01f));
+  return __fmul2_rn(x, q);
+}
+DEVINL float2 gelu_fast2(float2 x) {
+  float2 x2;
+  const float2 a = gelu_tanh_arg2(x, x2);
+  const float2 t = make_float2(fast_tanh(a.x), fast_tanh(a.y));
+  const float2 hx = __fmul2_rn(make_float2(0.5f, 0.5f), x);
+  return __ffma2_rn(hx, t, hx);
+}
+DEVINL float2 gelu_grad_fast2(float2 x) {
+  float2 x2;
+  const float2 a = gelu_tanh_arg2(x, x2);
+  const float2 t = make_float2(fast_tanh(a.x), fast_tanh(a.y));
+  const float2 cdf = __ffma2_rn(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f));
+  const float2 ea = __fmul2_rn(make_float2(-0.72134752044448170f, -0.72134752044448170f), x2);
+  const float2 e = make_float2(fast_ex2(ea.x), fast_ex2(ea.y));
+  return __ffma2_rn(__fmul2_rn(x, e), make_float2(0.3989422804014327f, 0.3989422804014327f), cdf);
+}
+
 // explicit shared-state-space 128-bit accesses (a generic pointer derived from the aligned dynamic-smem base makes
 // the compiler emit generic LD/ST, which issue slower than LDS/STS)
 DEVINL void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {

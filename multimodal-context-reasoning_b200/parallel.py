@@ -83,7 +83,7 @@ class GradReducer:
     reduces the accumulated ``.grad``.  ``finish()`` must follow exactly one synchronising backward: a parameter that is
     enqueued twice before ``finish()`` raises."""
 
-    def __init__(self, params, bucket_mb=25, group=None, comm_dtype=None, handoff=True, windows=False):
+    def __init__(self, params, bucket_mb=128, group=None, comm_dtype=None, handoff=True, windows=False):
         """``comm_dtype=torch.bfloat16`` halves the bytes on NVLink (the sum is then formed in bf16, like DDP's bf16
         compression hook); ``None`` reduces in the gradients' own dtype (fp32)."""
         global _ACTIVE
