@@ -59,6 +59,9 @@ class EncoderRun:
         # requires_grad of the inputs, so under torch.no_grad() (evaluate(), frozen encoders) nothing is saved
         self.want_grad = torch.is_grad_enabled()
         self.keep_attn, self.attn_debug = False, None    # lazy dense-attention debug path (AttentionsNotMaterialised)
+        # a caller-supplied [N,S,S] query-by-key mask (modeling_transfomres.py:630-631): every layer runs the bit-mask mode
+        # of the attention kernels with all S rows as "text" rows; ``cbits`` holds the [N,S,ceil(S/32)] bits
+        self.dense_mask = False
         self.N, self.T = input_ids.shape
         self.R = 0 if img_feats is None else img_feats.shape[1]
         self.S = self.n_pre + self.T + self.R
@@ -66,6 +69,9 @@ class EncoderRun:
     def layer_cfg(self, i):
         c = self.cfg
         mode, cross = 0, False
+        if self.dense_mask:
+            ac = E.AttnCfg(self.N, self.S, c["H"], c["heads"], 0, self.S, 1, self.kbias, self.cbits, self.cwords)
+            return ac, False
         if self.is_seq:
             if i < CHUNK_LAYERS:
                 mode = 1

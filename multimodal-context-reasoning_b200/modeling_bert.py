@@ -325,6 +325,36 @@ class _EncoderModelBase(CaptionPreTrainedModel):
         return self.resize_token_embeddings(new_num_tokens)
 
 
+def _prepare_mask(attention_mask, N, S, P, dev):
+    """The two mask forms of ``BertImgModel.forward`` (modeling/modeling_transfomres.py:628-641) -> (key bias [N,P+S],
+    query-by-key bits or None, words per bit row).
+
+    * 2-D ``[N, P+S]`` (or ``[N, S]``: the prefix keys are then always visible): key padding, the additive -10000 bias
+      per key that every mask mode of the attention kernels starts from;
+    * 3-D ``[N, S, S]`` (:630-631), 0 / 1 valued: one bit per (query, key), evaluated in registers by the bit-mask mode of
+      the kernels (a masked key gets the reference's additive -10000, so a row with no visible key is, as there, the
+      softmax of its unmasked scores shifted by -10000).  Without ``encoder_history_states`` only: the bit rows cover the
+      sequence keys."""
+    if attention_mask is None:
+        attention_mask = torch.ones((N, P + S), dtype=torch.float32, device=dev)
+    if attention_mask.dim() == 3:
+        if P > 0:
+            raise NotImplementedError("a 3-D attention_mask together with encoder_history_states is outside the ModCR "
+                                      "path (global_enc gets the 2-D input_mask, run_PMR_ModCR.py / v10:1041-1047)")
+        if tuple(attention_mask.shape) != (N, S, S):
+            raise ValueError("a 3-D attention_mask must be [N, S, S] = %s, got %s" % ((N, S, S), tuple(attention_mask.shape)))
+        cbits, cwords = E.make_chunk_bits(attention_mask)
+        kbias = E.make_key_bias(torch.ones((N, S), dtype=torch.float32, device=dev))
+        return kbias, cbits, cwords
+    if attention_mask.dim() != 2:
+        raise NotImplementedError("attention_mask must be 2-D or 3-D (modeling_transfomres.py:628-633)")
+    if attention_mask.shape[1] == S and P > 0:
+        attention_mask = torch.cat([torch.ones((N, P), dtype=attention_mask.dtype, device=dev), attention_mask], -1)
+    if attention_mask.shape[1] != P + S:
+        raise ValueError("attention_mask has %d keys, expected P+S = %d" % (attention_mask.shape[1], P + S))
+    return E.make_key_bias(attention_mask), None, 0
+
+
 class BertImgModel(_EncoderModelBase):
     """Expand from BertModel to handle image region features as input
     (modeling/modeling_transfomres.py:564-694; twin modeling/modeling_bert.py:158-291)."""
@@ -356,16 +386,11 @@ class BertImgModel(_EncoderModelBase):
         dev = input_ids.device
         if attention_mask is None:
             attention_mask = torch.ones((N, P + S), dtype=torch.float32, device=dev)
-        if attention_mask.dim() != 2:
-            raise NotImplementedError("only 2-D key-padding masks are implemented for BertImgModel "
-                                      "(3-D masks are built internally by SeqBertImgModel)")
-        if attention_mask.shape[1] == S and P > 0:
-            attention_mask = torch.cat([torch.ones((N, P), dtype=attention_mask.dtype, device=dev), attention_mask], -1)
-        if attention_mask.shape[1] != P + S:
-            raise ValueError("attention_mask has %d keys, expected P+S = %d" % (attention_mask.shape[1], P + S))
-        kbias = E.make_key_bias(attention_mask)
+        kbias, cbits, cwords = _prepare_mask(attention_mask, N, S, P, dev)
         ps, names, params = self._store()
-        run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P)
+        run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P,
+                         cbits=cbits, cwords=cwords)
+        run.dense_mask = cbits is not None
         run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
                                cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 1 << 20)
         run.keep_attn = bool(getattr(self, "materialise_attentions", False))
@@ -410,12 +435,6 @@ class BertImgModel_gtToken(_EncoderModelBase):
         dev = input_ids.device
         if attention_mask is None:
             attention_mask = torch.ones((N, P + S), dtype=torch.float32, device=dev)
-        if attention_mask.dim() != 2:
-            raise NotImplementedError("only 2-D key-padding masks are implemented for BertImgModel_gtToken")
-        if attention_mask.shape[1] == S and P > 0:
-            attention_mask = torch.cat([torch.ones((N, P), dtype=attention_mask.dtype, device=dev), attention_mask], -1)
-        if attention_mask.shape[1] != P + S:
-            raise ValueError("attention_mask has %d keys, expected P+S = %d" % (attention_mask.shape[1], P + S))
         extra = None
         if img_feats is not None:
             if img_pos_feat is None or tuple(img_pos_feat.shape) != (N, R, 7):
@@ -423,10 +442,11 @@ class BertImgModel_gtToken(_EncoderModelBase):
             if img_token_type_ids is None:
                 img_token_type_ids = torch.zeros((N, R), dtype=torch.int64, device=dev)
             extra = (img_pos_feat, img_token_type_ids)
-        kbias = E.make_key_bias(attention_mask)
+        kbias, cbits, cwords = _prepare_mask(attention_mask, N, S, P, dev)
         ps, names, params = self._store()
         run = EncoderRun(ps, names, engine_cfg(self.config), input_ids, token_type_ids, position_ids, img_feats, kbias, P,
-                         img_extra=extra)
+                         img_extra=extra, cbits=cbits, cwords=cwords)
+        run.dense_mask = cbits is not None
         run.drop = E.make_drop(self.training, cfg_get(self.config, "hidden_dropout_prob", 0.0),
                                cfg_get(self.config, "attention_probs_dropout_prob", 0.0), dev, 8 << 20)
         run.keep_attn = bool(getattr(self, "materialise_attentions", False))

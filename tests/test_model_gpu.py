@@ -487,6 +487,52 @@ def test_global_enc_without_img_layernorm_matches_oracle():
     assert max(errs.values()) < 5e-2, errs
 
 
+@pytest.mark.parametrize("T,R", [(20, 6), (150, 60)])       # persistent kernel (S <= 192) / tiled kernels (S = 210)
+def test_global_enc_3d_attention_mask_matches_oracle(T, R):
+    """``BertImgModel.forward`` with a 3-D ``[N, S, S]`` query-by-key mask (modeling_transfomres.py:630-631): the mask
+    is packed to one bit per (query, key) and evaluated inside the attention kernels; forward + gradients against the
+    restatement, which adds the reference's (1 - mask) * -10000."""
+    B = 1
+    cfg = BertConfig(vocab_size=CFG["vocab_size"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                     num_hidden_layers=2)
+    m = BertImgModel(cfg)
+    sd = params.fill_params({k: v for k, v in m.state_dict().items()}, 11)
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    b = synth.make_batch(B=B, T=T, R=R, seed=13)
+    bd = synth.to_device(b, DEV)
+    N, S = 4 * B, T + R
+    g = torch.Generator().manual_seed(3)
+    mask = (torch.rand(N, S, S, generator=g) < 0.6).float()
+    mask[:, torch.arange(S), torch.arange(S)] = 1.0          # every query sees itself
+    mask[1, 3] = 0.0                                         # one row with no visible key: uniform over all keys
+    mask[2, :, S - 5:] = 0.0                                 # keys nobody sees
+    out, pool = m(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=mask.to(DEV),
+                  img_feats=bd["img_feat"])[:2]
+    w_out = torch.randn(out.shape, generator=g)
+    (out.float() * w_out.to(DEV)).sum().backward()
+    sdr = {"global_enc." + k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    cfg_r = dict(CFG, num_hidden_layers=2)
+    o, p_, _ = restate.global_enc_forward(sdr, cfg_r, b["input_ids"], b["token_type_ids"], mask, b["img_feat"])
+    (o * w_out).sum().backward()
+    assert float((out.float().cpu() - o).abs().max()) < 3e-2
+    assert float((pool.float().cpu() - p_).abs().max()) < 2e-2
+    named = dict(m.named_parameters())
+    errs = {k: l2err(named[k].grad, sdr["global_enc." + k].grad)
+            for k in ("img_embedding.weight", "encoder.layer.0.attention.self.query.weight",
+                      "encoder.layer.0.attention.self.value.weight", "encoder.layer.1.attention.self.key.weight")}
+    print("3-D mask grad rel-L2 err:", {k: round(v, 4) for k, v in errs.items()})
+    assert max(errs.values()) < 5e-2, errs
+    # a 3-D mask together with prefix states is refused, a wrong shape is a ValueError
+    hist = [torch.zeros(N, 2, 768, device=DEV) for _ in range(2)]
+    with pytest.raises(NotImplementedError):
+        m(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=mask.to(DEV), img_feats=bd["img_feat"],
+          encoder_history_states=hist)
+    with pytest.raises(ValueError):
+        m(bd["input_ids"], token_type_ids=bd["token_type_ids"], attention_mask=mask[:, :-1].to(DEV),
+          img_feats=bd["img_feat"])
+
+
 def test_seq_enc_optional_residuals_match_oracle():
     """--add_residual / --add_local_residual (run_PMR_ModCR.py:574-575, 747-748): skip connections around the three
     cross-modal layers and from the input of layer 9 to the output (v10:212-223); forward and gradients against the
