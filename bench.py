@@ -92,14 +92,42 @@ def ncu_traffic(w):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / power / throttle reasons during the timed region: NVML polled every 10 ms when `pynvml` is there (the
+    same counters nvidia-smi prints, without a process spawn per sample), else `nvidia-smi` every 200 ms."""
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:                                   # local index -> physical index
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if idx < len(ids) and ids[idx].isdigit():
+                idx = int(ids[idx])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = int(get_reasons(h))
+            watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            self.rows.append([str(sm), str(mx), "%.1f" % watts] +
+                             ["Active" if bits & b else "Not Active" for b, _ in self.NVML_REASONS])
+            self._stop.wait(0.01)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:  # noqa: BLE001 -- no pynvml / NVML error: fall back to the nvidia-smi poll below
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -125,8 +153,9 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        watts = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), power_w=statistics.median(watts) if watts else None)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
