@@ -456,3 +456,26 @@ def test_restated_gttoken_region_embedding_matches_live_reference():
     assert float((ref[0] - seq).abs().max()) == 0.0 and float((ref[1] - pooled).abs().max()) == 0.0
     assert {"img_token_type_embeddings.weight", "img_pos_layer_norm.weight", "img_pos_layer_norm.bias", "img_pos_linear.weight",
             "img_pos_linear.bias"} <= set(sd.keys())
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present")
+def test_restated_3d_attention_mask_matches_live_reference():
+    """``BertImgModel.forward`` with a 3-D ``[N, S, S]`` mask (modeling/modeling_transfomres.py:630-631): the restatement
+    the GPU test ``test_global_enc_3d_attention_mask_matches_oracle`` compares against, pinned to the live class."""
+    ns = ref_shim.load()
+    cfg = ref_shim.make_config(ns, num_hidden_layers=2, output_attentions=False)
+    m = ns.tfm.BertImgModel(cfg)
+    sd = params.fill_params(m.state_dict(), 11)
+    m.load_state_dict(sd)
+    m.eval()
+    b = synth.make_batch(B=1, T=20, R=6, seed=13)
+    N, S = b["input_ids"].shape[0], 26
+    g = torch.Generator().manual_seed(3)
+    mask = (torch.rand(N, S, S, generator=g) < 0.6).float()
+    mask[:, torch.arange(S), torch.arange(S)] = 1.0
+    mask[1, 3] = 0.0                                          # a row with no visible key
+    with torch.no_grad():
+        ref = m(b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=mask, img_feats=b["img_feat"])
+        seq, pooled, _ = restate.global_enc_forward({k: v for k, v in sd.items()}, restate.default_cfg(num_hidden_layers=2),
+                                                    b["input_ids"], b["token_type_ids"], mask, b["img_feat"], None, pfx="")
+    assert float((ref[0] - seq).abs().max()) == 0.0 and float((ref[1] - pooled).abs().max()) == 0.0
