@@ -187,7 +187,7 @@ def oracle_step_fn(B, w, seed=88):
 
 
 REF_MAX_QUESTIONS = 8          # host-memory bound of the fp32 CPU path (dense [N,h,S,S] probabilities of 24 layers kept for backward)
-REF_BUDGET_S = 150.0           # the whole --steps K --warmup W run of the reference arm stays within a few minutes
+REF_BUDGET_S = float(os.environ.get("MODCR_REF_BUDGET_S", "150"))   # seconds of CPU work the reference arm may spend
 
 
 def run_reference(args):

@@ -190,3 +190,33 @@ def test_lr_schedules_match_transformers():
                 assert abs(ours - sch.get_last_lr()[0]) < 1e-12, (kind, warm, total, step)
                 opt.step()
                 sch.step()
+
+
+def test_bench_reference_arm_prints_the_contract_line_and_product_arm_refuses_the_cpu():
+    """`bench.py --impl reference` (the oracle port on the host cores, the one place besides tests / smoke that may run
+    `oracle/`): one JSON line with the same metric / unit / config dict as the product arm plus `impl`, `cpu_baseline`
+    and a zero-copy `e2e`.  The product arm itself must not fall back to the CPU."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, MODCR_REF_BUDGET_S="4", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
+    assert d["config"] == bench.config_dict(dict(bench.WORKLOADS["cfg2"]), 1, False)
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "questions" in cb["sample"]
+    assert d["e2e"] == dict(value=d["value"], unit=bench.UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    # the product arm: no device, no number
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
